@@ -1,0 +1,333 @@
+"""Generate golden fixtures by running the UNMODIFIED reference (NumPy path).
+
+Run in the dev container where /root/reference is mounted:
+
+    python tests/golden/make_golden.py
+
+Writes tests/golden/*.npz (inputs that are small + reference outputs).  Large inputs are
+regenerated from seeds by `oracle.numpy_oracle.synthetic_*`; a checksum of them is stored so a
+change in NumPy's generator stream would be detected.  Reference: qiskit-dynamics 0.6.0
+(/root/reference/qiskit_dynamics/VERSION.txt), imported through oracle/ref_shim.py.
+"""
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+import oracle.ref_shim as ref_shim  # noqa: E402
+
+if not ref_shim.reference_available():
+    raise SystemExit("reference not mounted at /root/reference; cannot regenerate goldens")
+
+from qiskit_dynamics import Signal, DiscreteSignal, solve_lmde, Solver  # noqa: E402
+from qiskit_dynamics.signals import SignalList, SignalSum  # noqa: E402
+from qiskit_dynamics.models import (  # noqa: E402
+    HamiltonianModel, LindbladModel, GeneratorModel, RotatingFrame)
+from qiskit_dynamics.models.operator_collections import (  # noqa: E402
+    OperatorCollection, LindbladCollection, VectorizedLindbladCollection)
+from qiskit_dynamics.solvers.fixed_step_solvers import get_fixed_step_sizes  # noqa: E402
+
+from oracle import numpy_oracle as orc  # noqa: E402
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"wrote {path}  ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
+def checksum(*arrays):
+    return np.array([np.sum(np.abs(a)) for a in arrays] + [np.sum(a).real for a in arrays])
+
+
+def sigs(spec):
+    return [Signal(a, nu, ph) for (a, nu, ph) in spec]
+
+
+# ---------------------------------------------------------------------------------------------
+def gen_collection():
+    rng = np.random.default_rng(342)
+    K, n, B = 5, 6, 7
+    ops = rng.standard_normal((K, n, n)) + 1j * rng.standard_normal((K, n, n))
+    stat = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    c_real = rng.standard_normal(K)
+    c_cplx = rng.standard_normal(K) + 1j * rng.standard_normal(K)
+    yv = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    ym = rng.standard_normal((n, B)) + 1j * rng.standard_normal((n, B))
+    full = OperatorCollection(static_operator=stat, operators=ops)
+    nostat = OperatorCollection(operators=ops)
+    onlystat = OperatorCollection(static_operator=stat)
+    save("collection", ops=ops, stat=stat, c_real=c_real, c_cplx=c_cplx, yv=yv, ym=ym,
+         eval_real=full.evaluate(c_real), eval_cplx=full.evaluate(c_cplx),
+         eval_nostat=nostat.evaluate(c_real), eval_onlystat=onlystat.evaluate(None),
+         rhs_v=full.evaluate_rhs(c_real, yv), rhs_m=full.evaluate_rhs(c_real, ym),
+         rhs_m_cplx=full.evaluate_rhs(c_cplx, ym), rhs_m_nostat=nostat(c_real, ym),
+         rhs_m_onlystat=onlystat(None, ym))
+
+
+def gen_frame():
+    rng = np.random.default_rng(4531)
+    n, B = 5, 3
+    H = orc.herm(rng, n) * 3
+    rf = RotatingFrame(H)
+    rf_anti = RotatingFrame(-1j * H)
+    rf1d = RotatingFrame(np.array([1.0, -0.5, 2.0, 0.25, 3.0]))
+    y = rng.standard_normal((n, B)) + 1j * rng.standard_normal((n, B))
+    op = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    sop = rng.standard_normal((n * n, n * n)) + 1j * rng.standard_normal((n * n, n * n))
+    t = 0.7312
+    save("frame", H=H, y=y, op=op, sop=sop, t=np.array(t), diag1d=np.array([1.0, -0.5, 2.0, 0.25, 3.0]),
+         frame_diag=rf.frame_diag, frame_basis=rf.frame_basis,
+         frame_diag_anti=rf_anti.frame_diag,
+         frame_diag_1d=rf1d.frame_diag,
+         into_fb=rf.state_into_frame(t, y, y_in_frame_basis=True, return_in_frame_basis=True),
+         outof_fb=rf.state_out_of_frame(t, y, y_in_frame_basis=True, return_in_frame_basis=True),
+         into_full=rf.state_into_frame(t, y),
+         outof_full=rf.state_out_of_frame(t, y),
+         op_into_fb=rf.operator_into_frame(t, op, operator_in_frame_basis=True, return_in_frame_basis=True),
+         op_into_full=rf.operator_into_frame(t, op),
+         op_outof_full=rf.operator_out_of_frame(t, op),
+         gen_into_full=rf.generator_into_frame(t, op),
+         gen_outof_full=rf.generator_out_of_frame(t, op),
+         gen_into_fb0=rf.generator_into_frame(0.0, op, return_in_frame_basis=True),
+         vec_into_fb=rf.vectorized_map_into_frame(t, sop, operator_in_frame_basis=True, return_in_frame_basis=True),
+         vec_into_full=rf.vectorized_map_into_frame(t, sop),
+         vec_basis=rf.vectorized_frame_basis,
+         state_into_basis=rf.state_into_frame_basis(y), state_outof_basis=rf.state_out_of_frame_basis(y),
+         op_into_basis=rf.operator_into_frame_basis(op), op_outof_basis=rf.operator_out_of_frame_basis(op),
+         into_1d=rf1d.state_into_frame(t, y), op_into_1d=rf1d.operator_into_frame(t, op))
+
+
+def gen_signals():
+    ts = np.array([0.0, 0.05, 0.1, 0.1 + 1e-17, 0.2, 0.29999999999999993, 0.3, 0.30000000000000004,
+                   0.31, -0.01, 1.0, 1.2, 1.5555555555555556, 2.9, 3.3])
+    samples = np.array([1.0, 2.0, 3.0 + 1j])
+    d1 = DiscreteSignal(dt=0.1, samples=samples, carrier_freq=1.3, phase=0.2)
+    d2 = DiscreteSignal(dt=0.1, samples=samples, start_time=1.0, carrier_freq=0.0)
+    s1 = Signal(0.7, 2.0, 0.4)
+    s2 = Signal(lambda t: np.exp(-t**2) * (1 + 0.5j), carrier_freq=0.9, phase=-1.1)
+    s3 = Signal(1.5)
+    ssum = s1 + s2
+    sprod = s1 * s2
+    dprod = d1 * d1
+    sl = SignalList([s1, s2, s3, d1, d2, ssum, 2.0])
+    # accumulated stage times with dt = 1/4.5, h = dt/2 (bin-edge trap)
+    dt = 1 / 4.5
+    h = dt / 2
+    tacc = [0.0]
+    for _ in range(20):
+        tacc.append(tacc[-1] + h)
+    tacc = np.array(tacc)
+    rng = np.random.default_rng(7)
+    dsamp = rng.standard_normal(8) + 1j * rng.standard_normal(8)
+    d3 = DiscreteSignal(dt=dt, samples=dsamp, carrier_freq=0.4)
+    save("signals", ts=ts, samples=samples,
+         d1=d1(ts), d1_cv=d1.complex_value(ts), d2=d2(ts), s1=s1(ts), s2=s2(ts), s2_cv=s2.complex_value(ts),
+         s3=s3(ts), ssum=ssum(ts), sprod=sprod(ts), dprod=dprod(ts),
+         siglist=sl(ts), siglist_scalar=sl(0.123), siglist_cv=sl.complex_value(ts),
+         drift=sl.drift, tacc=tacc, dsamp=dsamp, d3_acc=d3(tacc), d3_env_acc=d3.envelope(tacc),
+         conj_d1=d1.conjugate().complex_value(ts))
+
+
+def gen_step_grid():
+    cases = [([0.0, 1.0], None, 0.1), ([0.0, 1.0], None, 0.3), ([0.0, 1.0], [0.25, 0.5, 0.9], 0.1),
+             ([1.0, 0.0], [0.75, 0.5], 0.2), ([0.0, 1.0], None, 1e-3), ([0.0, 0.05], None, 1e-3),
+             ([0.0, 10.0], None, 1e-3), ([0.0, 1.0], [0.0, 0.5, 1.0], 0.11), ([0.0, 0.2], None, 1e-2),
+             ([0.0, 1.0], None, 5.0)]
+    out = {}
+    for i, (span, ev, mdt) in enumerate(cases):
+        t_list, h_list, n_list = get_fixed_step_sizes(span, ev, mdt)
+        out[f"span{i}"] = np.array(span)
+        out[f"eval{i}"] = np.array([]) if ev is None else np.array(ev)
+        out[f"has_eval{i}"] = np.array(ev is not None)
+        out[f"maxdt{i}"] = np.array(mdt)
+        out[f"t{i}"] = np.array(t_list)
+        out[f"h{i}"] = np.array(h_list)
+        out[f"n{i}"] = np.array(n_list)
+    out["ncases"] = np.array(len(cases))
+    save("step_grid", **out)
+
+
+def gen_hamiltonian_model():
+    n, K, B = 8, 3, 5
+    H0, Hs, Y, sig = orc.synthetic_schrodinger(n, K, B, 99)
+    out = dict(H0=H0, Hs=Hs, Y=Y, sig=np.array(sig), ts=np.array([0.0, 0.37, 2.5]))
+    for frame_name, frame in (("none", None), ("full", H0), ("diag", np.diag(H0).real)):
+        m = HamiltonianModel(static_operator=H0, operators=Hs, signals=sigs(sig), rotating_frame=frame)
+        for fb in (False, True):
+            m.in_frame_basis = fb
+            for i, t in enumerate(out["ts"]):
+                out[f"rhs_{frame_name}_fb{int(fb)}_{i}"] = m(t, Y)
+                out[f"gen_{frame_name}_fb{int(fb)}_{i}"] = m(t)
+            out[f"rhsvec_{frame_name}_fb{int(fb)}"] = m(0.37, Y[:, 0])
+        m.in_frame_basis = True
+        out[f"stat_{frame_name}"] = (np.zeros((n, n), complex) if m._operator_collection.static_operator is None
+                                     else m._operator_collection.static_operator)
+        out[f"ops_{frame_name}"] = m._operator_collection.operators
+    # no static operator, frame only
+    m = HamiltonianModel(operators=Hs, signals=sigs(sig), rotating_frame=H0, in_frame_basis=True)
+    out["rhs_nostatic"] = m(0.37, Y)
+    out["stat_nostatic"] = m._operator_collection.static_operator
+    # GeneratorModel (no -i fold), non-Hermitian generator
+    rng = np.random.default_rng(5)
+    Gs = rng.standard_normal((K, n, n)) + 1j * rng.standard_normal((K, n, n))
+    Gd = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    gm = GeneratorModel(static_operator=Gd, operators=Gs, signals=sigs(sig), rotating_frame=-1j * H0)
+    out["Gs"] = Gs
+    out["Gd"] = Gd
+    out["genmodel_rhs"] = gm(0.37, Y)
+    out["genmodel_gen"] = gm(0.37)
+    save("hamiltonian_model", **out)
+
+
+def gen_rk4_solves():
+    out = {}
+    # cfg1: 2-qubit, 1 Rabi drive, RK4, T shortened to 1.0 for fixture size
+    X = np.array([[0, 1], [1, 0]], dtype=complex)
+    Z = np.diag([1.0, -1.0]).astype(complex)
+    I2 = np.eye(2, dtype=complex)
+    H0 = 2 * np.pi * 5 * (np.kron(Z, I2) + np.kron(I2, Z)) / 2
+    H1 = 2 * np.pi * 0.1 * np.kron(X, I2) / 2
+    y0 = np.array([1.0, 0, 0, 0], dtype=complex)
+    m = HamiltonianModel(static_operator=H0, operators=[H1], signals=[Signal(1.0, 5.0)], rotating_frame=H0)
+    r = solve_lmde(m, t_span=[0, 10.0], y0=y0, method="RK4", max_dt=1e-3)
+    out["cfg1_H0"], out["cfg1_H1"], out["cfg1_y0"], out["cfg1_y"] = H0, H1, y0, r.y
+    # same through Solver.solve with array y0 (plumbing)
+    s = Solver(static_hamiltonian=H0, hamiltonian_operators=[H1], rotating_frame=H0)
+    r2 = s.solve(t_span=[0, 10.0], y0=y0, signals=[Signal(1.0, 5.0)], method="RK4", max_dt=1e-3)
+    out["cfg1_solver_y"] = r2.y
+
+    # cfg4-like: n=128, K=8, B=8 columns, 50 steps, frame = H0
+    n, K, B = 128, 8, 8
+    H0, Hs, Y, sig = orc.synthetic_schrodinger(n, K, B, 2004)
+    out["cfg4_check"] = checksum(H0, Hs, Y)
+    m = HamiltonianModel(static_operator=H0, operators=Hs, signals=sigs(sig), rotating_frame=H0)
+    r = solve_lmde(m, t_span=[0, 0.05], y0=Y, method="RK4", max_dt=1e-3)
+    out["cfg4_y"] = r.y[-1]
+    m.in_frame_basis = True
+    out["cfg4_rhs_fb"] = np.array([m(t, Y) for t in (0.0, 0.0135, 0.05)])
+    m.in_frame_basis = False
+    # t_eval + intermediate results, and a single RK4 step
+    r = solve_lmde(m, t_span=[0, 0.02], y0=Y, method="RK4", max_dt=1e-3, t_eval=[0.0, 0.005, 0.0125, 0.02])
+    out["cfg4_teval_t"], out["cfg4_teval_y"] = np.array(r.t), r.y
+    r = solve_lmde(m, t_span=[0, 1e-3], y0=Y, method="RK4", max_dt=1e-3)
+    out["cfg4_onestep_y"] = r.y[-1]
+    # backwards integration
+    r = solve_lmde(m, t_span=[0.02, 0.0], y0=Y, method="RK4", max_dt=1e-3)
+    out["cfg4_back_y"] = r.y[-1]
+
+    # cfg2-like sweep: n=32, K=8, B=16 per-column amplitudes a_{b,j} = a_j (0.5 + b/B), single y0
+    n, K, B = 32, 8, 16
+    H0, Hs, Y, sig = orc.synthetic_schrodinger(n, K, 1, 2002)
+    out["cfg2_check"] = checksum(H0, Hs, Y)
+    m = HamiltonianModel(static_operator=H0, operators=Hs, rotating_frame=H0)
+    cols = []
+    for b in range(B):
+        m.signals = [Signal(a * (0.5 + b / B), nu, ph) for (a, nu, ph) in sig]
+        r = solve_lmde(m, t_span=[0, 0.1], y0=Y[:, 0], method="RK4", max_dt=1e-3)
+        cols.append(r.y[-1])
+    out["cfg2_y"] = np.stack(cols, axis=-1)
+
+    # odd dimension (padding path): n=5, K=2, B=3, no frame / 1-d frame
+    n, K, B = 5, 2, 3
+    H0, Hs, Y, sig = orc.synthetic_schrodinger(n, K, B, 11)
+    out["odd_H0"], out["odd_Hs"], out["odd_Y"], out["odd_sig"] = H0, Hs, Y, np.array(sig)
+    m = HamiltonianModel(static_operator=H0, operators=Hs, signals=sigs(sig))
+    out["odd_noframe_y"] = solve_lmde(m, t_span=[0, 0.5], y0=Y, method="RK4", max_dt=0.01).y[-1]
+    m = HamiltonianModel(static_operator=H0, operators=Hs, signals=sigs(sig), rotating_frame=np.diag(H0).real)
+    out["odd_diagframe_y"] = solve_lmde(m, t_span=[0, 0.5], y0=Y, method="RK4", max_dt=0.01).y[-1]
+    out["odd_vec_y"] = solve_lmde(m, t_span=[0, 0.5], y0=Y[:, 0], method="RK4", max_dt=0.01).y[-1]
+    # square y0 (propagator) as in test_fixed_step_solvers
+    out["odd_eye_y"] = solve_lmde(m, t_span=[0, 0.5], y0=np.eye(n, dtype=complex), method="RK4", max_dt=0.01).y[-1]
+    # expm stepper on the Hamiltonian model
+    out["odd_expm_y"] = solve_lmde(m, t_span=[0, 0.5], y0=Y, method="scipy_expm", max_dt=0.01).y[-1]
+    m = HamiltonianModel(static_operator=H0, operators=Hs, signals=sigs(sig), rotating_frame=H0)
+    out["odd_expm_fullframe_y"] = solve_lmde(m, t_span=[0, 0.5], y0=Y, method="scipy_expm", max_dt=0.01).y[-1]
+
+    # DiscreteSignal drive with max_dt = sample width: every stage time on a bin edge (A.4)
+    n, K, B = 6, 2, 4
+    H0, Hs, Y, _ = orc.synthetic_schrodinger(n, K, B, 21)
+    dt = 1 / 4.5
+    rng = np.random.default_rng(22)
+    samp = rng.standard_normal((K, 9)) + 1j * rng.standard_normal((K, 9))
+    dsigs = [DiscreteSignal(dt=dt, samples=samp[j], carrier_freq=0.3 * (j + 1), phase=0.1 * j) for j in range(K)]
+    out["disc_H0"], out["disc_Hs"], out["disc_Y"], out["disc_samples"], out["disc_dt"] = H0, Hs, Y, samp, np.array(dt)
+    m = HamiltonianModel(static_operator=H0, operators=Hs, signals=dsigs, rotating_frame=H0)
+    out["disc_y"] = solve_lmde(m, t_span=[0, 2.0], y0=Y, method="RK4", max_dt=dt / 2).y[-1]
+    m2 = HamiltonianModel(static_operator=H0, operators=Hs, signals=dsigs)
+    out["disc_noframe_y"] = solve_lmde(m2, t_span=[0, 2.0], y0=Y, method="RK4", max_dt=dt / 2).y[-1]
+    save("rk4_solves", **out)
+
+
+def gen_lindblad():
+    out = {}
+    # small: n=3, 2 ham ops, 2 static + 2 time-dependent dissipators
+    n, K, B = 3, 2, 4
+    H0, Hs, Ls, Y, sig = orc.synthetic_lindblad(n, K, 4, B, 31)
+    Lstat, Ldyn = Ls[:2], Ls[2:] + 0.02j * Ls[:2]
+    dsig = [(0.3, 0.0, 0.0), (0.2, 0.11, 0.4)]
+    out.update(s_H0=H0, s_Hs=Hs, s_Lstat=Lstat, s_Ldyn=Ldyn, s_Y=Y, s_sig=np.array(sig), s_dsig=np.array(dsig))
+    for frame_name, frame in (("none", None), ("full", H0), ("diag", np.diag(H0).real)):
+        kw = dict(static_hamiltonian=H0, hamiltonian_operators=Hs, hamiltonian_signals=sigs(sig),
+                  static_dissipators=Lstat, dissipator_operators=Ldyn, dissipator_signals=sigs(dsig),
+                  rotating_frame=frame)
+        mv = LindbladModel(vectorized=True, **kw)
+        mm = LindbladModel(vectorized=False, **kw)
+        t = 0.41
+        for fb in (False, True):
+            mv.in_frame_basis = fb
+            mm.in_frame_basis = fb
+            out[f"s_vec_gen_{frame_name}_fb{int(fb)}"] = mv(t)
+            out[f"s_vec_rhs_{frame_name}_fb{int(fb)}"] = mv(t, Y)
+            rho = Y.T.reshape(B, n, n, order="F")[:, :, :]
+            rho = np.array([Y[:, b].reshape(n, n, order="F") for b in range(B)])
+            out[f"s_mat_rhs_{frame_name}_fb{int(fb)}"] = mm(t, rho)
+            out[f"s_mat_rhs1_{frame_name}_fb{int(fb)}"] = mm(t, rho[0])
+        mv.in_frame_basis = False
+        mm.in_frame_basis = False
+        out[f"s_expm_{frame_name}"] = solve_lmde(mv, t_span=[0, 0.5], y0=Y, method="scipy_expm", max_dt=0.05).y[-1]
+        out[f"s_rk4_{frame_name}"] = solve_lmde(mv, t_span=[0, 0.5], y0=Y, method="RK4", max_dt=0.01).y[-1]
+        rho = np.array([Y[:, b].reshape(n, n, order="F") for b in range(B)])
+        out[f"s_rk4_mat_{frame_name}"] = solve_lmde(mm, t_span=[0, 0.5], y0=rho, method="RK4", max_dt=0.01).y[-1]
+        mv.in_frame_basis = True
+        oc = mv._operator_collection._operator_collection
+        out[f"s_super_static_{frame_name}"] = oc.static_operator
+        out[f"s_super_ops_{frame_name}"] = oc.operators
+    # collection-level goldens (non-vectorised LindbladCollection with batch of rho)
+    lc = LindbladCollection(static_hamiltonian=H0, hamiltonian_operators=Hs, static_dissipators=Lstat,
+                            dissipator_operators=Ldyn)
+    rho = np.array([Y[:, b].reshape(n, n, order="F") for b in range(B)])
+    hc, dc = np.array([0.3, -0.7]), np.array([0.25, 0.4])
+    out["s_hc"], out["s_dc"] = hc, dc
+    out["s_coll_rhs"] = lc.evaluate_rhs(hc, dc, rho)
+    out["s_coll_rhs_hamonly"] = LindbladCollection(static_hamiltonian=H0, hamiltonian_operators=Hs).evaluate_rhs(hc, None, rho)
+    out["s_coll_rhs_statdis"] = LindbladCollection(static_hamiltonian=H0, static_dissipators=Lstat).evaluate_rhs(None, None, rho)
+    vc = VectorizedLindbladCollection(static_hamiltonian=H0, hamiltonian_operators=Hs, static_dissipators=Lstat,
+                                      dissipator_operators=Ldyn)
+    out["s_vcoll_eval"] = vc.evaluate(hc, dc)
+    out["s_vcoll_rhs"] = vc.evaluate_rhs(hc, dc, Y)
+
+    # cfg3-like: n=27 (729), 3 ham ops, 6 static dissipators, B=4, frame = diag(H0) (1-d), expm, 3 steps
+    n, K, B = 27, 3, 4
+    H0, Hs, Ls, Y, sig = orc.synthetic_lindblad(n, K, 6, B, 2003)
+    out["cfg3_check"] = checksum(H0, Hs, Ls, Y)
+    mv = LindbladModel(static_hamiltonian=H0, hamiltonian_operators=Hs, hamiltonian_signals=sigs(sig),
+                       static_dissipators=Ls, rotating_frame=np.diag(H0).real, vectorized=True)
+    out["cfg3_expm_y"] = solve_lmde(mv, t_span=[0, 0.03], y0=Y, method="scipy_expm", max_dt=1e-2).y[-1]
+    out["cfg3_rhs"] = mv(0.013, Y)
+    save("lindblad", **out)
+
+
+if __name__ == "__main__":
+    gen_collection()
+    gen_frame()
+    gen_signals()
+    gen_step_grid()
+    gen_hamiltonian_model()
+    gen_rk4_solves()
+    gen_lindblad()
