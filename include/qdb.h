@@ -1,0 +1,152 @@
+/*
+ * qdb.h -- C-ABI of libqdb.so, the B200 (sm_100a) time-evolution hot path.
+ *
+ * The reference (qiskit-dynamics 0.6.0) is pure Python and has no FFI of its own; the seams
+ * this library sits behind are its two string-selected factories and the model call protocol
+ * (SURVEY.md section 8(b)).  Every entry point below names the reference code it replaces
+ * (paths relative to /root/reference/qiskit_dynamics/).  The Python binding a reference
+ * maintainer would add is shown in INTEGRATION.md (ctypes, no torch types cross this boundary).
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers owned by the caller unless a parameter says "host".
+ *   - complex128 = interleaved (re, im) doubles ("qdb_c128"); matrices are row-major.
+ *   - A state batch y is (n, B): row i = basis component, B columns contiguous, leading
+ *     dimension ldy >= B (in complex elements).  This is the reference's own layout
+ *     (models/operator_collections.py:124-134: `G @ y`, batch = columns).
+ *   - Frame phases: mu[a] (real, length n) are the frame frequencies of row a.  The kernels use
+ *     p_a(t) = exp(-i mu_a t); RHS = conj(p) .* (G (p .* y)); generator = G .* outer(conj p, p)
+ *     (models/rotating_frame.py:255,350-353; vectorised states: :568-577, mu_{i+k n} = lam_i - lam_k).
+ *     mu == NULL means "no rotating frame".
+ *   - Functions enqueue work on `stream` (a cudaStream_t passed as void*), never synchronise
+ *     the device, never allocate persistent memory and never throw.  Scratch memory is passed
+ *     in by the caller (size from qdb_workspace_bytes).
+ *   - Return value: 0 = OK, negative = invalid argument (QDB_E_*), positive = cudaError_t.
+ *     qdb_last_error_string() gives the text of the last failure on the calling thread.
+ */
+#ifndef QDB_H
+#define QDB_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { double re, im; } qdb_c128;
+
+#define QDB_OK 0
+#define QDB_E_ARG (-1)        /* bad dimension / NULL pointer / unsupported flag */
+#define QDB_E_WORKSPACE (-2)  /* workspace too small */
+#define QDB_E_UNSUPPORTED (-3)/* shape outside what this build supports */
+
+/* layouts of an (n x n) operator in device memory */
+#define QDB_LAYOUT_ROWMAJOR 0 /* [n][n] */
+#define QDB_LAYOUT_PACKED 1   /* DMMA A-fragment order, zero padded to npad = 8*ceil(n/8):
+                                 element (r,c) at ((r/8)*(npad/4) + c/4)*32 + (r%8)*4 + c%4 */
+
+/* workspace kinds for qdb_workspace_bytes */
+#define QDB_WS_RHS 0
+#define QDB_WS_RK4 1
+#define QDB_WS_EXPM 2
+
+const char* qdb_last_error_string(void);
+int qdb_version(void);
+
+/* n rounded up to the DMMA tile (8) and the element count of one packed operator (npad*npad). */
+int qdb_npad(int n);
+size_t qdb_packed_elems(int n);
+
+/* Bytes of scratch the steppers need.  S = number of steps handled per call (the RK4 stepper
+ * accepts any workspace >= the S=1 size and chunks the step loop to fit). */
+size_t qdb_workspace_bytes(int kind, int n, int K, int B, int S);
+
+/* Re-order `count` row-major (n x n) operators into QDB_LAYOUT_PACKED (one-time, at model
+ * construction).  Replaces nothing in the reference; it is the HBM layout of
+ * OperatorCollection._operators / _static_operator (models/operator_collections.py:73-81). */
+int qdb_pack_operators(int n, int count, const qdb_c128* src, qdb_c128* dst, void* stream);
+
+/* a1 + a5: generator table.  For each of the T times
+ *     out[t] = scale * (stat + sum_j coeff[t][j] * ops[j]) .* outer(conj p(t), p(t))
+ * ops/stat/out all in `layout`.  coeff is [T][K] real, or [T][K] complex when coeff_complex != 0.
+ * stat or ops may be NULL (K = 0), not both.  times may be NULL when mu is NULL.
+ * Replaces OperatorCollection.evaluate (models/operator_collections.py:101-122 ->
+ * arraylias/register_functions/linear_combo.py:30-32) and RotatingFrame.operator_into_frame in
+ * the frame basis (models/rotating_frame.py:350-353), i.e. GeneratorModel.evaluate
+ * (models/generator_model.py:256-279) and LindbladModel.evaluate (models/lindblad_model.py:436-475). */
+int qdb_generator_c128(int n, int K, int T, int layout,
+                       const qdb_c128* ops, const qdb_c128* stat,
+                       const double* coeff, int coeff_complex,
+                       const double* mu, const double* times, double scale,
+                       qdb_c128* out, void* stream);
+
+/* General complex GEMM with the fused pro/epilogues the path needs:
+ *     C[m][b] = beta * C[m][b] + alpha * colscale[b] * post[m] * sum_k A[m][k] * pre[k] * Bm[k][b]
+ * colscale (real, length N), pre (length Kd) and post (length M) may each be NULL (= 1).
+ * Replaces np.matmul in _matmul (models/operator_collections.py:31-32,134), the frame-basis
+ * changes U^dag y0 / U y (solvers/solver_functions.py:396-403,436-448) and the products inside
+ * scipy.linalg.expm (solvers/fixed_step_solvers.py:22,104). */
+int qdb_zgemm_c128(int M, int N, int Kd,
+                   const qdb_c128* A, int lda, const qdb_c128* Bm, int ldb,
+                   qdb_c128* C, int ldc, qdb_c128 alpha, qdb_c128 beta,
+                   const double* colscale, const qdb_c128* pre, const qdb_c128* post,
+                   void* stream);
+
+/* a1 + a2 + a3 fused: one RHS evaluation  y_out = conj(p) .* ((stat + sum_j c_j ops_j)(p .* y_in)).
+ * coeff_per_col == 0: coeff is [K] (shared by all columns);
+ * coeff_per_col == 1: coeff is [K][ldc] real, column b uses coeff[j][b] ("sweep mode" -- the
+ *                     reference reaches this only through its sequential list-of-simulations loop,
+ *                     solvers/solver_classes.py:556-590).
+ * ops/stat row-major.  Replaces GeneratorModel.evaluate_rhs (models/generator_model.py:281-316),
+ * OperatorCollection.evaluate_rhs (models/operator_collections.py:124-134) and
+ * RotatingFrame.state_into_frame/state_out_of_frame (models/rotating_frame.py:225-284). */
+int qdb_rhs_c128(int n, int K, int B,
+                 const qdb_c128* ops, const qdb_c128* stat,
+                 const double* coeff, int coeff_per_col, int ldc,
+                 const double* mu, double t,
+                 const qdb_c128* y_in, qdb_c128* y_out, int ldy,
+                 void* workspace, size_t ws_bytes, void* stream);
+
+/* a7 + a8 inner loop: S fixed RK4 steps of size h, state resident on chip.
+ *   times  : HOST pointer, [2S+1] stage times t_0, t_0+h/2, t_1, ... t_S built with the
+ *            reference's accumulation (solvers/fixed_step_solvers.py:448-454, :64-66)
+ *   coeff  : device, signal table.  sig_mode 0: [2S+1][K] shared; sig_mode 1: [2S+1][K][ldc]
+ *            per column (sweep).
+ *   ops_packed / stat_packed : QDB_LAYOUT_PACKED (sig_mode 1 and the on-chip path), plus the
+ *            row-major copies ops_rm / stat_rm used when n is too large for the on-chip path.
+ * Replaces RK4_solver.take_step + the fixed_step_solver_template loop
+ * (solvers/fixed_step_solvers.py:43-77,441-454) applied to GeneratorModel.evaluate_rhs. */
+int qdb_rk4_steps_c128(int n, int K, int B, int S,
+                       const qdb_c128* ops_rm, const qdb_c128* stat_rm,
+                       const qdb_c128* ops_packed, const qdb_c128* stat_packed,
+                       const double* coeff, int sig_mode, int ldc,
+                       const double* mu, const double* times_host, double h,
+                       qdb_c128* y, int ldy,
+                       void* workspace, size_t ws_bytes, void* stream);
+
+/* a9: S exponential (Magnus order 1) steps  y <- expm(h * G_frame(t_s + h/2)) y  with a
+ * scaling-and-squaring Taylor propagator built from qdb_zgemm_c128 products.
+ *   times_mid_host : HOST [S] midpoints t_s + h/2;  coeff : device [S][K] at those midpoints
+ *   squarings_host : HOST [S] number of squarings per step (chosen by the caller from a norm
+ *                    bound so that no device->host sync is needed inside the loop)
+ * Replaces get_exponential_take_step(magnus_order=1) + scipy.linalg.expm
+ * (solvers/fixed_step_solvers.py:343-346,400-401,104). */
+int qdb_expm_steps_c128(int n, int K, int B, int S,
+                        const qdb_c128* ops_rm, const qdb_c128* stat_rm,
+                        const double* coeff, const double* mu,
+                        const double* times_mid_host, const int* squarings_host, double h,
+                        qdb_c128* y, int ldy,
+                        void* workspace, size_t ws_bytes, void* stream);
+
+/* Matrix exponential of one (n x n) row-major matrix with `squarings` halvings (building block
+ * of qdb_expm_steps_c128, exported for parity tests against scipy.linalg.expm). */
+int qdb_expm_c128(int n, const qdb_c128* A, int squarings, qdb_c128* out,
+                  void* workspace, size_t ws_bytes, void* stream);
+
+/* Number of kernels this library has launched on the calling process since load (bench.py's
+ * "gpu_launches" evidence). */
+unsigned long long qdb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QDB_H */

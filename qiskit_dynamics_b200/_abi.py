@@ -1,0 +1,217 @@
+"""ctypes binding of libqdb.so (include/qdb.h).  PyTorch is used only as the owner of device
+memory and streams: every call passes raw device pointers + sizes, no torch types cross the ABI.
+
+There is NO fallback: if the shared library is missing, or a tensor is not a CUDA complex128 /
+float64 tensor, the call raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libqdb.so")
+
+LAYOUT_ROWMAJOR = 0
+LAYOUT_PACKED = 1
+WS_RHS, WS_RK4, WS_EXPM = 0, 1, 2
+
+
+class QdbError(RuntimeError):
+    """A libqdb call failed (message from qdb_last_error_string)."""
+
+
+class c128(ctypes.Structure):
+    _fields_ = [("re", ctypes.c_double), ("im", ctypes.c_double)]
+
+
+_vp, _i, _d, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size_t
+
+# name -> (restype, argtypes); the single source of truth checked against include/qdb.h in tests
+SIGNATURES = {
+    "qdb_last_error_string": (ctypes.c_char_p, []),
+    "qdb_version": (_i, []),
+    "qdb_npad": (_i, [_i]),
+    "qdb_packed_elems": (_sz, [_i]),
+    "qdb_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "qdb_pack_operators": (_i, [_i, _i, _vp, _vp, _vp]),
+    "qdb_generator_c128": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _d, _vp, _vp]),
+    "qdb_zgemm_c128": (_i, [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, c128, c128, _vp, _vp, _vp, _vp]),
+    "qdb_rhs_c128": (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _d, _vp, _vp, _i, _vp, _sz, _vp]),
+    "qdb_rk4_steps_c128": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _d, _vp, _i, _vp, _sz, _vp]),
+    "qdb_expm_steps_c128": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _i, _vp, _sz, _vp]),
+    "qdb_expm_c128": (_i, [_i, _vp, _i, _vp, _vp, _sz, _vp]),
+    "qdb_launch_count": (ctypes.c_ulonglong, []),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libqdb.so (once).  Raises QdbError when it has not been built -- no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise QdbError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  qiskit_dynamics_b200 has no CPU fallback."
+            )
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().qdb_last_error_string().decode()
+        raise QdbError(f"{what} failed (rc={rc}): {msg}")
+
+
+def _ptr(t: Optional[torch.Tensor], dtype, name: str):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise QdbError(f"{name}: expected a CUDA tensor (the B200 path has no CPU fallback), got {type(t).__name__}"
+                       + (f" on {t.device}" if isinstance(t, torch.Tensor) else ""))
+    if t.dtype != dtype:
+        raise QdbError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise QdbError(f"{name}: tensor must be contiguous")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+C = torch.complex128
+F = torch.float64
+
+
+def npad(n: int) -> int:
+    return (n + 7) & ~7
+
+
+def workspace_bytes(kind: int, n: int, K: int, B: int, S: int = 1) -> int:
+    return int(lib().qdb_workspace_bytes(kind, n, K, B, S))
+
+
+def launch_count() -> int:
+    return int(lib().qdb_launch_count())
+
+
+def pack_operators(ops: torch.Tensor) -> torch.Tensor:
+    """(count, n, n) row-major -> (count, npad*npad) DMMA-fragment order."""
+    count, n, _ = ops.shape
+    out = torch.empty((count, npad(n) ** 2), dtype=C, device=ops.device)
+    _check(lib().qdb_pack_operators(n, count, _ptr(ops, C, "ops"), _ptr(out, C, "out"), _stream()), "qdb_pack_operators")
+    return out
+
+
+def generator(n, ops, stat, coeff, mu, times, scale=1.0, layout=LAYOUT_ROWMAJOR, out=None):
+    """out[t] = scale * (stat + sum_j coeff[t,j] ops[j]) .* outer(conj p(t), p(t)); coeff (T,K)."""
+    K = 0 if ops is None else ops.shape[0]
+    if coeff is not None:
+        T = coeff.shape[0]
+    elif times is not None:
+        T = times.shape[0]
+    else:
+        T = 1
+    cplx = coeff is not None and coeff.dtype == C
+    elems = npad(n) ** 2 if layout == LAYOUT_PACKED else n * n
+    dev = (ops if ops is not None else stat).device
+    if out is None:
+        out = torch.empty((T, elems), dtype=C, device=dev)
+    _check(lib().qdb_generator_c128(n, K, T, layout, _ptr(ops, C, "ops"), _ptr(stat, C, "stat"),
+                                    _ptr(coeff, C if cplx else F, "coeff"), int(cplx), _ptr(mu, F, "mu"),
+                                    _ptr(times, F, "times"), float(scale), _ptr(out, C, "out"), _stream()),
+           "qdb_generator_c128")
+    return out
+
+
+def zgemm(A, Bm, out=None, alpha=1.0 + 0j, beta=0.0 + 0j, colscale=None, pre=None, post=None):
+    M, Kd = A.shape
+    Kd2, N = Bm.shape
+    if Kd != Kd2:
+        raise QdbError(f"zgemm: inner dimensions differ ({Kd} vs {Kd2})")
+    if out is None:
+        out = torch.empty((M, N), dtype=C, device=A.device)
+    a, b = complex(alpha), complex(beta)
+    _check(lib().qdb_zgemm_c128(M, N, Kd, _ptr(A, C, "A"), Kd, _ptr(Bm, C, "B"), N, _ptr(out, C, "C"), N,
+                                c128(a.real, a.imag), c128(b.real, b.imag), _ptr(colscale, F, "colscale"),
+                                _ptr(pre, C, "pre"), _ptr(post, C, "post"), _stream()), "qdb_zgemm_c128")
+    return out
+
+
+def rhs(n, ops, stat, coeff, mu, t, y, per_col=False, out=None, workspace=None):
+    """One fused RHS evaluation on y (n, B)."""
+    K = 0 if ops is None else ops.shape[0]
+    B = y.shape[1]
+    if out is None:
+        out = torch.empty_like(y)
+    need = workspace_bytes(WS_RHS, n, K, B)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=y.device)
+    ldc = coeff.shape[-1] if (per_col and coeff is not None) else 0
+    _check(lib().qdb_rhs_c128(n, K, B, _ptr(ops, C, "ops"), _ptr(stat, C, "stat"), _ptr(coeff, F, "coeff"),
+                              int(per_col), ldc, _ptr(mu, F, "mu"), float(t), _ptr(y, C, "y_in"), _ptr(out, C, "y_out"),
+                              B, ctypes.c_void_p(workspace.data_ptr()), workspace.numel(), _stream()), "qdb_rhs_c128")
+    return out
+
+
+def rk4_steps(n, ops_rm, stat_rm, ops_packed, stat_packed, coeff, mu, times_host: np.ndarray, h, y, S,
+              per_col=False, workspace=None, max_ws_bytes=1 << 30):
+    """S fused RK4 steps in place on y (n, B).  times_host: float64 numpy array [2S+1]."""
+    K = 0 if (ops_rm is None and ops_packed is None) else (ops_rm if ops_rm is not None else ops_packed).shape[0]
+    B = y.shape[1]
+    times_host = np.ascontiguousarray(times_host, dtype=np.float64)
+    if times_host.shape[0] != 2 * S + 1:
+        raise QdbError(f"rk4_steps: need {2 * S + 1} stage times, got {times_host.shape[0]}")
+    if workspace is None:
+        need = min(workspace_bytes(WS_RK4, n, K, B, S), max(max_ws_bytes, workspace_bytes(WS_RK4, n, K, B, 1)))
+        workspace = torch.empty(need, dtype=torch.uint8, device=y.device)
+    ldc = coeff.shape[-1] if (per_col and coeff is not None) else 0
+    _check(lib().qdb_rk4_steps_c128(n, K, B, S, _ptr(ops_rm, C, "ops_rm"), _ptr(stat_rm, C, "stat_rm"),
+                                    _ptr(ops_packed, C, "ops_packed"), _ptr(stat_packed, C, "stat_packed"),
+                                    _ptr(coeff, F, "coeff"), int(per_col), ldc, _ptr(mu, F, "mu"),
+                                    times_host.ctypes.data_as(ctypes.c_void_p), float(h), _ptr(y, C, "y"), B,
+                                    ctypes.c_void_p(workspace.data_ptr()), workspace.numel(), _stream()),
+           "qdb_rk4_steps_c128")
+    return y
+
+
+def expm_steps(n, ops_rm, stat_rm, coeff, mu, times_mid_host: np.ndarray, squarings_host: np.ndarray, h, y, S,
+               workspace=None):
+    K = 0 if ops_rm is None else ops_rm.shape[0]
+    B = y.shape[1]
+    times_mid_host = np.ascontiguousarray(times_mid_host, dtype=np.float64)
+    squarings_host = np.ascontiguousarray(squarings_host, dtype=np.int32)
+    need = workspace_bytes(WS_EXPM, n, K, B)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=y.device)
+    _check(lib().qdb_expm_steps_c128(n, K, B, S, _ptr(ops_rm, C, "ops_rm"), _ptr(stat_rm, C, "stat_rm"),
+                                     _ptr(coeff, F, "coeff"), _ptr(mu, F, "mu"),
+                                     times_mid_host.ctypes.data_as(ctypes.c_void_p),
+                                     squarings_host.ctypes.data_as(ctypes.c_void_p), float(h), _ptr(y, C, "y"), B,
+                                     ctypes.c_void_p(workspace.data_ptr()), workspace.numel(), _stream()),
+           "qdb_expm_steps_c128")
+    return y
+
+
+def expm(A: torch.Tensor, squarings: int, out=None):
+    n = A.shape[0]
+    if out is None:
+        out = torch.empty_like(A)
+    ws = torch.empty(6 * n * n * 16, dtype=torch.uint8, device=A.device)
+    _check(lib().qdb_expm_c128(n, _ptr(A, C, "A"), int(squarings), _ptr(out, C, "out"), ctypes.c_void_p(ws.data_ptr()),
+                               ws.numel(), _stream()), "qdb_expm_c128")
+    return out

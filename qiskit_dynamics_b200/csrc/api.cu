@@ -1,0 +1,308 @@
+// extern "C" entry points of libqdb.so (see include/qdb.h for the contract of each).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "qdb_common.cuh"
+
+namespace qdb {
+
+static thread_local char g_err[512] = "no error";
+static std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return (int)e;
+}
+
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+}  // namespace qdb
+
+using namespace qdb;
+
+static inline const double2* D2(const qdb_c128* p) { return reinterpret_cast<const double2*>(p); }
+static inline double2* D2(qdb_c128* p) { return reinterpret_cast<double2*>(p); }
+
+#define QDB_REQUIRE(cond, ...)      \
+    do {                            \
+        if (!(cond)) {              \
+            set_error(__VA_ARGS__); \
+            return QDB_E_ARG;       \
+        }                           \
+    } while (0)
+
+extern "C" {
+
+const char* qdb_last_error_string(void) { return g_err; }
+int qdb_version(void) { return 100; }
+int qdb_npad(int n) { return round_up8(n); }
+size_t qdb_packed_elems(int n) { return (size_t)round_up8(n) * round_up8(n); }
+unsigned long long qdb_launch_count(void) { return g_launches.load(); }
+
+size_t qdb_workspace_bytes(int kind, int n, int K, int B, int S) {
+    const size_t n2 = (size_t)n * n * sizeof(double2);
+    const size_t np2 = qdb_packed_elems(n) * sizeof(double2);
+    const size_t yb = (size_t)n * B * sizeof(double2);
+    if (S < 1) S = 1;
+    switch (kind) {
+        case QDB_WS_RHS:
+            return align_up(n2) + 2 * align_up((size_t)n * sizeof(double2));
+        case QDB_WS_RK4:
+            if (rk4_fused_supported(n))
+                return align_up((size_t)(2 * S + 1) * np2) + align_up((size_t)(2 * S + 1) * sizeof(double));
+            return 3 * align_up(n2) + 3 * align_up(yb) + align_up(3 * sizeof(double));
+        case QDB_WS_EXPM:
+            return 7 * align_up(n2) + align_up(yb);
+        default:
+            return 0;
+    }
+    (void)K;
+}
+
+int qdb_pack_operators(int n, int count, const qdb_c128* src, qdb_c128* dst, void* stream) {
+    QDB_REQUIRE(n >= 1 && count >= 0, "qdb_pack_operators: bad n=%d count=%d", n, count);
+    if (count == 0) return QDB_OK;
+    QDB_REQUIRE(src && dst, "qdb_pack_operators: null pointer");
+    return launch_pack(n, count, D2(src), D2(dst), (cudaStream_t)stream);
+}
+
+int qdb_generator_c128(int n, int K, int T, int layout, const qdb_c128* ops, const qdb_c128* stat,
+                       const double* coeff, int coeff_complex, const double* mu, const double* times,
+                       double scale, qdb_c128* out, void* stream) {
+    QDB_REQUIRE(n >= 1 && K >= 0 && T >= 0, "qdb_generator_c128: bad n=%d K=%d T=%d", n, K, T);
+    QDB_REQUIRE(layout == QDB_LAYOUT_ROWMAJOR || layout == QDB_LAYOUT_PACKED, "qdb_generator_c128: bad layout %d", layout);
+    QDB_REQUIRE(out, "qdb_generator_c128: null output");
+    QDB_REQUIRE(stat || (ops && K > 0), "qdb_generator_c128: neither static operator nor operators given");
+    QDB_REQUIRE(K == 0 || (ops && coeff), "qdb_generator_c128: K=%d but ops/coeff missing", K);
+    QDB_REQUIRE(!mu || times, "qdb_generator_c128: frame given without times");
+    if (T == 0) return QDB_OK;
+    return launch_generator(n, K, T, layout, D2(ops), D2(stat), coeff, coeff_complex, mu, times, 0.0, scale, D2(out),
+                            (cudaStream_t)stream);
+}
+
+int qdb_zgemm_c128(int M, int N, int Kd, const qdb_c128* A, int lda, const qdb_c128* Bm, int ldb, qdb_c128* C, int ldc,
+                   qdb_c128 alpha, qdb_c128 beta, const double* colscale, const qdb_c128* pre, const qdb_c128* post,
+                   void* stream) {
+    QDB_REQUIRE(M >= 0 && N >= 0 && Kd >= 0, "qdb_zgemm_c128: negative dimension");
+    if (M == 0 || N == 0) return QDB_OK;
+    QDB_REQUIRE(A && Bm && C, "qdb_zgemm_c128: null pointer");
+    QDB_REQUIRE(lda >= Kd && ldb >= N && ldc >= N, "qdb_zgemm_c128: leading dimension too small");
+    return launch_zgemm(M, N, Kd, D2(A), lda, D2(Bm), ldb, D2(C), ldc, make_double2(alpha.re, alpha.im),
+                        make_double2(beta.re, beta.im), colscale, D2(pre), D2(post), (cudaStream_t)stream);
+}
+
+int qdb_rhs_c128(int n, int K, int B, const qdb_c128* ops, const qdb_c128* stat, const double* coeff, int coeff_per_col,
+                 int ldc, const double* mu, double t, const qdb_c128* y_in, qdb_c128* y_out, int ldy, void* workspace,
+                 size_t ws_bytes, void* stream) {
+    QDB_REQUIRE(n >= 1 && K >= 0 && B >= 0, "qdb_rhs_c128: bad n=%d K=%d B=%d", n, K, B);
+    QDB_REQUIRE(stat || (ops && K > 0), "qdb_rhs_c128: neither static operator nor operators given");
+    QDB_REQUIRE(K == 0 || (ops && coeff), "qdb_rhs_c128: K=%d but ops/coeff missing", K);
+    if (B == 0) return QDB_OK;
+    QDB_REQUIRE(y_in && y_out && ldy >= B, "qdb_rhs_c128: bad state pointers / ldy");
+    QDB_REQUIRE(y_in != y_out, "qdb_rhs_c128: y_in and y_out must not alias");
+    if (ws_bytes < qdb_workspace_bytes(QDB_WS_RHS, n, K, B, 1) || !workspace) {
+        set_error("qdb_rhs_c128: workspace too small (%zu < %zu)", ws_bytes, qdb_workspace_bytes(QDB_WS_RHS, n, K, B, 1));
+        return QDB_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)workspace;
+    double2* G = (double2*)ws;
+    double2* pre = (double2*)(ws + align_up((size_t)n * n * sizeof(double2)));
+    double2* post = (double2*)((char*)pre + align_up((size_t)n * sizeof(double2)));
+    const double2 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0);
+    int rc;
+    if (!coeff_per_col) {
+        // G_frame(t) once (a1 + a5), then one GEMM (a2); the frame phases ride inside G_frame
+        rc = launch_generator(n, K, 1, QDB_LAYOUT_ROWMAJOR, D2(ops), D2(stat), coeff, 0, mu, nullptr, t, 1.0, G, st);
+        if (rc != QDB_OK) return rc;
+        return launch_zgemm(n, B, n, G, n, D2(y_in), ldy, D2(y_out), ldy, one, zero, nullptr, nullptr, nullptr, st);
+    }
+    QDB_REQUIRE(ldc >= B, "qdb_rhs_c128: ldc < B");
+    const double2 *prep = nullptr, *postp = nullptr;
+    if (mu) {
+        rc = launch_phase_vectors(n, mu, t, pre, post, st);
+        if (rc != QDB_OK) return rc;
+        prep = pre;
+        postp = post;
+    }
+    bool first = true;
+    if (stat) {
+        rc = launch_zgemm(n, B, n, D2(stat), n, D2(y_in), ldy, D2(y_out), ldy, one, zero, nullptr, prep, postp, st);
+        if (rc != QDB_OK) return rc;
+        first = false;
+    }
+    for (int j = 0; j < K; ++j) {
+        rc = launch_zgemm(n, B, n, D2(ops) + (size_t)j * n * n, n, D2(y_in), ldy, D2(y_out), ldy, one, first ? zero : one,
+                          coeff + (size_t)j * ldc, prep, postp, st);
+        if (rc != QDB_OK) return rc;
+        first = false;
+    }
+    return QDB_OK;
+}
+
+int qdb_rk4_steps_c128(int n, int K, int B, int S, const qdb_c128* ops_rm, const qdb_c128* stat_rm,
+                       const qdb_c128* ops_packed, const qdb_c128* stat_packed, const double* coeff, int sig_mode, int ldc,
+                       const double* mu, const double* times_host, double h, qdb_c128* y, int ldy, void* workspace,
+                       size_t ws_bytes, void* stream) {
+    QDB_REQUIRE(n >= 1 && K >= 0 && B >= 0 && S >= 0, "qdb_rk4_steps_c128: bad n=%d K=%d B=%d S=%d", n, K, B, S);
+    QDB_REQUIRE(sig_mode == 0 || sig_mode == 1, "qdb_rk4_steps_c128: bad sig_mode %d", sig_mode);
+    if (B == 0 || S == 0) return QDB_OK;
+    QDB_REQUIRE(y && ldy >= B, "qdb_rk4_steps_c128: bad state pointer / ldy");
+    QDB_REQUIRE(K == 0 || coeff, "qdb_rk4_steps_c128: K=%d but no signal table", K);
+    QDB_REQUIRE(!mu || times_host, "qdb_rk4_steps_c128: frame given without stage times");
+    QDB_REQUIRE(workspace, "qdb_rk4_steps_c128: null workspace");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)workspace;
+    const bool fused = rk4_fused_supported(n);
+    int rc;
+
+    if (fused) {
+        QDB_REQUIRE(stat_packed || (ops_packed && K > 0), "qdb_rk4_steps_c128: packed operators missing");
+        const size_t np2 = qdb_packed_elems(n);
+        if (sig_mode == 1) {
+            QDB_REQUIRE(ldc >= B, "qdb_rk4_steps_c128: ldc < B");
+            // only the stage times go to the device; operators are used as stored
+            const size_t need = align_up((size_t)(2 * S + 1) * sizeof(double));
+            if (ws_bytes < need) {
+                set_error("qdb_rk4_steps_c128: workspace too small (%zu < %zu)", ws_bytes, need);
+                return QDB_E_WORKSPACE;
+            }
+            double* times_dev = (double*)ws;
+            if (mu) QDB_CUDA(cudaMemcpyAsync(times_dev, times_host, (size_t)(2 * S + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
+            return launch_rk4_fused_sweep(n, K, B, S, D2(stat_packed), D2(ops_packed), coeff, ldc, mu, times_dev, h, D2(y), ldy, st);
+        }
+        // shared signals: chunk the step loop so that the generator table fits the workspace
+        const size_t per_entry = np2 * sizeof(double2);
+        size_t budget = ws_bytes;
+        // entries E = 2 Sc + 1 need E*per_entry (+align) + E*8 (+align)
+        long long max_entries = (long long)((budget - 2 * 256) / (per_entry + sizeof(double)));
+        int Sc_max = (int)((max_entries - 1) / 2);
+        if (Sc_max < 1) {
+            set_error("qdb_rk4_steps_c128: workspace too small (%zu < %zu)", ws_bytes, qdb_workspace_bytes(QDB_WS_RK4, n, K, B, 1));
+            return QDB_E_WORKSPACE;
+        }
+        if (Sc_max > S) Sc_max = S;
+        double2* table = (double2*)ws;
+        double* times_dev = (double*)(ws + align_up((size_t)(2 * Sc_max + 1) * per_entry));
+        for (int s0 = 0; s0 < S; s0 += Sc_max) {
+            const int Sc = (S - s0 < Sc_max) ? S - s0 : Sc_max;
+            const int T = 2 * Sc + 1;
+            if (mu) QDB_CUDA(cudaMemcpyAsync(times_dev, times_host + 2 * s0, (size_t)T * sizeof(double), cudaMemcpyHostToDevice, st));
+            rc = launch_generator(n, K, T, QDB_LAYOUT_PACKED, D2(ops_packed), D2(stat_packed),
+                                  coeff ? coeff + (size_t)2 * s0 * K : nullptr, 0, mu, times_dev, 0.0, 1.0, table, st);
+            if (rc != QDB_OK) return rc;
+            rc = launch_rk4_fused_shared(n, B, Sc, table, h, D2(y), ldy, st);
+            if (rc != QDB_OK) return rc;
+        }
+        return QDB_OK;
+    }
+
+    // ---- generic path for large n: one GEMM per stage with the RK4 combine fused in its epilogue ----
+    if (sig_mode == 1) {
+        set_error("qdb_rk4_steps_c128: per-column signals need n <= 256 (got %d)", n);
+        return QDB_E_UNSUPPORTED;
+    }
+    QDB_REQUIRE(stat_rm || (ops_rm && K > 0), "qdb_rk4_steps_c128: row-major operators missing");
+    QDB_REQUIRE(ldy == B, "qdb_rk4_steps_c128: generic path needs ldy == B");
+    if (ws_bytes < qdb_workspace_bytes(QDB_WS_RK4, n, K, B, 1)) {
+        set_error("qdb_rk4_steps_c128: workspace too small (%zu < %zu)", ws_bytes, qdb_workspace_bytes(QDB_WS_RK4, n, K, B, 1));
+        return QDB_E_WORKSPACE;
+    }
+    const size_t n2 = align_up((size_t)n * n * sizeof(double2));
+    const size_t yb = align_up((size_t)n * B * sizeof(double2));
+    double2* G3 = (double2*)ws;  // three generators, contiguous stride n*n (unaligned stride is fine)
+    double2* ya = (double2*)(ws + 3 * n2);
+    double2* yb_ = (double2*)(ws + 3 * n2 + yb);
+    double2* acc = (double2*)(ws + 3 * n2 + 2 * yb);
+    double* times_dev = (double*)(ws + 3 * n2 + 3 * yb);
+    const size_t nn = (size_t)n * n;
+    for (int s = 0; s < S; ++s) {
+        if (mu) QDB_CUDA(cudaMemcpyAsync(times_dev, times_host + 2 * s, 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+        rc = launch_generator(n, K, 3, QDB_LAYOUT_ROWMAJOR, D2(ops_rm), D2(stat_rm), coeff ? coeff + (size_t)2 * s * K : nullptr,
+                              0, mu, times_dev, 0.0, 1.0, G3, st);
+        if (rc != QDB_OK) return rc;
+        double2* Y = D2(y);
+        // k1 = G0 y           ya = y + h/2 k1 ; acc  = k1
+        if ((rc = launch_zgemm_rk4stage(n, B, G3, Y, ldy, Y, ya, acc, 0.5 * h, 1.0, 1, st)) != QDB_OK) return rc;
+        // k2 = G1 ya          yb = y + h/2 k2 ; acc += 2 k2
+        if ((rc = launch_zgemm_rk4stage(n, B, G3 + nn, ya, ldy, Y, yb_, acc, 0.5 * h, 2.0, 0, st)) != QDB_OK) return rc;
+        // k3 = G1 yb          ya = y + h k3   ; acc += 2 k3
+        if ((rc = launch_zgemm_rk4stage(n, B, G3 + nn, yb_, ldy, Y, ya, acc, h, 2.0, 0, st)) != QDB_OK) return rc;
+        // k4 = G2 ya          yb = y (unused) ; acc += k4
+        if ((rc = launch_zgemm_rk4stage(n, B, G3 + 2 * nn, ya, ldy, Y, yb_, acc, 0.0, 1.0, 0, st)) != QDB_OK) return rc;
+        // y += (1/6) h acc
+        if ((rc = launch_axpby((size_t)n * B, Y, acc, (1.0 / 6) * h, Y, 1.0, st)) != QDB_OK) return rc;
+    }
+    return QDB_OK;
+}
+
+int qdb_expm_c128(int n, const qdb_c128* A, int squarings, qdb_c128* out, void* workspace, size_t ws_bytes, void* stream) {
+    QDB_REQUIRE(n >= 1 && squarings >= 0 && squarings < 64, "qdb_expm_c128: bad n=%d squarings=%d", n, squarings);
+    QDB_REQUIRE(A && out && workspace, "qdb_expm_c128: null pointer");
+    const size_t e = (size_t)n * n;
+    if (ws_bytes < 6 * e * sizeof(double2)) {
+        set_error("qdb_expm_c128: workspace too small (%zu < %zu)", ws_bytes, 6 * e * sizeof(double2));
+        return QDB_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    double2* As = (double2*)workspace;
+    int rc = launch_axpby(e, As, D2(A), ldexp(1.0, -squarings), nullptr, 0.0, st);
+    if (rc != QDB_OK) return rc;
+    return expm_core(n, As, squarings, D2(out), As + e, st);
+}
+
+int qdb_expm_steps_c128(int n, int K, int B, int S, const qdb_c128* ops_rm, const qdb_c128* stat_rm, const double* coeff,
+                        const double* mu, const double* times_mid_host, const int* squarings_host, double h, qdb_c128* y,
+                        int ldy, void* workspace, size_t ws_bytes, void* stream) {
+    QDB_REQUIRE(n >= 1 && K >= 0 && B >= 0 && S >= 0, "qdb_expm_steps_c128: bad n=%d K=%d B=%d S=%d", n, K, B, S);
+    if (S == 0) return QDB_OK;
+    QDB_REQUIRE(stat_rm || (ops_rm && K > 0), "qdb_expm_steps_c128: neither static operator nor operators given");
+    QDB_REQUIRE(K == 0 || coeff, "qdb_expm_steps_c128: K=%d but no signal table", K);
+    QDB_REQUIRE(squarings_host, "qdb_expm_steps_c128: squarings missing");
+    QDB_REQUIRE(!mu || times_mid_host, "qdb_expm_steps_c128: frame given without times");
+    QDB_REQUIRE(B == 0 || (y && ldy == B), "qdb_expm_steps_c128: need y with ldy == B");
+    if (ws_bytes < qdb_workspace_bytes(QDB_WS_EXPM, n, K, B, 1) || !workspace) {
+        set_error("qdb_expm_steps_c128: workspace too small (%zu < %zu)", ws_bytes, qdb_workspace_bytes(QDB_WS_EXPM, n, K, B, 1));
+        return QDB_E_WORKSPACE;
+    }
+    if (B == 0) return QDB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)workspace;
+    const size_t n2 = align_up((size_t)n * n * sizeof(double2));
+    double2* As = (double2*)ws;
+    double2* P = (double2*)(ws + n2);
+    double2* core_ws = (double2*)(ws + 2 * n2);  // 5 n^2 (contiguous, unaligned stride)
+    double2* ytmp = (double2*)(ws + 7 * n2);
+    double2* ycur = D2(y);
+    double2* ynext = ytmp;
+    const double2 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0);
+    int rc;
+    for (int s = 0; s < S; ++s) {
+        const int sq = squarings_host[s];
+        QDB_REQUIRE(sq >= 0 && sq < 64, "qdb_expm_steps_c128: bad squarings[%d]=%d", s, sq);
+        // As = (h / 2^sq) * G_frame(t_s + h/2)
+        rc = launch_generator(n, K, 1, QDB_LAYOUT_ROWMAJOR, D2(ops_rm), D2(stat_rm), coeff ? coeff + (size_t)s * K : nullptr, 0,
+                              mu, nullptr, mu ? times_mid_host[s] : 0.0, ldexp(h, -sq), As, st);
+        if (rc != QDB_OK) return rc;
+        if ((rc = expm_core(n, As, sq, P, core_ws, st)) != QDB_OK) return rc;
+        if ((rc = launch_zgemm(n, B, n, P, n, ycur, ldy, ynext, ldy, one, zero, nullptr, nullptr, nullptr, st)) != QDB_OK) return rc;
+        double2* t = ycur;
+        ycur = ynext;
+        ynext = t;
+    }
+    if (ycur != D2(y)) QDB_CUDA(cudaMemcpyAsync(y, ycur, (size_t)n * B * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+    return QDB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,113 @@
+// Shared device helpers for libqdb (sm_100a).  fp64 tensor work on Blackwell is the warp-level
+// DMMA (mma.sync m8n8k4 f64 -> SASS DMMA.8x8x4); tcgen05 has no f64 kind.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/qdb.h"
+
+namespace qdb {
+
+// ---- error plumbing (host) --------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+void count_launch(int n = 1);
+
+#define QDB_CUDA(call)                                        \
+    do {                                                      \
+        cudaError_t _e = (call);                              \
+        if (_e != cudaSuccess) return qdb::cuda_fail(_e, #call); \
+    } while (0)
+
+#define QDB_LAUNCH_CHECK(what)                                \
+    do {                                                      \
+        cudaError_t _e = cudaGetLastError();                  \
+        if (_e != cudaSuccess) return qdb::cuda_fail(_e, what); \
+        qdb::count_launch();                                  \
+    } while (0)
+
+// ---- packed (DMMA A-fragment) operator layout -------------------------------------------------
+// element (r, c) of an npad x npad matrix lives at ((r/8)*(npad/4) + c/4)*32 + (r%8)*4 + c%4
+__host__ __device__ inline int round_up8(int n) { return (n + 7) & ~7; }
+__host__ __device__ inline size_t packed_index(int npad, int r, int c) {
+    return ((size_t)(r >> 3) * (npad >> 2) + (c >> 2)) * 32 + ((r & 7) << 2) + (c & 3);
+}
+
+// ---- DMMA -------------------------------------------------------------------------------------
+// D(8x8) += A(8x4) * B(4x8); lane = 4*g + q holds A[g][q], B[q][g], C[g][2q], C[g][2q+1].
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+// sign flip on the integer pipe (keeps the fp64 pipe free for DMMA)
+__device__ __forceinline__ double negate(double x) {
+    return __longlong_as_double(__double_as_longlong(x) ^ (long long)0x8000000000000000ULL);
+}
+
+// complex helpers on double2
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cmul_conj_a(double2 a, double2 b) {  // conj(a) * b
+    return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+
+// p = exp(-i * mu * t)
+__device__ __forceinline__ double2 frame_phase(double mu, double t) {
+    double s, c;
+    sincos(mu * t, &s, &c);
+    return make_double2(c, -s);
+}
+
+// 16-byte streaming global load (read once per CTA per stage: do not allocate in L1)
+__device__ __forceinline__ double2 ldg_stream(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+// cp.async 16 B with zero fill when !pred
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    int bytes = pred ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+}  // namespace qdb
+
+// ---- internal launchers shared between translation units --------------------------------------
+namespace qdb {
+int launch_pack(int n, int count, const double2* src, double2* dst, cudaStream_t st);
+int launch_generator(int n, int K, int T, int layout, const double2* ops, const double2* stat,
+                     const double* coeff, int coeff_complex, const double* mu, const double* times,
+                     double t_scalar, double scale, double2* out, cudaStream_t st);
+int launch_phase_vectors(int n, const double* mu, double t, double2* pre, double2* post, cudaStream_t st);
+int launch_poly(int n, double c0, double c1, const double2* A1, double c2, const double2* A2, double c3,
+                const double2* A3, double c4, const double2* A4, double2* out, cudaStream_t st);
+int expm_core(int n, const double2* As, int squarings, double2* out, double2* ws /*5 n^2*/, cudaStream_t st);
+int launch_zgemm(int M, int N, int Kd, const double2* A, int lda, const double2* B, int ldb,
+                 double2* C, int ldc, double2 alpha, double2 beta, const double* colscale,
+                 const double2* pre, const double2* post, cudaStream_t st);
+// two-output RK4 stage epilogue variant (generic large-n path):
+//   k = G * yin ;  yout = ybase + a_next * k ;  acc = (first ? 0 : acc) + w * k
+int launch_zgemm_rk4stage(int n, int B, const double2* G, const double2* yin, int ldy,
+                          const double2* ybase, double2* yout, double2* acc, double a_next, double w,
+                          int first, cudaStream_t st);
+bool rk4_fused_supported(int n);
+int launch_rk4_fused_shared(int n, int B, int S, const double2* gen_table, double h, double2* y,
+                            int ldy, cudaStream_t st);
+int launch_rk4_fused_sweep(int n, int K, int B, int S, const double2* stat_packed /*or null*/,
+                           const double2* ops_packed /*[K]*/, const double* coeff, int ldc,
+                           const double* mu, const double* times_dev,
+                           double h, double2* y, int ldy, cudaStream_t st);
+int launch_axpby(size_t count, double2* dst, const double2* x, double a, const double2* y, double b,
+                 cudaStream_t st);
+}  // namespace qdb

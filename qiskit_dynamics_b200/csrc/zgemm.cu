@@ -1,0 +1,203 @@
+// General complex128 GEMM on the fp64 tensor pipe (DMMA m8n8k4), with the fused pro/epilogues of
+// the hot path.
+//
+// CTA tile 64 x 64, k-chunk 16, 8 warps as 4 (rows) x 2 (cols); each warp owns a 16 x 32 complex
+// tile = 2 x 4 DMMA tiles, i.e. 32 real DMMAs per k4-step fed by 2 + 4 LDS.128 -- the DMMA pipe
+// (16 issue cycles per DMMA per SM sub-partition) is the bound, not shared memory.
+// Operand tiles are staged with a 3-deep cp.async ring; rows are padded so that every fragment
+// load is bank-conflict free (A stride = 64 mod 128 B, B stride = 32 mod 128 B).
+#include "qdb_common.cuh"
+
+namespace qdb {
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, STAGES = 3;
+constexpr int A_LD = BK + 4;   // complex elements per smem row of A  (320 B)
+constexpr int B_LD = BN + 2;   // complex elements per smem row of B  (1056 B)
+constexpr int A_TILE = BM * A_LD;
+constexpr int B_TILE = BK * B_LD;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * (A_TILE + B_TILE) * sizeof(double2);
+
+struct EpiStd {
+    double2* C;
+    int ldc;
+    double2 alpha, beta;
+    const double* colscale;
+    const double2* post;
+};
+
+struct EpiRk4 {
+    const double2* ybase;
+    double2* yout;
+    double2* acc;
+    int ld;
+    double a_next, w;
+    int first;
+};
+
+__device__ __forceinline__ void epilogue(const EpiStd& e, int r, int c, double2 v) {
+    if (e.post) v = cmul(e.post[r], v);
+    double2 a = e.alpha;
+    if (e.colscale) {
+        const double s = e.colscale[c];
+        a.x *= s;
+        a.y *= s;
+    }
+    v = cmul(a, v);
+    double2* dst = e.C + (size_t)r * e.ldc + c;
+    if (e.beta.x != 0.0 || e.beta.y != 0.0) v = cadd(v, cmul(e.beta, *dst));
+    *dst = v;
+}
+
+__device__ __forceinline__ void epilogue(const EpiRk4& e, int r, int c, double2 k) {
+    const size_t i = (size_t)r * e.ld + c;
+    const double2 yb = e.ybase[i];
+    e.yout[i] = make_double2(fma(e.a_next, k.x, yb.x), fma(e.a_next, k.y, yb.y));
+    double2 a = make_double2(e.w * k.x, e.w * k.y);
+    if (!e.first) {
+        const double2 old = e.acc[i];
+        a.x += old.x;
+        a.y += old.y;
+    }
+    e.acc[i] = a;
+}
+
+template <typename Epi>
+__global__ void __launch_bounds__(256) zgemm_kernel(int M, int N, int Kd, const double2* __restrict__ A, int lda,
+                                                     const double2* __restrict__ Bm, int ldb,
+                                                     const double2* __restrict__ pre, Epi epi) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* sA = reinterpret_cast<double2*>(smem_raw);
+    double2* sB = sA + STAGES * A_TILE;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2;  // 4 x 2 warps
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int numK = (Kd + BK - 1) / BK;
+
+    auto load_stage = [&](int kt, int slot) {
+        const int k0 = kt * BK;
+        double2* a_dst = sA + slot * A_TILE;
+        double2* b_dst = sB + slot * B_TILE;
+#pragma unroll
+        for (int i = 0; i < (BM * BK) / 256; ++i) {
+            const int idx = tid + 256 * i;
+            const int r = idx / BK, c = idx % BK;
+            const bool ok = (m0 + r < M) && (k0 + c < Kd);
+            const double2* src = ok ? A + (size_t)(m0 + r) * lda + k0 + c : A;
+            cp_async16(a_dst + r * A_LD + c, src, ok);
+        }
+#pragma unroll
+        for (int i = 0; i < (BK * BN) / 256; ++i) {
+            const int idx = tid + 256 * i;
+            const int r = idx / BN, c = idx % BN;
+            const bool ok = (k0 + r < Kd) && (n0 + c < N);
+            const double2* src = ok ? Bm + (size_t)(k0 + r) * ldb + n0 + c : Bm;
+            cp_async16(b_dst + r * B_LD + c, src, ok);
+        }
+    };
+
+    double cr[2][4][2], ci[2][4][2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) cr[m][c][0] = cr[m][c][1] = ci[m][c][0] = ci[m][c][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < numK) load_stage(s, s);
+        cp_async_commit();
+    }
+
+    for (int kt = 0; kt < numK; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            const int nk = kt + STAGES - 1;
+            if (nk < numK) load_stage(nk, nk % STAGES);
+            cp_async_commit();
+        }
+        const double2* a_s = sA + (kt % STAGES) * A_TILE + (wm * 16 + g) * A_LD + q;
+        const double2* b_s = sB + (kt % STAGES) * B_TILE + q * B_LD + wn * 32 + g;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            double2 a[2], b[4];
+#pragma unroll
+            for (int m = 0; m < 2; ++m) a[m] = a_s[m * 8 * A_LD + kk * 4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) b[c] = b_s[kk * 4 * B_LD + c * 8];
+            if (pre != nullptr) {
+                const int k = kt * BK + kk * 4 + q;
+                const double2 p = k < Kd ? pre[k] : make_double2(0.0, 0.0);
+#pragma unroll
+                for (int m = 0; m < 2; ++m) a[m] = cmul(a[m], p);
+            }
+            double nai[2];
+#pragma unroll
+            for (int m = 0; m < 2; ++m) nai[m] = negate(a[m].y);
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    dmma(cr[m][c][0], cr[m][c][1], a[m].x, b[c].x);
+                    dmma(ci[m][c][0], ci[m][c][1], a[m].x, b[c].y);
+                }
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    dmma(cr[m][c][0], cr[m][c][1], nai[m], b[c].y);
+                    dmma(ci[m][c][0], ci[m][c][1], a[m].y, b[c].x);
+                }
+        }
+    }
+    cp_async_wait<0>();
+
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        const int r = m0 + wm * 16 + m * 8 + g;
+        if (r >= M) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int col = n0 + wn * 32 + c * 8 + 2 * q + i;
+                if (col < N) epilogue(epi, r, col, make_double2(cr[m][c][i], ci[m][c][i]));
+            }
+    }
+}
+
+template <typename Epi>
+int launch(int M, int N, int Kd, const double2* A, int lda, const double2* B, int ldb, const double2* pre,
+           const Epi& epi, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        QDB_CUDA(cudaFuncSetAttribute(zgemm_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        configured = true;
+    }
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+    zgemm_kernel<Epi><<<grid, 256, SMEM_BYTES, st>>>(M, N, Kd, A, lda, B, ldb, pre, epi);
+    QDB_LAUNCH_CHECK("zgemm_kernel");
+    return QDB_OK;
+}
+
+}  // namespace
+
+int launch_zgemm(int M, int N, int Kd, const double2* A, int lda, const double2* B, int ldb, double2* C, int ldc,
+                 double2 alpha, double2 beta, const double* colscale, const double2* pre, const double2* post,
+                 cudaStream_t st) {
+    if (M == 0 || N == 0) return QDB_OK;
+    EpiStd e{C, ldc, alpha, beta, colscale, post};
+    return launch(M, N, Kd, A, lda, B, ldb, pre, e, st);
+}
+
+int launch_zgemm_rk4stage(int n, int B, const double2* G, const double2* yin, int ldy, const double2* ybase,
+                          double2* yout, double2* acc, double a_next, double w, int first, cudaStream_t st) {
+    if (n == 0 || B == 0) return QDB_OK;
+    EpiRk4 e{ybase, yout, acc, ldy, a_next, w, first};
+    return launch(n, B, n, G, n, yin, ldy, (const double2*)nullptr, e, st);
+}
+
+}  // namespace qdb

@@ -1,0 +1,237 @@
+"""GPU parity tests of the C-ABI kernels (libqdb.so through ctypes) against the NumPy oracle.
+
+Tolerance: the north-star bar is max-over-columns L2 error < 1e-8 on final states; true fp64
+DMMA arithmetic lands at 1e-13..1e-15, so the tests assert 1e-11 (solves) / 1e-12 (single ops)
+to leave room only for summation-order differences.
+"""
+import numpy as np
+import pytest
+import scipy.linalg
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import numpy_oracle as orc  # noqa: E402
+from conftest import max_col_l2  # noqa: E402
+
+TOL_OP = 1e-12
+TOL_SOLVE = 1e-11
+
+
+@pytest.fixture(scope="module")
+def abi():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from qiskit_dynamics_b200 import _abi
+    _abi.lib()
+    return _abi
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def model_inputs(n, K, B, seed, frame="full"):
+    H0, Hs, Y, sig = orc.synthetic_schrodinger(n, K, B, seed)
+    fr = {"full": H0, "diag": np.diag(H0).real, "none": None}[frame]
+    Gd, G, d, U = orc.generator_model_operators(H0, Hs, fr)
+    yfb = Y if U is None else U.conj().T @ Y
+    specs = [orc.SigSpec(a, nu, ph) for (a, nu, ph) in sig]
+    mu = None if d is None else -np.imag(d)
+    return Gd, G, d, mu, yfb, specs
+
+
+def test_pack_and_generator(abi):
+    rng = np.random.default_rng(0)
+    for n, K, T in ((5, 2, 3), (8, 1, 1), (27, 3, 4), (128, 8, 5)):
+        ops = rng.standard_normal((K, n, n)) + 1j * rng.standard_normal((K, n, n))
+        stat = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        coeff = rng.standard_normal((T, K))
+        mu = rng.standard_normal(n) * 3
+        times = rng.uniform(0, 5, T)
+        d = -1j * mu
+        ref = np.array([orc.operator_into_frame(d, t, orc.collection_evaluate(c, ops, stat)) for t, c in zip(times, coeff)])
+        out = abi.generator(n, dev(ops), dev(stat), dev(coeff), dev(mu), dev(times), scale=0.5)
+        np.testing.assert_allclose(out.cpu().numpy().reshape(T, n, n), 0.5 * ref, rtol=0, atol=TOL_OP)
+        # packed layout round trip
+        npad = abi.npad(n)
+        pk_ops, pk_stat = abi.pack_operators(dev(ops)), abi.pack_operators(dev(stat[None]))[0]
+        outp = abi.generator(n, pk_ops, pk_stat, dev(coeff), dev(mu), dev(times), layout=abi.LAYOUT_PACKED).cpu().numpy()
+        r, c = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+        idx = ((r // 8) * (npad // 4) + c // 4) * 32 + (r % 8) * 4 + c % 4
+        np.testing.assert_allclose(outp[:, idx], ref, rtol=0, atol=TOL_OP)
+        mask = np.ones(npad * npad, bool)
+        mask[idx.ravel()] = False
+        assert np.all(outp[:, mask] == 0)
+        # complex coefficients, no frame, no static (reference test_operator_collections.py:82-94)
+        cc = rng.standard_normal((1, K)) + 1j * rng.standard_normal((1, K))
+        outc = abi.generator(n, dev(ops), None, dev(cc), None, None).cpu().numpy().reshape(n, n)
+        np.testing.assert_allclose(outc, np.tensordot(cc[0], ops, axes=1), rtol=0, atol=TOL_OP)
+        # static only
+        outs = abi.generator(n, None, dev(stat), None, None, None).cpu().numpy().reshape(n, n)
+        np.testing.assert_allclose(outs, stat, rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("M,N,Kd", [(1, 1, 1), (5, 3, 7), (64, 64, 16), (65, 67, 17), (128, 4096, 128), (729, 40, 729), (200, 130, 33)])
+def test_zgemm(abi, M, N, Kd):
+    rng = np.random.default_rng(M * 1000 + N)
+    A = rng.standard_normal((M, Kd)) + 1j * rng.standard_normal((M, Kd))
+    Bm = rng.standard_normal((Kd, N)) + 1j * rng.standard_normal((Kd, N))
+    C0 = rng.standard_normal((M, N)) + 1j * rng.standard_normal((M, N))
+    out = abi.zgemm(dev(A), dev(Bm)).cpu().numpy()
+    scale = np.sqrt(Kd)
+    np.testing.assert_allclose(out, A @ Bm, rtol=0, atol=TOL_OP * scale * 10)
+    alpha, beta = 0.3 - 1.2j, -0.7 + 0.4j
+    cs = rng.standard_normal(N)
+    pre = np.exp(1j * rng.standard_normal(Kd))
+    post = np.exp(1j * rng.standard_normal(M))
+    c = dev(C0)
+    abi.zgemm(dev(A), dev(Bm), out=c, alpha=alpha, beta=beta, colscale=dev(cs), pre=dev(pre), post=dev(post))
+    ref = beta * C0 + alpha * cs[None, :] * post[:, None] * (A @ (pre[:, None] * Bm))
+    np.testing.assert_allclose(c.cpu().numpy(), ref, rtol=0, atol=TOL_OP * scale * 10)
+
+
+@pytest.mark.parametrize("n,K,B,frame", [(8, 3, 5, "full"), (5, 2, 3, "diag"), (5, 2, 1, "none"), (128, 8, 64, "full"), (32, 8, 40, "full")])
+def test_rhs_shared_and_sweep(abi, n, K, B, frame):
+    Gd, G, d, mu, y, specs = model_inputs(n, K, B, 1234 + n, frame)
+    mu_d = None if mu is None else dev(mu)
+    for t in (0.0, 0.37, 2.5):
+        c = orc.signal_list_values(specs, t)
+        ref = orc.model_rhs(t, y, specs, G, Gd, d)
+        out = abi.rhs(n, dev(G), dev(Gd), dev(c), mu_d, t, dev(y)).cpu().numpy()
+        assert max_col_l2(out, ref) < TOL_OP * 10
+        # no static operator
+        ref2 = orc.model_rhs(t, y, specs, G, None, d)
+        out2 = abi.rhs(n, dev(G), None, dev(c), mu_d, t, dev(y)).cpu().numpy()
+        assert max_col_l2(out2, ref2) < TOL_OP * 10
+        # per-column coefficients: column b scaled amplitudes
+        amp = 0.5 + np.arange(B) / B
+        cb = c[:, None] * amp[None, :]  # (K, B)
+        ref3 = np.stack([orc.model_rhs(t, y[:, b], None, None, orc.collection_evaluate(cb[:, b], G, Gd), d) for b in range(B)], axis=-1)
+        out3 = abi.rhs(n, dev(G), dev(Gd), dev(cb), mu_d, t, dev(y), per_col=True).cpu().numpy()
+        assert max_col_l2(out3, ref3) < TOL_OP * 10
+
+
+def _oracle_rk4(Gd, G, d, specs, y, t0, h, S):
+    t = t0
+    for _ in range(S):
+        y = orc.rk4_step(lambda tt, yy: orc.model_rhs(tt, yy, specs, G, Gd, d), t, y, h)
+        t = t + h
+    return y
+
+
+@pytest.mark.parametrize("n,K,B,S,frame", [
+    (128, 8, 72, 20, "full"),    # headline shape, ragged column count
+    (128, 8, 4096, 2, "full"),   # headline batch
+    (5, 2, 3, 50, "diag"),       # odd dimension -> padding
+    (4, 1, 1, 30, "full"),       # cfg1-like single column
+    (32, 8, 100, 10, "full"),    # cfg2 dimension
+    (88, 3, 40, 5, "full"),      # 11 row tiles (uneven warp load)
+    (200, 2, 24, 3, "none"),     # MR = 4
+    (256, 1, 16, 2, "full"),
+])
+def test_rk4_fused_shared(abi, n, K, B, S, frame):
+    Gd, G, d, mu, y, specs = model_inputs(n, K, B, 77 + n, frame)
+    t0, h = 0.1, 1e-3 if n >= 32 else 0.01
+    times = orc.stage_time_grid(t0, h, S)
+    coeff = orc.signal_list_values(specs, times)
+    ref = _oracle_rk4(Gd, G, d, specs, y, t0, h, S)
+    Gdev, Gd_dev = dev(G), dev(Gd)
+    yd = dev(y)
+    abi.rk4_steps(n, Gdev, Gd_dev, abi.pack_operators(Gdev), abi.pack_operators(Gd_dev[None])[0], dev(coeff),
+                  None if mu is None else dev(mu), times, h, yd, S)
+    assert max_col_l2(yd.cpu().numpy(), ref) < TOL_SOLVE
+    # chunked step loop (tiny workspace) gives the same answer
+    yd2 = dev(y)
+    ws = torch.empty(abi.workspace_bytes(abi.WS_RK4, n, K, B, 2), dtype=torch.uint8, device="cuda")
+    abi.rk4_steps(n, Gdev, Gd_dev, abi.pack_operators(Gdev), abi.pack_operators(Gd_dev[None])[0], dev(coeff),
+                  None if mu is None else dev(mu), times, h, yd2, S, workspace=ws)
+    assert torch.equal(yd, yd2)
+
+
+@pytest.mark.parametrize("n,K,B,S,frame", [(32, 8, 48, 10, "full"), (5, 2, 3, 20, "diag"), (128, 8, 40, 3, "full"), (16, 2, 600, 4, "none")])
+def test_rk4_fused_sweep(abi, n, K, B, S, frame):
+    Gd, G, d, mu, y, specs = model_inputs(n, K, B, 99 + n, frame)
+    t0, h = 0.0, 1e-3 if n >= 32 else 0.01
+    times = orc.stage_time_grid(t0, h, S)
+    base = orc.signal_list_values(specs, times)  # (T, K)
+    amp = 0.5 + np.arange(B) / B
+    coeff = base[:, :, None] * amp[None, None, :]  # (T, K, B)
+    ref = np.empty_like(y)
+    for b in range(B):
+        sp = [orc.SigSpec(s.envelope * amp[b], s.carrier_freq, s.phase) for s in specs]
+        ref[:, b] = _oracle_rk4(Gd, G, d, sp, y[:, b], t0, h, S)
+    Gdev, Gd_dev = dev(G), dev(Gd)
+    yd = dev(y)
+    abi.rk4_steps(n, Gdev, Gd_dev, abi.pack_operators(Gdev), abi.pack_operators(Gd_dev[None])[0], dev(coeff),
+                  None if mu is None else dev(mu), times, h, yd, S, per_col=True)
+    assert max_col_l2(yd.cpu().numpy(), ref) < TOL_SOLVE
+    # no static operator
+    ref2 = np.empty_like(y)
+    for b in range(min(B, 4)):
+        sp = [orc.SigSpec(s.envelope * amp[b], s.carrier_freq, s.phase) for s in specs]
+        ref2[:, b] = _oracle_rk4(None, G, d, sp, y[:, b], t0, h, S)
+    yd = dev(y)
+    abi.rk4_steps(n, Gdev, None, abi.pack_operators(Gdev), None, dev(coeff), None if mu is None else dev(mu), times, h, yd, S, per_col=True)
+    assert max_col_l2(yd.cpu().numpy()[:, :4], ref2[:, :4]) < TOL_SOLVE
+
+
+def test_rk4_generic_large_n(abi):
+    n, K, B, S = 264, 2, 24, 3
+    Gd, G, d, mu, y, specs = model_inputs(n, K, B, 5, "full")
+    t0, h = 0.0, 1e-3
+    times = orc.stage_time_grid(t0, h, S)
+    coeff = orc.signal_list_values(specs, times)
+    ref = _oracle_rk4(Gd, G, d, specs, y, t0, h, S)
+    yd = dev(y)
+    abi.rk4_steps(n, dev(G), dev(Gd), None, None, dev(coeff), dev(mu), times, h, yd, S)
+    assert max_col_l2(yd.cpu().numpy(), ref) < TOL_SOLVE
+
+
+@pytest.mark.parametrize("n,norm", [(2, 3.0), (9, 0.3), (27, 5.0), (64, 40.0), (200, 1.0)])
+def test_expm_matches_scipy(abi, n, norm):
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    A = A - A.conj().T  # anti-Hermitian-ish generator, keeps exp bounded
+    A = A * (norm / np.linalg.norm(A, 1)) + 0.01 * rng.standard_normal((n, n))
+    s = max(0, int(np.ceil(np.log2(np.linalg.norm(A, 1) / 0.7))))
+    out = abi.expm(dev(A), s).cpu().numpy()
+    ref = scipy.linalg.expm(A)
+    assert np.max(np.abs(out - ref)) < 1e-12 * max(1.0, norm)
+
+
+def test_expm_steps(abi):
+    # vectorised Lindblad, n = 3 -> 9, with 1-d frame, against the oracle's scipy_expm stepping
+    n, K, B = 3, 2, 4
+    H0, Hs, Ls, Y, sig = orc.synthetic_lindblad(n, K, 4, B, 31)
+    specs = [orc.SigSpec(a, nu, ph) for (a, nu, ph) in sig]
+    Hd, Hops, Ds, Do, d, U = orc.lindblad_model_operators(H0, Hs, Ls, None, np.diag(H0).real)
+    Sst, ops = orc.vectorized_lindblad_collection(Hd, Hops, Ds, Do)
+    mu = orc.vec_frame_phase(d)
+    t0, h, S = 0.0, 0.05, 10
+    y = Y.copy()
+    t = t0
+    for _ in range(S):
+        y = orc.expm_step(lambda tt: orc.vectorized_map_into_frame(d, tt, orc.collection_evaluate(orc.signal_list_values(specs, tt), ops, Sst)), t, y, h)
+        t = t + h
+    starts = orc.stage_time_grid(t0, h, S)[0::2][:-1]
+    mids = starts + h / 2
+    coeff = orc.signal_list_values(specs, mids)
+    bound = abs(h) * (np.linalg.norm(Sst, 1) + np.abs(coeff) @ np.array([np.linalg.norm(o, 1) for o in ops]))
+    sq = np.maximum(0, np.ceil(np.log2(np.maximum(bound, 1e-300) / 0.7))).astype(np.int32)
+    yd = dev(Y)
+    abi.expm_steps(n * n, dev(ops), dev(Sst), dev(coeff), dev(mu), mids, sq, h, yd, S)
+    assert max_col_l2(yd.cpu().numpy(), y) < TOL_SOLVE
+
+
+def test_argument_errors(abi):
+    y = torch.zeros((4, 2), dtype=torch.complex128, device="cuda")
+    with pytest.raises(abi.QdbError):
+        abi.rhs(4, None, None, None, None, 0.0, y)  # empty collection (operator_collections.py:119-122)
+    with pytest.raises(abi.QdbError):
+        abi.rhs(4, None, torch.zeros((4, 4), dtype=torch.complex128), None, None, 0.0, y)  # CPU tensor: no fallback
+    with pytest.raises(abi.QdbError):
+        abi.zgemm(torch.zeros((4, 3), dtype=torch.complex128, device="cuda"), torch.zeros((4, 3), dtype=torch.complex128, device="cuda"))
