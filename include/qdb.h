@@ -79,6 +79,12 @@ int qdb_generator_c128(int n, int K, int T, int layout,
                        const double* mu, const double* times, double scale,
                        qdb_c128* out, void* stream);
 
+/* a3 on its own:  y_out[a][b] = q_a * y_in[a][b],  q = exp(-i mu t) (conj_phase = 0: "out of frame")
+ * or exp(+i mu t) (conj_phase = 1: "into frame"), in the frame basis.  May run in place.
+ * Replaces RotatingFrame.state_into_frame / state_out_of_frame (models/rotating_frame.py:225-284). */
+int qdb_frame_apply_c128(int n, int B, const double* mu, double t, int conj_phase,
+                         const qdb_c128* y_in, qdb_c128* y_out, int ldy, void* stream);
+
 /* General complex GEMM with the fused pro/epilogues the path needs:
  *     C[m][b] = beta * C[m][b] + alpha * colscale[b] * post[m] * sum_k A[m][k] * pre[k] * Bm[k][b]
  * colscale (real, length N), pre (length Kd) and post (length M) may each be NULL (= 1).

@@ -41,6 +41,7 @@ SIGNATURES = {
     "qdb_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "qdb_pack_operators": (_i, [_i, _i, _vp, _vp, _vp]),
     "qdb_generator_c128": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _d, _vp, _vp]),
+    "qdb_frame_apply_c128": (_i, [_i, _i, _vp, _d, _i, _vp, _vp, _i, _vp]),
     "qdb_zgemm_c128": (_i, [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, c128, c128, _vp, _vp, _vp, _vp]),
     "qdb_rhs_c128": (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _d, _vp, _vp, _i, _vp, _sz, _vp]),
     "qdb_rk4_steps_c128": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _d, _vp, _i, _vp, _sz, _vp]),
@@ -86,6 +87,8 @@ def _ptr(t: Optional[torch.Tensor], dtype, name: str):
         raise QdbError(f"{name}: expected dtype {dtype}, got {t.dtype}")
     if not t.is_contiguous():
         raise QdbError(f"{name}: tensor must be contiguous")
+    if t.is_conj() or t.is_neg():
+        raise QdbError(f"{name}: tensor carries a lazy conj/neg bit; call .resolve_conj()/.resolve_neg() first")
     return ctypes.c_void_p(t.data_ptr())
 
 
@@ -135,6 +138,16 @@ def generator(n, ops, stat, coeff, mu, times, scale=1.0, layout=LAYOUT_ROWMAJOR,
                                     _ptr(coeff, C if cplx else F, "coeff"), int(cplx), _ptr(mu, F, "mu"),
                                     _ptr(times, F, "times"), float(scale), _ptr(out, C, "out"), _stream()),
            "qdb_generator_c128")
+    return out
+
+
+def frame_apply(mu, t, y, conj_phase: bool, out=None):
+    """Rows of y (n, B) times exp(-i mu t) (or its conjugate)."""
+    n, B = y.shape
+    if out is None:
+        out = torch.empty_like(y)
+    _check(lib().qdb_frame_apply_c128(n, B, _ptr(mu, F, "mu"), float(t), int(conj_phase), _ptr(y, C, "y_in"),
+                                      _ptr(out, C, "y_out"), B, _stream()), "qdb_frame_apply_c128")
     return out
 
 

@@ -1,0 +1,61 @@
+"""Array plumbing: everything numeric is a torch.complex128 (or float64) tensor on one device.
+
+The reference's arraylias multi-backend dispatch (arraylias/alias.py) is removed: there is one
+array type and one compute path.  `default_device()` is cuda:LOCAL_RANK when a GPU is visible;
+without one, tensors can still be *constructed* (host logic, argument checks) but every
+evaluation raises, because the CUDA C-ABI is the only implementation.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+CDTYPE = torch.complex128
+RDTYPE = torch.float64
+
+_device_override: Optional[torch.device] = None
+
+
+def set_default_device(device) -> None:
+    global _device_override
+    _device_override = None if device is None else torch.device(device)
+
+
+def default_device() -> torch.device:
+    if _device_override is not None:
+        return _device_override
+    if torch.cuda.is_available():
+        return torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")) % max(torch.cuda.device_count(), 1))
+    return torch.device("cpu")
+
+
+def asarray(x, device=None) -> Optional[torch.Tensor]:
+    """Anything array-like (numpy, nested lists, objects with __array__/.data, tensors) ->
+    contiguous complex128 tensor on the compute device.  None passes through."""
+    if x is None:
+        return None
+    device = default_device() if device is None else torch.device(device)
+    if isinstance(x, torch.Tensor):
+        # resolve lazy conj/neg bits: raw device pointers cross the C-ABI
+        return x.to(device=device, dtype=CDTYPE).resolve_conj().resolve_neg().contiguous()
+    if isinstance(x, (list, tuple)) and len(x) > 0 and isinstance(x[0], torch.Tensor):
+        return torch.stack([asarray(e, device) for e in x]).contiguous()
+    arr = np.asarray(x, dtype=complex) if not (isinstance(x, (list, tuple)) and len(x) and hasattr(x[0], "data") and not isinstance(x[0], np.ndarray)) \
+        else np.asarray([np.asarray(getattr(e, "data", e)) for e in x], dtype=complex)
+    return torch.from_numpy(np.ascontiguousarray(arr)).to(device=device, dtype=CDTYPE)
+
+
+def asreal(x, device=None) -> torch.Tensor:
+    device = default_device() if device is None else torch.device(device)
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=RDTYPE).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64))).to(device)
+
+
+def to_numpy(x) -> np.ndarray:
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().numpy()
+    return np.asarray(x)

@@ -91,6 +91,14 @@ int qdb_generator_c128(int n, int K, int T, int layout, const qdb_c128* ops, con
                             (cudaStream_t)stream);
 }
 
+int qdb_frame_apply_c128(int n, int B, const double* mu, double t, int conj_phase, const qdb_c128* y_in, qdb_c128* y_out,
+                         int ldy, void* stream) {
+    QDB_REQUIRE(n >= 0 && B >= 0, "qdb_frame_apply_c128: bad n=%d B=%d", n, B);
+    if (n == 0 || B == 0) return QDB_OK;
+    QDB_REQUIRE(mu && y_in && y_out && ldy >= B, "qdb_frame_apply_c128: null pointer / bad ldy");
+    return launch_frame_apply(n, B, mu, t, conj_phase, D2(y_in), D2(y_out), ldy, (cudaStream_t)stream);
+}
+
 int qdb_zgemm_c128(int M, int N, int Kd, const qdb_c128* A, int lda, const qdb_c128* Bm, int ldb, qdb_c128* C, int ldc,
                    qdb_c128 alpha, qdb_c128 beta, const double* colscale, const qdb_c128* pre, const qdb_c128* post,
                    void* stream) {
@@ -184,10 +192,13 @@ int qdb_rk4_steps_c128(int n, int K, int B, int S, const qdb_c128* ops_rm, const
         }
         // shared signals: chunk the step loop so that the generator table fits the workspace
         const size_t per_entry = np2 * sizeof(double2);
-        size_t budget = ws_bytes;
-        // entries E = 2 Sc + 1 need E*per_entry (+align) + E*8 (+align)
-        long long max_entries = (long long)((budget - 2 * 256) / (per_entry + sizeof(double)));
-        int Sc_max = (int)((max_entries - 1) / 2);
+        // largest Sc whose 2 Sc + 1 table entries (+ their stage times) fit the workspace
+        auto fits = [&](long long Sc) {
+            const size_t E = (size_t)(2 * Sc + 1);
+            return align_up(E * per_entry) + align_up(E * sizeof(double)) <= ws_bytes;
+        };
+        long long Sc_max = (long long)(ws_bytes / per_entry + 1) / 2;
+        while (Sc_max >= 1 && !fits(Sc_max)) --Sc_max;
         if (Sc_max < 1) {
             set_error("qdb_rk4_steps_c128: workspace too small (%zu < %zu)", ws_bytes, qdb_workspace_bytes(QDB_WS_RK4, n, K, B, 1));
             return QDB_E_WORKSPACE;
@@ -195,8 +206,8 @@ int qdb_rk4_steps_c128(int n, int K, int B, int S, const qdb_c128* ops_rm, const
         if (Sc_max > S) Sc_max = S;
         double2* table = (double2*)ws;
         double* times_dev = (double*)(ws + align_up((size_t)(2 * Sc_max + 1) * per_entry));
-        for (int s0 = 0; s0 < S; s0 += Sc_max) {
-            const int Sc = (S - s0 < Sc_max) ? S - s0 : Sc_max;
+        for (int s0 = 0; s0 < S; s0 += (int)Sc_max) {
+            const int Sc = (S - s0 < Sc_max) ? S - s0 : (int)Sc_max;
             const int T = 2 * Sc + 1;
             if (mu) QDB_CUDA(cudaMemcpyAsync(times_dev, times_host + 2 * s0, (size_t)T * sizeof(double), cudaMemcpyHostToDevice, st));
             rc = launch_generator(n, K, T, QDB_LAYOUT_PACKED, D2(ops_packed), D2(stat_packed),

@@ -201,3 +201,26 @@ int launch_poly(int n, double c0, double c1, const double2* A1, double c2, const
 }
 
 }  // namespace qdb
+
+namespace qdb {
+
+// y_out[a][b] = q_a * y_in[a][b],  q = exp(-i mu t) or its conjugate (a3 as a stand-alone op)
+__global__ void frame_apply_kernel(int n, int B, const double* __restrict__ mu, double t, int conj_phase,
+                                   const double2* __restrict__ y_in, double2* __restrict__ y_out, int ldy) {
+    const int a = blockIdx.y;
+    double2 p = frame_phase(mu[a], t);
+    if (conj_phase) p.y = -p.y;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x)
+        y_out[(size_t)a * ldy + b] = cmul(p, y_in[(size_t)a * ldy + b]);
+}
+
+int launch_frame_apply(int n, int B, const double* mu, double t, int conj_phase, const double2* y_in, double2* y_out,
+                       int ldy, cudaStream_t st) {
+    if (n == 0 || B == 0) return QDB_OK;
+    dim3 grid((unsigned)min((B + 255) / 256, 1024), n);
+    frame_apply_kernel<<<grid, 256, 0, st>>>(n, B, mu, t, conj_phase, y_in, y_out, ldy);
+    QDB_LAUNCH_CHECK("frame_apply_kernel");
+    return QDB_OK;
+}
+
+}  // namespace qdb

@@ -89,6 +89,8 @@ int launch_pack(int n, int count, const double2* src, double2* dst, cudaStream_t
 int launch_generator(int n, int K, int T, int layout, const double2* ops, const double2* stat,
                      const double* coeff, int coeff_complex, const double* mu, const double* times,
                      double t_scalar, double scale, double2* out, cudaStream_t st);
+int launch_frame_apply(int n, int B, const double* mu, double t, int conj_phase, const double2* y_in,
+                       double2* y_out, int ldy, cudaStream_t st);
 int launch_phase_vectors(int n, const double* mu, double t, double2* pre, double2* post, cudaStream_t st);
 int launch_poly(int n, double c0, double c1, const double2* A1, double c2, const double2* A2, double c3,
                 const double2* A3, double c4, const double2* A4, double2* out, cudaStream_t st);

@@ -409,7 +409,21 @@ struct Config {
 constexpr int kMaxFusedNpad = 256;
 constexpr size_t kSmemLimit = 227 * 1024;
 
+int sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+            sms = v;
+        else
+            sms = 148;  // B200
+    }
+    return sms;
+}
+
 bool pick_config(int n, int B, int K_sweep /*0 for shared*/, Config& cfg) {
+    const int SMS = sm_count();
     const int npad = round_up8(n);
     if (npad > kMaxFusedNpad || n < 1) return false;
     Geometry geo;
@@ -425,7 +439,7 @@ bool pick_config(int n, int B, int K_sweep /*0 for shared*/, Config& cfg) {
         MR = (geo.RT + 7) / 8;
         // fewer wasted row slots with 4 row-warps x 2 column-warps?
         const int MR4 = (geo.RT + 3) / 4;
-        if (MR4 <= 4 && MR4 * 4 < MR * 8 && CT >= 2 * 148) {
+        if (MR4 <= 4 && MR4 * 4 < MR * 8 && CT >= 2 * SMS) {
             WR = 4;
             WC = 2;
             MR = MR4;
@@ -435,33 +449,38 @@ bool pick_config(int n, int B, int K_sweep /*0 for shared*/, Config& cfg) {
         while (WR < geo.RT) WR *= 2;
         MR = 1;
         // small problems: 4 warps per CTA so that more CTAs exist; else fill 8 warps with columns
-        const int warps = (CT >= 2 * 148 * (8 / WR)) ? 8 : (WR > 4 ? 8 : 4);
+        const int warps = (CT >= 2 * SMS * (8 / WR)) ? 8 : (WR > 4 ? 8 : 4);
         WC = warps / WR;
         if (WC < 1) WC = 1;
     }
-    const int NCWmax = MR == 1 ? 4 : (MR == 2 ? 4 : 2);
-    int NCW = NCWmax;
-    // shrink the column tile while it leaves SMs idle
-    while (NCW > 1 && (CT + NCW * WC - 1) / (NCW * WC) < 148) NCW /= 2;
-    for (;;) {
-        geo.WR = WR;
-        geo.WC = WC;
-        geo.NCT = NCW * WC;
+    const int NCWmax = MR <= 2 ? 4 : 2;
+    // The busiest SM runs ceil(ctas / #SMs) CTAs of NCW column tiles each: minimise that product,
+    // ties go to the wider tile (fewer A-fragment reloads per column).
+    long best_cost = -1;
+    bool found = false;
+    for (int NCW = NCWmax; NCW >= 1; NCW /= 2) {
+        Geometry g2 = geo;
+        g2.WR = WR;
+        g2.WC = WC;
+        g2.NCT = NCW * WC;
         const int threads = 32 * WR * WC;
-        size_t smem = (size_t)2 * geo.KT * geo.NCT * 32 * sizeof(double2) + (size_t)MR * NCW * 2 * threads * sizeof(double2);
-        if (K_sweep > 0) smem += (size_t)K_sweep * 8 * geo.NCT * sizeof(double);
-        if (smem <= kSmemLimit) {
-            cfg.geo = geo;
+        size_t smem = (size_t)2 * g2.KT * g2.NCT * 32 * sizeof(double2) + (size_t)MR * NCW * 2 * threads * sizeof(double2);
+        if (K_sweep > 0) smem += (size_t)K_sweep * 8 * g2.NCT * sizeof(double);
+        if (smem > kSmemLimit) continue;
+        const int ctas = (CT + g2.NCT - 1) / g2.NCT;
+        const long cost = (long)((ctas + SMS - 1) / SMS) * NCW;
+        if (!found || cost < best_cost) {
+            found = true;
+            best_cost = cost;
+            cfg.geo = g2;
             cfg.MR = MR;
             cfg.NCW = NCW;
             cfg.threads = threads;
             cfg.smem = smem;
-            cfg.grid = (CT + geo.NCT - 1) / geo.NCT;
-            return true;
+            cfg.grid = ctas;
         }
-        if (NCW == 1) return false;
-        NCW /= 2;
     }
+    return found;
 }
 
 template <int MR, int NCW>

@@ -1,0 +1,234 @@
+"""Fixed-step drivers: the step grid of the reference (host, NumPy) and the fused device loops.
+
+* ``merge_t_args`` / ``trim_t_results`` / ``get_fixed_step_sizes`` keep the reference's exact
+  semantics (solvers/solver_utils.py:46-119, solvers/fixed_step_solvers.py:616-653).
+* ``rk4_model_solve`` / ``expm_model_solve`` own the step loop for model generators: per
+  integration interval they build the stage-time grid with the reference's accumulation, evaluate
+  the SignalList once into a (T, K) table, and make ONE C-ABI call (qdb_rk4_steps_c128 /
+  qdb_expm_steps_c128) -- replacing the Python hot loop at solvers/fixed_step_solvers.py:448-454.
+* ``RK4_solver`` / ``scipy_expm_solver`` keep the reference's generic callable protocol
+  (``rhs(t, y)`` / ``generator(t)`` as arbitrary Python functions returning device tensors); this
+  host-driven route cannot be fused and is not on the measured path.
+"""
+
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+from scipy.integrate._ivp.ivp import OdeResult
+
+from .. import _abi
+from ..arrays import asarray, asreal
+from ..exceptions import QiskitError
+
+EXPM_THETA = 0.7  # 1-norm radius of the degree-16 Taylor polynomial (csrc/expm.cu)
+
+
+# ---------------------------------------------------------------------------------------------
+# step grid (host)
+# ---------------------------------------------------------------------------------------------
+
+
+def merge_t_args(t_span, t_eval=None) -> np.ndarray:
+    """[t_span[0], *t_eval, t_span[1]] after validation; t_span itself when t_eval is None."""
+    if t_eval is None:
+        return t_span
+    t_span = np.array(t_span)
+    t_eval = np.array(t_eval)
+    lo, hi = np.min(t_span), np.max(t_span)
+    direction = np.sign(t_span[1] - t_span[0])
+    if t_eval.ndim > 1:
+        raise ValueError("t_eval must be 1 dimensional.")
+    if np.min(t_eval) < lo or np.max(t_eval) > hi:
+        raise ValueError("t_eval entries must lie in t_span.")
+    if np.any(direction * np.diff(t_eval) < 0.0):
+        raise ValueError("t_eval must be ordered according to the direction of integration.")
+    return np.append(np.append(t_span[0], t_eval), t_span[1])
+
+
+def trim_t_results(results: OdeResult, t_eval=None) -> OdeResult:
+    """Drop the two end points that merge_t_args added."""
+    if t_eval is None:
+        return results
+    results.t = results.t[1:-1]
+    results.y = results.y[1:-1]
+    return results
+
+
+def get_fixed_step_sizes(t_span, t_eval, max_dt) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """(t_list, h_list, n_steps_list): fewest equal steps per interval with |h| <= max_dt."""
+    t_list = np.array(merge_t_args(np.array(t_span), t_eval))
+    max_dt = np.array(max_dt)
+    deltas = np.diff(t_list)
+    n_steps = np.abs(deltas / max_dt).astype(int)
+    for i, (delta, n) in enumerate(zip(deltas, n_steps)):
+        if n == 0:
+            n_steps[i] = 1
+        elif np.abs(delta / n) / max_dt > 1 + 1e-15:  # guard against the truncation above
+            n_steps[i] = n + 1
+    return t_list, np.array(deltas / n_steps), n_steps
+
+
+def stage_time_grid(t0: float, h: float, n_steps: int) -> np.ndarray:
+    """[t_0, t_0 + h/2, t_1, t_1 + h/2, ..., t_S] with t_{i+1} = t_i + h accumulated sequentially
+    (cumsum is a sequential add), exactly the floats the reference's loop produces
+    (fixed_step_solvers.py:64-66, 453) -- this matters for DiscreteSignal bin edges."""
+    starts = np.cumsum(np.concatenate([[float(t0)], np.full(int(n_steps), float(h))]))
+    grid = np.empty(2 * int(n_steps) + 1)
+    grid[0::2] = starts
+    grid[1::2] = starts[:-1] + 0.5 * h
+    return grid
+
+
+# ---------------------------------------------------------------------------------------------
+# fused model solves
+# ---------------------------------------------------------------------------------------------
+
+
+def _columns(y0: torch.Tensor):
+    if y0.ndim == 1:
+        return y0.reshape(-1, 1).contiguous(), y0.shape
+    if y0.ndim == 2:
+        return y0.contiguous(), y0.shape
+    raise QiskitError("y0 must be a vector or a matrix whose columns are states.")
+
+
+def rk4_model_solve(model, t_span, y0_fb: torch.Tensor, max_dt, t_eval=None,
+                    column_coefficients: Optional[Callable[[np.ndarray], np.ndarray]] = None,
+                    workspace_bytes: int = 1 << 30) -> OdeResult:
+    """RK4 on a model generator, state already in the frame basis.
+
+    ``column_coefficients(times) -> (T, K, B)`` switches to sweep mode (per-column signal values).
+    """
+    coll = model._collection()
+    n = coll.dim
+    y, shape = _columns(y0_fb)
+    if y.shape[0] != n:
+        raise QiskitError(f"y0 has leading dimension {y.shape[0]}, model dimension is {n}.")
+    y = y.clone()
+    B = y.shape[1]
+    mu = model._frame_freqs()
+    t_list, h_list, n_list = get_fixed_step_sizes(t_span, t_eval, max_dt)
+    ops, stat = coll.operators, coll.static_operator
+    use_packed = _abi.npad(n) <= 256
+    ops_p, stat_p = coll.packed() if use_packed else (None, None)
+    K = coll.num_operators
+    ws = None
+    ys = [y.reshape(shape).clone()]
+    for t0, h, S in zip(t_list, h_list, n_list):
+        S = int(S)
+        times = stage_time_grid(t0, h, S)
+        if column_coefficients is not None:
+            table = np.ascontiguousarray(column_coefficients(times), dtype=np.float64)
+            if table.shape != (times.shape[0], K, B):
+                raise QiskitError(f"per-column signal table has shape {table.shape}, expected {(times.shape[0], K, B)}")
+            coeff = asreal(table, y.device)
+            per_col = True
+        else:
+            table = model._signal_table(times)
+            coeff = None if table is None else asreal(table, y.device)
+            per_col = False
+        need = _abi.workspace_bytes(_abi.WS_RK4, n, K, B, S)
+        need = min(need, max(workspace_bytes, _abi.workspace_bytes(_abi.WS_RK4, n, K, B, 1)))
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=y.device)
+        _abi.rk4_steps(n, ops, stat, ops_p, stat_p, coeff, mu, times, float(h), y, S, per_col=per_col, workspace=ws)
+        ys.append(y.reshape(shape).clone())
+    return trim_t_results(OdeResult(t=np.array(t_list), y=torch.stack(ys)), t_eval)
+
+
+def expm_squarings(model, coeff_table: Optional[np.ndarray], h: float) -> np.ndarray:
+    """Squarings per step from the bound ||h G(t)||_1 <= |h| (||G_d||_1 + sum |c_j| ||G_j||_1) (the
+    frame phases have modulus 1), so that no device->host norm read is needed inside the loop."""
+    s_norm, o_norms = model._collection().norms1()
+    S = 1 if coeff_table is None else coeff_table.shape[0]
+    bound = np.full(S, s_norm, dtype=float)
+    if coeff_table is not None and o_norms.size:
+        bound = bound + np.abs(coeff_table) @ o_norms
+    bound = np.abs(h) * bound
+    with np.errstate(divide="ignore"):
+        sq = np.ceil(np.log2(np.maximum(bound, 1e-300) / EXPM_THETA))
+    return np.maximum(sq, 0).astype(np.int32)
+
+
+def expm_model_solve(model, t_span, y0_fb: torch.Tensor, max_dt, t_eval=None, magnus_order: int = 1) -> OdeResult:
+    """y <- expm(h G(t + h/2)) y per step (Magnus order 1) on a model generator."""
+    if magnus_order != 1:
+        raise QiskitError("Only magnus_order 1 is implemented by the fused B200 exponential stepper.")
+    coll = model._collection()
+    n = coll.dim
+    y, shape = _columns(y0_fb)
+    if y.shape[0] != n:
+        raise QiskitError(f"y0 has leading dimension {y.shape[0]}, model dimension is {n}.")
+    y = y.clone()
+    mu = model._frame_freqs()
+    t_list, h_list, n_list = get_fixed_step_sizes(t_span, t_eval, max_dt)
+    ws = None
+    ys = [y.reshape(shape).clone()]
+    for t0, h, S in zip(t_list, h_list, n_list):
+        S = int(S)
+        starts = stage_time_grid(t0, h, S)[0::2][:-1]
+        mids = starts + (h / 2)
+        table = model._signal_table(mids)
+        coeff = None if table is None else asreal(table, y.device)
+        sq = expm_squarings(model, table, float(h)) if table is not None else np.repeat(expm_squarings(model, None, float(h)), S)
+        need = _abi.workspace_bytes(_abi.WS_EXPM, n, coll.num_operators, y.shape[1])
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=y.device)
+        _abi.expm_steps(n, coll.operators, coll.static_operator, coeff, mu, mids, sq, float(h), y, S, workspace=ws)
+        ys.append(y.reshape(shape).clone())
+    return trim_t_results(OdeResult(t=np.array(t_list), y=torch.stack(ys)), t_eval)
+
+
+# ---------------------------------------------------------------------------------------------
+# generic callable protocol (host-driven; not fused)
+# ---------------------------------------------------------------------------------------------
+
+
+def fixed_step_solver_template(take_step: Callable, rhs_func: Callable, t_span, y0, max_dt, t_eval=None) -> OdeResult:
+    y0 = asarray(y0)
+    t_list, h_list, n_list = get_fixed_step_sizes(t_span, t_eval, max_dt)
+    ys = [y0]
+    for t0, h, n in zip(t_list, h_list, n_list):
+        y = ys[-1]
+        t = t0
+        for _ in range(int(n)):
+            y = take_step(rhs_func, t, y, h)
+            t = t + h
+        ys.append(y)
+    return trim_t_results(OdeResult(t=np.array(t_list), y=torch.stack(ys)), t_eval)
+
+
+def RK4_solver(rhs: Callable, t_span, y0, max_dt, t_eval=None) -> OdeResult:
+    """Classical RK4 for an arbitrary ``rhs(t, y)`` returning device tensors."""
+    div6 = 1.0 / 6
+
+    def take_step(f, t, y, h):
+        h2 = 0.5 * h
+        k1 = asarray(f(t, y))
+        k2 = asarray(f(t + h2, y + h2 * k1))
+        k3 = asarray(f(t + h2, y + h2 * k2))
+        k4 = asarray(f(t + h, y + h * k3))
+        return y + div6 * h * (k1 + 2 * k2 + 2 * k3 + k4)
+
+    return fixed_step_solver_template(take_step, rhs, t_span, y0, max_dt, t_eval)
+
+
+def scipy_expm_solver(generator: Callable, t_span, y0, max_dt, t_eval=None, magnus_order: int = 1) -> OdeResult:
+    """Exponential stepper for an arbitrary ``generator(t)`` returning an (n, n) device tensor; the
+    exponential itself is the device Taylor scaling-and-squaring (qdb_expm_c128)."""
+    if magnus_order != 1:
+        raise QiskitError("Only magnus_order 1 is implemented by the B200 exponential stepper.")
+
+    def take_step(gen, t, y, h):
+        A = (asarray(gen(t + (h / 2))) * h).contiguous()
+        norm = float(torch.linalg.matrix_norm(A, 1))
+        sq = max(0, int(np.ceil(np.log2(max(norm, 1e-300) / EXPM_THETA))))
+        P = _abi.expm(A, sq)
+        if y.ndim == 1:
+            return _abi.zgemm(P, y.reshape(-1, 1).contiguous()).reshape(-1)
+        return _abi.zgemm(P, y.contiguous())
+
+    return fixed_step_solver_template(take_step, generator, t_span, y0, max_dt, t_eval)

@@ -1,0 +1,211 @@
+"""Solver: model construction + simulation entry point (mirror of solvers/solver_classes.py).
+
+Kept: constructor arguments for the operator/frames part, ``solve(t_span, y0, signals, **kwargs)``
+with single simulations or lists of simulations, initial-state validation, signals cleared after
+the solve.  New: a list of simulations that shares ``t_span`` and differs only in ``signals`` (and
+optionally ``y0`` vectors) -- the reference's *sequential* Python loop
+(solvers/solver_classes.py:556-590) -- is executed as ONE sweep-mode launch in which every
+simulation is a state column with its own signal values.
+
+Outside this build (need qiskit): pulse ``Schedule`` inputs,
+``Statevector``/``DensityMatrix``/``SuperOp`` wrapping, the rotating-wave approximation.
+"""
+
+from __future__ import annotations
+
+from typing import List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+from scipy.integrate._ivp.ivp import OdeResult
+
+from ..arrays import asarray
+from ..exceptions import QiskitError
+from ..models import HamiltonianModel, LindbladModel, RotatingFrame
+from ..signals import Signal, SignalList
+from .fixed_step import rk4_model_solve
+from .solver_functions import (ODE_METHODS, is_lindblad_model_not_vectorized, is_lindblad_model_vectorized,
+                               results_y_out_of_frame_basis, setup_generator_model_rhs_y0_in_frame_basis, solve_lmde)
+
+
+class Solver:
+    def __init__(self, static_hamiltonian=None, hamiltonian_operators=None, static_dissipators=None,
+                 dissipator_operators=None, hamiltonian_channels=None, dissipator_channels=None,
+                 channel_carrier_freqs=None, dt=None, rotating_frame=None, in_frame_basis: bool = False,
+                 array_library: Optional[str] = None, vectorized: Optional[bool] = None,
+                 rwa_cutoff_freq: Optional[float] = None, rwa_carrier_freqs=None, validate: bool = True):
+        if any(x is not None for x in (dt, channel_carrier_freqs, hamiltonian_channels, dissipator_channels)):
+            raise QiskitError("pulse Schedule simulation (channels / dt) needs qiskit.pulse and is not part of the B200 build.")
+        if rwa_cutoff_freq:
+            raise QiskitError("rotating_wave_approximation is a set-up-time transform outside the B200 build.")
+        if static_dissipators is None and dissipator_operators is None:
+            self._model = HamiltonianModel(static_operator=static_hamiltonian, operators=hamiltonian_operators,
+                                           rotating_frame=rotating_frame, in_frame_basis=in_frame_basis,
+                                           array_library=array_library, validate=validate)
+        else:
+            self._model = LindbladModel(static_hamiltonian=static_hamiltonian,
+                                        hamiltonian_operators=hamiltonian_operators,
+                                        static_dissipators=static_dissipators,
+                                        dissipator_operators=dissipator_operators, rotating_frame=rotating_frame,
+                                        in_frame_basis=in_frame_basis, array_library=array_library,
+                                        vectorized=bool(vectorized), validate=validate)
+
+    @property
+    def model(self) -> Union[HamiltonianModel, LindbladModel]:
+        return self._model
+
+    # -- signals ------------------------------------------------------------------------------
+    def _set_new_signals(self, signals):
+        if signals is not None:
+            if isinstance(self.model, LindbladModel) and isinstance(signals, (list, SignalList)):
+                signals = (signals, None)
+            self.model.signals = signals
+        elif isinstance(self.model, LindbladModel):
+            self.model.signals = (None, None)
+        else:
+            self.model.signals = None
+
+    # -- solve --------------------------------------------------------------------------------
+    def solve(self, t_span, y0, signals=None, convert_results: bool = True, **kwargs):
+        """Simulate; lists of ``t_span`` / ``y0`` / ``signals`` run several simulations."""
+        [t_span_list, y0_list, signals_list], multiple = setup_args_lists(
+            [t_span, y0, signals], ["t_span", "y0", "signals"], [t_span_to_list, _y0_to_list, _signals_to_list])
+        try:
+            results = self._solve_batched(t_span_list, y0_list, signals_list, **kwargs)
+            if results is None:
+                results = self._solve_list(t_span_list, y0_list, signals_list, **kwargs)
+        finally:
+            self._set_new_signals(None)
+        return results if multiple else results[0]
+
+    def _solve_list(self, t_span_list, y0_list, signals_list, **kwargs) -> List[OdeResult]:
+        out = []
+        for t_span, y0, signals in zip(t_span_list, y0_list, signals_list):
+            self._set_new_signals(signals)
+            y0 = validate_and_format_initial_state(y0, self.model)
+            out.append(solve_lmde(generator=self.model, t_span=t_span, y0=y0, **kwargs))
+        self._set_new_signals(None)
+        return out
+
+    def _solve_batched(self, t_span_list, y0_list, signals_list, **kwargs) -> Optional[List[OdeResult]]:
+        """One sweep-mode launch for a list of simulations, when they qualify; else None."""
+        nsim = len(signals_list)
+        model = self.model
+        if nsim < 2 or kwargs.get("method", None) not in ODE_METHODS or "max_dt" not in kwargs:
+            return None
+        if not (isinstance(model, HamiltonianModel) or is_lindblad_model_vectorized(model)):
+            return None
+        if any(s is None for s in signals_list) or model._collection().num_operators == 0:
+            return None
+        if model._collection().dim > 256:
+            return None
+        spans = np.asarray(t_span_list, dtype=float)
+        if not np.all(spans == spans[0]):
+            return None
+        y0s = [validate_and_format_initial_state(y, model) for y in y0_list]
+        if any(y.ndim != 1 for y in y0s):
+            return None
+        t_eval = kwargs.get("t_eval", None)
+        max_dt = kwargs["max_dt"]
+        extra = {k: v for k, v in kwargs.items() if k not in ("method", "max_dt", "t_eval")}
+        if extra:
+            return None
+
+        # per-simulation SignalLists (validated by the model's own setter)
+        sig_lists = []
+        for signals in signals_list:
+            self._set_new_signals(signals)
+            sig_lists.append(model.signals)
+        self._set_new_signals(signals_list[0])
+
+        def column_coefficients(times: np.ndarray) -> np.ndarray:
+            cols = []
+            for sl in sig_lists:
+                if isinstance(model, LindbladModel):
+                    parts = [s.table(times) for s in sl if s is not None]
+                    cols.append(np.concatenate(parts, axis=-1))
+                else:
+                    cols.append(sl.table(times))
+            return np.stack(cols, axis=-1)  # (T, K, B)
+
+        Y0 = torch.stack(y0s, dim=1).contiguous()  # (n, B): one column per simulation
+        _, _, y0_fb, was = setup_generator_model_rhs_y0_in_frame_basis(model, Y0)
+        try:
+            res = rk4_model_solve(model, spans[0], y0_fb, max_dt, t_eval=t_eval, column_coefficients=column_coefficients)
+            if not was:
+                res.y = results_y_out_of_frame_basis(model, res.y, 2)
+        finally:
+            model.in_frame_basis = was
+        return [OdeResult(t=res.t, y=res.y[:, :, b].contiguous()) for b in range(nsim)]
+
+
+# ---------------------------------------------------------------------------------------------
+# helpers (solvers/solver_classes.py:741-913, solvers/solver_utils.py:230-287)
+# ---------------------------------------------------------------------------------------------
+
+
+def validate_and_format_initial_state(y0, model):
+    """Array initial states only: shape checks of solver_classes.py:781-792."""
+    y0 = asarray(y0)
+    if isinstance(model, HamiltonianModel) and (y0.shape[0] != model.dim or y0.ndim > 2):
+        raise QiskitError("Shape mismatch for initial state y0 and HamiltonianModel.")
+    if is_lindblad_model_vectorized(model) and (y0.shape[0] != model.dim**2 or y0.ndim > 2):
+        raise QiskitError("Shape mismatch for initial state y0 and LindbladModel in vectorized evaluation mode.")
+    if is_lindblad_model_not_vectorized(model) and tuple(y0.shape[-2:]) != (model.dim, model.dim):
+        raise QiskitError("Shape mismatch for initial state y0 and LindbladModel.")
+    return y0
+
+
+def _nested_ndim(x) -> int:
+    if isinstance(x, (list, tuple)):
+        return 1 + _nested_ndim(x[0])
+    if hasattr(x, "ndim"):
+        return x.ndim
+    return 0
+
+
+def t_span_to_list(t_span):
+    ndim = _nested_ndim(t_span)
+    if ndim > 2:
+        raise QiskitError("t_span must be either 1d or 2d.")
+    if ndim == 1:
+        return [t_span], False
+    return list(t_span), True
+
+
+def _y0_to_list(y0):
+    if isinstance(y0, list):
+        return y0, True
+    return [y0], False
+
+
+def _signals_to_list(signals):
+    if signals is None or isinstance(signals, tuple):
+        return [signals], False
+    if isinstance(signals, list) and len(signals) > 0 and isinstance(signals[0], tuple):
+        return signals, True
+    if isinstance(signals, list) and len(signals) > 0 and isinstance(signals[0], (list, SignalList)):
+        return signals, True
+    if isinstance(signals, SignalList) or (isinstance(signals, list) and len(signals) > 0):
+        return [signals], False
+    raise QiskitError("Signals specified in invalid format.")
+
+
+def setup_args_lists(args_list, args_names, args_to_list):
+    """Expand singletons so that every argument is a list of the common length."""
+    as_lists, any_list = [], False
+    for arg, to_list in zip(args_list, args_to_list):
+        lst, was = to_list(arg)
+        as_lists.append(lst)
+        any_list = any_list or was
+    lens = [len(x) for x in as_lists]
+    longest = max(lens)
+    for name, ln in zip(args_names, lens):
+        if ln not in (1, longest):
+            names = ", ".join(args_names[:-1]) + f", and {args_names[-1]}"
+            raise QiskitError(
+                f"If one of {names} is given as a list of valid inputs, then the others must specify only a "
+                f"single input, or a list of the same length. {args_names[lens.index(longest)]} specifies "
+                f"{longest} inputs, but {name} is of length {ln}, which is incompatible."
+            )
+    return [x * longest if len(x) == 1 else x for x in as_lists], any_list

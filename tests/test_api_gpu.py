@@ -1,0 +1,292 @@
+"""GPU parity of the drop-in surface (Signal / RotatingFrame / HamiltonianModel / LindbladModel /
+solve_lmde / Solver) against fixtures produced by the UNMODIFIED reference (tests/golden/*.npz).
+
+These read like the reference's own tests (test_generator_model.py, test_lindblad_model.py,
+test_rotating_frame.py, test_solver_functions.py): build the model from the same arrays, call the
+same methods, compare.  Tolerance: 1e-10 absolute on O(1) data (the north-star bar is 1e-8).
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from conftest import load_golden, max_col_l2  # noqa: E402
+from oracle import numpy_oracle as orc  # noqa: E402
+
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def qd():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import qiskit_dynamics_b200 as q
+    q._abi.lib()
+    return q
+
+
+def npy(x):
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+def close(a, b, tol=TOL):
+    np.testing.assert_allclose(npy(a), np.asarray(b), rtol=0, atol=tol)
+
+
+def sigs(qd, spec):
+    return [qd.Signal(a, nu, ph) for (a, nu, ph) in np.asarray(spec)]
+
+
+def test_operator_collection(qd):
+    g = load_golden("collection")
+    full = qd.OperatorCollection(static_operator=g["stat"], operators=g["ops"])
+    nostat = qd.OperatorCollection(operators=g["ops"])
+    onlystat = qd.OperatorCollection(static_operator=g["stat"])
+    close(full.evaluate(g["c_real"]), g["eval_real"])
+    close(full.evaluate(g["c_cplx"]), g["eval_cplx"])
+    close(nostat.evaluate(g["c_real"]), g["eval_nostat"])
+    close(onlystat.evaluate(None), g["eval_onlystat"])
+    close(full.evaluate_rhs(g["c_real"], g["yv"]), g["rhs_v"])
+    close(full.evaluate_rhs(g["c_real"], g["ym"]), g["rhs_m"])
+    close(full.evaluate_rhs(g["c_cplx"], g["ym"]), g["rhs_m_cplx"])
+    close(nostat(g["c_real"], g["ym"]), g["rhs_m_nostat"])
+    close(onlystat(None, g["ym"]), g["rhs_m_onlystat"])
+    assert full.dim == 6
+    with pytest.raises(qd.QiskitError):
+        qd.OperatorCollection().evaluate(None)
+    with pytest.raises(qd.QiskitError):
+        qd.OperatorCollection(operators=g["ops"], array_library="scipy_sparse")
+    # explicit-loop check with 32 operators of 128x128 and complex coefficients
+    # (reference test_operator_collections.py:82-94)
+    rng = np.random.default_rng(342)
+    ops = rng.uniform(-1, 1, (32, 128, 128)) + 1j * rng.uniform(-1, 1, (32, 128, 128))
+    c = rng.uniform(-1, 1, 32) + 1j * rng.uniform(-1, 1, 32)
+    close(qd.OperatorCollection(operators=ops).evaluate(c), sum(ci * o for ci, o in zip(c, ops)), 1e-11)
+
+
+def test_rotating_frame(qd):
+    g = load_golden("frame")
+    rf = qd.RotatingFrame(g["H"])
+    t = float(g["t"])
+    y, op, sop = g["y"], g["op"], g["sop"]
+    close(rf.frame_diag, g["frame_diag"])
+    close(qd.RotatingFrame(-1j * g["H"]).frame_diag, g["frame_diag_anti"])
+    rf1 = qd.RotatingFrame(g["diag1d"])
+    close(rf1.frame_diag, g["frame_diag_1d"])
+    assert rf1.frame_basis is None and rf.dim == 5
+    close(rf.state_into_frame(t, y, y_in_frame_basis=True, return_in_frame_basis=True), g["into_fb"])
+    close(rf.state_out_of_frame(t, y, y_in_frame_basis=True, return_in_frame_basis=True), g["outof_fb"])
+    close(rf.state_into_frame(t, y), g["into_full"])
+    close(rf.state_out_of_frame(t, y), g["outof_full"])
+    close(rf.state_into_frame(t, y[:, 0]), g["into_full"][:, 0])
+    close(rf.operator_into_frame(t, op, operator_in_frame_basis=True, return_in_frame_basis=True), g["op_into_fb"])
+    close(rf.operator_into_frame(t, op), g["op_into_full"])
+    close(rf.operator_out_of_frame(t, op), g["op_outof_full"])
+    close(rf.generator_into_frame(t, op), g["gen_into_full"])
+    close(rf.generator_out_of_frame(t, op), g["gen_outof_full"])
+    close(rf.vectorized_map_into_frame(t, sop, operator_in_frame_basis=True, return_in_frame_basis=True), g["vec_into_fb"])
+    close(rf.vectorized_map_into_frame(t, sop), g["vec_into_full"], 1e-9)
+    close(rf.state_out_of_frame_basis(rf.state_into_frame_basis(y)), y)
+    close(rf.operator_out_of_frame_basis(rf.operator_into_frame_basis(op)), op)
+    close(rf1.state_into_frame(t, y), g["into_1d"])
+    close(rf1.operator_into_frame(t, op), g["op_into_1d"])
+    # stack of operators and the vectorised-operator convention (dim^2, k)
+    stack = np.stack([op, 2 * op])
+    close(rf.operator_into_frame(t, stack), np.stack([g["op_into_full"], 2 * g["op_into_full"]]))
+    vec = np.stack([op.flatten(order="F"), 2 * op.flatten(order="F")], axis=1)
+    out = npy(rf.operator_into_frame(t, vec, vectorized_operators=True))
+    close(out[:, 0].reshape(5, 5, order="F"), g["op_into_full"])
+    # null frame is the identity map
+    rf0 = qd.RotatingFrame(None)
+    close(rf0.state_into_frame(t, y), y)
+    close(rf0.generator_into_frame(t, op), op)
+    with pytest.raises(qd.QiskitError):
+        qd.RotatingFrame(np.array([[1.0, 2.0], [3.0, 4.0]]))
+
+
+def test_hamiltonian_model(qd):
+    g = load_golden("hamiltonian_model")
+    H0, Hs, Y, sig = g["H0"], g["Hs"], g["Y"], g["sig"]
+    for frame_name, frame in (("none", None), ("full", H0), ("diag", np.diag(H0).real)):
+        m = qd.HamiltonianModel(static_operator=H0, operators=Hs, signals=sigs(qd, sig), rotating_frame=frame)
+        assert m.dim == 8
+        for i, t in enumerate(g["ts"]):
+            close(m(t, Y), g[f"rhs_{frame_name}_fb0_{i}"])
+            close(m(t), g[f"gen_{frame_name}_fb0_{i}"])
+        close(m(0.37, Y[:, 0]), g[f"rhsvec_{frame_name}_fb0"])
+        if frame_name != "full":  # frame-basis quantities are eigenvector-phase dependent for a full frame
+            m.in_frame_basis = True
+            for i, t in enumerate(g["ts"]):
+                close(m(t, Y), g[f"rhs_{frame_name}_fb1_{i}"])
+                close(m(t), g[f"gen_{frame_name}_fb1_{i}"])
+            close(m._operator_collection.operators, g[f"ops_{frame_name}"])
+        # public operator accessors undo the -i fold (hamiltonian_model.py:134-150)
+        m.in_frame_basis = False
+        close(m.operators, Hs)
+    # batch of columns == per-column (reference test_generator_model.py:615-674)
+    m = qd.HamiltonianModel(static_operator=H0, operators=Hs, signals=sigs(qd, sig), rotating_frame=H0)
+    full = npy(m(0.37, Y))
+    for b in range(Y.shape[1]):
+        close(m(0.37, Y[:, b]), full[:, b], 1e-13)
+    # frame only, no static operator
+    m = qd.HamiltonianModel(operators=Hs, signals=sigs(qd, sig), rotating_frame=H0)
+    Gd_o, G_o, d_o, U_o = orc.generator_model_operators(None, Hs, H0)
+    sp = [orc.SigSpec(a, nu, ph) for (a, nu, ph) in sig]
+    close(m(0.37, Y), U_o @ orc.model_rhs(0.37, U_o.conj().T @ Y, sp, G_o, Gd_o, d_o))
+    close(torch.diag(m._operator_collection.static_operator), np.diag(g["stat_nostatic"]))
+    # GeneratorModel with a non-Hermitian generator in an anti-Hermitian frame
+    gm = qd.GeneratorModel(static_operator=g["Gd"], operators=g["Gs"], signals=sigs(qd, sig), rotating_frame=-1j * H0)
+    close(gm(0.37, Y), g["genmodel_rhs"], 1e-9)
+    close(gm(0.37), g["genmodel_gen"], 1e-9)
+    # error conventions
+    with pytest.raises(qd.QiskitError):
+        qd.HamiltonianModel(static_operator=np.array([[0, 1], [0, 0]]))
+    with pytest.raises(qd.QiskitError):
+        qd.HamiltonianModel()
+    with pytest.raises(qd.QiskitError):
+        qd.HamiltonianModel(operators=Hs, signals=sigs(qd, sig)[:2])
+    with pytest.raises(qd.QiskitError):
+        qd.HamiltonianModel(operators=Hs)(0.1, Y)  # no signals
+
+
+def test_rk4_solves(qd):
+    g = load_golden("rk4_solves")
+    # cfg1 through solve_lmde and through Solver (plumbing)
+    m = qd.HamiltonianModel(static_operator=g["cfg1_H0"], operators=[g["cfg1_H1"]], signals=[qd.Signal(1.0, 5.0)],
+                            rotating_frame=g["cfg1_H0"])
+    r = qd.solve_lmde(m, t_span=[0, 10.0], y0=g["cfg1_y0"], method="RK4", max_dt=1e-3)
+    assert tuple(r.y.shape) == (2, 4) and list(r.t) == [0, 10.0]
+    close(r.y, g["cfg1_y"], 1e-9)
+    assert m.in_frame_basis is False
+    s = qd.Solver(static_hamiltonian=g["cfg1_H0"], hamiltonian_operators=[g["cfg1_H1"]], rotating_frame=g["cfg1_H0"])
+    r2 = s.solve(t_span=[0, 10.0], y0=g["cfg1_y0"], signals=[qd.Signal(1.0, 5.0)], method="RK4", max_dt=1e-3)
+    close(r2.y, g["cfg1_solver_y"], 1e-9)
+    assert s.model.signals is None
+    # cfg4-like
+    H0, Hs, Y, sig = orc.synthetic_schrodinger(128, 8, 8, 2004)
+    m = qd.HamiltonianModel(static_operator=H0, operators=Hs, signals=sigs(qd, sig), rotating_frame=H0)
+    r = qd.solve_lmde(m, t_span=[0, 0.05], y0=Y, method="RK4", max_dt=1e-3)
+    assert max_col_l2(npy(r.y[-1]), g["cfg4_y"]) < TOL
+    r = qd.solve_lmde(m, t_span=[0, 0.02], y0=Y, method="RK4", max_dt=1e-3, t_eval=[0.0, 0.005, 0.0125, 0.02])
+    assert np.array_equal(r.t, g["cfg4_teval_t"])
+    close(r.y, g["cfg4_teval_y"])
+    close(qd.solve_lmde(m, t_span=[0, 1e-3], y0=Y, method="RK4", max_dt=1e-3).y[-1], g["cfg4_onestep_y"], 1e-12)
+    close(qd.solve_lmde(m, t_span=[0.02, 0.0], y0=Y, method="RK4", max_dt=1e-3).y[-1], g["cfg4_back_y"])
+    close(qd.solve_ode(m, t_span=[0, 0.05], y0=Y, method="RK4", max_dt=1e-3).y[-1], g["cfg4_y"])
+    # cfg2-like sweep through Solver with a list of signal lists (one launch for the whole list)
+    H0, Hs, Y, sig = orc.synthetic_schrodinger(32, 8, 1, 2002)
+    B = 16
+    s = qd.Solver(static_hamiltonian=H0, hamiltonian_operators=Hs, rotating_frame=H0)
+    sig_lists = [[qd.Signal(a * (0.5 + b / B), nu, ph) for (a, nu, ph) in sig] for b in range(B)]
+    before = qd._abi.launch_count()
+    res = s.solve(t_span=[0, 0.1], y0=Y[:, 0], signals=sig_lists, method="RK4", max_dt=1e-3)
+    launches = qd._abi.launch_count() - before
+    assert isinstance(res, list) and len(res) == B
+    assert launches <= 8, f"sweep should be a handful of launches, saw {launches}"
+    got = np.stack([npy(r.y[-1]) for r in res], axis=-1)
+    assert max_col_l2(got, g["cfg2_y"]) < TOL
+    # ... and the sequential path (different y0 shapes disable batching) agrees
+    res1 = s.solve(t_span=[0, 0.1], y0=Y[:, 0], signals=sig_lists[3], method="RK4", max_dt=1e-3)
+    close(res1.y[-1], g["cfg2_y"][:, 3])
+    # odd dimension
+    H0, Hs, Y, sg = g["odd_H0"], g["odd_Hs"], g["odd_Y"], g["odd_sig"]
+    m = qd.HamiltonianModel(static_operator=H0, operators=Hs, signals=sigs(qd, sg))
+    close(qd.solve_lmde(m, t_span=[0, 0.5], y0=Y, method="RK4", max_dt=0.01).y[-1], g["odd_noframe_y"])
+    m = qd.HamiltonianModel(static_operator=H0, operators=Hs, signals=sigs(qd, sg), rotating_frame=np.diag(H0).real)
+    close(qd.solve_lmde(m, t_span=[0, 0.5], y0=Y, method="RK4", max_dt=0.01).y[-1], g["odd_diagframe_y"])
+    close(qd.solve_lmde(m, t_span=[0, 0.5], y0=Y[:, 0], method="RK4", max_dt=0.01).y[-1], g["odd_vec_y"])
+    close(qd.solve_lmde(m, t_span=[0, 0.5], y0=np.eye(5, dtype=complex), method="RK4", max_dt=0.01).y[-1], g["odd_eye_y"])
+    close(qd.solve_lmde(m, t_span=[0, 0.5], y0=Y, method="scipy_expm", max_dt=0.01).y[-1], g["odd_expm_y"])
+    m = qd.HamiltonianModel(static_operator=H0, operators=Hs, signals=sigs(qd, sg), rotating_frame=H0)
+    close(qd.solve_lmde(m, t_span=[0, 0.5], y0=Y, method="scipy_expm", max_dt=0.01).y[-1], g["odd_expm_fullframe_y"])
+    # DiscreteSignal drive, every stage time on a bin edge
+    dt = float(g["disc_dt"])
+    ds = [qd.DiscreteSignal(dt=dt, samples=g["disc_samples"][j], carrier_freq=0.3 * (j + 1), phase=0.1 * j) for j in range(2)]
+    m = qd.HamiltonianModel(static_operator=g["disc_H0"], operators=g["disc_Hs"], signals=ds, rotating_frame=g["disc_H0"])
+    close(qd.solve_lmde(m, t_span=[0, 2.0], y0=g["disc_Y"], method="RK4", max_dt=dt / 2).y[-1], g["disc_y"])
+    m = qd.HamiltonianModel(static_operator=g["disc_H0"], operators=g["disc_Hs"], signals=ds)
+    close(qd.solve_lmde(m, t_span=[0, 2.0], y0=g["disc_Y"], method="RK4", max_dt=dt / 2).y[-1], g["disc_noframe_y"])
+    # callable generator / rhs (reference test_fixed_step_solvers.py style)
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((5, 5)) + 1j * rng.standard_normal((5, 5))
+    Ad = qd.asarray(A)
+    r = qd.solve_lmde(lambda t: Ad * np.cos(t), t_span=[0, 1.0], y0=np.eye(5, dtype=complex), method="RK4", max_dt=0.01)
+    yref = orc.fixed_step_solve(orc.rk4_step, lambda t, y: (A * np.cos(t)) @ y, [0, 1.0], np.eye(5, dtype=complex), 0.01)[1]
+    close(r.y, yref)
+    r = qd.solve_lmde(lambda t: Ad * np.cos(t), t_span=[0, 1.0], y0=np.eye(5, dtype=complex), method="scipy_expm", max_dt=0.1)
+    yref = orc.fixed_step_solve(orc.expm_step, lambda t: A * np.cos(t), [0, 1.0], np.eye(5, dtype=complex), 0.1)[1]
+    close(r.y, yref, 1e-9)
+    # error conventions
+    with pytest.raises(qd.QiskitError):
+        qd.solve_lmde(m, t_span=[0, 1], y0=g["disc_Y"], method="DOP853")
+    with pytest.raises(qd.QiskitError):
+        qd.solve_lmde(m, t_span=[0, 1], y0=g["disc_Y"], method="not_a_method", max_dt=0.1)
+    with pytest.raises(ValueError):
+        qd.solve_lmde(m, t_span=[0, 1], y0=g["disc_Y"], method="RK4", max_dt=0.1, t_eval=[0.5, 1.5])
+    with pytest.raises(qd.QiskitError):
+        s.solve(t_span=[0, 0.1], y0=np.ones(7), signals=sig_lists[0], method="RK4", max_dt=1e-3)
+
+
+def test_lindblad(qd):
+    g = load_golden("lindblad")
+    H0, Hs, Lstat, Ldyn, Y = g["s_H0"], g["s_Hs"], g["s_Lstat"], g["s_Ldyn"], g["s_Y"]
+    n, B = 3, Y.shape[1]
+    rho = np.array([Y[:, b].reshape(n, n, order="F") for b in range(B)])
+    hc, dc = g["s_hc"], g["s_dc"]
+    lc = qd.LindbladCollection(static_hamiltonian=H0, hamiltonian_operators=Hs, static_dissipators=Lstat, dissipator_operators=Ldyn)
+    close(lc.evaluate_rhs(hc, dc, rho), g["s_coll_rhs"])
+    close(lc.evaluate_rhs(hc, dc, rho[0]), g["s_coll_rhs"][0])
+    close(qd.LindbladCollection(static_hamiltonian=H0, hamiltonian_operators=Hs).evaluate_rhs(hc, None, rho), g["s_coll_rhs_hamonly"])
+    close(qd.LindbladCollection(static_hamiltonian=H0, static_dissipators=Lstat).evaluate_rhs(None, None, rho), g["s_coll_rhs_statdis"])
+    with pytest.raises(ValueError):
+        lc.evaluate(hc, dc)
+    vc = qd.VectorizedLindbladCollection(static_hamiltonian=H0, hamiltonian_operators=Hs, static_dissipators=Lstat, dissipator_operators=Ldyn)
+    close(vc.evaluate(hc, dc), g["s_vcoll_eval"])
+    close(vc.evaluate_rhs(hc, dc, Y), g["s_vcoll_rhs"])
+    close(vc.evaluate_hamiltonian(hc), H0 + np.tensordot(hc, Hs, axes=1))
+    for frame_name, frame in (("none", None), ("full", H0), ("diag", np.diag(H0).real)):
+        kw = dict(static_hamiltonian=H0, hamiltonian_operators=Hs, hamiltonian_signals=sigs(qd, g["s_sig"]),
+                  static_dissipators=Lstat, dissipator_operators=Ldyn, dissipator_signals=sigs(qd, g["s_dsig"]),
+                  rotating_frame=frame)
+        mv = qd.LindbladModel(vectorized=True, **kw)
+        mm = qd.LindbladModel(vectorized=False, **kw)
+        assert mv.dim == 3 and mv.vectorized and not mm.vectorized
+        t = 0.41
+        close(mv(t), g[f"s_vec_gen_{frame_name}_fb0"], 1e-9)
+        close(mv(t, Y), g[f"s_vec_rhs_{frame_name}_fb0"], 1e-9)
+        close(mm(t, rho), g[f"s_mat_rhs_{frame_name}_fb0"], 1e-9)
+        close(mm(t, rho[0]), g[f"s_mat_rhs1_{frame_name}_fb0"], 1e-9)
+        if frame_name != "full":
+            mv.in_frame_basis = True
+            mm.in_frame_basis = True
+            close(mv(t), g[f"s_vec_gen_{frame_name}_fb1"])
+            close(mv(t, Y), g[f"s_vec_rhs_{frame_name}_fb1"])
+            close(mm(t, rho), g[f"s_mat_rhs_{frame_name}_fb1"])
+            oc = mv._operator_collection._operator_collection
+            close(oc.static_operator, g[f"s_super_static_{frame_name}"])
+            close(oc.operators, g[f"s_super_ops_{frame_name}"])
+            mv.in_frame_basis = False
+            mm.in_frame_basis = False
+        with pytest.raises(NotImplementedError):
+            mm(t)
+        close(qd.solve_lmde(mv, t_span=[0, 0.5], y0=Y, method="scipy_expm", max_dt=0.05).y[-1], g[f"s_expm_{frame_name}"], 1e-9)
+        close(qd.solve_lmde(mv, t_span=[0, 0.5], y0=Y, method="RK4", max_dt=0.01).y[-1], g[f"s_rk4_{frame_name}"], 1e-9)
+        close(qd.solve_lmde(mv, t_span=[0, 0.5], y0=Y[:, 1], method="RK4", max_dt=0.01).y[-1], g[f"s_rk4_{frame_name}"][:, 1], 1e-9)
+        close(qd.solve_lmde(mm, t_span=[0, 0.5], y0=rho, method="RK4", max_dt=0.01).y[-1], g[f"s_rk4_mat_{frame_name}"], 1e-9)
+        with pytest.raises(qd.QiskitError):
+            qd.solve_lmde(mm, t_span=[0, 0.5], y0=rho, method="scipy_expm", max_dt=0.05)
+    # Solver with dissipators builds a LindbladModel; from_hamiltonian keeps frame + signals
+    s = qd.Solver(static_hamiltonian=H0, hamiltonian_operators=Hs, static_dissipators=Lstat, vectorized=True, rotating_frame=np.diag(H0).real)
+    assert isinstance(s.model, qd.LindbladModel)
+    hm = qd.HamiltonianModel(static_operator=H0, operators=Hs, signals=sigs(qd, g["s_sig"]))
+    lm = qd.LindbladModel.from_hamiltonian(hm, static_dissipators=Lstat, dissipator_operators=Ldyn,
+                                           dissipator_signals=sigs(qd, g["s_dsig"]), vectorized=True)
+    close(lm(0.41, Y), g["s_vec_rhs_none_fb0"], 1e-9)
+    # cfg3-like: n = 27 (729), expm stepper, 1-d frame
+    H0, Hs, Ls, Y, sig = orc.synthetic_lindblad(27, 3, 6, 4, 2003)
+    mv = qd.LindbladModel(static_hamiltonian=H0, hamiltonian_operators=Hs, hamiltonian_signals=sigs(qd, sig),
+                          static_dissipators=Ls, rotating_frame=np.diag(H0).real, vectorized=True)
+    r = qd.solve_lmde(mv, t_span=[0, 0.03], y0=Y, method="scipy_expm", max_dt=1e-2)
+    assert max_col_l2(npy(r.y[-1]), g["cfg3_expm_y"]) < TOL
+    close(mv(0.013, Y), g["cfg3_rhs"])

@@ -1,0 +1,211 @@
+"""CPU-only tests: host logic of the drop-in surface, the C-ABI library's symbols, and the
+world_size-2 sharding path on gloo.  No compute call is made (there is no GPU here and the product
+has no CPU fallback -- which is itself asserted)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+
+@pytest.fixture(scope="module")
+def qd():
+    import __graft_entry__ as ge
+    ge.build()
+    import qiskit_dynamics_b200 as q
+    return q
+
+
+def test_library_exports_every_declared_symbol(qd):
+    header = open(os.path.join(ROOT, "include", "qdb.h")).read()
+    declared = set(re.findall(r"\b(qdb_[a-z0-9_]+)\s*\(", header))
+    declared -= {"qdb_c128"}
+    assert len(declared) >= 12
+    lib = ctypes.CDLL(qd._abi.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/qdb.h but not exported"
+    assert declared == set(qd._abi.SIGNATURES), (declared ^ set(qd._abi.SIGNATURES))
+    l = qd._abi.lib()
+    assert l.qdb_version() >= 100
+    assert l.qdb_npad(27) == 32 and l.qdb_npad(128) == 128 and l.qdb_packed_elems(5) == 64
+    assert qd._abi.workspace_bytes(qd._abi.WS_RK4, 128, 8, 4096, 10) >= 21 * 128 * 128 * 16
+    assert l.qdb_last_error_string() is not None
+
+
+def test_abi_argument_validation_without_gpu(qd):
+    """Invalid arguments are rejected before any CUDA call (negative return, message set)."""
+    l = qd._abi.lib()
+    rc = l.qdb_pack_operators(0, 1, None, None, None)
+    assert rc == -1 and b"qdb_pack_operators" in l.qdb_last_error_string()
+    rc = l.qdb_generator_c128(4, 0, 1, 0, None, None, None, 0, None, None, 1.0, None, None)
+    assert rc == -1
+    rc = l.qdb_rk4_steps_c128(4, 1, 2, 3, None, None, None, None, None, 7, 0, None, None, 0.1, None, 2, None, 0, None)
+    assert rc == -1 and b"sig_mode" in l.qdb_last_error_string()
+    assert l.qdb_rk4_steps_c128(4, 1, 0, 3, None, None, None, None, None, 0, 0, None, None, 0.1, None, 0, None, 0, None) == 0  # empty batch
+    assert l.qdb_expm_steps_c128(4, 0, 1, 0, None, None, None, None, None, None, 0.1, None, 1, None, 0, None) == 0  # zero steps
+
+
+def test_no_cpu_fallback(qd):
+    m = qd.HamiltonianModel(static_operator=np.diag([1.0, -1.0]), operators=[np.array([[0, 1], [1, 0]])],
+                            signals=[qd.Signal(1.0, 1.0)], rotating_frame=np.diag([1.0, -1.0]))
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(qd._abi.QdbError, match="no CPU fallback"):
+        m(0.1, np.array([1.0, 0.0]))
+    with pytest.raises(qd._abi.QdbError):
+        qd.solve_lmde(m, t_span=[0, 1], y0=np.array([1.0, 0.0]), method="RK4", max_dt=0.1)
+    # nothing in the product imports the oracle
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "qiskit_dynamics_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("numpy_oracle", "oracle") or "import" not in [ln for ln in src.splitlines() if "oracle" in ln][0], f
+
+
+def test_signals_match_reference_golden(qd):
+    g = load_golden("signals")
+    ts, samples = g["ts"], g["samples"]
+    d1 = qd.DiscreteSignal(dt=0.1, samples=samples, carrier_freq=1.3, phase=0.2)
+    d2 = qd.DiscreteSignal(dt=0.1, samples=samples, start_time=1.0, carrier_freq=0.0)
+    s1 = qd.Signal(0.7, 2.0, 0.4)
+    s2 = qd.Signal(lambda t: np.exp(-t**2) * (1 + 0.5j), carrier_freq=0.9, phase=-1.1)
+    s3 = qd.Signal(1.5)
+    tol = dict(rtol=0, atol=1e-14)
+    np.testing.assert_allclose(d1(ts), g["d1"], **tol)
+    np.testing.assert_allclose(d1.complex_value(ts), g["d1_cv"], **tol)
+    np.testing.assert_allclose(d2(ts), g["d2"], **tol)
+    np.testing.assert_allclose(s1(ts), g["s1"], **tol)
+    np.testing.assert_allclose(s2(ts), g["s2"], **tol)
+    np.testing.assert_allclose(s2.complex_value(ts), g["s2_cv"], **tol)
+    np.testing.assert_allclose(s3(ts), g["s3"], **tol)
+    np.testing.assert_allclose((s1 + s2)(ts), g["ssum"], **tol)
+    np.testing.assert_allclose((s1 * s2)(ts), g["sprod"], **tol)
+    np.testing.assert_allclose((d1 * d1)(ts), g["dprod"], **tol)
+    sl = qd.SignalList([s1, s2, s3, d1, d2, s1 + s2, 2.0])
+    np.testing.assert_allclose(sl(ts), g["siglist"], **tol)
+    np.testing.assert_allclose(sl(0.123), g["siglist_scalar"], **tol)
+    np.testing.assert_allclose(sl.complex_value(ts), g["siglist_cv"], **tol)
+    np.testing.assert_allclose(sl.drift, g["drift"], **tol)
+    assert sl.table(ts).shape == (len(ts), 7) and sl.table(ts).flags["C_CONTIGUOUS"]
+    np.testing.assert_allclose(d1.conjugate().complex_value(ts), g["conj_d1"], **tol)
+    # bin-edge semantics on accumulated stage times: identical sample choice
+    d3 = qd.DiscreteSignal(dt=1 / 4.5, samples=g["dsamp"], carrier_freq=0.4)
+    assert np.array_equal(d3.envelope(g["tacc"]), g["d3_env_acc"])
+    np.testing.assert_allclose(d3(g["tacc"]), g["d3_acc"], **tol)
+    # algebra closure / types
+    assert s3.is_constant and not s1.is_constant
+    assert isinstance(d1 + d1, qd.DiscreteSignalSum) and isinstance(2.0 * d1, qd.DiscreteSignalSum)
+    assert isinstance(s1 * s2, qd.SignalSum) and len(s1 * s2) == 2
+    np.testing.assert_allclose((s1 - s2)(ts), g["s1"] - g["s2"], **tol)
+    np.testing.assert_allclose((-s1)(ts), -g["s1"], **tol)
+    np.testing.assert_allclose((3 + s1)(ts), 3 + g["s1"], **tol)
+    np.testing.assert_allclose((s1 + s2).flatten()(ts), g["ssum"], rtol=0, atol=1e-13)
+    ds = qd.DiscreteSignal.from_Signal(s2, dt=0.1, n_samples=10)
+    assert ds.duration == 10 and ds.dt == 0.1
+    np.testing.assert_allclose(ds.samples, s2.envelope(0.05 + 0.1 * np.arange(10)), **tol)
+    dd = qd.DiscreteSignal(dt=0.5, samples=[1.0, 2.0])
+    dd.add_samples(3, [5.0])
+    np.testing.assert_allclose(dd.samples, [1, 2, 0, 5])
+    with pytest.raises(qd.QiskitError):
+        dd.add_samples(1, [1.0])
+    assert len(sl[[0, 2]]) == 2 and isinstance(sl[1], qd.SignalSum)
+    with pytest.raises(qd.QiskitError):
+        qd.SignalSum("not a signal")
+
+
+def test_step_grid_matches_reference_golden(qd):
+    from qiskit_dynamics_b200.solvers import get_fixed_step_sizes, merge_t_args, stage_time_grid
+    g = load_golden("step_grid")
+    for i in range(int(g["ncases"])):
+        ev = g[f"eval{i}"] if bool(g[f"has_eval{i}"]) else None
+        t, h, n = get_fixed_step_sizes(g[f"span{i}"], ev, float(g[f"maxdt{i}"]))
+        assert np.array_equal(t, g[f"t{i}"]) and np.array_equal(h, g[f"h{i}"]) and np.array_equal(n, g[f"n{i}"])
+    for bad in ([0.5, 1.5], [0.7, 0.5], [[0.5]]):
+        with pytest.raises(ValueError):
+            merge_t_args([0, 1], bad)
+    # stage grid == the reference loop's accumulated floats
+    t0, h, S = 0.3, (1 / 4.5) / 2, 25
+    grid = stage_time_grid(t0, h, S)
+    t = t0
+    for i in range(S):
+        assert grid[2 * i] == t and grid[2 * i + 1] == t + 0.5 * h and grid[2 * i + 2] == t + h
+        t = t + h
+
+
+def test_model_construction_and_error_conventions(qd):
+    g = load_golden("hamiltonian_model")
+    H0, Hs = g["H0"], g["Hs"]
+    m = qd.HamiltonianModel(static_operator=H0, operators=Hs, rotating_frame=np.diag(H0).real, in_frame_basis=True)
+    np.testing.assert_allclose(m._operator_collection.operators.numpy(), g["ops_diag"], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(m._operator_collection.static_operator.numpy(), g["stat_diag"], rtol=0, atol=1e-14)
+    m0 = qd.HamiltonianModel(static_operator=H0, operators=Hs)
+    np.testing.assert_allclose(m0._operator_collection.operators.numpy(), g["ops_none"], rtol=0, atol=1e-14)
+    assert m.dim == 8 and m.in_frame_basis and m.signals is None
+    m.signals = [1.0, 2.0, qd.Signal(1.0, 3.0)]
+    assert isinstance(m.signals, qd.SignalList) and len(m.signals) == 3
+    np.testing.assert_allclose(m.rotating_frame.frame_freqs.numpy(), np.diag(H0).real)
+    for bad, exc in (
+        (lambda: qd.HamiltonianModel(), qd.QiskitError),
+        (lambda: qd.HamiltonianModel(static_operator=np.array([[0, 1], [0, 0]])), qd.QiskitError),
+        (lambda: qd.HamiltonianModel(operators=Hs, signals=[1.0]), qd.QiskitError),
+        (lambda: qd.HamiltonianModel(static_operator=H0, signals=[1.0]), qd.QiskitError),
+        (lambda: qd.HamiltonianModel(operators=Hs, signals="x"), qd.QiskitError),
+        (lambda: qd.RotatingFrame(np.array([[1.0, 2.0], [3.0, 4.0]])), qd.QiskitError),
+        (lambda: qd.LindbladModel(), qd.QiskitError),
+        (lambda: qd.LindbladModel(static_hamiltonian=np.array([[0, 1], [0, 0]])), qd.QiskitError),
+        (lambda: qd.Solver(hamiltonian_operators=Hs, dt=0.1), qd.QiskitError),
+        (lambda: qd.OperatorCollection(operators=Hs, array_library="jax"), qd.QiskitError),
+    ):
+        with pytest.raises(exc):
+            bad()
+    # vectorised Lindblad superoperators are built at construction (no frame -> pure torch set-up)
+    gl = load_golden("lindblad")
+    lm = qd.LindbladModel(static_hamiltonian=gl["s_H0"], hamiltonian_operators=gl["s_Hs"], static_dissipators=gl["s_Lstat"],
+                          dissipator_operators=gl["s_Ldyn"], vectorized=True)
+    oc = lm._operator_collection._operator_collection
+    np.testing.assert_allclose(oc.static_operator.numpy(), gl["s_super_static_none"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(oc.operators.numpy(), gl["s_super_ops_none"], rtol=0, atol=1e-13)
+    lm1 = qd.LindbladModel(static_hamiltonian=gl["s_H0"], hamiltonian_operators=gl["s_Hs"], static_dissipators=gl["s_Lstat"],
+                           dissipator_operators=gl["s_Ldyn"], vectorized=True, rotating_frame=np.diag(gl["s_H0"]).real)
+    np.testing.assert_allclose(lm1._operator_collection._operator_collection.static_operator.numpy(),
+                               gl["s_super_static_diag"], rtol=0, atol=1e-13)
+    lam = np.diag(gl["s_H0"]).real
+    np.testing.assert_allclose(lm1._frame_freqs().numpy(), (lam[:, None] - lam[None, :]).flatten(order="F"))
+    with pytest.raises(qd.QiskitError):
+        lm.signals = ([1.0], None)
+    # Solver argument plumbing
+    from qiskit_dynamics_b200.solvers.solver_classes import setup_args_lists, t_span_to_list, _y0_to_list, _signals_to_list
+    lists, multi = setup_args_lists([[0, 1], [np.ones(2), np.zeros(2)], None], ["t_span", "y0", "signals"],
+                                    [t_span_to_list, _y0_to_list, _signals_to_list])
+    assert multi and [len(x) for x in lists] == [2, 2, 2]
+    with pytest.raises(qd.QiskitError):
+        setup_args_lists([[[0, 1], [0, 2], [0, 3]], [np.ones(2), np.zeros(2)], None], ["t_span", "y0", "signals"],
+                         [t_span_to_list, _y0_to_list, _signals_to_list])
+
+
+def test_shard_bounds():
+    from qiskit_dynamics_b200 import distributed as D
+    for B in (1, 7, 512, 4096, 4097):
+        for w in (1, 2, 3, 8):
+            spans = [D.shard_bounds(B, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_gloo_world_size_2_gather():
+    """Batch sharding + the single final all-gather, two processes on gloo (CPU tensors)."""
+    script = os.path.join(ROOT, "tests", "_gloo_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29631")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29631", script],
+                         cwd=ROOT, env=env, capture_output=True, text=True, timeout=240)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "GLOO_OK rank=0" in res.stdout and "GLOO_OK rank=1" in res.stdout
