@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: RHS evals/sec, dim-128 Schrodinger in the rotating frame,
+fp64 (complex128), batch 4096 per GPU, fixed-step RK4 (BASELINE.json configs[3]).
+
+    python bench.py --gpus N --steps K --warmup W            # the B200 arm
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's NumPy path (CPU)
+
+A "step" is one pass of the hot path over one batch: a fused solve of RK4_STEPS fixed RK4 steps
+(4 RHS evaluations each) on all B columns.  Metric = state-RHS evaluations per second, whole job
+(sum over the N ranks; weak scaling: B columns per GPU).
+
+  value  : inputs already resident in HBM (operators, signal table, state); timed per step with
+           CUDA events on the launching stream, L2 flushed between steps, max over ranks.
+  e2e    : the same workload through the public API (`solve_lmde(model, ...)`) from a pinned HOST
+           y0 to a pinned HOST final state -- host-side signal table, H2D, basis changes, D2H and
+           (N > 1) the single NCCL gather of final observables are all inside the timed region.
+  roofline : the dominant kernel (rk4_shared_kernel, one launch per step) against the fp64
+           tensor pipe: algorithmic flops per launch / its mean CUDA-event duration, over the
+           live-measured DMMA peak (MEASURED_PEAKS.json has no fp64 entry; datasheet 37-40 TF).
+  cpu_baseline : the oracle port of the reference's NumPy path (same BLAS calls) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_DIM, K_OPS, BATCH = 128, 8, 4096
+RK4_STEPS = 100       # RK4 steps per bench step (400 RHS evaluations per column)
+MAX_DT = 1e-3
+SEED = 2004
+REF_RK4_STEPS = 3     # bounded CPU sample per reference step
+
+
+def flops_per_column_step(n):
+    """4 (8 n^2 + 12 n) + 28 n per RK4 step per column."""
+    return 4 * (8 * n * n + 12 * n) + 28 * n
+
+
+def workload(n, K, B, seed):
+    from oracle import numpy_oracle as orc  # synthetic-input generator shared with the tests
+    H0, Hs, Y, sig = orc.synthetic_schrodinger(n, K, B, seed)
+    return H0, Hs, Y, sig
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's NumPy path
+# ---------------------------------------------------------------------------------------------
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        blas = [p for p in threadpool_info() if p.get("user_api") == "blas"]
+        if blas:
+            return int(max(p["num_threads"] for p in blas))
+    except Exception:  # noqa: BLE001
+        pass
+    return os.cpu_count() or 1
+
+
+def cpu_reference_rate(n, K, B, steps, warmup, rk4_steps, seed=SEED):
+    """state-RHS/s of solve_lmde(method='RK4') restated in NumPy (oracle), all host BLAS threads."""
+    from oracle import numpy_oracle as orc
+    H0, Hs, Y, sig = workload(n, K, B, seed)
+    specs = [orc.SigSpec(a, nu, ph) for a, nu, ph in sig]
+    Gd, G, d, U = orc.generator_model_operators(H0, Hs, H0)
+    yfb = U.conj().T @ Y
+    rhs = lambda t, y: orc.model_rhs(t, y, specs, G, Gd, d)  # noqa: E731
+    span = [0.0, rk4_steps * MAX_DT]
+    for _ in range(warmup):
+        orc.fixed_step_solve(orc.rk4_step, rhs, span, yfb, MAX_DT)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.fixed_step_solve(orc.rk4_step, rhs, span, yfb, MAX_DT)
+    dt = time.perf_counter() - t0
+    return 4.0 * rk4_steps * B * steps / dt, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = cpu_threads()
+    rate, sec_per_step = cpu_reference_rate(N_DIM, K_OPS, BATCH, args.steps, args.warmup, REF_RK4_STEPS)
+    sample = f"{REF_RK4_STEPS} RK4 steps ({4 * REF_RK4_STEPS} batched RHS calls) on the full n={N_DIM}, K={K_OPS}, B={BATCH} batch per step"
+    line = {
+        "impl": "reference", "metric": "rhs_evals_per_sec", "value": rate, "unit": "state-RHS/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+        "config": {"workload": f"cfg4: dim-{N_DIM} Schrodinger, rotating frame, K={K_OPS}, batch {BATCH}, RK4 max_dt={MAX_DT}",
+                   "note": "reference arm = NumPy port of qiskit-dynamics solve_lmde(method='RK4') (oracle/), host cores only; "
+                           "the reference is pure Python and cannot be compiled to oracle/_ref"},
+        "cpu_baseline": {"value": rate, "unit": "state-RHS/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "state-RHS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling
+# ---------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": float(max(power))}
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import __graft_entry__ as ge
+    ge.build()
+    import qiskit_dynamics_b200 as qd
+    from qiskit_dynamics_b200 import _abi as abi
+    from qiskit_dynamics_b200 import distributed as D
+    from qiskit_dynamics_b200.solvers import stage_time_grid
+
+    qd.set_default_device(f"cuda:{local_rank}")
+    dev = torch.device("cuda", local_rank)
+    n, K, B, S = N_DIM, K_OPS, BATCH, RK4_STEPS
+    H0, Hs, Y, sig = workload(n, K, B, SEED + rank)  # every rank owns its own B columns (weak scaling)
+    signals = [qd.Signal(a, nu, ph) for a, nu, ph in sig]
+    model = qd.HamiltonianModel(static_operator=H0, operators=Hs, signals=signals, rotating_frame=H0)
+    t_span = [0.0, S * MAX_DT]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2
+
+    # ---------------- device-resident arm: generator table + fused RK4 kernel ----------------
+    coll = model._collection()
+    ops_p, stat_p = coll.packed()
+    mu = model._frame_freqs()
+    times = stage_time_grid(0.0, MAX_DT, S)
+    coeff = torch.from_numpy(model._signal_table(times)).to(dev)
+    times_d = torch.from_numpy(times).to(dev)
+    y_fb = model.rotating_frame.state_into_frame_basis(qd.asarray(Y))
+    y_work = y_fb.clone()
+    table = torch.empty((2 * S + 1, abi.packed_elems(n)), dtype=torch.complex128, device=dev)
+
+    def device_step(record=None):
+        y_work.copy_(y_fb)
+        abi.generator(n, ops_p, stat_p, coeff, mu, times_d, layout=abi.LAYOUT_PACKED, out=table)
+        if record is not None:
+            record[0].record()
+        abi.rk4_table_steps(n, table, MAX_DT, y_work, S)
+        if record is not None:
+            record[1].record()
+
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = abi.launch_count()
+    step_ms, kern_ms = [], []
+    barrier()
+    for _ in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        device_step((k0, k1))
+        e1.record()
+        torch.cuda.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        kern_ms.append(k0.elapsed_time(k1))
+    barrier()
+    launches = abi.launch_count() - launches0
+    dev_ms = max_over_ranks(float(np.mean(step_ms)))
+    kern_mean_ms = float(np.mean(kern_ms))
+    value = 4.0 * S * B * world / (dev_ms * 1e-3)
+
+    # ---------------- end-to-end arm: public API, pinned host in / pinned host out ----------------
+    y0_host = torch.from_numpy(Y).pin_memory()
+    out_host = torch.empty((n, B), dtype=torch.complex128).pin_memory()
+    obs_host = torch.empty(B * world, dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        res = qd.solve_lmde(model, t_span=t_span, y0=y0_host, method="RK4", max_dt=MAX_DT)
+        yf = res.y[-1]
+        out_host.copy_(yf, non_blocking=True)
+        if world > 1:  # the single collective of the path: gather of final observables over NVLink
+            obs = D.all_gather_columns((yf.real**2 + yf.imag**2).sum(dim=0), B * world)
+            obs_host.copy_(obs, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        e2e_step()
+    barrier()
+    e2e_s = []
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e2e_step()
+        e2e_s.append(time.perf_counter() - t0)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_ms = max_over_ranks(float(np.mean(e2e_s)) * 1e3)
+    e2e_value = 4.0 * S * B * world / (e2e_ms * 1e-3)
+
+    # ---------------- roofline of the dominant kernel ----------------
+    peak_tf = abi.dmma_probe()
+    flops_launch = float(S) * B * flops_per_column_step(n)
+    achieved_tf = flops_launch / (kern_mean_ms * 1e-3) * 1e-12
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "rk4_shared_traffic.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            traffic = None
+
+    # parity spot check of the timed configuration (not timed): norm preservation of the unitary flow
+    norms = torch.linalg.vector_norm(y_work, dim=0)
+    norm_dev = float((norms - 1.0).abs().max().item())
+
+    if rank == 0:
+        threads = cpu_threads()
+        cpu_rate, cpu_sec = cpu_reference_rate(n, K, B, steps=2, warmup=1, rk4_steps=REF_RK4_STEPS)
+        line = {
+            "metric": "rhs_evals_per_sec", "value": value, "unit": "state-RHS/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+            "config": {"workload": f"cfg4: dim-{n} Schrodinger in rotating frame, K={K} drive operators, batch {B} per GPU, "
+                                   f"fixed-step RK4 max_dt={MAX_DT}; one bench step = {S} RK4 steps = {4 * S} RHS evals per column",
+                       "l2": "flushed between timed iterations (256 MB write)", "rk4_steps_per_step": S,
+                       "batch_per_gpu": B, "max_unitarity_drift": norm_dev},
+            "e2e": {"value": e2e_value, "unit": "state-RHS/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(n * B * 16 + coeff.numel() * 8 + times.size * 8),
+                    "d2h_bytes_per_step": int(n * B * 16 + (8 * B * world if world > 1 else 0))},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "rk4_shared_kernel<2,4>", "achieved": achieved_tf, "peak": peak_tf,
+                         "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
+                         "flops_per_launch": flops_launch, "kernel_ms": kern_mean_ms,
+                         "peak_source": "live DMMA m8n8k4 issue-rate probe (qdb_dmma_probe); MEASURED_PEAKS.json has no "
+                                        "fp64 entry; B200 datasheet fp64 tensor 37-40 TFLOP/s"},
+            "cpu_baseline": {"value": cpu_rate, "unit": "state-RHS/s", "cores": threads, "kind": "port",
+                             "sample": f"{REF_RK4_STEPS} RK4 steps of the same n={n}, K={K}, B={B} batch x 2 repeats "
+                                       f"({cpu_sec:.2f} s each), NumPy/OpenBLAS port of the reference path"},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

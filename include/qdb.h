@@ -41,8 +41,9 @@ typedef struct { double re, im; } qdb_c128;
 
 /* layouts of an (n x n) operator in device memory */
 #define QDB_LAYOUT_ROWMAJOR 0 /* [n][n] */
-#define QDB_LAYOUT_PACKED 1   /* DMMA A-fragment order, zero padded to npad = 8*ceil(n/8):
-                                 element (r,c) at ((r/8)*(npad/4) + c/4)*32 + (r%8)*4 + c%4 */
+#define QDB_LAYOUT_PACKED 1   /* DMMA A-fragment order, zero padded to npad = 8*ceil(n/8) rows and
+                                 kpad = 16*ceil(n/16) columns:
+                                 element (r,c) at ((r/8)*(kpad/4) + c/4)*32 + (r%8)*4 + c%4 */
 
 /* workspace kinds for qdb_workspace_bytes */
 #define QDB_WS_RHS 0
@@ -52,7 +53,7 @@ typedef struct { double re, im; } qdb_c128;
 const char* qdb_last_error_string(void);
 int qdb_version(void);
 
-/* n rounded up to the DMMA tile (8) and the element count of one packed operator (npad*npad). */
+/* n rounded up to the DMMA tile (8) and the element count of one packed operator (npad*kpad). */
 int qdb_npad(int n);
 size_t qdb_packed_elems(int n);
 
@@ -128,6 +129,18 @@ int qdb_rk4_steps_c128(int n, int K, int B, int S,
                        const double* mu, const double* times_host, double h,
                        qdb_c128* y, int ldy,
                        void* workspace, size_t ws_bytes, void* stream);
+
+/* The on-chip RK4 kernel alone: S steps from a prebuilt generator table
+ * gen_table_packed[2S+1][npad*npad] (QDB_LAYOUT_PACKED entries G_frame(t) at the stage times, as
+ * produced by qdb_generator_c128).  n <= 256.  This is the dominant launch of
+ * qdb_rk4_steps_c128 in shared-signal mode; exported so that it can be timed/profiled alone. */
+int qdb_rk4_table_steps_c128(int n, int B, int S, const qdb_c128* gen_table_packed, double h,
+                             qdb_c128* y, int ldy, void* stream);
+
+/* fp64 tensor-pipe (DMMA m8n8k4) issue-rate probe: launches register-resident DMMA chains on every
+ * SM; *flops_out (host) receives the flop count of the launch.  Timed by the caller with CUDA
+ * events, it gives the live roofline denominator for the fp64 kernels. */
+int qdb_dmma_probe(double* sink, int iters, double* flops_out, void* stream);
 
 /* a9: S exponential (Magnus order 1) steps  y <- expm(h * G_frame(t_s + h/2)) y  with a
  * scaling-and-squaring Taylor propagator built from qdb_zgemm_c128 products.

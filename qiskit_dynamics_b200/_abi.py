@@ -46,6 +46,8 @@ SIGNATURES = {
     "qdb_rhs_c128": (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _d, _vp, _vp, _i, _vp, _sz, _vp]),
     "qdb_rk4_steps_c128": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _d, _vp, _i, _vp, _sz, _vp]),
     "qdb_expm_steps_c128": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _i, _vp, _sz, _vp]),
+    "qdb_rk4_table_steps_c128": (_i, [_i, _i, _i, _vp, _d, _vp, _i, _vp]),
+    "qdb_dmma_probe": (_i, [_vp, _i, _vp, _vp]),
     "qdb_expm_c128": (_i, [_i, _vp, _i, _vp, _vp, _sz, _vp]),
     "qdb_launch_count": (ctypes.c_ulonglong, []),
 }
@@ -104,6 +106,11 @@ def npad(n: int) -> int:
     return (n + 7) & ~7
 
 
+def packed_elems(n: int) -> int:
+    """Elements of one operator in QDB_LAYOUT_PACKED (rows padded to 8, columns to 16)."""
+    return ((n + 7) & ~7) * ((n + 15) & ~15)
+
+
 def workspace_bytes(kind: int, n: int, K: int, B: int, S: int = 1) -> int:
     return int(lib().qdb_workspace_bytes(kind, n, K, B, S))
 
@@ -115,7 +122,7 @@ def launch_count() -> int:
 def pack_operators(ops: torch.Tensor) -> torch.Tensor:
     """(count, n, n) row-major -> (count, npad*npad) DMMA-fragment order."""
     count, n, _ = ops.shape
-    out = torch.empty((count, npad(n) ** 2), dtype=C, device=ops.device)
+    out = torch.empty((count, packed_elems(n)), dtype=C, device=ops.device)
     _check(lib().qdb_pack_operators(n, count, _ptr(ops, C, "ops"), _ptr(out, C, "out"), _stream()), "qdb_pack_operators")
     return out
 
@@ -130,7 +137,7 @@ def generator(n, ops, stat, coeff, mu, times, scale=1.0, layout=LAYOUT_ROWMAJOR,
     else:
         T = 1
     cplx = coeff is not None and coeff.dtype == C
-    elems = npad(n) ** 2 if layout == LAYOUT_PACKED else n * n
+    elems = packed_elems(n) if layout == LAYOUT_PACKED else n * n
     dev = (ops if ops is not None else stat).device
     if out is None:
         out = torch.empty((T, elems), dtype=C, device=dev)
@@ -228,3 +235,29 @@ def expm(A: torch.Tensor, squarings: int, out=None):
     _check(lib().qdb_expm_c128(n, _ptr(A, C, "A"), int(squarings), _ptr(out, C, "out"), ctypes.c_void_p(ws.data_ptr()),
                                ws.numel(), _stream()), "qdb_expm_c128")
     return out
+
+
+def rk4_table_steps(n, table, h, y, S):
+    """The on-chip RK4 kernel alone, from a prebuilt packed generator table (2S+1, npad^2)."""
+    B = y.shape[1]
+    if table.shape[0] < 2 * S + 1:
+        raise QdbError(f"rk4_table_steps: table has {table.shape[0]} entries, need {2 * S + 1}")
+    _check(lib().qdb_rk4_table_steps_c128(n, B, S, _ptr(table, C, "table"), float(h), _ptr(y, C, "y"), B, _stream()),
+           "qdb_rk4_table_steps_c128")
+    return y
+
+
+def dmma_probe(iters: int = 20000, reps: int = 5) -> float:
+    """Measured fp64 tensor-pipe peak in TFLOP/s (best of `reps`, CUDA events)."""
+    sink = torch.zeros(1, dtype=F, device="cuda")
+    flops = ctypes.c_double(0.0)
+    best = float("inf")
+    for r in range(reps + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _check(lib().qdb_dmma_probe(_ptr(sink, F, "sink"), int(iters), ctypes.byref(flops), _stream()), "qdb_dmma_probe")
+        e1.record()
+        torch.cuda.synchronize()
+        if r > 0:
+            best = min(best, e0.elapsed_time(e1))
+    return flops.value / best * 1e-9

@@ -47,7 +47,7 @@ extern "C" {
 const char* qdb_last_error_string(void) { return g_err; }
 int qdb_version(void) { return 100; }
 int qdb_npad(int n) { return round_up8(n); }
-size_t qdb_packed_elems(int n) { return (size_t)round_up8(n) * round_up8(n); }
+size_t qdb_packed_elems(int n) { return (size_t)round_up8(n) * round_up16(n); }
 unsigned long long qdb_launch_count(void) { return g_launches.load(); }
 
 size_t qdb_workspace_bytes(int kind, int n, int K, int B, int S) {
@@ -256,6 +256,26 @@ int qdb_rk4_steps_c128(int n, int K, int B, int S, const qdb_c128* ops_rm, const
         if ((rc = launch_axpby((size_t)n * B, Y, acc, (1.0 / 6) * h, Y, 1.0, st)) != QDB_OK) return rc;
     }
     return QDB_OK;
+}
+
+int qdb_rk4_table_steps_c128(int n, int B, int S, const qdb_c128* gen_table_packed, double h, qdb_c128* y, int ldy,
+                             void* stream) {
+    QDB_REQUIRE(n >= 1 && B >= 0 && S >= 0, "qdb_rk4_table_steps_c128: bad n=%d B=%d S=%d", n, B, S);
+    if (B == 0 || S == 0) return QDB_OK;
+    QDB_REQUIRE(gen_table_packed && y && ldy >= B, "qdb_rk4_table_steps_c128: null pointer / bad ldy");
+    if (!rk4_fused_supported(n)) {
+        set_error("qdb_rk4_table_steps_c128: on-chip path needs n <= 256 (got %d)", n);
+        return QDB_E_UNSUPPORTED;
+    }
+    return launch_rk4_fused_shared(n, B, S, D2(gen_table_packed), h, D2(y), ldy, (cudaStream_t)stream);
+}
+
+int qdb_dmma_probe(double* sink, int iters, double* flops_out, void* stream) {
+    QDB_REQUIRE(sink && iters > 0, "qdb_dmma_probe: bad arguments");
+    int grid = 0;
+    const int rc = launch_dmma_probe(sink, iters, &grid, (cudaStream_t)stream);
+    if (rc == QDB_OK && flops_out) *flops_out = (double)grid * 8.0 /*warps*/ * iters * 16.0 * 512.0;
+    return rc;
 }
 
 int qdb_expm_c128(int n, const qdb_c128* A, int squarings, qdb_c128* out, void* workspace, size_t ws_bytes, void* stream) {

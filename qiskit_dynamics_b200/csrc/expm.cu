@@ -51,3 +51,40 @@ int expm_core(int n, const double2* As, int squarings, double2* out, double2* ws
 }
 
 }  // namespace qdb
+
+// ------------------------------------------------------------------------------------------------
+// fp64 tensor-pipe peak probe: every warp issues independent DMMA m8n8k4 chains from registers.
+// Used by bench.py as the live roofline denominator (MEASURED_PEAKS.json has no fp64 entry).
+// ------------------------------------------------------------------------------------------------
+namespace qdb {
+
+__global__ void __launch_bounds__(256) dmma_probe_kernel(double* sink, int iters, double a0, double b0) {
+    double c[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i][0] = c[i][1] = 0.0;
+    const double a = a0 + threadIdx.x * 1e-9, b = b0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1])
+                         : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+    if (s == 123.456) sink[0] = s;  // never true; keeps the chains alive
+}
+
+int launch_dmma_probe(double* sink, int iters, int* grid_out, cudaStream_t st) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = sms * 2;
+    dmma_probe_kernel<<<grid, 256, 0, st>>>(sink, iters, 1.0, 1.0);
+    QDB_LAUNCH_CHECK("dmma_probe_kernel");
+    if (grid_out) *grid_out = grid;
+    return QDB_OK;
+}
+
+}  // namespace qdb

@@ -12,19 +12,20 @@ __global__ void pack_kernel(int n, int npad, size_t per_src, size_t per_dst, con
     const int j = blockIdx.y;
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= per_dst) return;
-    const int KT = npad >> 2;
+    const int KT = round_up16(n) >> 2;
     const size_t tile = e >> 5;
     const int lane = (int)(e & 31);
     const int r = (int)(tile / KT) * 8 + (lane >> 2);
     const int c = (int)(tile % KT) * 4 + (lane & 3);
     double2 v = make_double2(0.0, 0.0);
     if (r < n && c < n) v = src[(size_t)j * per_src + (size_t)r * n + c];
+    (void)npad;
     dst[(size_t)j * per_dst + e] = v;
 }
 
 int launch_pack(int n, int count, const double2* src, double2* dst, cudaStream_t st) {
     const int npad = round_up8(n);
-    const size_t per_dst = (size_t)npad * npad;
+    const size_t per_dst = (size_t)npad * round_up16(n);
     dim3 grid((unsigned)((per_dst + 255) / 256), count);
     pack_kernel<<<grid, 256, 0, st>>>(n, npad, (size_t)n * n, per_dst, src, dst);
     QDB_LAUNCH_CHECK("pack_kernel");
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(256) generator_kernel(int n, int npad, int K, 
         rr[u] = cc[u] = 0;
         if (live[u]) {
             if (layout == QDB_LAYOUT_PACKED) {
-                const int KT = npad >> 2;
+                const int KT = round_up16(n) >> 2;
                 const size_t tile = e >> 5;
                 const int lane = (int)(e & 31);
                 rr[u] = (int)(tile / KT) * 8 + (lane >> 2);
@@ -120,7 +121,7 @@ int launch_generator(int n, int K, int T, int layout, const double2* ops, const 
                      const double* coeff, int coeff_complex, const double* mu, const double* times,
                      double t_scalar, double scale, double2* out, cudaStream_t st) {
     const int npad = round_up8(n);
-    const size_t elems = layout == QDB_LAYOUT_PACKED ? (size_t)npad * npad : (size_t)n * n;
+    const size_t elems = layout == QDB_LAYOUT_PACKED ? (size_t)npad * round_up16(n) : (size_t)n * n;
     const size_t smem = mu ? (size_t)n * sizeof(double2) : 0;
     dim3 grid((unsigned)((elems + 511) / 512), T);
     if (coeff_complex) {

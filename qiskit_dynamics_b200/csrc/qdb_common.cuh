@@ -27,10 +27,13 @@ void count_launch(int n = 1);
     } while (0)
 
 // ---- packed (DMMA A-fragment) operator layout -------------------------------------------------
-// element (r, c) of an npad x npad matrix lives at ((r/8)*(npad/4) + c/4)*32 + (r%8)*4 + c%4
+// rows padded to npad = 8*ceil(n/8), columns (the GEMM k dimension) to kpad = 16*ceil(n/16) so that the
+// k-tile count kpad/4 is a multiple of the 4-deep fragment ring of the fused steppers;
+// element (r, c) lives at ((r/8)*(kpad/4) + c/4)*32 + (r%8)*4 + c%4
 __host__ __device__ inline int round_up8(int n) { return (n + 7) & ~7; }
-__host__ __device__ inline size_t packed_index(int npad, int r, int c) {
-    return ((size_t)(r >> 3) * (npad >> 2) + (c >> 2)) * 32 + ((r & 7) << 2) + (c & 3);
+__host__ __device__ inline int round_up16(int n) { return (n + 15) & ~15; }
+__host__ __device__ inline size_t packed_index(int kpad, int r, int c) {
+    return ((size_t)(r >> 3) * (kpad >> 2) + (c >> 2)) * 32 + ((r & 7) << 2) + (c & 3);
 }
 
 // ---- DMMA -------------------------------------------------------------------------------------
@@ -103,6 +106,7 @@ int launch_zgemm(int M, int N, int Kd, const double2* A, int lda, const double2*
 int launch_zgemm_rk4stage(int n, int B, const double2* G, const double2* yin, int ldy,
                           const double2* ybase, double2* yout, double2* acc, double a_next, double w,
                           int first, cudaStream_t st);
+int launch_dmma_probe(double* sink, int iters, int* grid_out, cudaStream_t st);
 bool rk4_fused_supported(int n);
 int launch_rk4_fused_shared(int n, int B, int S, const double2* gen_table, double h, double2* y,
                             int ldy, cudaStream_t st);

@@ -4,12 +4,15 @@
 // Decomposition.  Every state column evolves independently, so a CTA owns 8*NCT whole columns for
 // the entire launch: no inter-CTA communication, HBM traffic = read y once + write y once.
 //   * A operand (the generator) streams L2 -> registers directly in DMMA A-fragment order
-//     (QDB_LAYOUT_PACKED: one coalesced 512 B LDG.128 per warp per fragment).  Each warp owns
-//     distinct row tiles, so there is no intra-CTA reuse that shared-memory staging could exploit.
+//     (QDB_LAYOUT_PACKED: one coalesced 512 B LDG.128 per warp per fragment) through a 4-deep
+//     register ring that runs 3 k-tiles ahead and keeps streaming across stage boundaries.  Each
+//     warp owns distinct row tiles, so there is no intra-CTA reuse that shared-memory staging
+//     could exploit.
 //   * B operand (the stage vector) lives in shared memory in DMMA B-fragment order, double
-//     buffered; the epilogue of stage s writes the stage s+1 input there (XOR-swizzled so both the
-//     fragment loads and the scattered epilogue stores are bank-conflict free).
-//   * The RK4 accumulator lives in registers, y itself in a thread-private shared-memory slab.
+//     buffered; fragments are fetched one k-tile ahead; the epilogue of stage s writes the stage
+//     s+1 input (XOR-swizzled so both the fragment loads and the scattered epilogue stores are
+//     bank-conflict free).
+//   * The RK4 k-sum lives in registers, y itself in a thread-private shared-memory slab.
 //
 // Shared-signal mode: A = precomputed generator table entry G_frame(t_stage) (frame phases folded
 // in by generator_kernel).  Sweep mode: A = the K+1 stored operators, the per-column signal value
@@ -23,15 +26,16 @@ namespace qdb {
 
 namespace {
 
-constexpr int PF = 4;  // A-fragment prefetch depth (k4-steps)
+constexpr int RING = 4;  // A-fragment register ring; prefetch distance RING-1 k-tiles (KT % RING == 0)
 
 struct Geometry {
-    int n, npad, KT, RT;
-    int WR, WC;   // warps along rows / columns
-    int NCT;      // column tiles per CTA
+    int n, npad, KT, RT;  // KT = kpad/4 k-tiles (kpad = n rounded to 16), RT = npad/8 row tiles
+    int WR, WC;           // warps along rows / columns
+    int NCT;              // column tiles per CTA
 };
 
-// position of state element (row, col-in-CTA) in the B-fragment-ordered stage buffer
+// position of state element (row tile rt, row-in-tile g, column tile ct, column-in-tile cin) in the
+// B-fragment-ordered stage buffer: k-tile = 2 rt + g/4, lane = g%4 + 4 cin, 16 B slot XOR-swizzled
 __device__ __forceinline__ int yin_pos(int NCT, int rt, int g, int ct, int cin) {
     const int kt = 2 * rt + (g >> 2);
     const int lane_b = (g & 3) + 4 * cin;
@@ -49,28 +53,37 @@ struct Accum {
     }
 };
 
+// 4 MR NCW real DMMAs of one complex k-tile; dependent DMMAs on the same accumulator are 2 MR NCW apart
 template <int MR, int NCW>
 __device__ __forceinline__ void mma_block(Accum<MR, NCW>& acc, const double2 (&a)[MR], const double2 (&b)[NCW]) {
-    double nai[MR];
 #pragma unroll
-    for (int m = 0; m < MR; ++m) nai[m] = negate(a[m].y);
-#pragma unroll
-    for (int m = 0; m < MR; ++m) {
+    for (int m = 0; m < MR; ++m)
 #pragma unroll
         for (int c = 0; c < NCW; ++c) {
             dmma(acc.cr[m][c][0], acc.cr[m][c][1], a[m].x, b[c].x);
             dmma(acc.ci[m][c][0], acc.ci[m][c][1], a[m].x, b[c].y);
         }
-    }
 #pragma unroll
-    for (int m = 0; m < MR; ++m) {
+    for (int m = 0; m < MR; ++m)
 #pragma unroll
         for (int c = 0; c < NCW; ++c) {
-            dmma(acc.cr[m][c][0], acc.cr[m][c][1], nai[m], b[c].y);
+            dmma(acc.cr[m][c][0], acc.cr[m][c][1], -a[m].y, b[c].y);  // SASS: DMMA with negated operand
             dmma(acc.ci[m][c][0], acc.ci[m][c][1], a[m].y, b[c].x);
         }
-    }
 }
+
+// RK4 stage combine shared by both kernels.  k-sum weights 1,2,2,1; next-input step h/2, h/2, h;
+// final update y + ((1/6) h) * ksum  (reference: fixed_step_solvers.py:60-73).
+struct StageCoef {
+    bool last;
+    double keep, wk, astep;
+    __device__ __forceinline__ StageCoef(int stage, double h) {
+        last = (stage == 3);
+        keep = stage == 0 ? 0.0 : 1.0;
+        wk = (stage == 1 || stage == 2) ? 2.0 : 1.0;
+        astep = stage < 2 ? 0.5 * h : (stage == 2 ? h : (1.0 / 6) * h);
+    }
+};
 
 // ------------------------------------------------------------------------------------------------
 // shared-signal mode
@@ -79,19 +92,18 @@ template <int MR, int NCW>
 __global__ void __launch_bounds__(256, 1)
 rk4_shared_kernel(Geometry geo, int B, int S, const double2* __restrict__ gen, double h, double2* __restrict__ y,
                   int ldy) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(16) double2 sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int wr = warp % geo.WR, wc = warp / geo.WR;
     const int KT = geo.KT, NCT = geo.NCT, n = geo.n;
-    const size_t npad2 = (size_t)geo.npad * geo.npad;
+    const size_t entry_elems = (size_t)geo.npad * KT * 4;
     const int yin_elems = KT * NCT * 32;
-    double2* yin[2] = {reinterpret_cast<double2*>(smem_raw), reinterpret_cast<double2*>(smem_raw) + yin_elems};
-    double2* yst = reinterpret_cast<double2*>(smem_raw) + 2 * yin_elems;  // [MR*NCW*2][blockDim]
+    const int yst_off = 2 * yin_elems;  // thread-private y slab: [MR*NCW*2][blockDim]
     const int nthr = blockDim.x;
     const int col0 = blockIdx.x * 8 * NCT;
 
-    int rt[MR], rtl[MR];  // row tile owned / row tile loaded (clamped: surplus warps recompute the last tile)
+    int rt[MR], rtl[MR];  // row tile owned / loaded (surplus warps recompute the last tile, results dropped)
     bool mvalid[MR];
 #pragma unroll
     for (int m = 0; m < MR; ++m) {
@@ -100,7 +112,9 @@ rk4_shared_kernel(Geometry geo, int B, int S, const double2* __restrict__ gen, d
         rtl[m] = mvalid[m] ? rt[m] : geo.RT - 1;
     }
 
-    // ---- load y tile: thread-private slab + stage-0 input ----
+    // ---- zero both stage buffers (k rows beyond npad stay zero), load y ----
+    for (int i = tid; i < 2 * yin_elems; i += nthr) sm[i] = make_double2(0.0, 0.0);
+    __syncthreads();
 #pragma unroll
     for (int m = 0; m < MR; ++m)
 #pragma unroll
@@ -112,10 +126,9 @@ rk4_shared_kernel(Geometry geo, int B, int S, const double2* __restrict__ gen, d
                 const int col = col0 + 8 * ct + 2 * q + i;
                 double2 v = make_double2(0.0, 0.0);
                 if (mvalid[m] && row < n && col < B) v = y[(size_t)row * ldy + col];
-                yst[((m * NCW + c) * 2 + i) * nthr + tid] = v;
-                if (mvalid[m]) yin[0][yin_pos(NCT, rt[m], g, ct, 2 * q + i)] = v;
+                sm[yst_off + ((m * NCW + c) * 2 + i) * nthr + tid] = v;
+                if (mvalid[m]) sm[yin_pos(NCT, rt[m], g, ct, 2 * q + i)] = v;
             }
-    __syncthreads();
 
     Accum<MR, NCW> acc;
     acc.zero();
@@ -124,70 +137,83 @@ rk4_shared_kernel(Geometry geo, int B, int S, const double2* __restrict__ gen, d
     for (int m = 0; m < MR; ++m)
 #pragma unroll
         for (int c = 0; c < NCW; ++c) kr[m][c][0] = kr[m][c][1] = ki[m][c][0] = ki[m][c][1] = 0.0;
-    int cur = 0;
-    const double h2 = 0.5 * h;
-    const double h6 = (1.0 / 6) * h;  // reference: div6 * h * (...)  (fixed_step_solvers.py:60,73)
 
-    for (int step = 0; step < S; ++step) {
+    // A-fragment offsets of this warp's row tiles inside one table entry
+    size_t aoff[MR];
+#pragma unroll
+    for (int m = 0; m < MR; ++m) aoff[m] = (size_t)rtl[m] * KT * 32 + lane;
+
+    // prime the ring with k-tiles 0 .. RING-2 of the first stage
+    double2 ring[RING][MR];
+#pragma unroll
+    for (int u = 0; u < RING - 1; ++u)
+#pragma unroll
+        for (int m = 0; m < MR; ++m) ring[u][m] = ldg_stream(gen + aoff[m] + (size_t)u * 32);
+
+    int cur = 0;
+    __syncthreads();
+
+    const int total_stages = 4 * S;
 #pragma unroll 1
-        for (int stage = 0; stage < 4; ++stage) {
-            const int entry = 2 * step + (stage == 0 ? 0 : (stage == 3 ? 2 : 1));
-            const double2* gsrc = gen + (size_t)entry * npad2 + lane;
-            const double2* ysrc = yin[cur] + (wc * NCW) * 32;
-            // ---- main loop over k4 tiles, A fragments prefetched PF tiles ahead ----
-            double2 abuf[PF][MR];
+    for (int sidx = 0; sidx < total_stages; ++sidx) {
+        const int step = sidx >> 2, stage = sidx & 3;
+        const int entry = 2 * step + (stage == 0 ? 0 : (stage == 3 ? 2 : 1));
+        // table entry of the NEXT stage (the ring streams into it during the last RING-1 k-tiles)
+        const int nstage = (stage + 1) & 3, nstep = step + (stage == 3 ? 1 : 0);
+        const int nentry = (sidx + 1 < total_stages) ? 2 * nstep + (nstage == 0 ? 0 : (nstage == 3 ? 2 : 1)) : entry;
+        const double2* gcur = gen + (size_t)entry * entry_elems;
+        const double2* gnxt = gen + (size_t)nentry * entry_elems;
+        const int ybase = cur * yin_elems + (wc * NCW) * 32;
+
+        double2 bfrag[2][NCW];
 #pragma unroll
-            for (int u = 0; u < PF; ++u)
+        for (int c = 0; c < NCW; ++c) bfrag[0][c] = sm[ybase + c * 32 + lane];  // k-tile 0: swizzle bit = 0
+
+#pragma unroll 1
+        for (int kt0 = 0; kt0 < KT; kt0 += RING) {
 #pragma unroll
-                for (int m = 0; m < MR; ++m)
-                    if (u < KT) abuf[u][m] = ldg_stream(gsrc + ((size_t)rtl[m] * KT + u) * 32);
-            for (int kt0 = 0; kt0 < KT; kt0 += PF) {
+            for (int u = 0; u < RING; ++u) {
+                const int kt = kt0 + u;
+                // A fragments of k-tile kt + RING-1 into the ring slot the previous k-tile just released
+                {
+                    const int ktn = kt + RING - 1;
+                    const double2* src = ktn < KT ? gcur + (size_t)ktn * 32 : gnxt + (size_t)(ktn - KT) * 32;
 #pragma unroll
-                for (int u = 0; u < PF; ++u) {
-                    const int kt = kt0 + u;
-                    if (kt < KT) {
-                        double2 a[MR], b[NCW];
-#pragma unroll
-                        for (int m = 0; m < MR; ++m) a[m] = abuf[u][m];
-#pragma unroll
-                        for (int m = 0; m < MR; ++m)
-                            if (kt + PF < KT) abuf[u][m] = ldg_stream(gsrc + ((size_t)rtl[m] * KT + kt + PF) * 32);
-                        const int sw = lane ^ ((kt & 1) << 2);
-#pragma unroll
-                        for (int c = 0; c < NCW; ++c) b[c] = ysrc[(kt * NCT + c) * 32 + sw];
-                        mma_block<MR, NCW>(acc, a, b);
-                    }
+                    for (int m = 0; m < MR; ++m) ring[(u + RING - 1) % RING][m] = ldg_stream(src + aoff[m]);
                 }
-            }
-            // ---- epilogue: RK4 stage combine, write next stage input ----
-            double2* ydst = yin[cur ^ 1];
-            // k-sum weights 1,2,2,1; next-input step h/2, h/2, h; final update (1/6) h * ksum
-            const bool last = (stage == 3);
-            const double keep = stage == 0 ? 0.0 : 1.0;
-            const double wk = (stage == 1 || stage == 2) ? 2.0 : 1.0;
-            const double astep = stage < 2 ? h2 : (stage == 2 ? h : h6);
+                // B fragments of k-tile kt + 1 (clamped at the stage end: a harmless reload)
+                {
+                    const int ktb = min(kt + 1, KT - 1);
+                    const int sw = lane ^ ((ktb & 1) << 2);
 #pragma unroll
-            for (int m = 0; m < MR; ++m) {
-#pragma unroll
-                for (int c = 0; c < NCW; ++c) {
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const double k_r = acc.cr[m][c][i], k_i = acc.ci[m][c][i];
-                        const int slab = ((m * NCW + c) * 2 + i) * nthr + tid;
-                        const double2 yv = yst[slab];
-                        kr[m][c][i] = keep * kr[m][c][i] + wk * k_r;
-                        ki[m][c][i] = keep * ki[m][c][i] + wk * k_i;
-                        const double v_r = last ? kr[m][c][i] : k_r, v_i = last ? ki[m][c][i] : k_i;
-                        const double2 nxt = make_double2(yv.x + astep * v_r, yv.y + astep * v_i);
-                        if (last) yst[slab] = nxt;
-                        if (mvalid[m]) ydst[yin_pos(NCT, rt[m], g, wc * NCW + c, 2 * q + i)] = nxt;
-                    }
+                    for (int c = 0; c < NCW; ++c) bfrag[(u + 1) & 1][c] = sm[ybase + (ktb * NCT + c) * 32 + sw];
                 }
+                mma_block<MR, NCW>(acc, ring[u], bfrag[u & 1]);
             }
-            acc.zero();
-            cur ^= 1;
-            __syncthreads();
         }
+
+        // ---- epilogue: RK4 stage combine, write next stage input ----
+        const StageCoef sc(stage, h);
+        const int ydst = (cur ^ 1) * yin_elems;
+#pragma unroll
+        for (int m = 0; m < MR; ++m)
+#pragma unroll
+            for (int c = 0; c < NCW; ++c)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const double k_r = acc.cr[m][c][i], k_i = acc.ci[m][c][i];
+                    const int slab = yst_off + ((m * NCW + c) * 2 + i) * nthr + tid;
+                    const double2 yv = sm[slab];
+                    kr[m][c][i] = sc.keep * kr[m][c][i] + sc.wk * k_r;
+                    ki[m][c][i] = sc.keep * ki[m][c][i] + sc.wk * k_i;
+                    const double v_r = sc.last ? kr[m][c][i] : k_r, v_i = sc.last ? ki[m][c][i] : k_i;
+                    const double2 nxt = make_double2(yv.x + sc.astep * v_r, yv.y + sc.astep * v_i);
+                    if (sc.last) sm[slab] = nxt;
+                    if (mvalid[m]) sm[ydst + yin_pos(NCT, rt[m], g, wc * NCW + c, 2 * q + i)] = nxt;
+                }
+        acc.zero();
+        cur ^= 1;
+        __syncthreads();
     }
 
     // ---- store y ----
@@ -199,7 +225,8 @@ rk4_shared_kernel(Geometry geo, int B, int S, const double2* __restrict__ gen, d
             for (int i = 0; i < 2; ++i) {
                 const int row = 8 * rt[m] + g;
                 const int col = col0 + 8 * (wc * NCW + c) + 2 * q + i;
-                if (mvalid[m] && row < n && col < B) y[(size_t)row * ldy + col] = yst[((m * NCW + c) * 2 + i) * nthr + tid];
+                if (mvalid[m] && row < n && col < B)
+                    y[(size_t)row * ldy + col] = sm[yst_off + ((m * NCW + c) * 2 + i) * nthr + tid];
             }
 }
 
@@ -209,22 +236,22 @@ rk4_shared_kernel(Geometry geo, int B, int S, const double2* __restrict__ gen, d
 template <int MR, int NCW>
 __global__ void __launch_bounds__(256, 1)
 rk4_sweep_kernel(Geometry geo, int K, int B, int S, const double2* __restrict__ stat /*packed or null*/,
-                 const double2* __restrict__ ops /*[K] packed*/,
-                 const double* __restrict__ coeff /*[2S+1][K][ldc]*/, int ldc, const double* __restrict__ mu,
-                 const double* __restrict__ times /*[2S+1]*/, double h, double2* __restrict__ y, int ldy) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+                 const double2* __restrict__ ops /*[K] packed*/, const double* __restrict__ coeff /*[2S+1][K][ldc]*/,
+                 int ldc, const double* __restrict__ mu, const double* __restrict__ times /*[2S+1]*/, double h,
+                 double2* __restrict__ y, int ldy) {
+    extern __shared__ __align__(16) double2 sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int wr = warp % geo.WR, wc = warp / geo.WR;
     const int KT = geo.KT, NCT = geo.NCT, n = geo.n;
-    const size_t npad2 = (size_t)geo.npad * geo.npad;
+    const size_t entry_elems = (size_t)geo.npad * KT * 4;
     const int yin_elems = KT * NCT * 32;
     const int nthr = blockDim.x;
     const int ncols = 8 * NCT;
-    double2* yin[2] = {reinterpret_cast<double2*>(smem_raw), reinterpret_cast<double2*>(smem_raw) + yin_elems};
-    double2* yst = reinterpret_cast<double2*>(smem_raw) + 2 * yin_elems;  // [MR*NCW*2][nthr]
-    double* scoef = reinterpret_cast<double*>(yst + MR * NCW * 2 * nthr);  // [K][ncols]
+    const int yst_off = 2 * yin_elems;                                              // [MR*NCW*2][nthr]
+    double* scoef = reinterpret_cast<double*>(sm + yst_off + MR * NCW * 2 * nthr);  // [K][ncols]
     const int col0 = blockIdx.x * ncols;
+    const bool framed = (mu != nullptr);
 
     int rt[MR], rtl[MR];
     bool mvalid[MR];
@@ -235,9 +262,8 @@ rk4_sweep_kernel(Geometry geo, int K, int B, int S, const double2* __restrict__ 
         mvalid[m] = rt[m] < geo.RT;
         rtl[m] = mvalid[m] ? rt[m] : geo.RT - 1;
         const int row = 8 * rt[m] + g;
-        mu_row[m] = (mu != nullptr && mvalid[m] && row < n) ? mu[row] : 0.0;
+        mu_row[m] = (framed && mvalid[m] && row < n) ? mu[row] : 0.0;
     }
-    const bool framed = (mu != nullptr);
 
     // phases of this thread's rows at the current stage time: p = exp(-i mu t)
     double2 ph[MR];
@@ -247,6 +273,8 @@ rk4_sweep_kernel(Geometry geo, int K, int B, int S, const double2* __restrict__ 
         for (int m = 0; m < MR; ++m) ph[m] = framed ? frame_phase(mu_row[m], t0) : make_double2(1.0, 0.0);
     }
 
+    for (int i = tid; i < 2 * yin_elems; i += nthr) sm[i] = make_double2(0.0, 0.0);
+    __syncthreads();
 #pragma unroll
     for (int m = 0; m < MR; ++m)
 #pragma unroll
@@ -258,8 +286,8 @@ rk4_sweep_kernel(Geometry geo, int K, int B, int S, const double2* __restrict__ 
                 const int col = col0 + 8 * ct + 2 * q + i;
                 double2 v = make_double2(0.0, 0.0);
                 if (mvalid[m] && row < n && col < B) v = y[(size_t)row * ldy + col];
-                yst[((m * NCW + c) * 2 + i) * nthr + tid] = v;
-                if (mvalid[m]) yin[0][yin_pos(NCT, rt[m], g, ct, 2 * q + i)] = cmul(ph[m], v);  // pre-phase
+                sm[yst_off + ((m * NCW + c) * 2 + i) * nthr + tid] = v;
+                if (mvalid[m]) sm[yin_pos(NCT, rt[m], g, ct, 2 * q + i)] = cmul(ph[m], v);  // pre-phase
             }
 
     Accum<MR, NCW> acc;
@@ -269,119 +297,109 @@ rk4_sweep_kernel(Geometry geo, int K, int B, int S, const double2* __restrict__ 
     for (int m = 0; m < MR; ++m)
 #pragma unroll
         for (int c = 0; c < NCW; ++c) kr[m][c][0] = kr[m][c][1] = ki[m][c][0] = ki[m][c][1] = 0.0;
-    int cur = 0;
-    const double h2 = 0.5 * h;
-    const double h6 = (1.0 / 6) * h;
+
     const int has_static = stat != nullptr ? 1 : 0;
-    const int J = K + has_static;  // operator passes per k4 tile; pass 0 = static if present
-    const int total = KT * J;
+    const int J = K + has_static;  // operator passes per k-tile; pass 0 = static operator if present
+    const int total = KT * J;      // multiple of RING because KT is
 
-    for (int step = 0; step < S; ++step) {
+    size_t aoff[MR];
+#pragma unroll
+    for (int m = 0; m < MR; ++m) aoff[m] = (size_t)rtl[m] * KT * 32 + lane;
+    auto a_src = [&](int kt, int j) -> const double2* {
+        const double2* base = (has_static && j == 0) ? stat : ops + (size_t)(j - has_static) * entry_elems;
+        return base + (size_t)kt * 32;
+    };
+
+    // ring primed with the first RING-1 (kt, j) passes; (pk, pj) = next pass to prefetch
+    double2 ring[RING][MR];
+    int pk = 0, pj = 0;
+#pragma unroll
+    for (int u = 0; u < RING - 1; ++u) {
+        const double2* src = a_src(pk, pj);
+#pragma unroll
+        for (int m = 0; m < MR; ++m) ring[u][m] = __ldg(src + aoff[m]);
+        if (++pj == J) { pj = 0; if (++pk == KT) pk = 0; }
+    }
+
+    int cur = 0;
+    const int total_stages = 4 * S;
 #pragma unroll 1
-        for (int stage = 0; stage < 4; ++stage) {
-            const int entry = 2 * step + (stage == 0 ? 0 : (stage == 3 ? 2 : 1));
-            // signal values of this CTA's columns at this stage time
-            for (int idx = tid; idx < K * ncols; idx += nthr) {
-                const int j = idx / ncols, cc = idx - j * ncols;
-                const int col = col0 + cc;
-                scoef[idx] = col < B ? coeff[((size_t)entry * K + j) * ldc + col] : 0.0;
-            }
-            __syncthreads();  // scoef + previous epilogue's yin writes visible
+    for (int sidx = 0; sidx < total_stages; ++sidx) {
+        const int step = sidx >> 2, stage = sidx & 3;
+        const int entry = 2 * step + (stage == 0 ? 0 : (stage == 3 ? 2 : 1));
+        // signal values of this CTA's columns at this stage time
+        for (int idx = tid; idx < K * ncols; idx += nthr) {
+            const int j = idx / ncols, cc = idx - j * ncols;
+            const int col = col0 + cc;
+            scoef[idx] = col < B ? coeff[((size_t)entry * K + j) * ldc + col] : 0.0;
+        }
+        __syncthreads();  // scoef + previous epilogue's stage-buffer writes visible
 
-            const double2* ysrc = yin[cur] + (wc * NCW) * 32;
-            const double* csrc = scoef + (wc * NCW) * 8 + g;  // B-fragment lane holds column 8 ct + g
+        const int ybase = cur * yin_elems + (wc * NCW) * 32;
+        const double* csrc = scoef + (wc * NCW) * 8 + g;  // B-fragment lane holds column 8 ct + g
 
-            // flattened (kt, j) loop with PF-deep A prefetch
-            auto a_ptr = [&](int kt, int j, int m) {  // pass 0 is the static operator when present
-                const double2* base = (has_static && j == 0) ? stat : ops + (size_t)(j - has_static) * npad2;
-                return base + ((size_t)rtl[m] * KT + kt) * 32 + lane;
-            };
-            double2 abuf[PF][MR];
-            int pk = 0, pj = 0;  // (kt, j) of the next fragment to prefetch
+        int kt = 0, j = 0;
+        double2 b[NCW];
+#pragma unroll 1
+        for (int it0 = 0; it0 < total; it0 += RING) {
 #pragma unroll
-            for (int u = 0; u < PF; ++u) {
-                if (pk < KT) {
+            for (int u = 0; u < RING; ++u) {
+                {   // prefetch pass it + RING-1 (wraps to the start: the operators are time independent)
+                    const double2* src = a_src(pk, pj);
 #pragma unroll
-                    for (int m = 0; m < MR; ++m) abuf[u][m] = __ldg(a_ptr(pk, pj, m));
-                    if (++pj == J) { pj = 0; ++pk; }
+                    for (int m = 0; m < MR; ++m) ring[(u + RING - 1) % RING][m] = __ldg(src + aoff[m]);
+                    if (++pj == J) { pj = 0; if (++pk == KT) pk = 0; }
                 }
-            }
-            int kt = 0, j = 0;
-            double2 b[NCW];
-            for (int it0 = 0; it0 < total; it0 += PF) {
+                if (j == 0) {
+                    const int sw = lane ^ ((kt & 1) << 2);
 #pragma unroll
-                for (int u = 0; u < PF; ++u) {
-                    if (it0 + u < total) {
-                        double2 a[MR];
-#pragma unroll
-                        for (int m = 0; m < MR; ++m) a[m] = abuf[u][m];
-                        if (pk < KT) {
-#pragma unroll
-                            for (int m = 0; m < MR; ++m) abuf[u][m] = __ldg(a_ptr(pk, pj, m));
-                            if (++pj == J) { pj = 0; ++pk; }
-                        }
-                        if (j == 0) {
-                            const int sw = lane ^ ((kt & 1) << 2);
-#pragma unroll
-                            for (int c = 0; c < NCW; ++c) b[c] = ysrc[(kt * NCT + c) * 32 + sw];
-                        }
-                        const int sig = has_static ? j - 1 : j;  // -1 -> static operator, coefficient 1
-                        if (sig < 0) {
-                            mma_block<MR, NCW>(acc, a, b);
-                        } else {
-                            double2 bs[NCW];
-#pragma unroll
-                            for (int c = 0; c < NCW; ++c) {
-                                const double s = csrc[sig * ncols + c * 8];
-                                bs[c] = make_double2(b[c].x * s, b[c].y * s);
-                            }
-                            mma_block<MR, NCW>(acc, a, bs);
-                        }
-                        if (++j == J) { j = 0; ++kt; }
-                    }
+                    for (int c = 0; c < NCW; ++c) b[c] = sm[ybase + (kt * NCT + c) * 32 + sw];
                 }
-            }
-
-            // ---- epilogue ----
-            // post-phase conj(p(t_stage)) on k; pre-phase p(t_next) on the next stage input
-            double2 ph_next[MR];
-            {
-                const int next_entry = stage == 3 ? 2 * step + 2 : (stage == 0 ? 2 * step + 1 : (stage == 1 ? 2 * step + 1 : 2 * step + 2));
-                const double tn = framed ? times[next_entry] : 0.0;
-#pragma unroll
-                for (int m = 0; m < MR; ++m)
-                    ph_next[m] = (framed && next_entry != entry) ? frame_phase(mu_row[m], tn) : ph[m];
-            }
-            double2* ydst = yin[cur ^ 1];
-            // k-sum weights 1,2,2,1; next-input step h/2, h/2, h; final update (1/6) h * ksum
-            const bool last = (stage == 3);
-            const double keep = stage == 0 ? 0.0 : 1.0;
-            const double wk = (stage == 1 || stage == 2) ? 2.0 : 1.0;
-            const double astep = stage < 2 ? h2 : (stage == 2 ? h : h6);
-#pragma unroll
-            for (int m = 0; m < MR; ++m) {
+                const int sig = j - has_static;  // -1 -> static operator, coefficient 1
+                double2 bs[NCW];
 #pragma unroll
                 for (int c = 0; c < NCW; ++c) {
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const double2 k = cmul_conj_a(ph[m], make_double2(acc.cr[m][c][i], acc.ci[m][c][i]));
-                        const int slab = ((m * NCW + c) * 2 + i) * nthr + tid;
-                        const double2 yv = yst[slab];
-                        kr[m][c][i] = keep * kr[m][c][i] + wk * k.x;
-                        ki[m][c][i] = keep * ki[m][c][i] + wk * k.y;
-                        const double v_r = last ? kr[m][c][i] : k.x, v_i = last ? ki[m][c][i] : k.y;
-                        const double2 nxt = make_double2(yv.x + astep * v_r, yv.y + astep * v_i);
-                        if (last) yst[slab] = nxt;
-                        if (mvalid[m]) ydst[yin_pos(NCT, rt[m], g, wc * NCW + c, 2 * q + i)] = cmul(ph_next[m], nxt);
-                    }
+                    const double s = sig < 0 ? 1.0 : csrc[sig * ncols + c * 8];
+                    bs[c] = make_double2(b[c].x * s, b[c].y * s);
                 }
+                mma_block<MR, NCW>(acc, ring[u], bs);
+                if (++j == J) { j = 0; ++kt; }
             }
-#pragma unroll
-            for (int m = 0; m < MR; ++m) ph[m] = ph_next[m];
-            acc.zero();
-            cur ^= 1;
-            __syncthreads();  // all warps done reading scoef / yin[old cur] before they are rewritten
         }
+
+        // ---- epilogue: post-phase conj(p(t_stage)) on k; pre-phase p(t_next) on the next stage input ----
+        double2 ph_next[MR];
+        {
+            const int nstage = (stage + 1) & 3, nstep = step + (stage == 3 ? 1 : 0);
+            const int next_entry = (sidx + 1 < total_stages) ? 2 * nstep + (nstage == 0 ? 0 : (nstage == 3 ? 2 : 1)) : entry;
+            const double tn = framed ? times[next_entry] : 0.0;
+#pragma unroll
+            for (int m = 0; m < MR; ++m)
+                ph_next[m] = (framed && next_entry != entry) ? frame_phase(mu_row[m], tn) : ph[m];
+        }
+        const StageCoef sc(stage, h);
+        const int ydst = (cur ^ 1) * yin_elems;
+#pragma unroll
+        for (int m = 0; m < MR; ++m)
+#pragma unroll
+            for (int c = 0; c < NCW; ++c)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const double2 k = cmul_conj_a(ph[m], make_double2(acc.cr[m][c][i], acc.ci[m][c][i]));
+                    const int slab = yst_off + ((m * NCW + c) * 2 + i) * nthr + tid;
+                    const double2 yv = sm[slab];
+                    kr[m][c][i] = sc.keep * kr[m][c][i] + sc.wk * k.x;
+                    ki[m][c][i] = sc.keep * ki[m][c][i] + sc.wk * k.y;
+                    const double v_r = sc.last ? kr[m][c][i] : k.x, v_i = sc.last ? ki[m][c][i] : k.y;
+                    const double2 nxt = make_double2(yv.x + sc.astep * v_r, yv.y + sc.astep * v_i);
+                    if (sc.last) sm[slab] = nxt;
+                    if (mvalid[m]) sm[ydst + yin_pos(NCT, rt[m], g, wc * NCW + c, 2 * q + i)] = cmul(ph_next[m], nxt);
+                }
+#pragma unroll
+        for (int m = 0; m < MR; ++m) ph[m] = ph_next[m];
+        acc.zero();
+        cur ^= 1;
+        __syncthreads();  // all warps done reading scoef / the old stage buffer before they are rewritten
     }
 
 #pragma unroll
@@ -392,7 +410,8 @@ rk4_sweep_kernel(Geometry geo, int K, int B, int S, const double2* __restrict__ 
             for (int i = 0; i < 2; ++i) {
                 const int row = 8 * rt[m] + g;
                 const int col = col0 + 8 * (wc * NCW + c) + 2 * q + i;
-                if (mvalid[m] && row < n && col < B) y[(size_t)row * ldy + col] = yst[((m * NCW + c) * 2 + i) * nthr + tid];
+                if (mvalid[m] && row < n && col < B)
+                    y[(size_t)row * ldy + col] = sm[yst_off + ((m * NCW + c) * 2 + i) * nthr + tid];
             }
 }
 
@@ -429,7 +448,7 @@ bool pick_config(int n, int B, int K_sweep /*0 for shared*/, Config& cfg) {
     Geometry geo;
     geo.n = n;
     geo.npad = npad;
-    geo.KT = npad / 4;
+    geo.KT = round_up16(n) / 4;
     geo.RT = npad / 8;
     const int CT = (B + 7) / 8;  // column tiles in the batch
     int WR, WC, MR;

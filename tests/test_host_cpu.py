@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(qd):
     assert declared == set(qd._abi.SIGNATURES), (declared ^ set(qd._abi.SIGNATURES))
     l = qd._abi.lib()
     assert l.qdb_version() >= 100
-    assert l.qdb_npad(27) == 32 and l.qdb_npad(128) == 128 and l.qdb_packed_elems(5) == 64
+    assert l.qdb_npad(27) == 32 and l.qdb_npad(128) == 128 and l.qdb_packed_elems(5) == 8 * 16
     assert qd._abi.workspace_bytes(qd._abi.WS_RK4, 128, 8, 4096, 10) >= 21 * 128 * 128 * 16
     assert l.qdb_last_error_string() is not None
 

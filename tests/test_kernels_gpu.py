@@ -57,13 +57,13 @@ def test_pack_and_generator(abi):
         out = abi.generator(n, dev(ops), dev(stat), dev(coeff), dev(mu), dev(times), scale=0.5)
         np.testing.assert_allclose(out.cpu().numpy().reshape(T, n, n), 0.5 * ref, rtol=0, atol=TOL_OP)
         # packed layout round trip
-        npad = abi.npad(n)
+        npad, kpad = abi.npad(n), (n + 15) // 16 * 16
         pk_ops, pk_stat = abi.pack_operators(dev(ops)), abi.pack_operators(dev(stat[None]))[0]
         outp = abi.generator(n, pk_ops, pk_stat, dev(coeff), dev(mu), dev(times), layout=abi.LAYOUT_PACKED).cpu().numpy()
         r, c = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
-        idx = ((r // 8) * (npad // 4) + c // 4) * 32 + (r % 8) * 4 + c % 4
+        idx = ((r // 8) * (kpad // 4) + c // 4) * 32 + (r % 8) * 4 + c % 4
         np.testing.assert_allclose(outp[:, idx], ref, rtol=0, atol=TOL_OP)
-        mask = np.ones(npad * npad, bool)
+        mask = np.ones(npad * kpad, bool)
         mask[idx.ravel()] = False
         assert np.all(outp[:, mask] == 0)
         # complex coefficients, no frame, no static (reference test_operator_collections.py:82-94)
