@@ -55,14 +55,25 @@ def workload(n, K, B, seed):
 # ---------------------------------------------------------------------------------------------
 
 def cpu_threads():
-    try:
-        from threadpoolctl import threadpool_info
-        blas = [p for p in threadpool_info() if p.get("user_api") == "blas"]
-        if blas:
-            return int(max(p["num_threads"] for p in blas))
-    except Exception:  # noqa: BLE001
-        pass
+    """BLAS threads the CPU legs run with: all host cores (torchrun exports OMP_NUM_THREADS=1, so
+    the limit is raised explicitly)."""
     return os.cpu_count() or 1
+
+
+class all_host_threads:
+    def __enter__(self):
+        try:
+            from threadpoolctl import threadpool_limits
+            self.ctx = threadpool_limits(limits=cpu_threads(), user_api="blas")
+            self.ctx.__enter__()
+        except Exception:  # noqa: BLE001
+            self.ctx = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
 
 
 def cpu_reference_rate(n, K, B, steps, warmup, rk4_steps, seed=SEED):
@@ -74,12 +85,13 @@ def cpu_reference_rate(n, K, B, steps, warmup, rk4_steps, seed=SEED):
     yfb = U.conj().T @ Y
     rhs = lambda t, y: orc.model_rhs(t, y, specs, G, Gd, d)  # noqa: E731
     span = [0.0, rk4_steps * MAX_DT]
-    for _ in range(warmup):
-        orc.fixed_step_solve(orc.rk4_step, rhs, span, yfb, MAX_DT)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        orc.fixed_step_solve(orc.rk4_step, rhs, span, yfb, MAX_DT)
-    dt = time.perf_counter() - t0
+    with all_host_threads():
+        for _ in range(warmup):
+            orc.fixed_step_solve(orc.rk4_step, rhs, span, yfb, MAX_DT)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            orc.fixed_step_solve(orc.rk4_step, rhs, span, yfb, MAX_DT)
+        dt = time.perf_counter() - t0
     return 4.0 * rk4_steps * B * steps / dt, dt / steps
 
 

@@ -1,0 +1,164 @@
+"""Size-independent properties at BASELINE.json's full sizes, plus edge cases (GPU).
+
+The oracle is too slow at n=128, B=4096, S=1000 (minutes), so at full size parity is checked through
+properties the domain offers: unitarity of the Schrodinger flow, linearity in y0, forward/backward
+round trip, agreement of independent code paths (fused on-chip kernel vs the per-stage GEMM path vs
+sweep mode with identical columns), chunking invariance, and column-permutation equivariance.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import numpy_oracle as orc  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def qd():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import qiskit_dynamics_b200 as q
+    q._abi.lib()
+    return q
+
+
+@pytest.fixture(scope="module")
+def headline(qd):
+    n, K, B = 128, 8, 4096
+    H0, Hs, Y, sig = orc.synthetic_schrodinger(n, K, B, 2004)
+    m = qd.HamiltonianModel(static_operator=H0, operators=Hs, signals=[qd.Signal(*s) for s in sig], rotating_frame=H0)
+    return m, qd.asarray(Y)
+
+
+def col_err(a, b):
+    return float(torch.linalg.vector_norm(a - b, dim=0).max())
+
+
+def test_full_size_unitarity_and_round_trip(qd, headline):
+    m, Y = headline
+    r = qd.solve_lmde(m, t_span=[0, 1.0], y0=Y, method="RK4", max_dt=1e-3)  # cfg4: 1000 steps, 4000 RHS/column
+    yf = r.y[-1]
+    assert tuple(r.y.shape) == (2, 128, 4096)
+    norms = torch.linalg.vector_norm(yf, dim=0)
+    assert float((norms - 1).abs().max()) < 1e-11  # RK4 norm drift of the reference itself: 2.5e-14
+    back = qd.solve_lmde(m, t_span=[1.0, 0.0], y0=yf, method="RK4", max_dt=1e-3).y[-1]
+    assert col_err(back, Y) < 1e-9  # RK4 is not time-symmetric: round trip error = truncation, ~h^4
+    # linearity: solve(a y1 + b y2) == a solve(y1) + b solve(y2)
+    a, b = 0.3 - 0.8j, -1.1 + 0.2j
+    mix = (a * Y[:, :64] + b * Y[:, 64:128]).contiguous()
+    rm = qd.solve_lmde(m, t_span=[0, 1.0], y0=mix, method="RK4", max_dt=1e-3).y[-1]
+    assert col_err(rm, a * yf[:, :64] + b * yf[:, 64:128]) < 1e-11
+    # column-permutation equivariance and batch-size independence (tile shapes change with B)
+    perm = torch.randperm(4096, device=Y.device)[:200]
+    rp = qd.solve_lmde(m, t_span=[0, 1.0], y0=Y[:, perm].contiguous(), method="RK4", max_dt=1e-3).y[-1]
+    assert col_err(rp, yf[:, perm]) < 1e-12
+
+
+def test_full_size_independent_paths_agree(qd, headline):
+    m, Y = headline
+    abi = qd._abi
+    from qiskit_dynamics_b200.solvers import stage_time_grid
+    S, h = 50, 1e-3
+    coll = m._collection()
+    mu = m._frame_freqs()
+    yfb = m.rotating_frame.state_into_frame_basis(Y)
+    times = stage_time_grid(0.0, h, S)
+    table = m._signal_table(times)
+    coeff = torch.from_numpy(table).cuda()
+    ops_p, stat_p = coll.packed()
+    # (1) fused shared-signal kernel
+    y1 = yfb.clone()
+    abi.rk4_steps(128, coll.operators, coll.static_operator, ops_p, stat_p, coeff, mu, times, h, y1, S)
+    # (2) sweep kernel with every column given the same signal values
+    y2 = yfb[:, :512].clone()
+    coeff_cols = coeff[:, :, None].expand(-1, -1, 512).contiguous()
+    abi.rk4_steps(128, coll.operators, coll.static_operator, ops_p, stat_p, coeff_cols, mu, times, h, y2, S, per_col=True)
+    assert col_err(y2, y1[:, :512]) < 1e-12
+    # (3) unfused: RK4 written with single fused-RHS calls (qdb_rhs_c128), 5 steps
+    y3 = yfb[:, :256].clone()
+    for s in range(5):
+        t = times[2 * s]
+        f = lambda tt, yy, idx: abi.rhs(128, coll.operators, coll.static_operator, coeff[idx].contiguous(), mu, tt, yy.contiguous())  # noqa: E731
+        k1 = f(t, y3, 2 * s)
+        k2 = f(times[2 * s + 1], y3 + 0.5 * h * k1, 2 * s + 1)
+        k3 = f(times[2 * s + 1], y3 + 0.5 * h * k2, 2 * s + 1)
+        k4 = f(times[2 * s + 2], y3 + h * k3, 2 * s + 2)
+        y3 = y3 + (1.0 / 6) * h * (k1 + 2 * k2 + 2 * k3 + k4)
+    y1b = yfb[:, :256].clone()
+    abi.rk4_steps(128, coll.operators, coll.static_operator, ops_p, stat_p, coeff, mu, times[:11], h, y1b, 5)
+    assert col_err(y3, y1b) < 1e-13
+    # (4) chunked step loop == single launch, bit for bit
+    y4 = yfb.clone()
+    ws = torch.empty(abi.workspace_bytes(abi.WS_RK4, 128, 8, 4096, 7), dtype=torch.uint8, device="cuda")
+    abi.rk4_steps(128, coll.operators, coll.static_operator, ops_p, stat_p, coeff, mu, times, h, y4, S, workspace=ws)
+    assert torch.equal(y4, y1)
+
+
+def test_vectorized_lindblad_full_dimension_properties(qd):
+    """cfg3 dimension (n=27 -> 729), expm stepper: trace preservation and Hermiticity of rho."""
+    n, K, B = 27, 3, 64
+    H0, Hs, Ls, Y, sig = orc.synthetic_lindblad(n, K, 6, B, 2003)
+    mv = qd.LindbladModel(static_hamiltonian=H0, hamiltonian_operators=Hs, hamiltonian_signals=[qd.Signal(*s) for s in sig],
+                          static_dissipators=Ls, rotating_frame=np.diag(H0).real, vectorized=True)
+    r = qd.solve_lmde(mv, t_span=[0, 0.2], y0=Y, method="scipy_expm", max_dt=1e-2)
+    rho = r.y[-1].cpu().numpy().reshape(n, n, B, order="F")
+    tr = np.einsum("iib->b", rho)
+    assert np.max(np.abs(tr - 1)) < 1e-11
+    assert np.max(np.abs(rho - rho.conj().transpose(1, 0, 2))) < 1e-11
+    # RK4 (generic per-stage GEMM path, n^2 = 729 > 256) agrees with expm to RK4/Magnus truncation
+    r4 = qd.solve_lmde(mv, t_span=[0, 0.2], y0=Y, method="RK4", max_dt=1e-3)
+    assert col_err(r4.y[-1], r.y[-1]) < 1e-5
+    tr4 = np.einsum("iib->b", r4.y[-1].cpu().numpy().reshape(n, n, B, order="F"))
+    assert np.max(np.abs(tr4 - 1)) < 1e-11
+
+
+def test_edge_cases(qd):
+    abi = qd._abi
+    rng = np.random.default_rng(1)
+    # n = 1, single column, K = 0 (static only), complex generator
+    g = qd.GeneratorModel(static_operator=np.array([[0.3 - 2.0j]]))
+    r = qd.solve_lmde(g, t_span=[0, 1.0], y0=np.array([1.0 + 0j]), method="RK4", max_dt=1e-3)
+    assert abs(complex(r.y[-1][0]) - np.exp(0.3 - 2.0j)) < 1e-11
+    r = qd.solve_lmde(g, t_span=[0, 1.0], y0=np.array([1.0 + 0j]), method="scipy_expm", max_dt=0.25)
+    assert abs(complex(r.y[-1][0]) - np.exp(0.3 - 2.0j)) < 1e-13
+    # empty batch and zero steps are no-ops
+    H = orc.herm(rng, 6)
+    m = qd.HamiltonianModel(static_operator=H, operators=[H], signals=[1.0])
+    r = qd.solve_lmde(m, t_span=[0, 0.1], y0=np.zeros((6, 0), dtype=complex), method="RK4", max_dt=0.01)
+    assert tuple(r.y.shape) == (2, 6, 0)
+    y = torch.randn(6, 3, dtype=torch.complex128, device="cuda")
+    y0 = y.clone()
+    coll = m._collection()
+    ops_p, stat_p = coll.packed()
+    abi.rk4_steps(6, coll.operators, coll.static_operator, ops_p, stat_p, torch.ones(1, 1, dtype=torch.float64, device="cuda"),
+                  None, np.zeros(1), 0.01, y, 0)
+    assert torch.equal(y, y0)
+    # t_eval equal to the end points, repeated points, single interior point
+    r = qd.solve_lmde(m, t_span=[0, 0.1], y0=np.eye(6, dtype=complex), method="RK4", max_dt=0.01, t_eval=[0.0, 0.05, 0.05, 0.1])
+    assert tuple(r.y.shape) == (4, 6, 6) and torch.equal(r.y[1], r.y[2])
+    assert torch.equal(r.y[0], qd.asarray(np.eye(6, dtype=complex)))
+    # max_dt larger than the interval -> exactly one step
+    r1 = qd.solve_lmde(m, t_span=[0, 0.1], y0=np.eye(6, dtype=complex), method="RK4", max_dt=5.0)
+    U = orc.rk4_step(lambda t, yy: (-2j * H) @ yy, 0.0, np.eye(6, dtype=complex), 0.1)
+    assert np.max(np.abs(r1.y[-1].cpu().numpy() - U)) < 1e-14
+    # largest on-chip dimension (256) against the generic per-stage path on the same inputs
+    n, B, S = 256, 40, 3
+    H0, Hs, Y, sig = orc.synthetic_schrodinger(n, 2, B, 3)
+    mm = qd.HamiltonianModel(static_operator=H0, operators=Hs, signals=[qd.Signal(*s) for s in sig], rotating_frame=H0)
+    rf = qd.solve_lmde(mm, t_span=[0, 3e-3], y0=Y, method="RK4", max_dt=1e-3).y[-1]
+    c = mm._collection()
+    from qiskit_dynamics_b200.solvers import stage_time_grid
+    times = stage_time_grid(0.0, 1e-3, S)
+    yg = mm.rotating_frame.state_into_frame_basis(qd.asarray(Y)).clone()
+    wsb = 3 * ((n * n * 16 + 255) // 256 * 256) + 3 * ((n * B * 16 + 255) // 256 * 256) + 256
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    # per-stage GEMM path, forced by calling the stage kernels through zgemm-based RHS
+    for s in range(S):
+        f = lambda tt, yy, i: abi.rhs(n, c.operators, c.static_operator, torch.from_numpy(mm._signal_table(np.array([tt]))[0]).cuda(), mm._frame_freqs(), tt, yy.contiguous())  # noqa: E731
+        k1 = f(times[2 * s], yg, 0)
+        k2 = f(times[2 * s + 1], yg + 0.5e-3 * k1, 0)
+        k3 = f(times[2 * s + 1], yg + 0.5e-3 * k2, 0)
+        k4 = f(times[2 * s + 2], yg + 1e-3 * k3, 0)
+        yg = yg + (1.0 / 6) * 1e-3 * (k1 + 2 * k2 + 2 * k3 + k4)
+    assert col_err(mm.rotating_frame.state_out_of_frame_basis(yg), rf) < 1e-12
