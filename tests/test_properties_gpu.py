@@ -106,9 +106,13 @@ def test_vectorized_lindblad_full_dimension_properties(qd):
     tr = np.einsum("iib->b", rho)
     assert np.max(np.abs(tr - 1)) < 1e-11
     assert np.max(np.abs(rho - rho.conj().transpose(1, 0, 2))) < 1e-11
-    # RK4 (generic per-stage GEMM path, n^2 = 729 > 256) agrees with expm to RK4/Magnus truncation
+    # RK4 (generic per-stage GEMM path, n^2 = 729 > 256) agrees with expm up to the O(h^2) error of
+    # the order-1 Magnus stepper; refining the expm step 4x must shrink the gap ~16x
     r4 = qd.solve_lmde(mv, t_span=[0, 0.2], y0=Y, method="RK4", max_dt=1e-3)
-    assert col_err(r4.y[-1], r.y[-1]) < 1e-5
+    gap_coarse = col_err(r4.y[-1], r.y[-1])
+    r_fine = qd.solve_lmde(mv, t_span=[0, 0.2], y0=Y, method="scipy_expm", max_dt=2.5e-3)
+    gap_fine = col_err(r4.y[-1], r_fine.y[-1])
+    assert gap_coarse < 1e-3 and gap_fine < gap_coarse / 10
     tr4 = np.einsum("iib->b", r4.y[-1].cpu().numpy().reshape(n, n, B, order="F"))
     assert np.max(np.abs(tr4 - 1)) < 1e-11
 
