@@ -20,6 +20,9 @@
 // frame phases are applied to B rows on write and to C rows on read.
 //
 // Roofline: fp64 tensor pipe.  Algorithmic flops per column per step = 4(8n^2 + 12n) + 28n.
+#include <cstdio>
+#include <cstdlib>
+
 #include "qdb_common.cuh"
 
 namespace qdb {
@@ -472,7 +475,17 @@ bool pick_config(int n, int B, int K_sweep /*0 for shared*/, Config& cfg) {
         WC = warps / WR;
         if (WC < 1) WC = 1;
     }
-    const int NCWmax = MR <= 2 ? 4 : 2;
+    int NCWmax = MR <= 2 ? 4 : 2;
+    // experiment hook: QDB_FORCE_CFG="WR,WC,MR,NCW" pins the tiling (profiling only)
+    if (const char* force = getenv("QDB_FORCE_CFG")) {
+        int fwr, fwc, fmr, fncw;
+        if (sscanf(force, "%d,%d,%d,%d", &fwr, &fwc, &fmr, &fncw) == 4 && fwr * fmr >= geo.RT && fwr * fwc <= 8) {
+            WR = fwr;
+            WC = fwc;
+            MR = fmr;
+            NCWmax = fncw;
+        }
+    }
     // The busiest SM runs ceil(ctas / #SMs) CTAs of NCW column tiles each: minimise that product,
     // ties go to the wider tile (fewer A-fragment reloads per column).
     long best_cost = -1;
