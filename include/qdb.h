@@ -137,6 +137,13 @@ int qdb_rk4_steps_c128(int n, int K, int B, int S,
 int qdb_rk4_table_steps_c128(int n, int B, int S, const qdb_c128* gen_table_packed, double h,
                              qdb_c128* y, int ldy, void* stream);
 
+/* Tiling the on-chip RK4 kernels pick for a shape (diagnostic: reported by bench.py, asserted by the
+ * tests).  sweep_K = 0 asks about the shared-signal kernel, > 0 about the per-column kernel.
+ * out[0..7] = {warps along rows, warps along columns, row tiles per warp, own column tiles per warp,
+ * split (1 = 2-CTA clusters sharing one column octet through DSMEM), CTAs, threads per CTA,
+ * dynamic shared memory bytes}.  Returns QDB_E_UNSUPPORTED when n is outside the on-chip path. */
+int qdb_rk4_tiling(int n, int B, int sweep_K, int* out /* host, 8 ints */);
+
 /* fp64 tensor-pipe (DMMA m8n8k4) issue-rate probe: launches register-resident DMMA chains on every
  * SM; *flops_out (host) receives the flop count of the launch.  Timed by the caller with CUDA
  * events, it gives the live roofline denominator for the fp64 kernels. */

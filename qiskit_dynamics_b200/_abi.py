@@ -47,6 +47,7 @@ SIGNATURES = {
     "qdb_rk4_steps_c128": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _d, _vp, _i, _vp, _sz, _vp]),
     "qdb_expm_steps_c128": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _i, _vp, _sz, _vp]),
     "qdb_rk4_table_steps_c128": (_i, [_i, _i, _i, _vp, _d, _vp, _i, _vp]),
+    "qdb_rk4_tiling": (_i, [_i, _i, _i, _vp]),
     "qdb_dmma_probe": (_i, [_vp, _i, _vp, _vp]),
     "qdb_expm_c128": (_i, [_i, _vp, _i, _vp, _vp, _sz, _vp]),
     "qdb_launch_count": (ctypes.c_ulonglong, []),
@@ -117,6 +118,14 @@ def workspace_bytes(kind: int, n: int, K: int, B: int, S: int = 1) -> int:
 
 def launch_count() -> int:
     return int(lib().qdb_launch_count())
+
+
+def rk4_tiling(n: int, B: int, sweep_K: int = 0) -> dict:
+    """Tiling the on-chip RK4 kernel picks for (n, B) -- diagnostic (qdb_rk4_tiling)."""
+    out = (ctypes.c_int * 8)()
+    _check(lib().qdb_rk4_tiling(n, B, sweep_K, ctypes.cast(out, ctypes.c_void_p)), "qdb_rk4_tiling")
+    keys = ("warps_rows", "warps_cols", "row_tiles_per_warp", "col_tiles_per_warp", "split", "ctas", "threads", "smem_bytes")
+    return dict(zip(keys, (int(v) for v in out)))
 
 
 def pack_operators(ops: torch.Tensor) -> torch.Tensor:

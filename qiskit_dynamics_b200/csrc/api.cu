@@ -270,6 +270,15 @@ int qdb_rk4_table_steps_c128(int n, int B, int S, const qdb_c128* gen_table_pack
     return launch_rk4_fused_shared(n, B, S, D2(gen_table_packed), h, D2(y), ldy, (cudaStream_t)stream);
 }
 
+int qdb_rk4_tiling(int n, int B, int sweep_K, int* out) {
+    QDB_REQUIRE(out && n >= 1 && B >= 1 && sweep_K >= 0, "qdb_rk4_tiling: bad arguments");
+    if (!rk4_fused_tiling(n, B, sweep_K, out)) {
+        set_error("qdb_rk4_tiling: on-chip path needs n <= 256 (got %d)", n);
+        return QDB_E_UNSUPPORTED;
+    }
+    return QDB_OK;
+}
+
 int qdb_dmma_probe(double* sink, int iters, double* flops_out, void* stream) {
     QDB_REQUIRE(sink && iters > 0, "qdb_dmma_probe: bad arguments");
     int grid = 0;

@@ -108,6 +108,7 @@ int launch_zgemm_rk4stage(int n, int B, const double2* G, const double2* yin, in
                           int first, cudaStream_t st);
 int launch_dmma_probe(double* sink, int iters, int* grid_out, cudaStream_t st);
 bool rk4_fused_supported(int n);
+bool rk4_fused_tiling(int n, int B, int sweep_K, int* out);
 int launch_rk4_fused_shared(int n, int B, int S, const double2* gen_table, double h, double2* y,
                             int ldy, cudaStream_t st);
 int launch_rk4_fused_sweep(int n, int K, int B, int S, const double2* stat_packed /*or null*/,

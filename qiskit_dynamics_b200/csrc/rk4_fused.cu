@@ -11,13 +11,21 @@
 //   * B operand (the stage vector) lives in shared memory in DMMA B-fragment order, double
 //     buffered; fragments are fetched one k-tile ahead; the epilogue of stage s writes the stage
 //     s+1 input (XOR-swizzled so both the fragment loads and the scattered epilogue stores are
-//     bank-conflict free).
+//     bank-conflict free per quarter warp, the unit in which 16 B shared accesses are served).
 //   * The RK4 k-sum lives in registers, y itself in a thread-private shared-memory slab.
 //
 // Shared-signal mode: A = precomputed generator table entry G_frame(t_stage) (frame phases folded
 // in by generator_kernel).  Sweep mode: A = the K+1 stored operators, the per-column signal value
 // scales the B fragment (so the operator sum accumulates in the same DMMA accumulators) and the
 // frame phases are applied to B rows on write and to C rows on read.
+//
+// Split mode (shared-signal kernel): whole-column CTAs quantise the batch in units of 8 NCW columns
+// per SM (4096 columns = 512 octets over 148 SMs -> 4 octets on the busiest SM = 86.5 % of the
+// chip).  A 2-CTA cluster instead owns 2 NCW + 1 octets: NCW octets per CTA plus one octet whose
+// output ROWS are split between the two CTAs (row tile m < MR/2 on rank 0, m >= MR/2 on rank 1).
+// Only that octet's stage vector crosses DSMEM (8 KiB per CTA per stage at n=128), and the per-stage
+// __syncthreads becomes a cluster barrier.  74 clusters x 7 octets cover 4096 columns with 98.8 %
+// of the SM-time busy.
 //
 // Roofline: fp64 tensor pipe.  Algorithmic flops per column per step = 4(8n^2 + 12n) + 28n.
 #include <cstdio>
@@ -38,11 +46,15 @@ struct Geometry {
 };
 
 // position of state element (row tile rt, row-in-tile g, column tile ct, column-in-tile cin) in the
-// B-fragment-ordered stage buffer: k-tile = 2 rt + g/4, lane = g%4 + 4 cin, 16 B slot XOR-swizzled
+// B-fragment-ordered stage buffer: k-tile = 2 rt + g/4, fragment lane L = g%4 + 4 cin (bits: k0 k1 c0 c1 c2).
+// A 16 B shared access is served per quarter warp (8 lanes -> 8 distinct 16 B bank groups = slot mod 8):
+//   fragment load : the 8 lanes vary (k0, k1, c0);  epilogue store (C-fragment order, fixed i): (k0, c1, c2).
+// slot = L ^ ((L >> 2) & 6) sends (k0, k1^c1, c0^c2) to the bank bits: distinct in both cases.
+__device__ __forceinline__ int frag_swizzle(int L) { return L ^ ((L >> 2) & 6); }
 __device__ __forceinline__ int yin_pos(int NCT, int rt, int g, int ct, int cin) {
     const int kt = 2 * rt + (g >> 2);
     const int lane_b = (g & 3) + 4 * cin;
-    return (kt * NCT + ct) * 32 + (lane_b ^ ((g >> 2) << 2));
+    return (kt * NCT + ct) * 32 + frag_swizzle(lane_b);
 }
 
 template <int MR, int NCW>
@@ -75,6 +87,85 @@ __device__ __forceinline__ void mma_block(Accum<MR, NCW>& acc, const double2 (&a
         }
 }
 
+// split mode: own tiles (MR x NCW) plus MS = MR/2 row tiles of the shared octet (B fragment b[NCW]);
+// a_s = this rank's half of the A fragments.  Dependent DMMAs are 2 MR NCW + 2 MS apart.
+template <int MR, int NCW, int MS>
+struct AccumS {
+    double cr[MS][2], ci[MS][2];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int m = 0; m < MS; ++m) cr[m][0] = cr[m][1] = ci[m][0] = ci[m][1] = 0.0;
+    }
+};
+
+template <int MR, int NCW, int MS>
+__device__ __forceinline__ void mma_block_split(Accum<MR, NCW>& acc, AccumS<MR, NCW, MS>& accs, const double2 (&a)[MR],
+                                                const double2 (&a_s)[MS], const double2 (&b)[NCW + 1]) {
+#pragma unroll
+    for (int m = 0; m < MR; ++m)
+#pragma unroll
+        for (int c = 0; c < NCW; ++c) {
+            dmma(acc.cr[m][c][0], acc.cr[m][c][1], a[m].x, b[c].x);
+            dmma(acc.ci[m][c][0], acc.ci[m][c][1], a[m].x, b[c].y);
+        }
+#pragma unroll
+    for (int m = 0; m < MS; ++m) {
+        dmma(accs.cr[m][0], accs.cr[m][1], a_s[m].x, b[NCW].x);
+        dmma(accs.ci[m][0], accs.ci[m][1], a_s[m].x, b[NCW].y);
+    }
+#pragma unroll
+    for (int m = 0; m < MR; ++m)
+#pragma unroll
+        for (int c = 0; c < NCW; ++c) {
+            dmma(acc.cr[m][c][0], acc.cr[m][c][1], -a[m].y, b[c].y);
+            dmma(acc.ci[m][c][0], acc.ci[m][c][1], a[m].y, b[c].x);
+        }
+#pragma unroll
+    for (int m = 0; m < MS; ++m) {
+        dmma(accs.cr[m][0], accs.cr[m][1], -a_s[m].y, b[NCW].y);
+        dmma(accs.ci[m][0], accs.ci[m][1], a_s[m].y, b[NCW].x);
+    }
+}
+
+// ---- cluster helpers (split mode) ----
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// mbarrier plumbing for the per-stage DSMEM exchange: the producer's st.async carries its own completion
+// (complete_tx on the CONSUMER's mbarrier), so no cluster-wide barrier or memory fence sits in the stage loop.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(a), "r"(parity)
+        : "memory");
+}
+// 16 B into the peer CTA's shared memory at the offset of local pointer p, completing on the peer's copy of bar
+__device__ __forceinline__ void st_async_peer(const double2* p, const uint64_t* bar, unsigned peer, double2 v) {
+    uint32_t rp, rb;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rp) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(peer));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(peer));
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1,%2}, [%3];" ::"r"(rp), "d"(v.x),
+                 "d"(v.y), "r"(rb)
+                 : "memory");
+}
+
 // RK4 stage combine shared by both kernels.  k-sum weights 1,2,2,1; next-input step h/2, h/2, h;
 // final update y + ((1/6) h) * ksum  (reference: fixed_step_solvers.py:60-73).
 struct StageCoef {
@@ -91,20 +182,35 @@ struct StageCoef {
 // ------------------------------------------------------------------------------------------------
 // shared-signal mode
 // ------------------------------------------------------------------------------------------------
-template <int MR, int NCW>
+template <int MR, int NCW, bool SPLIT>
 __global__ void __launch_bounds__(256, 1)
 rk4_shared_kernel(Geometry geo, int B, int S, const double2* __restrict__ gen, double h, double2* __restrict__ y,
                   int ldy) {
+    static_assert(!SPLIT || MR % 2 == 0, "split mode halves the row tiles of the shared octet");
+    constexpr int MS = SPLIT ? MR / 2 : 1;         // row tiles of the shared octet per warp (1 = unused dummy)
+    constexpr int NB = NCW + (SPLIT ? 1 : 0);      // B fragments per k-tile per warp
+    constexpr int SLOTS = (MR * NCW + (SPLIT ? MS : 0)) * 2;  // y-slab entries per thread
     extern __shared__ __align__(16) double2 sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
-    const int wr = warp % geo.WR, wc = warp / geo.WR;
+    const int swl = frag_swizzle(lane);
+    const int wr = warp % geo.WR, wc = warp / geo.WR;  // split mode: WC == 1
     const int KT = geo.KT, NCT = geo.NCT, n = geo.n;
     const size_t entry_elems = (size_t)geo.npad * KT * 4;
     const int yin_elems = KT * NCT * 32;
-    const int yst_off = 2 * yin_elems;  // thread-private y slab: [MR*NCW*2][blockDim]
+    const int yst_off = 2 * yin_elems;  // thread-private y slab: [SLOTS][blockDim]
     const int nthr = blockDim.x;
-    const int col0 = blockIdx.x * 8 * NCT;
+    // first global column of this warp's own tiles / of the shared octet; local stage-buffer tile index
+    const unsigned rank = SPLIT ? cluster_ctarank() : 0u;
+    const int ct0 = wc * NCW;  // local index of own tile 0
+    int colw, cols = 0;
+    if (SPLIT) {
+        const int base = (blockIdx.x >> 1) * (2 * NCW + 1);
+        colw = 8 * (base + (int)rank * (NCW + 1));
+        cols = 8 * (base + NCW);
+    } else {
+        colw = 8 * (blockIdx.x * NCT + ct0);
+    }
 
     int rt[MR], rtl[MR];  // row tile owned / loaded (surplus warps recompute the last tile, results dropped)
     bool mvalid[MR];
@@ -113,6 +219,13 @@ rk4_shared_kernel(Geometry geo, int B, int S, const double2* __restrict__ gen, d
         rt[m] = wr + geo.WR * m;
         mvalid[m] = rt[m] < geo.RT;
         rtl[m] = mvalid[m] ? rt[m] : geo.RT - 1;
+    }
+    int rts[MS];  // this rank's row tiles of the shared octet
+    bool svalid[MS];
+#pragma unroll
+    for (int mm = 0; mm < MS; ++mm) {
+        rts[mm] = wr + geo.WR * ((int)rank * MS + mm);
+        svalid[mm] = SPLIT && rts[mm] < geo.RT;
     }
 
     // ---- zero both stage buffers (k rows beyond npad stay zero), load y ----
@@ -125,21 +238,40 @@ rk4_shared_kernel(Geometry geo, int B, int S, const double2* __restrict__ gen, d
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const int row = 8 * rt[m] + g;
-                const int ct = wc * NCW + c;
-                const int col = col0 + 8 * ct + 2 * q + i;
+                const int col = colw + 8 * c + 2 * q + i;
                 double2 v = make_double2(0.0, 0.0);
                 if (mvalid[m] && row < n && col < B) v = y[(size_t)row * ldy + col];
                 sm[yst_off + ((m * NCW + c) * 2 + i) * nthr + tid] = v;
-                if (mvalid[m]) sm[yin_pos(NCT, rt[m], g, ct, 2 * q + i)] = v;
+                if (mvalid[m]) sm[yin_pos(NCT, rt[m], g, ct0 + c, 2 * q + i)] = v;
             }
+    if (SPLIT) {
+        // shared octet: every CTA stages ALL rows, but keeps only its own half in the y slab
+#pragma unroll
+        for (int m = 0; m < MR; ++m)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int row = 8 * rt[m] + g;
+                const int col = cols + 2 * q + i;
+                double2 v = make_double2(0.0, 0.0);
+                if (mvalid[m] && row < n && col < B) v = y[(size_t)row * ldy + col];
+                if (mvalid[m]) sm[yin_pos(NCT, rt[m], g, NCW, 2 * q + i)] = v;
+                const int mm = m - (int)rank * MS;
+                if (mm >= 0 && mm < MS) sm[yst_off + ((MR * NCW + mm) * 2 + i) * nthr + tid] = v;
+            }
+    }
 
     Accum<MR, NCW> acc;
     acc.zero();
+    AccumS<MR, NCW, MS> accs;
+    accs.zero();
     double kr[MR][NCW][2], ki[MR][NCW][2];  // running k1 + 2 k2 + 2 k3 + k4
 #pragma unroll
     for (int m = 0; m < MR; ++m)
 #pragma unroll
         for (int c = 0; c < NCW; ++c) kr[m][c][0] = kr[m][c][1] = ki[m][c][0] = ki[m][c][1] = 0.0;
+    double ksr[MS][2], ksi[MS][2];
+#pragma unroll
+    for (int mm = 0; mm < MS; ++mm) ksr[mm][0] = ksr[mm][1] = ksi[mm][0] = ksi[mm][1] = 0.0;
 
     // A-fragment offsets of this warp's row tiles inside one table entry
     size_t aoff[MR];
@@ -154,7 +286,22 @@ rk4_shared_kernel(Geometry geo, int B, int S, const double2* __restrict__ gen, d
         for (int m = 0; m < MR; ++m) ring[u][m] = ldg_stream(gen + aoff[m] + (size_t)u * 32);
 
     int cur = 0;
-    __syncthreads();
+    // split mode: two mbarriers (stage parity) count the bytes the peer sends per stage
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + yst_off + SLOTS * nthr);
+    unsigned tx_bytes = 0;
+    if (SPLIT) {
+        const int first = (int)(rank ^ 1u) * MS * geo.WR;  // peer's row tiles of the shared octet
+        const int cnt = max(0, min(geo.RT - first, MS * geo.WR));
+        tx_bytes = (unsigned)cnt * 64u * (unsigned)sizeof(double2);
+        if (tid == 0) {
+            mbar_init(mbar, 1);
+            mbar_init(mbar + 1, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        cluster_barrier();  // peer's buffers and mbarriers are initialised before the first remote store can land
+    } else {
+        __syncthreads();
+    }
 
     const int total_stages = 4 * S;
 #pragma unroll 1
@@ -166,11 +313,12 @@ rk4_shared_kernel(Geometry geo, int B, int S, const double2* __restrict__ gen, d
         const int nentry = (sidx + 1 < total_stages) ? 2 * nstep + (nstage == 0 ? 0 : (nstage == 3 ? 2 : 1)) : entry;
         const double2* gcur = gen + (size_t)entry * entry_elems;
         const double2* gnxt = gen + (size_t)nentry * entry_elems;
-        const int ybase = cur * yin_elems + (wc * NCW) * 32;
+        const int ybase = cur * yin_elems + ct0 * 32;
+        if (SPLIT && tid == 0) mbar_expect_tx(mbar + (sidx & 1), tx_bytes);
 
-        double2 bfrag[2][NCW];
+        double2 bfrag[2][NB];
 #pragma unroll
-        for (int c = 0; c < NCW; ++c) bfrag[0][c] = sm[ybase + c * 32 + lane];  // k-tile 0: swizzle bit = 0
+        for (int c = 0; c < NB; ++c) bfrag[0][c] = sm[ybase + c * 32 + swl];
 
 #pragma unroll 1
         for (int kt0 = 0; kt0 < KT; kt0 += RING) {
@@ -187,37 +335,73 @@ rk4_shared_kernel(Geometry geo, int B, int S, const double2* __restrict__ gen, d
                 // B fragments of k-tile kt + 1 (clamped at the stage end: a harmless reload)
                 {
                     const int ktb = min(kt + 1, KT - 1);
-                    const int sw = lane ^ ((ktb & 1) << 2);
 #pragma unroll
-                    for (int c = 0; c < NCW; ++c) bfrag[(u + 1) & 1][c] = sm[ybase + (ktb * NCT + c) * 32 + sw];
+                    for (int c = 0; c < NB; ++c) bfrag[(u + 1) & 1][c] = sm[ybase + (ktb * NCT + c) * 32 + swl];
                 }
-                mma_block<MR, NCW>(acc, ring[u], bfrag[u & 1]);
+                if constexpr (SPLIT) {
+                    double2 a_s[MS];
+#pragma unroll
+                    for (int mm = 0; mm < MS; ++mm) a_s[mm] = rank ? ring[u][MS + mm] : ring[u][mm];
+                    mma_block_split<MR, NCW, MS>(acc, accs, ring[u], a_s, bfrag[u & 1]);
+                } else {
+                    mma_block<MR, NCW>(acc, ring[u], bfrag[u & 1]);
+                }
             }
         }
 
         // ---- epilogue: RK4 stage combine, write next stage input ----
         const StageCoef sc(stage, h);
         const int ydst = (cur ^ 1) * yin_elems;
+        if constexpr (SPLIT) {
+            // shared octet first: its remote stores are in flight while the own tiles are combined
 #pragma unroll
-        for (int m = 0; m < MR; ++m)
+            for (int mm = 0; mm < MS; ++mm)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const double k_r = accs.cr[mm][i], k_i = accs.ci[mm][i];
+                    const int slab = yst_off + ((MR * NCW + mm) * 2 + i) * nthr + tid;
+                    const double2 yv = sm[slab];
+                    ksr[mm][i] = sc.keep * ksr[mm][i] + sc.wk * k_r;
+                    ksi[mm][i] = sc.keep * ksi[mm][i] + sc.wk * k_i;
+                    const double v_r = sc.last ? ksr[mm][i] : k_r, v_i = sc.last ? ksi[mm][i] : k_i;
+                    const double2 nxt = make_double2(yv.x + sc.astep * v_r, yv.y + sc.astep * v_i);
+                    if (sc.last) sm[slab] = nxt;
+                    if (svalid[mm]) {
+                        double2* dst = sm + ydst + yin_pos(NCT, rts[mm], g, NCW, 2 * q + i);
+                        *dst = nxt;
+                        st_async_peer(dst, mbar + (sidx & 1), rank ^ 1u, nxt);
+                    }
+                }
+            accs.zero();
+        }
+        // one row tile at a time: all y-slab loads first, then the stores (the compiler cannot hoist a shared
+        // load above a shared store it cannot disambiguate, which would serialise on the LDS latency)
+#pragma unroll
+        for (int m = 0; m < MR; ++m) {
+            double2 yv[NCW][2];
+#pragma unroll
+            for (int c = 0; c < NCW; ++c)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) yv[c][i] = sm[yst_off + ((m * NCW + c) * 2 + i) * nthr + tid];
 #pragma unroll
             for (int c = 0; c < NCW; ++c)
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const double k_r = acc.cr[m][c][i], k_i = acc.ci[m][c][i];
-                    const int slab = yst_off + ((m * NCW + c) * 2 + i) * nthr + tid;
-                    const double2 yv = sm[slab];
                     kr[m][c][i] = sc.keep * kr[m][c][i] + sc.wk * k_r;
                     ki[m][c][i] = sc.keep * ki[m][c][i] + sc.wk * k_i;
                     const double v_r = sc.last ? kr[m][c][i] : k_r, v_i = sc.last ? ki[m][c][i] : k_i;
-                    const double2 nxt = make_double2(yv.x + sc.astep * v_r, yv.y + sc.astep * v_i);
-                    if (sc.last) sm[slab] = nxt;
-                    if (mvalid[m]) sm[ydst + yin_pos(NCT, rt[m], g, wc * NCW + c, 2 * q + i)] = nxt;
+                    const double2 nxt = make_double2(yv[c][i].x + sc.astep * v_r, yv[c][i].y + sc.astep * v_i);
+                    if (sc.last) sm[yst_off + ((m * NCW + c) * 2 + i) * nthr + tid] = nxt;
+                    if (mvalid[m]) sm[ydst + yin_pos(NCT, rt[m], g, ct0 + c, 2 * q + i)] = nxt;
                 }
+        }
         acc.zero();
         cur ^= 1;
         __syncthreads();
+        if (SPLIT) mbar_wait(mbar + (sidx & 1), (sidx >> 1) & 1);  // the peer's half of the shared octet has landed
     }
+    if (SPLIT) cluster_barrier();  // neither CTA retires while the other could still address its shared memory
 
     // ---- store y ----
 #pragma unroll
@@ -227,10 +411,21 @@ rk4_shared_kernel(Geometry geo, int B, int S, const double2* __restrict__ gen, d
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const int row = 8 * rt[m] + g;
-                const int col = col0 + 8 * (wc * NCW + c) + 2 * q + i;
+                const int col = colw + 8 * c + 2 * q + i;
                 if (mvalid[m] && row < n && col < B)
                     y[(size_t)row * ldy + col] = sm[yst_off + ((m * NCW + c) * 2 + i) * nthr + tid];
             }
+    if (SPLIT) {
+#pragma unroll
+        for (int mm = 0; mm < MS; ++mm)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int row = 8 * rts[mm] + g;
+                const int col = cols + 2 * q + i;
+                if (svalid[mm] && row < n && col < B)
+                    y[(size_t)row * ldy + col] = sm[yst_off + ((MR * NCW + mm) * 2 + i) * nthr + tid];
+            }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -245,6 +440,7 @@ rk4_sweep_kernel(Geometry geo, int K, int B, int S, const double2* __restrict__ 
     extern __shared__ __align__(16) double2 sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
+    const int swl = frag_swizzle(lane);
     const int wr = warp % geo.WR, wc = warp / geo.WR;
     const int KT = geo.KT, NCT = geo.NCT, n = geo.n;
     const size_t entry_elems = (size_t)geo.npad * KT * 4;
@@ -354,9 +550,8 @@ rk4_sweep_kernel(Geometry geo, int K, int B, int S, const double2* __restrict__ 
                     if (++pj == J) { pj = 0; if (++pk == KT) pk = 0; }
                 }
                 if (j == 0) {
-                    const int sw = lane ^ ((kt & 1) << 2);
 #pragma unroll
-                    for (int c = 0; c < NCW; ++c) b[c] = sm[ybase + (kt * NCT + c) * 32 + sw];
+                    for (int c = 0; c < NCW; ++c) b[c] = sm[ybase + (kt * NCT + c) * 32 + swl];
                 }
                 const int sig = j - has_static;  // -1 -> static operator, coefficient 1
                 double2 bs[NCW];
@@ -426,6 +621,7 @@ struct Config {
     int MR, NCW, threads;
     size_t smem;
     int grid;
+    bool split;  // 2-CTA clusters, 2 NCW + 1 column tiles per cluster (shared-signal kernel only)
 };
 
 constexpr int kMaxFusedNpad = 256;
@@ -486,9 +682,12 @@ bool pick_config(int n, int B, int K_sweep /*0 for shared*/, Config& cfg) {
             NCWmax = fncw;
         }
     }
-    // The busiest SM runs ceil(ctas / #SMs) CTAs of NCW column tiles each: minimise that product,
-    // ties go to the wider tile (fewer A-fragment reloads per column).
-    long best_cost = -1;
+    // The busiest SM runs ceil(ctas / #SMs) CTAs one after the other, each costing a fixed part (epilogue,
+    // barrier, pipeline fill; also the poorer A-fragment reuse of narrow tiles) plus a part proportional to
+    // its column tiles.  Measured at n=128 (profiles/probe/cfg_sweep.py): 28.0 / 41.2 / 75.4 us per step for
+    // NCW = 1 / 2 / 4, i.e. about 9.5 + 16.5 NCW.  Ties go to the wider tile.
+    constexpr double kFixedTiles = 0.6;
+    double best_cost = -1;
     bool found = false;
     for (int NCW = NCWmax; NCW >= 1; NCW /= 2) {
         Geometry g2 = geo;
@@ -500,7 +699,7 @@ bool pick_config(int n, int B, int K_sweep /*0 for shared*/, Config& cfg) {
         if (K_sweep > 0) smem += (size_t)K_sweep * 8 * g2.NCT * sizeof(double);
         if (smem > kSmemLimit) continue;
         const int ctas = (CT + g2.NCT - 1) / g2.NCT;
-        const long cost = (long)((ctas + SMS - 1) / SMS) * NCW;
+        const double cost = (double)((ctas + SMS - 1) / SMS) * (kFixedTiles + NCW);
         if (!found || cost < best_cost) {
             found = true;
             best_cost = cost;
@@ -510,6 +709,35 @@ bool pick_config(int n, int B, int K_sweep /*0 for shared*/, Config& cfg) {
             cfg.threads = threads;
             cfg.smem = smem;
             cfg.grid = ctas;
+            cfg.split = false;
+        }
+    }
+    // Split candidates (shared-signal kernel, all warps along rows, two row tiles per warp): a 2-CTA cluster
+    // owns 2 NCW + 1 column tiles, the busiest SM computes NCW + 1/2 tiles per row tile and wave.
+    const char* nosplit = getenv("QDB_NO_SPLIT");
+    if (found && K_sweep == 0 && WC == 1 && MR == 2 && SMS >= 2 && !(nosplit && nosplit[0] == '1')) {
+        for (int NCW = 3; NCW >= 1; --NCW) {
+            Geometry g2 = geo;
+            g2.WR = WR;
+            g2.WC = 1;
+            g2.NCT = NCW + 1;
+            const int threads = 32 * WR;
+            const size_t smem = (size_t)2 * g2.KT * g2.NCT * 32 * sizeof(double2) +
+                                (size_t)(MR * NCW + MR / 2) * 2 * threads * sizeof(double2) + 16 /*mbarriers*/;
+            if (smem > kSmemLimit) continue;
+            const int clusters = (CT + 2 * NCW) / (2 * NCW + 1);
+            const int slots = SMS / 2;
+            const double cost = (double)((clusters + slots - 1) / slots) * (kFixedTiles + NCW + 0.5);
+            if (cost < best_cost) {
+                best_cost = cost;
+                cfg.geo = g2;
+                cfg.MR = MR;
+                cfg.NCW = NCW;
+                cfg.threads = threads;
+                cfg.smem = smem;
+                cfg.grid = 2 * clusters;
+                cfg.split = true;
+            }
         }
     }
     return found;
@@ -517,9 +745,30 @@ bool pick_config(int n, int B, int K_sweep /*0 for shared*/, Config& cfg) {
 
 template <int MR, int NCW>
 int launch_shared_t(const Config& cfg, int B, int S, const double2* gen, double h, double2* y, int ldy, cudaStream_t st) {
-    QDB_CUDA(cudaFuncSetAttribute(rk4_shared_kernel<MR, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-    rk4_shared_kernel<MR, NCW><<<cfg.grid, cfg.threads, cfg.smem, st>>>(cfg.geo, B, S, gen, h, y, ldy);
+    QDB_CUDA(cudaFuncSetAttribute(rk4_shared_kernel<MR, NCW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+    rk4_shared_kernel<MR, NCW, false><<<cfg.grid, cfg.threads, cfg.smem, st>>>(cfg.geo, B, S, gen, h, y, ldy);
     QDB_LAUNCH_CHECK("rk4_shared_kernel");
+    return QDB_OK;
+}
+
+template <int MR, int NCW>
+int launch_split_t(const Config& cfg, int B, int S, const double2* gen, double h, double2* y, int ldy, cudaStream_t st) {
+    auto kern = rk4_shared_kernel<MR, NCW, true>;
+    QDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(cfg.grid);
+    lc.blockDim = dim3(cfg.threads);
+    lc.dynamicSmemBytes = cfg.smem;
+    lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    QDB_CUDA(cudaLaunchKernelEx(&lc, kern, cfg.geo, B, S, gen, h, y, ldy));
+    QDB_LAUNCH_CHECK("rk4_shared_kernel<split>");
     return QDB_OK;
 }
 
@@ -539,6 +788,20 @@ int launch_sweep_t(const Config& cfg, int K, int B, int S, const double2* stat, 
 
 bool rk4_fused_supported(int n) { return n >= 1 && round_up8(n) <= kMaxFusedNpad; }
 
+bool rk4_fused_tiling(int n, int B, int sweep_K, int* out) {
+    Config cfg;
+    if (!pick_config(n, B, sweep_K, cfg)) return false;
+    out[0] = cfg.geo.WR;
+    out[1] = cfg.geo.WC;
+    out[2] = cfg.MR;
+    out[3] = cfg.NCW;
+    out[4] = cfg.split ? 1 : 0;
+    out[5] = cfg.grid;
+    out[6] = cfg.threads;
+    out[7] = (int)cfg.smem;
+    return true;
+}
+
 int launch_rk4_fused_shared(int n, int B, int S, const double2* gen_table, double h, double2* y, int ldy, cudaStream_t st) {
     Config cfg;
     if (!pick_config(n, B, 0, cfg)) {
@@ -546,6 +809,11 @@ int launch_rk4_fused_shared(int n, int B, int S, const double2* gen_table, doubl
         return QDB_E_UNSUPPORTED;
     }
 #define ARGS cfg, B, S, gen_table, h, y, ldy, st
+    if (cfg.split) {
+        QDB_DISPATCH(2, 1, (launch_split_t<2, 1>(ARGS)));
+        QDB_DISPATCH(2, 2, (launch_split_t<2, 2>(ARGS)));
+        QDB_DISPATCH(2, 3, (launch_split_t<2, 3>(ARGS)));
+    }
     QDB_DISPATCH(1, 1, (launch_shared_t<1, 1>(ARGS)));
     QDB_DISPATCH(1, 2, (launch_shared_t<1, 2>(ARGS)));
     QDB_DISPATCH(1, 4, (launch_shared_t<1, 4>(ARGS)));

@@ -152,6 +152,55 @@ def test_rk4_fused_shared(abi, n, K, B, S, frame):
     assert torch.equal(yd, yd2)
 
 
+@pytest.mark.parametrize("n,B,S", [
+    (128, 4096, 3),   # headline: 74 clusters x 7 octets
+    (128, 4000, 2),   # ragged batch: last cluster partly empty
+    (128, 3001, 2),   # ragged inside an octet
+    (100, 2500, 2),   # 13 row tiles: rank 1 owns 5 of its 8 shared row tiles
+    (72, 6000, 2),    # 9 row tiles: rank 1 owns a single shared row tile
+    (128, 8192, 1),   # two waves of clusters
+])
+def test_rk4_split_clusters_bit_identical(abi, n, B, S):
+    """Split mode (2-CTA clusters exchanging one column octet over DSMEM) performs the same DMMA
+    sequence per element as whole-column CTAs, so the two tilings must agree bit for bit; the
+    whole-column tiling is the one checked against the oracle in test_rk4_fused_shared."""
+    import os
+    rng = np.random.default_rng(n + B)
+    table = dev((rng.standard_normal((2 * S + 1, n, n)) + 1j * rng.standard_normal((2 * S + 1, n, n))) * (3.0 / np.sqrt(n)))
+    packed = abi.pack_operators(table)
+    y0 = dev(rng.standard_normal((n, B)) + 1j * rng.standard_normal((n, B)))
+    old = os.environ.pop("QDB_NO_SPLIT", None)
+    try:
+        tiling = abi.rk4_tiling(n, B)
+        if n != 72:
+            assert tiling["split"] == 1, tiling
+        y1 = y0.clone()
+        abi.rk4_table_steps(n, packed, 1e-2, y1, S)
+        os.environ["QDB_NO_SPLIT"] = "1"
+        assert abi.rk4_tiling(n, B)["split"] == 0
+        y2 = y0.clone()
+        abi.rk4_table_steps(n, packed, 1e-2, y2, S)
+    finally:
+        os.environ.pop("QDB_NO_SPLIT", None)
+        if old is not None:
+            os.environ["QDB_NO_SPLIT"] = old
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y2)
+    # and against a plain fp64 torch restatement of RK4 on the same table (first 16 columns + the last 8)
+    cols = torch.cat([torch.arange(16), torch.arange(B - 8, B)]).cuda()
+    y = y0[:, cols]
+    h = 1e-2
+    for s in range(S):
+        G0, G1, G2 = table[2 * s], table[2 * s + 1], table[2 * s + 2]
+        k1 = G0 @ y
+        k2 = G1 @ (y + 0.5 * h * k1)
+        k3 = G1 @ (y + 0.5 * h * k2)
+        k4 = G2 @ (y + h * k3)
+        y = y + (1.0 / 6) * h * (k1 + 2 * k2 + 2 * k3 + k4)
+    err = torch.linalg.vector_norm(y1[:, cols] - y, dim=0).max().item()
+    assert err < TOL_SOLVE
+
+
 @pytest.mark.parametrize("n,K,B,S,frame", [(32, 8, 48, 10, "full"), (5, 2, 3, 20, "diag"), (128, 8, 40, 3, "full"), (16, 2, 600, 4, "none")])
 def test_rk4_fused_sweep(abi, n, K, B, S, frame):
     Gd, G, d, mu, y, specs = model_inputs(n, K, B, 99 + n, frame)
