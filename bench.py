@@ -36,7 +36,8 @@ N_DIM, K_OPS, BATCH = 128, 8, 4096
 RK4_STEPS = 100       # RK4 steps per bench step (400 RHS evaluations per column)
 MAX_DT = 1e-3
 SEED = 2004
-REF_RK4_STEPS = 3     # bounded CPU sample per reference step
+REF_RK4_STEPS = 20    # bounded CPU sample per reference-arm step (same batch, 20 of the 100 RK4 steps)
+CPU_BASELINE_RK4_STEPS = 100  # cpu_baseline leg of the B200 arm: one full bench step, repeated
 
 
 def flops_per_column_step(n):
@@ -298,13 +299,18 @@ def run_b200(args):
     peak_tf = abi.dmma_probe()
     flops_launch = float(S) * B * flops_per_column_step(n)
     achieved_tf = flops_launch / (kern_mean_ms * 1e-3) * 1e-12
+    # DRAM traffic per launch from the committed ncu --set full capture (profiles/rk4_shared_traffic.json):
+    # measured per RK4 step there (the generator table dominates), scaled to this launch's S steps
     traffic = None
     prof = os.path.join(ROOT, "profiles", "rk4_shared_traffic.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            traffic = float(json.load(open(prof))["dram_bytes_per_rk4_step"]) * S
         except Exception:  # noqa: BLE001
             traffic = None
+    tiling = abi.rk4_tiling(n, B)
+    kernel_name = (f"rk4_shared_kernel<{tiling['row_tiles_per_warp']},{tiling['col_tiles_per_warp']},"
+                   f"{'split' if tiling['split'] else 'whole'}>")
 
     # parity spot check of the timed configuration (not timed): norm preservation of the unitary flow
     norms = torch.linalg.vector_norm(y_work, dim=0)
@@ -312,7 +318,7 @@ def run_b200(args):
 
     if rank == 0:
         threads = cpu_threads()
-        cpu_rate, cpu_sec = cpu_reference_rate(n, K, B, steps=2, warmup=1, rk4_steps=REF_RK4_STEPS)
+        cpu_rate, cpu_sec = cpu_reference_rate(n, K, B, steps=2, warmup=1, rk4_steps=CPU_BASELINE_RK4_STEPS)
         line = {
             "metric": "rhs_evals_per_sec", "value": value, "unit": "state-RHS/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
@@ -326,14 +332,15 @@ def run_b200(args):
                     "d2h_bytes_per_step": int(n * B * 16 + (8 * B * world if world > 1 else 0))},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "rk4_shared_kernel<2,4>", "achieved": achieved_tf, "peak": peak_tf,
+            "roofline": {"bound": "tensor", "kernel": kernel_name, "tiling": tiling, "achieved": achieved_tf, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
                          "flops_per_launch": flops_launch, "kernel_ms": kern_mean_ms,
                          "peak_source": "live DMMA m8n8k4 issue-rate probe (qdb_dmma_probe); MEASURED_PEAKS.json has no "
                                         "fp64 entry; B200 datasheet fp64 tensor 37-40 TFLOP/s"},
             "cpu_baseline": {"value": cpu_rate, "unit": "state-RHS/s", "cores": threads, "kind": "port",
-                             "sample": f"{REF_RK4_STEPS} RK4 steps of the same n={n}, K={K}, B={B} batch x 2 repeats "
-                                       f"({cpu_sec:.2f} s each), NumPy/OpenBLAS port of the reference path"},
+                             "sample": f"{CPU_BASELINE_RK4_STEPS} RK4 steps (one full bench step) of the same n={n}, K={K}, "
+                                       f"B={B} batch x 2 repeats after 1 warm-up ({cpu_sec:.2f} s each), NumPy/OpenBLAS "
+                                       f"port of the reference path, {threads} BLAS threads"},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
