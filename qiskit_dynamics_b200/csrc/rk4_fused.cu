@@ -30,6 +30,7 @@
 // Roofline: fp64 tensor pipe.  Algorithmic flops per column per step = 4(8n^2 + 12n) + 28n.
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "qdb_common.cuh"
 
@@ -57,73 +58,97 @@ __device__ __forceinline__ int yin_pos(int NCT, int rt, int g, int ct, int cin) 
     return (kt * NCT + ct) * 32 + frag_swizzle(lane_b);
 }
 
-template <int MR, int NCW>
+// Complex tile product as real DMMAs.
+//   M3 = false ("4M"): cr += ar br - ai bi, ci += ar bi + ai br            -> 4 DMMAs per k-tile
+//   M3 = true  ("3M"): p1 += ar br, p2 += ai bi, p3 += (ar+ai)(br+bi);     -> 3 DMMAs per k-tile
+//                      re = p1 - p2, im = p3 - p1 - p2 (formed once per stage in the epilogue)
+// 3M trades a quarter of the tensor-pipe work for one more accumulator per tile, two DADDs per fragment
+// and a normwise (instead of componentwise) error bound of a few ulp of |A||B| -- five orders of
+// magnitude inside the 1e-8 parity bar.
+template <int MR, int NCW, bool M3>
 struct Accum {
-    double cr[MR][NCW][2], ci[MR][NCW][2];
+    static constexpr int NA = M3 ? 3 : 2;
+    double p[NA][MR][NCW][2];
     __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+#pragma unroll
+            for (int m = 0; m < MR; ++m)
+#pragma unroll
+                for (int c = 0; c < NCW; ++c) p[a][m][c][0] = p[a][m][c][1] = 0.0;
+    }
+    __device__ __forceinline__ double re(int m, int c, int i) const { return M3 ? p[0][m][c][i] - p[1][m][c][i] : p[0][m][c][i]; }
+    __device__ __forceinline__ double im(int m, int c, int i) const {
+        return M3 ? (p[NA - 1][m][c][i] - p[0][m][c][i]) - p[1][m][c][i] : p[1][m][c][i];
+    }
+};
+
+// own tiles (MR x NCW) plus, in split mode, MS row tiles of the shared octet (B fragment b[NCW], A fragments a_s
+// = this rank's half).  Every accumulator is touched once (3M) or twice half a block apart (4M) per k-tile.
+template <int MR, int NCW, int MS, bool SPLIT, bool M3>
+__device__ __forceinline__ void mma_block(Accum<MR, NCW, M3>& acc, Accum<MS, 1, M3>& accs, const double2 (&a)[MR],
+                                          const double2 (&a_s)[MS], const double2 (&b)[NCW + (SPLIT ? 1 : 0)]) {
+    if constexpr (M3) {
+        double as[MR], ass[MS], bs[NCW + (SPLIT ? 1 : 0)];
+#pragma unroll
+        for (int m = 0; m < MR; ++m) as[m] = a[m].x + a[m].y;
+#pragma unroll
+        for (int c = 0; c < NCW + (SPLIT ? 1 : 0); ++c) bs[c] = b[c].x + b[c].y;
+#pragma unroll
+        for (int m = 0; m < MS; ++m) ass[m] = a_s[m].x + a_s[m].y;
 #pragma unroll
         for (int m = 0; m < MR; ++m)
 #pragma unroll
-            for (int c = 0; c < NCW; ++c) cr[m][c][0] = cr[m][c][1] = ci[m][c][0] = ci[m][c][1] = 0.0;
-    }
-};
-
-// 4 MR NCW real DMMAs of one complex k-tile; dependent DMMAs on the same accumulator are 2 MR NCW apart
-template <int MR, int NCW>
-__device__ __forceinline__ void mma_block(Accum<MR, NCW>& acc, const double2 (&a)[MR], const double2 (&b)[NCW]) {
+            for (int c = 0; c < NCW; ++c) dmma(acc.p[0][m][c][0], acc.p[0][m][c][1], a[m].x, b[c].x);
+        if constexpr (SPLIT) {
 #pragma unroll
-    for (int m = 0; m < MR; ++m)
-#pragma unroll
-        for (int c = 0; c < NCW; ++c) {
-            dmma(acc.cr[m][c][0], acc.cr[m][c][1], a[m].x, b[c].x);
-            dmma(acc.ci[m][c][0], acc.ci[m][c][1], a[m].x, b[c].y);
+            for (int m = 0; m < MS; ++m) dmma(accs.p[0][m][0][0], accs.p[0][m][0][1], a_s[m].x, b[NCW].x);
         }
 #pragma unroll
-    for (int m = 0; m < MR; ++m)
+        for (int m = 0; m < MR; ++m)
 #pragma unroll
-        for (int c = 0; c < NCW; ++c) {
-            dmma(acc.cr[m][c][0], acc.cr[m][c][1], -a[m].y, b[c].y);  // SASS: DMMA with negated operand
-            dmma(acc.ci[m][c][0], acc.ci[m][c][1], a[m].y, b[c].x);
-        }
-}
-
-// split mode: own tiles (MR x NCW) plus MS = MR/2 row tiles of the shared octet (B fragment b[NCW]);
-// a_s = this rank's half of the A fragments.  Dependent DMMAs are 2 MR NCW + 2 MS apart.
-template <int MR, int NCW, int MS>
-struct AccumS {
-    double cr[MS][2], ci[MS][2];
-    __device__ __forceinline__ void zero() {
+            for (int c = 0; c < NCW; ++c) dmma(acc.p[1][m][c][0], acc.p[1][m][c][1], a[m].y, b[c].y);
+        if constexpr (SPLIT) {
 #pragma unroll
-        for (int m = 0; m < MS; ++m) cr[m][0] = cr[m][1] = ci[m][0] = ci[m][1] = 0.0;
-    }
-};
-
-template <int MR, int NCW, int MS>
-__device__ __forceinline__ void mma_block_split(Accum<MR, NCW>& acc, AccumS<MR, NCW, MS>& accs, const double2 (&a)[MR],
-                                                const double2 (&a_s)[MS], const double2 (&b)[NCW + 1]) {
-#pragma unroll
-    for (int m = 0; m < MR; ++m)
-#pragma unroll
-        for (int c = 0; c < NCW; ++c) {
-            dmma(acc.cr[m][c][0], acc.cr[m][c][1], a[m].x, b[c].x);
-            dmma(acc.ci[m][c][0], acc.ci[m][c][1], a[m].x, b[c].y);
+            for (int m = 0; m < MS; ++m) dmma(accs.p[1][m][0][0], accs.p[1][m][0][1], a_s[m].y, b[NCW].y);
         }
 #pragma unroll
-    for (int m = 0; m < MS; ++m) {
-        dmma(accs.cr[m][0], accs.cr[m][1], a_s[m].x, b[NCW].x);
-        dmma(accs.ci[m][0], accs.ci[m][1], a_s[m].x, b[NCW].y);
-    }
+        for (int m = 0; m < MR; ++m)
 #pragma unroll
-    for (int m = 0; m < MR; ++m)
+            for (int c = 0; c < NCW; ++c) dmma(acc.p[2][m][c][0], acc.p[2][m][c][1], as[m], bs[c]);
+        if constexpr (SPLIT) {
 #pragma unroll
-        for (int c = 0; c < NCW; ++c) {
-            dmma(acc.cr[m][c][0], acc.cr[m][c][1], -a[m].y, b[c].y);
-            dmma(acc.ci[m][c][0], acc.ci[m][c][1], a[m].y, b[c].x);
+            for (int m = 0; m < MS; ++m) dmma(accs.p[2][m][0][0], accs.p[2][m][0][1], ass[m], bs[NCW]);
+        }
+    } else {
+#pragma unroll
+        for (int m = 0; m < MR; ++m)
+#pragma unroll
+            for (int c = 0; c < NCW; ++c) {
+                dmma(acc.p[0][m][c][0], acc.p[0][m][c][1], a[m].x, b[c].x);
+                dmma(acc.p[1][m][c][0], acc.p[1][m][c][1], a[m].x, b[c].y);
+            }
+        if constexpr (SPLIT) {
+#pragma unroll
+            for (int m = 0; m < MS; ++m) {
+                dmma(accs.p[0][m][0][0], accs.p[0][m][0][1], a_s[m].x, b[NCW].x);
+                dmma(accs.p[1][m][0][0], accs.p[1][m][0][1], a_s[m].x, b[NCW].y);
+            }
         }
 #pragma unroll
-    for (int m = 0; m < MS; ++m) {
-        dmma(accs.cr[m][0], accs.cr[m][1], -a_s[m].y, b[NCW].y);
-        dmma(accs.ci[m][0], accs.ci[m][1], a_s[m].y, b[NCW].x);
+        for (int m = 0; m < MR; ++m)
+#pragma unroll
+            for (int c = 0; c < NCW; ++c) {
+                dmma(acc.p[0][m][c][0], acc.p[0][m][c][1], -a[m].y, b[c].y);  // SASS: DMMA with negated operand
+                dmma(acc.p[1][m][c][0], acc.p[1][m][c][1], a[m].y, b[c].x);
+            }
+        if constexpr (SPLIT) {
+#pragma unroll
+            for (int m = 0; m < MS; ++m) {
+                dmma(accs.p[0][m][0][0], accs.p[0][m][0][1], -a_s[m].y, b[NCW].y);
+                dmma(accs.p[1][m][0][0], accs.p[1][m][0][1], a_s[m].y, b[NCW].x);
+            }
+        }
     }
 }
 
@@ -182,11 +207,22 @@ struct StageCoef {
 // ------------------------------------------------------------------------------------------------
 // shared-signal mode
 // ------------------------------------------------------------------------------------------------
-template <int MR, int NCW, bool SPLIT>
+template <int MR, int NCW, bool SPLIT, int SKT>
+struct StaticGeo {
+    int n;
+    static constexpr int npad = 4 * SKT, KT = SKT, RT = 8 * MR, WR = 8, WC = 1, NCT = NCW + (SPLIT ? 1 : 0);
+};
+
+// SKT > 0 fixes the geometry at compile time (KT = SKT k-tiles, 8 row warps x 1 column warp, 256 threads,
+// RT = 8 MR row tiles, NCT = NCW (+1 in split mode)): addresses become immediates and about 25 registers
+// that otherwise carry precomputed epilogue offsets across the main loop are freed.
+template <int MR, int NCW, bool SPLIT, int SKT, bool M3>
 __global__ void __launch_bounds__(256, 1)
-rk4_shared_kernel(Geometry geo, int B, int S, const double2* __restrict__ gen, double h, double2* __restrict__ y,
+rk4_shared_kernel(Geometry geo_rt, int B, int S, const double2* __restrict__ gen, double h, double2* __restrict__ y,
                   int ldy) {
     static_assert(!SPLIT || MR % 2 == 0, "split mode halves the row tiles of the shared octet");
+    typename std::conditional<(SKT > 0), StaticGeo<MR, NCW, SPLIT, SKT>, Geometry>::type geo;
+    if constexpr (SKT > 0) geo.n = geo_rt.n; else geo = geo_rt;
     constexpr int MS = SPLIT ? MR / 2 : 1;         // row tiles of the shared octet per warp (1 = unused dummy)
     constexpr int NB = NCW + (SPLIT ? 1 : 0);      // B fragments per k-tile per warp
     constexpr int SLOTS = (MR * NCW + (SPLIT ? MS : 0)) * 2;  // y-slab entries per thread
@@ -199,7 +235,7 @@ rk4_shared_kernel(Geometry geo, int B, int S, const double2* __restrict__ gen, d
     const size_t entry_elems = (size_t)geo.npad * KT * 4;
     const int yin_elems = KT * NCT * 32;
     const int yst_off = 2 * yin_elems;  // thread-private y slab: [SLOTS][blockDim]
-    const int nthr = blockDim.x;
+    const int nthr = SKT > 0 ? 256 : blockDim.x;
     // first global column of this warp's own tiles / of the shared octet; local stage-buffer tile index
     const unsigned rank = SPLIT ? cluster_ctarank() : 0u;
     const int ct0 = wc * NCW;  // local index of own tile 0
@@ -260,9 +296,9 @@ rk4_shared_kernel(Geometry geo, int B, int S, const double2* __restrict__ gen, d
             }
     }
 
-    Accum<MR, NCW> acc;
+    Accum<MR, NCW, M3> acc;
     acc.zero();
-    AccumS<MR, NCW, MS> accs;
+    Accum<MS, 1, M3> accs;  // shared octet (split mode)
     accs.zero();
     double kr[MR][NCW][2], ki[MR][NCW][2];  // running k1 + 2 k2 + 2 k3 + k4
 #pragma unroll
@@ -338,14 +374,12 @@ rk4_shared_kernel(Geometry geo, int B, int S, const double2* __restrict__ gen, d
 #pragma unroll
                     for (int c = 0; c < NB; ++c) bfrag[(u + 1) & 1][c] = sm[ybase + (ktb * NCT + c) * 32 + swl];
                 }
+                double2 a_s[MS];
                 if constexpr (SPLIT) {
-                    double2 a_s[MS];
 #pragma unroll
                     for (int mm = 0; mm < MS; ++mm) a_s[mm] = rank ? ring[u][MS + mm] : ring[u][mm];
-                    mma_block_split<MR, NCW, MS>(acc, accs, ring[u], a_s, bfrag[u & 1]);
-                } else {
-                    mma_block<MR, NCW>(acc, ring[u], bfrag[u & 1]);
                 }
+                mma_block<MR, NCW, MS, SPLIT, M3>(acc, accs, ring[u], a_s, bfrag[u & 1]);
             }
         }
 
@@ -358,7 +392,7 @@ rk4_shared_kernel(Geometry geo, int B, int S, const double2* __restrict__ gen, d
             for (int mm = 0; mm < MS; ++mm)
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    const double k_r = accs.cr[mm][i], k_i = accs.ci[mm][i];
+                    const double k_r = accs.re(mm, 0, i), k_i = accs.im(mm, 0, i);
                     const int slab = yst_off + ((MR * NCW + mm) * 2 + i) * nthr + tid;
                     const double2 yv = sm[slab];
                     ksr[mm][i] = sc.keep * ksr[mm][i] + sc.wk * k_r;
@@ -387,7 +421,7 @@ rk4_shared_kernel(Geometry geo, int B, int S, const double2* __restrict__ gen, d
             for (int c = 0; c < NCW; ++c)
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    const double k_r = acc.cr[m][c][i], k_i = acc.ci[m][c][i];
+                    const double k_r = acc.re(m, c, i), k_i = acc.im(m, c, i);
                     kr[m][c][i] = sc.keep * kr[m][c][i] + sc.wk * k_r;
                     ki[m][c][i] = sc.keep * ki[m][c][i] + sc.wk * k_i;
                     const double v_r = sc.last ? kr[m][c][i] : k_r, v_i = sc.last ? ki[m][c][i] : k_i;
@@ -489,8 +523,9 @@ rk4_sweep_kernel(Geometry geo, int K, int B, int S, const double2* __restrict__ 
                 if (mvalid[m]) sm[yin_pos(NCT, rt[m], g, ct, 2 * q + i)] = cmul(ph[m], v);  // pre-phase
             }
 
-    Accum<MR, NCW> acc;
+    Accum<MR, NCW, false> acc;
     acc.zero();
+    Accum<1, 1, false> acc_unused;
     double kr[MR][NCW][2], ki[MR][NCW][2];
 #pragma unroll
     for (int m = 0; m < MR; ++m)
@@ -560,7 +595,10 @@ rk4_sweep_kernel(Geometry geo, int K, int B, int S, const double2* __restrict__ 
                     const double s = sig < 0 ? 1.0 : csrc[sig * ncols + c * 8];
                     bs[c] = make_double2(b[c].x * s, b[c].y * s);
                 }
-                mma_block<MR, NCW>(acc, ring[u], bs);
+                {
+                    const double2 a_unused[1] = {};
+                    mma_block<MR, NCW, 1, false, false>(acc, acc_unused, ring[u], a_unused, bs);
+                }
                 if (++j == J) { j = 0; ++kt; }
             }
         }
@@ -583,7 +621,7 @@ rk4_sweep_kernel(Geometry geo, int K, int B, int S, const double2* __restrict__ 
             for (int c = 0; c < NCW; ++c)
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    const double2 k = cmul_conj_a(ph[m], make_double2(acc.cr[m][c][i], acc.ci[m][c][i]));
+                    const double2 k = cmul_conj_a(ph[m], make_double2(acc.re(m, c, i), acc.im(m, c, i)));
                     const int slab = yst_off + ((m * NCW + c) * 2 + i) * nthr + tid;
                     const double2 yv = sm[slab];
                     kr[m][c][i] = sc.keep * kr[m][c][i] + sc.wk * k.x;
@@ -745,15 +783,15 @@ bool pick_config(int n, int B, int K_sweep /*0 for shared*/, Config& cfg) {
 
 template <int MR, int NCW>
 int launch_shared_t(const Config& cfg, int B, int S, const double2* gen, double h, double2* y, int ldy, cudaStream_t st) {
-    QDB_CUDA(cudaFuncSetAttribute(rk4_shared_kernel<MR, NCW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-    rk4_shared_kernel<MR, NCW, false><<<cfg.grid, cfg.threads, cfg.smem, st>>>(cfg.geo, B, S, gen, h, y, ldy);
+    QDB_CUDA(cudaFuncSetAttribute(rk4_shared_kernel<MR, NCW, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+    rk4_shared_kernel<MR, NCW, false, 0, false><<<cfg.grid, cfg.threads, cfg.smem, st>>>(cfg.geo, B, S, gen, h, y, ldy);
     QDB_LAUNCH_CHECK("rk4_shared_kernel");
     return QDB_OK;
 }
 
-template <int MR, int NCW>
+template <int MR, int NCW, int SKT, bool M3>
 int launch_split_t(const Config& cfg, int B, int S, const double2* gen, double h, double2* y, int ldy, cudaStream_t st) {
-    auto kern = rk4_shared_kernel<MR, NCW, true>;
+    auto kern = rk4_shared_kernel<MR, NCW, true, SKT, M3>;
     QDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(cfg.grid);
@@ -810,9 +848,14 @@ int launch_rk4_fused_shared(int n, int B, int S, const double2* gen_table, doubl
     }
 #define ARGS cfg, B, S, gen_table, h, y, ldy, st
     if (cfg.split) {
-        QDB_DISPATCH(2, 1, (launch_split_t<2, 1>(ARGS)));
-        QDB_DISPATCH(2, 2, (launch_split_t<2, 2>(ARGS)));
-        QDB_DISPATCH(2, 3, (launch_split_t<2, 3>(ARGS)));
+        // headline geometry (n = 121..128: 32 k-tiles, 16 row tiles) compiled with static geometry
+        const bool static128 = cfg.geo.KT == 32 && cfg.geo.RT == 16 && cfg.geo.WR == 8 && cfg.geo.npad == 128;
+        const char* m3 = getenv("QDB_3M");
+        if (static128 && m3 && m3[0] == '1') QDB_DISPATCH(2, 3, (launch_split_t<2, 3, 32, true>(ARGS)));
+        if (static128) QDB_DISPATCH(2, 3, (launch_split_t<2, 3, 32, false>(ARGS)));
+        QDB_DISPATCH(2, 1, (launch_split_t<2, 1, 0, false>(ARGS)));
+        QDB_DISPATCH(2, 2, (launch_split_t<2, 2, 0, false>(ARGS)));
+        QDB_DISPATCH(2, 3, (launch_split_t<2, 3, 0, false>(ARGS)));
     }
     QDB_DISPATCH(1, 1, (launch_shared_t<1, 1>(ARGS)));
     QDB_DISPATCH(1, 2, (launch_shared_t<1, 2>(ARGS)));
