@@ -230,14 +230,16 @@ def run_b200(args):
     times_d = torch.from_numpy(times).to(dev)
     y_fb = model.rotating_frame.state_into_frame_basis(qd.asarray(Y))
     y_work = y_fb.clone()
-    table = torch.empty((2 * S + 1, abi.packed_elems(n)), dtype=torch.complex128, device=dev)
+    layout = abi.rk4_table_layout(n, B)  # PACKED3M when the 3-product kernel serves this shape
+    entry_elems = abi.packed_elems(n) * (3 if layout == abi.LAYOUT_PACKED3M else 2) // 2
+    table = torch.empty((2 * S + 1, entry_elems), dtype=torch.complex128, device=dev)
 
     def device_step(record=None):
         y_work.copy_(y_fb)
-        abi.generator(n, ops_p, stat_p, coeff, mu, times_d, layout=abi.LAYOUT_PACKED, out=table)
+        abi.generator(n, ops_p, stat_p, coeff, mu, times_d, layout=layout, out=table)
         if record is not None:
             record[0].record()
-        abi.rk4_table_steps(n, table, MAX_DT, y_work, S)
+        abi.rk4_table_steps(n, table, MAX_DT, y_work, S, layout=layout)
         if record is not None:
             record[1].record()
 
@@ -299,18 +301,19 @@ def run_b200(args):
     peak_tf = abi.dmma_probe()
     flops_launch = float(S) * B * flops_per_column_step(n)
     achieved_tf = flops_launch / (kern_mean_ms * 1e-3) * 1e-12
-    # DRAM traffic per launch from the committed ncu --set full capture (profiles/rk4_shared_traffic.json):
-    # measured per RK4 step there (the generator table dominates), scaled to this launch's S steps
+    # DRAM traffic per launch from the committed ncu --set full capture (profiles/rk4_shared_traffic.json): the state
+    # read (fixed) plus the generator-table entries, each read from HBM once; scaled to this launch's 2S+1 entries
     traffic = None
     prof = os.path.join(ROOT, "profiles", "rk4_shared_traffic.json")
     if os.path.exists(prof):
         try:
-            traffic = float(json.load(open(prof))["dram_bytes_per_rk4_step"]) * S
+            pj = json.load(open(prof))
+            traffic = float(pj["dram_bytes_fixed"]) + float(pj["dram_bytes_per_table_entry"]) * (2 * S + 1)
         except Exception:  # noqa: BLE001
             traffic = None
     tiling = abi.rk4_tiling(n, B)
-    kernel_name = (f"rk4_shared_kernel<{tiling['row_tiles_per_warp']},{tiling['col_tiles_per_warp']},"
-                   f"{'split' if tiling['split'] else 'whole'}>")
+    kernel_name = (f"{'rk4_shared3m_kernel' if tiling['m3'] else 'rk4_shared_kernel'}<{tiling['row_tiles_per_warp']},"
+                   f"{tiling['col_tiles_per_warp']},{'split' if tiling['split'] else 'whole'}>")
 
     # parity spot check of the timed configuration (not timed): norm preservation of the unitary flow
     norms = torch.linalg.vector_norm(y_work, dim=0)
@@ -335,6 +338,12 @@ def run_b200(args):
             "roofline": {"bound": "tensor", "kernel": kernel_name, "tiling": tiling, "achieved": achieved_tf, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
                          "flops_per_launch": flops_launch, "kernel_ms": kern_mean_ms,
+                         "executed_tflops": achieved_tf * (0.75 if tiling["m3"] else 1.0),
+                         "pipe_frac": achieved_tf * (0.75 if tiling["m3"] else 1.0) / peak_tf,
+                         "note": ("achieved = ALGORITHMIC flops (8 per complex multiply-add, SURVEY 8(d)) / kernel time; the "
+                                  "3-product kernel issues 6 per complex multiply-add (re*re, im*im, (re+im)*(re+im)), so "
+                                  "frac can exceed 1; pipe_frac = executed DMMA flops / peak is the tensor-pipe utilisation")
+                         if tiling["m3"] else "achieved = algorithmic = executed flops",
                          "peak_source": "live DMMA m8n8k4 issue-rate probe (qdb_dmma_probe); MEASURED_PEAKS.json has no "
                                         "fp64 entry; B200 datasheet fp64 tensor 37-40 TFLOP/s"},
             "cpu_baseline": {"value": cpu_rate, "unit": "state-RHS/s", "cores": threads, "kind": "port",

@@ -45,6 +45,12 @@ typedef struct { double re, im; } qdb_c128;
                                  kpad = 16*ceil(n/16) columns:
                                  element (r,c) at ((r/8)*(kpad/4) + c/4)*32 + (r%8)*4 + c%4 */
 
+#define QDB_LAYOUT_PACKED3M 2 /* generator tables only: a PACKED complex plane (npad*kpad elements) followed by a
+                                 plane of npad*kpad doubles holding re + im of each element -- 24 bytes per
+                                 element.  The on-chip RK4 kernel multiplies complex tiles with three real
+                                 tensor-core products (re*re, im*im, (re+im)*(re+im)) and reads the sums from
+                                 this plane instead of forming them in its inner loop. */
+
 /* workspace kinds for qdb_workspace_bytes */
 #define QDB_WS_RHS 0
 #define QDB_WS_RK4 1
@@ -68,7 +74,8 @@ int qdb_pack_operators(int n, int count, const qdb_c128* src, qdb_c128* dst, voi
 
 /* a1 + a5: generator table.  For each of the T times
  *     out[t] = scale * (stat + sum_j coeff[t][j] * ops[j]) .* outer(conj p(t), p(t))
- * ops/stat/out all in `layout`.  coeff is [T][K] real, or [T][K] complex when coeff_complex != 0.
+ * ops/stat/out all in `layout` (QDB_LAYOUT_PACKED3M: ops/stat PACKED, out PACKED3M).
+ * coeff is [T][K] real, or [T][K] complex when coeff_complex != 0.
  * stat or ops may be NULL (K = 0), not both.  times may be NULL when mu is NULL.
  * Replaces OperatorCollection.evaluate (models/operator_collections.py:101-122 ->
  * arraylias/register_functions/linear_combo.py:30-32) and RotatingFrame.operator_into_frame in
@@ -130,19 +137,28 @@ int qdb_rk4_steps_c128(int n, int K, int B, int S,
                        qdb_c128* y, int ldy,
                        void* workspace, size_t ws_bytes, void* stream);
 
-/* The on-chip RK4 kernel alone: S steps from a prebuilt generator table
- * gen_table_packed[2S+1][npad*npad] (QDB_LAYOUT_PACKED entries G_frame(t) at the stage times, as
- * produced by qdb_generator_c128).  n <= 256.  This is the dominant launch of
- * qdb_rk4_steps_c128 in shared-signal mode; exported so that it can be timed/profiled alone. */
-int qdb_rk4_table_steps_c128(int n, int B, int S, const qdb_c128* gen_table_packed, double h,
+/* The on-chip RK4 kernel alone: S steps from a prebuilt generator table of 2S+1 entries G_frame(t) at the
+ * stage times, as produced by qdb_generator_c128 in `table_layout` (QDB_LAYOUT_PACKED: 4-product kernels;
+ * QDB_LAYOUT_PACKED3M: the 3-product kernel, available when qdb_rk4_table_layout says so).  n <= 256.
+ * This is the dominant launch of qdb_rk4_steps_c128 in shared-signal mode; exported so that it can be
+ * timed/profiled alone. */
+int qdb_rk4_table_steps_c128(int n, int B, int S, const qdb_c128* gen_table, int table_layout, double h,
                              qdb_c128* y, int ldy, void* stream);
 
+/* Table layout qdb_rk4_steps_c128 uses for this shape (QDB_LAYOUT_PACKED or QDB_LAYOUT_PACKED3M), and the
+ * bytes of one table entry in a layout. */
+int qdb_rk4_table_layout(int n, int B);
+size_t qdb_table_entry_bytes(int n, int layout);
+
 /* Tiling the on-chip RK4 kernels pick for a shape (diagnostic: reported by bench.py, asserted by the
- * tests).  sweep_K = 0 asks about the shared-signal kernel, > 0 about the per-column kernel.
+ * tests).  sweep_K = 0 asks about the shared-signal solve (the better of the 3- and 4-product kernels),
+ * sweep_K < 0 about the 4-product shared-signal kernel (what a QDB_LAYOUT_PACKED table runs on), > 0 about
+ * the per-column kernel.
  * out[0..7] = {warps along rows, warps along columns, row tiles per warp, own column tiles per warp,
  * split (1 = 2-CTA clusters sharing one column octet through DSMEM), CTAs, threads per CTA,
- * dynamic shared memory bytes}.  Returns QDB_E_UNSUPPORTED when n is outside the on-chip path. */
-int qdb_rk4_tiling(int n, int B, int sweep_K, int* out /* host, 8 ints */);
+ * dynamic shared memory bytes, 3M (1 = three-product complex tiles)}.  Returns QDB_E_UNSUPPORTED when n is
+ * outside the on-chip path. */
+int qdb_rk4_tiling(int n, int B, int sweep_K, int* out /* host, 9 ints */);
 
 /* fp64 tensor-pipe (DMMA m8n8k4) issue-rate probe: launches register-resident DMMA chains on every
  * SM; *flops_out (host) receives the flop count of the launch.  Timed by the caller with CUDA

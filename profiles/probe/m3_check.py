@@ -10,10 +10,13 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     A = torch.randn(2 * S + 1, n, n, dtype=torch.complex128, device="cuda")
     G = (A - A.conj().transpose(1, 2)) * (10.0 / (2 * n) ** 0.5) * 0.5
     table = abi.pack_operators(G.contiguous())
+    layout = abi.LAYOUT_PACKED3M if os.environ.get("QDB_3M") == "1" else abi.LAYOUT_PACKED
+    if layout == abi.LAYOUT_PACKED3M:
+        table = abi.to_packed3m(table)
     y0 = torch.randn(n, B, dtype=torch.complex128, device="cuda")
     y0 /= torch.linalg.vector_norm(y0, dim=0, keepdim=True)
     y = y0.clone()
-    abi.rk4_table_steps(n, table, 1e-3, y, S)
+    abi.rk4_table_steps(n, table, 1e-3, y, S, layout=layout)
     torch.cuda.synchronize()
     torch.save(y.cpu(), f"/tmp/m3_{os.environ.get('QDB_3M', '0')}.pt")
     # torch fp64 restatement on 64 columns
@@ -26,14 +29,14 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     best = 1e30
     for _ in range(5):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); abi.rk4_table_steps(n, table, 1e-3, y, S); e1.record(); torch.cuda.synchronize()
+        e0.record(); abi.rk4_table_steps(n, table, 1e-3, y, S, layout=layout); e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     flops = S * B * (4 * (8 * n * n + 12 * n) + 28 * n)
     print(json.dumps({"m3": os.environ.get("QDB_3M", "0"), "n": n, "B": B, "S": S, "err_vs_torch": err,
                       "us_per_step": best * 1e3 / S, "alg_tflops": flops / best * 1e-9}))
 else:
     import torch
-    for n, B, S in ((128, 4096, 100), (128, 4096, 1000)):
+    for n, B, S in ((128, 4096, 100), (128, 4096, 1000), (128, 512, 100), (64, 4096, 100), (100, 4096, 100), (200, 4096, 50), (128, 8192, 50)):
         for m3 in ("0", "1"):
             env = dict(os.environ, QDB_3M=m3)
             r = subprocess.run([sys.executable, __file__, "child", str(n), str(B), str(S)], env=env, capture_output=True, text=True)

@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libqdb.so")
 
 LAYOUT_ROWMAJOR = 0
 LAYOUT_PACKED = 1
+LAYOUT_PACKED3M = 2
 WS_RHS, WS_RK4, WS_EXPM = 0, 1, 2
 
 
@@ -46,7 +47,9 @@ SIGNATURES = {
     "qdb_rhs_c128": (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _d, _vp, _vp, _i, _vp, _sz, _vp]),
     "qdb_rk4_steps_c128": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _d, _vp, _i, _vp, _sz, _vp]),
     "qdb_expm_steps_c128": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _i, _vp, _sz, _vp]),
-    "qdb_rk4_table_steps_c128": (_i, [_i, _i, _i, _vp, _d, _vp, _i, _vp]),
+    "qdb_rk4_table_steps_c128": (_i, [_i, _i, _i, _vp, _i, _d, _vp, _i, _vp]),
+    "qdb_rk4_table_layout": (_i, [_i, _i]),
+    "qdb_table_entry_bytes": (_sz, [_i, _i]),
     "qdb_rk4_tiling": (_i, [_i, _i, _i, _vp]),
     "qdb_dmma_probe": (_i, [_vp, _i, _vp, _vp]),
     "qdb_expm_c128": (_i, [_i, _vp, _i, _vp, _vp, _sz, _vp]),
@@ -122,9 +125,10 @@ def launch_count() -> int:
 
 def rk4_tiling(n: int, B: int, sweep_K: int = 0) -> dict:
     """Tiling the on-chip RK4 kernel picks for (n, B) -- diagnostic (qdb_rk4_tiling)."""
-    out = (ctypes.c_int * 8)()
+    out = (ctypes.c_int * 9)()
     _check(lib().qdb_rk4_tiling(n, B, sweep_K, ctypes.cast(out, ctypes.c_void_p)), "qdb_rk4_tiling")
-    keys = ("warps_rows", "warps_cols", "row_tiles_per_warp", "col_tiles_per_warp", "split", "ctas", "threads", "smem_bytes")
+    keys = ("warps_rows", "warps_cols", "row_tiles_per_warp", "col_tiles_per_warp", "split", "ctas", "threads", "smem_bytes",
+            "m3")
     return dict(zip(keys, (int(v) for v in out)))
 
 
@@ -146,7 +150,7 @@ def generator(n, ops, stat, coeff, mu, times, scale=1.0, layout=LAYOUT_ROWMAJOR,
     else:
         T = 1
     cplx = coeff is not None and coeff.dtype == C
-    elems = packed_elems(n) if layout == LAYOUT_PACKED else n * n
+    elems = {LAYOUT_ROWMAJOR: n * n, LAYOUT_PACKED: packed_elems(n), LAYOUT_PACKED3M: packed_elems(n) * 3 // 2}[layout]
     dev = (ops if ops is not None else stat).device
     if out is None:
         out = torch.empty((T, elems), dtype=C, device=dev)
@@ -246,13 +250,28 @@ def expm(A: torch.Tensor, squarings: int, out=None):
     return out
 
 
-def rk4_table_steps(n, table, h, y, S):
-    """The on-chip RK4 kernel alone, from a prebuilt packed generator table (2S+1, npad^2)."""
+def rk4_table_layout(n: int, B: int) -> int:
+    """Generator-table layout the fused shared-signal solve uses for this shape (PACKED or PACKED3M)."""
+    return int(lib().qdb_rk4_table_layout(n, B))
+
+
+def to_packed3m(table: torch.Tensor) -> torch.Tensor:
+    """(T, npad*kpad) PACKED complex table -> (T, 3/2 npad*kpad) PACKED3M (complex plane + re+im plane)."""
+    sums = (table.real + table.imag).contiguous()
+    return torch.cat([table, torch.view_as_complex(sums.view(table.shape[0], -1, 2))], dim=1).contiguous()
+
+
+def rk4_table_steps(n, table, h, y, S, layout=LAYOUT_PACKED):
+    """The on-chip RK4 kernel alone, from a prebuilt generator table of 2S+1 entries in `layout`
+    (LAYOUT_PACKED: (T, npad*kpad) -> 4-product kernels; LAYOUT_PACKED3M: (T, 3/2 npad*kpad) -> 3-product kernel)."""
     B = y.shape[1]
     if table.shape[0] < 2 * S + 1:
         raise QdbError(f"rk4_table_steps: table has {table.shape[0]} entries, need {2 * S + 1}")
-    _check(lib().qdb_rk4_table_steps_c128(n, B, S, _ptr(table, C, "table"), float(h), _ptr(y, C, "y"), B, _stream()),
-           "qdb_rk4_table_steps_c128")
+    want = packed_elems(n) * (3 if layout == LAYOUT_PACKED3M else 2) // 2
+    if table.shape[1] != want:
+        raise QdbError(f"rk4_table_steps: table entries have {table.shape[1]} elements, layout {layout} needs {want}")
+    _check(lib().qdb_rk4_table_steps_c128(n, B, S, _ptr(table, C, "table"), int(layout), float(h), _ptr(y, C, "y"), B,
+                                          _stream()), "qdb_rk4_table_steps_c128")
     return y
 
 

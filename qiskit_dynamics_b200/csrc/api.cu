@@ -48,11 +48,19 @@ const char* qdb_last_error_string(void) { return g_err; }
 int qdb_version(void) { return 100; }
 int qdb_npad(int n) { return round_up8(n); }
 size_t qdb_packed_elems(int n) { return (size_t)round_up8(n) * round_up16(n); }
+size_t qdb_table_entry_bytes(int n, int layout) {
+    if (layout == QDB_LAYOUT_ROWMAJOR) return (size_t)n * n * sizeof(double2);
+    return qdb_packed_elems(n) * (layout == QDB_LAYOUT_PACKED3M ? 24 : 16);
+}
+int qdb_rk4_table_layout(int n, int B) {
+    if (n < 1 || B < 1 || !rk4_fused_supported(n)) return QDB_LAYOUT_PACKED;
+    return rk4_fused_table_layout(n, B);
+}
 unsigned long long qdb_launch_count(void) { return g_launches.load(); }
 
 size_t qdb_workspace_bytes(int kind, int n, int K, int B, int S) {
     const size_t n2 = (size_t)n * n * sizeof(double2);
-    const size_t np2 = qdb_packed_elems(n) * sizeof(double2);
+    const size_t np2 = qdb_packed_elems(n) * 24;  // a PACKED3M table entry (the larger of the two table layouts)
     const size_t yb = (size_t)n * B * sizeof(double2);
     if (S < 1) S = 1;
     switch (kind) {
@@ -81,7 +89,8 @@ int qdb_generator_c128(int n, int K, int T, int layout, const qdb_c128* ops, con
                        const double* coeff, int coeff_complex, const double* mu, const double* times,
                        double scale, qdb_c128* out, void* stream) {
     QDB_REQUIRE(n >= 1 && K >= 0 && T >= 0, "qdb_generator_c128: bad n=%d K=%d T=%d", n, K, T);
-    QDB_REQUIRE(layout == QDB_LAYOUT_ROWMAJOR || layout == QDB_LAYOUT_PACKED, "qdb_generator_c128: bad layout %d", layout);
+    QDB_REQUIRE(layout == QDB_LAYOUT_ROWMAJOR || layout == QDB_LAYOUT_PACKED || layout == QDB_LAYOUT_PACKED3M,
+                "qdb_generator_c128: bad layout %d", layout);
     QDB_REQUIRE(out, "qdb_generator_c128: null output");
     QDB_REQUIRE(stat || (ops && K > 0), "qdb_generator_c128: neither static operator nor operators given");
     QDB_REQUIRE(K == 0 || (ops && coeff), "qdb_generator_c128: K=%d but ops/coeff missing", K);
@@ -191,7 +200,8 @@ int qdb_rk4_steps_c128(int n, int K, int B, int S, const qdb_c128* ops_rm, const
             return launch_rk4_fused_sweep(n, K, B, S, D2(stat_packed), D2(ops_packed), coeff, ldc, mu, times_dev, h, D2(y), ldy, st);
         }
         // shared signals: chunk the step loop so that the generator table fits the workspace
-        const size_t per_entry = np2 * sizeof(double2);
+        const int table_layout = rk4_fused_table_layout(n, B);
+        const size_t per_entry = qdb_table_entry_bytes(n, table_layout);
         // largest Sc whose 2 Sc + 1 table entries (+ their stage times) fit the workspace
         auto fits = [&](long long Sc) {
             const size_t E = (size_t)(2 * Sc + 1);
@@ -210,10 +220,10 @@ int qdb_rk4_steps_c128(int n, int K, int B, int S, const qdb_c128* ops_rm, const
             const int Sc = (S - s0 < Sc_max) ? S - s0 : (int)Sc_max;
             const int T = 2 * Sc + 1;
             if (mu) QDB_CUDA(cudaMemcpyAsync(times_dev, times_host + 2 * s0, (size_t)T * sizeof(double), cudaMemcpyHostToDevice, st));
-            rc = launch_generator(n, K, T, QDB_LAYOUT_PACKED, D2(ops_packed), D2(stat_packed),
+            rc = launch_generator(n, K, T, table_layout, D2(ops_packed), D2(stat_packed),
                                   coeff ? coeff + (size_t)2 * s0 * K : nullptr, 0, mu, times_dev, 0.0, 1.0, table, st);
             if (rc != QDB_OK) return rc;
-            rc = launch_rk4_fused_shared(n, B, Sc, table, h, D2(y), ldy, st);
+            rc = launch_rk4_fused_shared(n, B, Sc, table, table_layout, h, D2(y), ldy, st);
             if (rc != QDB_OK) return rc;
         }
         return QDB_OK;
@@ -258,20 +268,22 @@ int qdb_rk4_steps_c128(int n, int K, int B, int S, const qdb_c128* ops_rm, const
     return QDB_OK;
 }
 
-int qdb_rk4_table_steps_c128(int n, int B, int S, const qdb_c128* gen_table_packed, double h, qdb_c128* y, int ldy,
-                             void* stream) {
+int qdb_rk4_table_steps_c128(int n, int B, int S, const qdb_c128* gen_table_packed, int table_layout, double h, qdb_c128* y,
+                             int ldy, void* stream) {
     QDB_REQUIRE(n >= 1 && B >= 0 && S >= 0, "qdb_rk4_table_steps_c128: bad n=%d B=%d S=%d", n, B, S);
+    QDB_REQUIRE(table_layout == QDB_LAYOUT_PACKED || table_layout == QDB_LAYOUT_PACKED3M,
+                "qdb_rk4_table_steps_c128: bad table layout %d", table_layout);
     if (B == 0 || S == 0) return QDB_OK;
     QDB_REQUIRE(gen_table_packed && y && ldy >= B, "qdb_rk4_table_steps_c128: null pointer / bad ldy");
     if (!rk4_fused_supported(n)) {
         set_error("qdb_rk4_table_steps_c128: on-chip path needs n <= 256 (got %d)", n);
         return QDB_E_UNSUPPORTED;
     }
-    return launch_rk4_fused_shared(n, B, S, D2(gen_table_packed), h, D2(y), ldy, (cudaStream_t)stream);
+    return launch_rk4_fused_shared(n, B, S, D2(gen_table_packed), table_layout, h, D2(y), ldy, (cudaStream_t)stream);
 }
 
 int qdb_rk4_tiling(int n, int B, int sweep_K, int* out) {
-    QDB_REQUIRE(out && n >= 1 && B >= 1 && sweep_K >= 0, "qdb_rk4_tiling: bad arguments");
+    QDB_REQUIRE(out && n >= 1 && B >= 1, "qdb_rk4_tiling: bad arguments");
     if (!rk4_fused_tiling(n, B, sweep_K, out)) {
         set_error("qdb_rk4_tiling: on-chip path needs n <= 256 (got %d)", n);
         return QDB_E_UNSUPPORTED;

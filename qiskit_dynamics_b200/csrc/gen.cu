@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) generator_kernel(int n, int npad, int K, 
         acc[u] = make_double2(0.0, 0.0);
         rr[u] = cc[u] = 0;
         if (live[u]) {
-            if (layout == QDB_LAYOUT_PACKED) {
+            if (layout != QDB_LAYOUT_ROWMAJOR) {
                 const int KT = round_up16(n) >> 2;
                 const size_t tile = e >> 5;
                 const int lane = (int)(e & 31);
@@ -113,7 +113,14 @@ __global__ void __launch_bounds__(256) generator_kernel(int n, int npad, int K, 
         }
         v.x *= scale;
         v.y *= scale;
-        out[(size_t)t_idx * elems + e0 + u] = v;
+        if (layout == QDB_LAYOUT_PACKED3M) {
+            // entry = complex plane [elems] followed by the (re + im) plane [elems] the 3M kernel multiplies with
+            double2* entry = out + (size_t)t_idx * (elems + elems / 2);
+            entry[e0 + u] = v;
+            reinterpret_cast<double*>(entry + elems)[e0 + u] = v.x + v.y;
+        } else {
+            out[(size_t)t_idx * elems + e0 + u] = v;
+        }
     }
 }
 
@@ -121,7 +128,7 @@ int launch_generator(int n, int K, int T, int layout, const double2* ops, const 
                      const double* coeff, int coeff_complex, const double* mu, const double* times,
                      double t_scalar, double scale, double2* out, cudaStream_t st) {
     const int npad = round_up8(n);
-    const size_t elems = layout == QDB_LAYOUT_PACKED ? (size_t)npad * round_up16(n) : (size_t)n * n;
+    const size_t elems = layout != QDB_LAYOUT_ROWMAJOR ? (size_t)npad * round_up16(n) : (size_t)n * n;
     const size_t smem = mu ? (size_t)n * sizeof(double2) : 0;
     dim3 grid((unsigned)((elems + 511) / 512), T);
     if (coeff_complex) {

@@ -109,8 +109,9 @@ int launch_zgemm_rk4stage(int n, int B, const double2* G, const double2* yin, in
 int launch_dmma_probe(double* sink, int iters, int* grid_out, cudaStream_t st);
 bool rk4_fused_supported(int n);
 bool rk4_fused_tiling(int n, int B, int sweep_K, int* out);
-int launch_rk4_fused_shared(int n, int B, int S, const double2* gen_table, double h, double2* y,
-                            int ldy, cudaStream_t st);
+int launch_rk4_fused_shared(int n, int B, int S, const double2* gen_table, int table_layout, double h,
+                            double2* y, int ldy, cudaStream_t st);
+int rk4_fused_table_layout(int n, int B);
 int launch_rk4_fused_sweep(int n, int K, int B, int S, const double2* stat_packed /*or null*/,
                            const double2* ops_packed /*[K]*/, const double* coeff, int ldc,
                            const double* mu, const double* times_dev,

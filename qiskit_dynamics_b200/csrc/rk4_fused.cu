@@ -85,70 +85,72 @@ struct Accum {
 
 // own tiles (MR x NCW) plus, in split mode, MS row tiles of the shared octet (B fragment b[NCW], A fragments a_s
 // = this rank's half).  Every accumulator is touched once (3M) or twice half a block apart (4M) per k-tile.
-template <int MR, int NCW, int MS, bool SPLIT, bool M3>
-__device__ __forceinline__ void mma_block(Accum<MR, NCW, M3>& acc, Accum<MS, 1, M3>& accs, const double2 (&a)[MR],
+template <int MR, int NCW, int MS, bool SPLIT>
+__device__ __forceinline__ void mma_block(Accum<MR, NCW, false>& acc, Accum<MS, 1, false>& accs, const double2 (&a)[MR],
                                           const double2 (&a_s)[MS], const double2 (&b)[NCW + (SPLIT ? 1 : 0)]) {
-    if constexpr (M3) {
-        double as[MR], ass[MS], bs[NCW + (SPLIT ? 1 : 0)];
 #pragma unroll
-        for (int m = 0; m < MR; ++m) as[m] = a[m].x + a[m].y;
+    for (int m = 0; m < MR; ++m)
 #pragma unroll
-        for (int c = 0; c < NCW + (SPLIT ? 1 : 0); ++c) bs[c] = b[c].x + b[c].y;
-#pragma unroll
-        for (int m = 0; m < MS; ++m) ass[m] = a_s[m].x + a_s[m].y;
-#pragma unroll
-        for (int m = 0; m < MR; ++m)
-#pragma unroll
-            for (int c = 0; c < NCW; ++c) dmma(acc.p[0][m][c][0], acc.p[0][m][c][1], a[m].x, b[c].x);
-        if constexpr (SPLIT) {
-#pragma unroll
-            for (int m = 0; m < MS; ++m) dmma(accs.p[0][m][0][0], accs.p[0][m][0][1], a_s[m].x, b[NCW].x);
+        for (int c = 0; c < NCW; ++c) {
+            dmma(acc.p[0][m][c][0], acc.p[0][m][c][1], a[m].x, b[c].x);
+            dmma(acc.p[1][m][c][0], acc.p[1][m][c][1], a[m].x, b[c].y);
         }
+    if constexpr (SPLIT) {
 #pragma unroll
-        for (int m = 0; m < MR; ++m)
-#pragma unroll
-            for (int c = 0; c < NCW; ++c) dmma(acc.p[1][m][c][0], acc.p[1][m][c][1], a[m].y, b[c].y);
-        if constexpr (SPLIT) {
-#pragma unroll
-            for (int m = 0; m < MS; ++m) dmma(accs.p[1][m][0][0], accs.p[1][m][0][1], a_s[m].y, b[NCW].y);
+        for (int m = 0; m < MS; ++m) {
+            dmma(accs.p[0][m][0][0], accs.p[0][m][0][1], a_s[m].x, b[NCW].x);
+            dmma(accs.p[1][m][0][0], accs.p[1][m][0][1], a_s[m].x, b[NCW].y);
         }
+    }
 #pragma unroll
-        for (int m = 0; m < MR; ++m)
+    for (int m = 0; m < MR; ++m)
 #pragma unroll
-            for (int c = 0; c < NCW; ++c) dmma(acc.p[2][m][c][0], acc.p[2][m][c][1], as[m], bs[c]);
-        if constexpr (SPLIT) {
-#pragma unroll
-            for (int m = 0; m < MS; ++m) dmma(accs.p[2][m][0][0], accs.p[2][m][0][1], ass[m], bs[NCW]);
+        for (int c = 0; c < NCW; ++c) {
+            dmma(acc.p[0][m][c][0], acc.p[0][m][c][1], -a[m].y, b[c].y);  // SASS: DMMA with negated operand
+            dmma(acc.p[1][m][c][0], acc.p[1][m][c][1], a[m].y, b[c].x);
         }
-    } else {
+    if constexpr (SPLIT) {
 #pragma unroll
-        for (int m = 0; m < MR; ++m)
-#pragma unroll
-            for (int c = 0; c < NCW; ++c) {
-                dmma(acc.p[0][m][c][0], acc.p[0][m][c][1], a[m].x, b[c].x);
-                dmma(acc.p[1][m][c][0], acc.p[1][m][c][1], a[m].x, b[c].y);
-            }
-        if constexpr (SPLIT) {
-#pragma unroll
-            for (int m = 0; m < MS; ++m) {
-                dmma(accs.p[0][m][0][0], accs.p[0][m][0][1], a_s[m].x, b[NCW].x);
-                dmma(accs.p[1][m][0][0], accs.p[1][m][0][1], a_s[m].x, b[NCW].y);
-            }
+        for (int m = 0; m < MS; ++m) {
+            dmma(accs.p[0][m][0][0], accs.p[0][m][0][1], -a_s[m].y, b[NCW].y);
+            dmma(accs.p[1][m][0][0], accs.p[1][m][0][1], a_s[m].y, b[NCW].x);
         }
+    }
+}
+
+// 3M block: fragments arrive with their (re + im) sums precomputed (A: third plane of the generator table,
+// B: third plane of the stage buffer written by the epilogue), so the k loop issues DMMAs only -- a DADD in
+// the loop costs about 9 cycles of the same fp64 pipe the DMMAs need.
+struct Frag3 {
+    double2 c;  // (re, im)
+    double s;   // re + im
+};
+template <int MR, int NCW, int MS, bool SPLIT>
+__device__ __forceinline__ void mma_block3(Accum<MR, NCW, true>& acc, Accum<MS, 1, true>& accs, const Frag3 (&a)[MR],
+                                           const Frag3 (&a_s)[MS], const Frag3 (&b)[NCW + (SPLIT ? 1 : 0)]) {
 #pragma unroll
-        for (int m = 0; m < MR; ++m)
+    for (int m = 0; m < MR; ++m)
 #pragma unroll
-            for (int c = 0; c < NCW; ++c) {
-                dmma(acc.p[0][m][c][0], acc.p[0][m][c][1], -a[m].y, b[c].y);  // SASS: DMMA with negated operand
-                dmma(acc.p[1][m][c][0], acc.p[1][m][c][1], a[m].y, b[c].x);
-            }
-        if constexpr (SPLIT) {
+        for (int c = 0; c < NCW; ++c) dmma(acc.p[0][m][c][0], acc.p[0][m][c][1], a[m].c.x, b[c].c.x);
+    if constexpr (SPLIT) {
 #pragma unroll
-            for (int m = 0; m < MS; ++m) {
-                dmma(accs.p[0][m][0][0], accs.p[0][m][0][1], -a_s[m].y, b[NCW].y);
-                dmma(accs.p[1][m][0][0], accs.p[1][m][0][1], a_s[m].y, b[NCW].x);
-            }
-        }
+        for (int m = 0; m < MS; ++m) dmma(accs.p[0][m][0][0], accs.p[0][m][0][1], a_s[m].c.x, b[NCW].c.x);
+    }
+#pragma unroll
+    for (int m = 0; m < MR; ++m)
+#pragma unroll
+        for (int c = 0; c < NCW; ++c) dmma(acc.p[1][m][c][0], acc.p[1][m][c][1], a[m].c.y, b[c].c.y);
+    if constexpr (SPLIT) {
+#pragma unroll
+        for (int m = 0; m < MS; ++m) dmma(accs.p[1][m][0][0], accs.p[1][m][0][1], a_s[m].c.y, b[NCW].c.y);
+    }
+#pragma unroll
+    for (int m = 0; m < MR; ++m)
+#pragma unroll
+        for (int c = 0; c < NCW; ++c) dmma(acc.p[2][m][c][0], acc.p[2][m][c][1], a[m].s, b[c].s);
+    if constexpr (SPLIT) {
+#pragma unroll
+        for (int m = 0; m < MS; ++m) dmma(accs.p[2][m][0][0], accs.p[2][m][0][1], a_s[m].s, b[NCW].s);
     }
 }
 
@@ -216,7 +218,7 @@ struct StaticGeo {
 // SKT > 0 fixes the geometry at compile time (KT = SKT k-tiles, 8 row warps x 1 column warp, 256 threads,
 // RT = 8 MR row tiles, NCT = NCW (+1 in split mode)): addresses become immediates and about 25 registers
 // that otherwise carry precomputed epilogue offsets across the main loop are freed.
-template <int MR, int NCW, bool SPLIT, int SKT, bool M3>
+template <int MR, int NCW, bool SPLIT, int SKT>
 __global__ void __launch_bounds__(256, 1)
 rk4_shared_kernel(Geometry geo_rt, int B, int S, const double2* __restrict__ gen, double h, double2* __restrict__ y,
                   int ldy) {
@@ -296,9 +298,9 @@ rk4_shared_kernel(Geometry geo_rt, int B, int S, const double2* __restrict__ gen
             }
     }
 
-    Accum<MR, NCW, M3> acc;
+    Accum<MR, NCW, false> acc;
     acc.zero();
-    Accum<MS, 1, M3> accs;  // shared octet (split mode)
+    Accum<MS, 1, false> accs;  // shared octet (split mode)
     accs.zero();
     double kr[MR][NCW][2], ki[MR][NCW][2];  // running k1 + 2 k2 + 2 k3 + k4
 #pragma unroll
@@ -379,7 +381,7 @@ rk4_shared_kernel(Geometry geo_rt, int B, int S, const double2* __restrict__ gen
 #pragma unroll
                     for (int mm = 0; mm < MS; ++mm) a_s[mm] = rank ? ring[u][MS + mm] : ring[u][mm];
                 }
-                mma_block<MR, NCW, MS, SPLIT, M3>(acc, accs, ring[u], a_s, bfrag[u & 1]);
+                mma_block<MR, NCW, MS, SPLIT>(acc, accs, ring[u], a_s, bfrag[u & 1]);
             }
         }
 
@@ -458,6 +460,329 @@ rk4_shared_kernel(Geometry geo_rt, int B, int S, const double2* __restrict__ gen
                 const int col = cols + 2 * q + i;
                 if (svalid[mm] && row < n && col < B)
                     y[(size_t)row * ldy + col] = sm[yst_off + ((MR * NCW + mm) * 2 + i) * nthr + tid];
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared-signal mode, 3M complex products
+// ------------------------------------------------------------------------------------------------
+// Same decomposition as rk4_shared_kernel, with three changes that make the 3-DMMA complex product pay:
+//   * the generator table is QDB_LAYOUT_PACKED3M: every entry carries a third plane re + im, streamed
+//     beside the complex plane (LDG.128 + LDG.64 per fragment);
+//   * the stage buffer carries a third plane too, written ONCE per element by the epilogue instead of being
+//     re-derived by every warp in the k loop;
+//   * to pay for that plane the own-tile stage buffer is single buffered (barrier before and after the
+//     epilogue stores); only the shared octet, which the peer CTA writes asynchronously, stays double buffered.
+template <int MR, int NCW, bool SPLIT, int SKT>
+struct StaticGeo3 {
+    int n;
+    static constexpr int npad = 4 * SKT, KT = SKT, RT = 8 * MR, WR = 8, WC = 1, NCT = NCW;  // NCT = own tiles
+};
+
+__device__ __forceinline__ double ldg_stream_f64(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_async_peer_f64(const double* p, const uint64_t* bar, unsigned peer, double v) {
+    uint32_t rp, rb;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rp) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(peer));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(peer));
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(rp), "d"(v), "r"(rb)
+                 : "memory");
+}
+
+template <int MR, int NCW, bool SPLIT, int SKT>
+__global__ void __launch_bounds__(256, 1)
+rk4_shared3m_kernel(Geometry geo_rt, int B, int S, const double2* __restrict__ gen, double h, double2* __restrict__ y,
+                    int ldy) {
+    static_assert(!SPLIT || MR % 2 == 0, "split mode halves the row tiles of the shared octet");
+    typename std::conditional<(SKT > 0), StaticGeo3<MR, NCW, SPLIT, SKT>, Geometry>::type geo;
+    if constexpr (SKT > 0) geo.n = geo_rt.n; else geo = geo_rt;
+    constexpr int MS = SPLIT ? MR / 2 : 1;
+    constexpr int NB = NCW + (SPLIT ? 1 : 0);
+    constexpr int SLOTS = (MR * NCW + (SPLIT ? MS : 0)) * 2;
+    extern __shared__ __align__(16) double2 sm[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int swl = frag_swizzle(lane);
+    const int wr = warp % geo.WR, wc = warp / geo.WR;
+    const int KT = geo.KT, NCO = geo.NCT, n = geo.n;  // NCO = own column tiles of the CTA
+    const size_t entry_elems = (size_t)geo.npad * KT * 4;
+    const int nthr = SKT > 0 ? 256 : blockDim.x;
+    // shared-memory carve-up: complex planes first, then the sum planes
+    const int own_elems = KT * NCO * 32, sh_elems = SPLIT ? KT * 32 : 0;
+    double2* own_c = sm;
+    double2* sh_c = own_c + own_elems;     // [2][sh_elems]
+    double2* slab = sh_c + 2 * sh_elems;   // [SLOTS][nthr] thread-private y
+    double* own_s = reinterpret_cast<double*>(slab + SLOTS * nthr);
+    double* sh_s = own_s + own_elems;      // [2][sh_elems]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(sh_s + 2 * sh_elems);
+
+    const unsigned rank = SPLIT ? cluster_ctarank() : 0u;
+    const int ct0 = wc * NCW;
+    int colw, cols = 0;
+    if (SPLIT) {
+        const int base = (blockIdx.x >> 1) * (2 * NCW + 1);
+        colw = 8 * (base + (int)rank * (NCW + 1));
+        cols = 8 * (base + NCW);
+    } else {
+        colw = 8 * (blockIdx.x * NCO + ct0);
+    }
+
+    int rt[MR], rtl[MR];
+    bool mvalid[MR];
+#pragma unroll
+    for (int m = 0; m < MR; ++m) {
+        rt[m] = wr + geo.WR * m;
+        mvalid[m] = rt[m] < geo.RT;
+        rtl[m] = mvalid[m] ? rt[m] : geo.RT - 1;
+    }
+    int rts[MS];
+    bool svalid[MS];
+#pragma unroll
+    for (int mm = 0; mm < MS; ++mm) {
+        rts[mm] = wr + geo.WR * ((int)rank * MS + mm);
+        svalid[mm] = SPLIT && rts[mm] < geo.RT;
+    }
+
+    // ---- zero the stage planes (k rows beyond n stay zero), load y ----
+    for (int i = tid; i < own_elems + 2 * sh_elems; i += nthr) sm[i] = make_double2(0.0, 0.0);
+    for (int i = tid; i < own_elems + 2 * sh_elems; i += nthr) own_s[i] = 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < MR; ++m)
+#pragma unroll
+        for (int c = 0; c < NCW; ++c)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int row = 8 * rt[m] + g;
+                const int col = colw + 8 * c + 2 * q + i;
+                double2 v = make_double2(0.0, 0.0);
+                if (mvalid[m] && row < n && col < B) v = y[(size_t)row * ldy + col];
+                slab[((m * NCW + c) * 2 + i) * nthr + tid] = v;
+                if (mvalid[m]) {
+                    const int pos = yin_pos(NCO, rt[m], g, ct0 + c, 2 * q + i);
+                    own_c[pos] = v;
+                    own_s[pos] = v.x + v.y;
+                }
+            }
+    if (SPLIT) {
+#pragma unroll
+        for (int m = 0; m < MR; ++m)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int row = 8 * rt[m] + g;
+                const int col = cols + 2 * q + i;
+                double2 v = make_double2(0.0, 0.0);
+                if (mvalid[m] && row < n && col < B) v = y[(size_t)row * ldy + col];
+                if (mvalid[m]) {
+                    const int pos = yin_pos(1, rt[m], g, 0, 2 * q + i);
+                    sh_c[pos] = v;
+                    sh_s[pos] = v.x + v.y;
+                }
+                const int mm = m - (int)rank * MS;
+                if (mm >= 0 && mm < MS) slab[((MR * NCW + mm) * 2 + i) * nthr + tid] = v;
+            }
+    }
+
+    Accum<MR, NCW, true> acc;
+    acc.zero();
+    Accum<MS, 1, true> accs;
+    accs.zero();
+    double kr[MR][NCW][2], ki[MR][NCW][2];
+#pragma unroll
+    for (int m = 0; m < MR; ++m)
+#pragma unroll
+        for (int c = 0; c < NCW; ++c) kr[m][c][0] = kr[m][c][1] = ki[m][c][0] = ki[m][c][1] = 0.0;
+    double ksr[MS][2], ksi[MS][2];
+#pragma unroll
+    for (int mm = 0; mm < MS; ++mm) ksr[mm][0] = ksr[mm][1] = ksi[mm][0] = ksi[mm][1] = 0.0;
+
+    size_t aoff[MR];
+#pragma unroll
+    for (int m = 0; m < MR; ++m) aoff[m] = (size_t)rtl[m] * KT * 32 + lane;
+    // entry e: complex plane at gen + e * (3/2) entry_elems, sum plane right behind it
+    const size_t entry_stride = entry_elems + entry_elems / 2;  // in double2 units (entry_elems is even)
+
+    Frag3 ring[RING][MR];
+#pragma unroll
+    for (int u = 0; u < RING - 1; ++u)
+#pragma unroll
+        for (int m = 0; m < MR; ++m) {
+            ring[u][m].c = ldg_stream(gen + aoff[m] + (size_t)u * 32);
+            ring[u][m].s = ldg_stream_f64(reinterpret_cast<const double*>(gen + entry_elems) + aoff[m] + (size_t)u * 32);
+        }
+
+    int cur = 0;
+    unsigned tx_bytes = 0;
+    if (SPLIT) {
+        const int first = (int)(rank ^ 1u) * MS * geo.WR;
+        const int cnt = max(0, min(geo.RT - first, MS * geo.WR));
+        tx_bytes = (unsigned)cnt * 64u * 24u;  // complex + sum plane
+        if (tid == 0) {
+            mbar_init(mbar, 1);
+            mbar_init(mbar + 1, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        cluster_barrier();
+    } else {
+        __syncthreads();
+    }
+
+    const int total_stages = 4 * S;
+#pragma unroll 1
+    for (int sidx = 0; sidx < total_stages; ++sidx) {
+        const int step = sidx >> 2, stage = sidx & 3;
+        const int entry = 2 * step + (stage == 0 ? 0 : (stage == 3 ? 2 : 1));
+        const int nstage = (stage + 1) & 3, nstep = step + (stage == 3 ? 1 : 0);
+        const int nentry = (sidx + 1 < total_stages) ? 2 * nstep + (nstage == 0 ? 0 : (nstage == 3 ? 2 : 1)) : entry;
+        const double2* gcur = gen + (size_t)entry * entry_stride;
+        const double2* gnxt = gen + (size_t)nentry * entry_stride;
+        const double2* bc = own_c + ct0 * 32 + swl;
+        const double* bs = own_s + ct0 * 32 + swl;
+        const double2* shc = sh_c + cur * sh_elems + swl;
+        const double* shs = sh_s + cur * sh_elems + swl;
+        if (SPLIT && tid == 0) mbar_expect_tx(mbar + (sidx & 1), tx_bytes);
+
+        Frag3 bfrag[2][NB];
+#pragma unroll
+        for (int c = 0; c < NCW; ++c) {
+            bfrag[0][c].c = bc[c * 32];
+            bfrag[0][c].s = bs[c * 32];
+        }
+        if constexpr (SPLIT) {
+            bfrag[0][NCW].c = shc[0];
+            bfrag[0][NCW].s = shs[0];
+        }
+
+#pragma unroll 1
+        for (int kt0 = 0; kt0 < KT; kt0 += RING) {
+#pragma unroll
+            for (int u = 0; u < RING; ++u) {
+                const int kt = kt0 + u;
+                {
+                    const int ktn = kt + RING - 1;
+                    const double2* ebase = ktn < KT ? gcur : gnxt;  // entry the fragment comes from
+                    const size_t koff = (size_t)(ktn < KT ? ktn : ktn - KT) * 32;
+                    const double* sbase = reinterpret_cast<const double*>(ebase + entry_elems);
+#pragma unroll
+                    for (int m = 0; m < MR; ++m) {
+                        ring[(u + RING - 1) % RING][m].c = ldg_stream(ebase + koff + aoff[m]);
+                        ring[(u + RING - 1) % RING][m].s = ldg_stream_f64(sbase + koff + aoff[m]);
+                    }
+                }
+                {
+                    const int ktb = min(kt + 1, KT - 1);
+#pragma unroll
+                    for (int c = 0; c < NCW; ++c) {
+                        bfrag[(u + 1) & 1][c].c = bc[(ktb * NCO + c) * 32];
+                        bfrag[(u + 1) & 1][c].s = bs[(ktb * NCO + c) * 32];
+                    }
+                    if constexpr (SPLIT) {
+                        bfrag[(u + 1) & 1][NCW].c = shc[ktb * 32];
+                        bfrag[(u + 1) & 1][NCW].s = shs[ktb * 32];
+                    }
+                }
+                Frag3 a_s[MS];
+                if constexpr (SPLIT) {
+#pragma unroll
+                    for (int mm = 0; mm < MS; ++mm) a_s[mm] = rank ? ring[u][MS + mm] : ring[u][mm];
+                }
+                mma_block3<MR, NCW, MS, SPLIT>(acc, accs, ring[u], a_s, bfrag[u & 1]);
+            }
+        }
+
+        // ---- epilogue ----
+        const StageCoef sc(stage, h);
+        if constexpr (SPLIT) {
+            // shared octet: goes to the OTHER buffer here and in the peer CTA, no hazard with the reads above
+            double2* dc = sh_c + (cur ^ 1) * sh_elems;
+            double* ds = sh_s + (cur ^ 1) * sh_elems;
+#pragma unroll
+            for (int mm = 0; mm < MS; ++mm)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const double k_r = accs.re(mm, 0, i), k_i = accs.im(mm, 0, i);
+                    double2* sl = slab + ((MR * NCW + mm) * 2 + i) * nthr + tid;
+                    const double2 yv = *sl;
+                    ksr[mm][i] = sc.keep * ksr[mm][i] + sc.wk * k_r;
+                    ksi[mm][i] = sc.keep * ksi[mm][i] + sc.wk * k_i;
+                    const double v_r = sc.last ? ksr[mm][i] : k_r, v_i = sc.last ? ksi[mm][i] : k_i;
+                    const double2 nxt = make_double2(yv.x + sc.astep * v_r, yv.y + sc.astep * v_i);
+                    if (sc.last) *sl = nxt;
+                    if (svalid[mm]) {
+                        const int pos = yin_pos(1, rts[mm], g, 0, 2 * q + i);
+                        const double sum = nxt.x + nxt.y;
+                        dc[pos] = nxt;
+                        ds[pos] = sum;
+                        st_async_peer(dc + pos, mbar + (sidx & 1), rank ^ 1u, nxt);
+                        st_async_peer_f64(ds + pos, mbar + (sidx & 1), rank ^ 1u, sum);
+                    }
+                }
+            accs.zero();
+        }
+        // own tiles: combine into registers first (the accumulators die here), then wait until every warp has
+        // finished reading the single-buffered stage planes, then overwrite them
+        double2 nx[MR][NCW][2];
+#pragma unroll
+        for (int m = 0; m < MR; ++m) {
+            double2 yv[NCW][2];
+#pragma unroll
+            for (int c = 0; c < NCW; ++c)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) yv[c][i] = slab[((m * NCW + c) * 2 + i) * nthr + tid];
+#pragma unroll
+            for (int c = 0; c < NCW; ++c)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const double k_r = acc.re(m, c, i), k_i = acc.im(m, c, i);
+                    kr[m][c][i] = sc.keep * kr[m][c][i] + sc.wk * k_r;
+                    ki[m][c][i] = sc.keep * ki[m][c][i] + sc.wk * k_i;
+                    const double v_r = sc.last ? kr[m][c][i] : k_r, v_i = sc.last ? ki[m][c][i] : k_i;
+                    nx[m][c][i] = make_double2(yv[c][i].x + sc.astep * v_r, yv[c][i].y + sc.astep * v_i);
+                    if (sc.last) slab[((m * NCW + c) * 2 + i) * nthr + tid] = nx[m][c][i];
+                }
+        }
+        acc.zero();
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < MR; ++m)
+#pragma unroll
+            for (int c = 0; c < NCW; ++c)
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    if (mvalid[m]) {
+                        const int pos = yin_pos(NCO, rt[m], g, ct0 + c, 2 * q + i);
+                        own_c[pos] = nx[m][c][i];
+                        own_s[pos] = nx[m][c][i].x + nx[m][c][i].y;
+                    }
+        cur ^= 1;
+        __syncthreads();
+        if (SPLIT) mbar_wait(mbar + (sidx & 1), (sidx >> 1) & 1);
+    }
+    if (SPLIT) cluster_barrier();
+
+    // ---- store y ----
+#pragma unroll
+    for (int m = 0; m < MR; ++m)
+#pragma unroll
+        for (int c = 0; c < NCW; ++c)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int row = 8 * rt[m] + g;
+                const int col = colw + 8 * c + 2 * q + i;
+                if (mvalid[m] && row < n && col < B) y[(size_t)row * ldy + col] = slab[((m * NCW + c) * 2 + i) * nthr + tid];
+            }
+    if (SPLIT) {
+#pragma unroll
+        for (int mm = 0; mm < MS; ++mm)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int row = 8 * rts[mm] + g;
+                const int col = cols + 2 * q + i;
+                if (svalid[mm] && row < n && col < B) y[(size_t)row * ldy + col] = slab[((MR * NCW + mm) * 2 + i) * nthr + tid];
             }
     }
 }
@@ -597,7 +922,7 @@ rk4_sweep_kernel(Geometry geo, int K, int B, int S, const double2* __restrict__ 
                 }
                 {
                     const double2 a_unused[1] = {};
-                    mma_block<MR, NCW, 1, false, false>(acc, acc_unused, ring[u], a_unused, bs);
+                    mma_block<MR, NCW, 1, false>(acc, acc_unused, ring[u], a_unused, bs);
                 }
                 if (++j == J) { j = 0; ++kt; }
             }
@@ -660,6 +985,7 @@ struct Config {
     size_t smem;
     int grid;
     bool split;  // 2-CTA clusters, 2 NCW + 1 column tiles per cluster (shared-signal kernel only)
+    bool m3;     // rk4_shared3m_kernel (needs a QDB_LAYOUT_PACKED3M table); geo.NCT = own tiles only
 };
 
 constexpr int kMaxFusedNpad = 256;
@@ -678,7 +1004,7 @@ int sm_count() {
     return sms;
 }
 
-bool pick_config(int n, int B, int K_sweep /*0 for shared*/, Config& cfg) {
+bool pick_config(int n, int B, int K_sweep /*0 for shared*/, Config& cfg, double* cost_out = nullptr) {
     const int SMS = sm_count();
     const int npad = round_up8(n);
     if (npad > kMaxFusedNpad || n < 1) return false;
@@ -778,20 +1104,103 @@ bool pick_config(int n, int B, int K_sweep /*0 for shared*/, Config& cfg) {
             }
         }
     }
+    cfg.m3 = false;
+    if (cost_out) *cost_out = best_cost;
     return found;
+}
+
+// 3M kernel (rk4_shared3m_kernel): 8 row warps, MR = ceil(RT / 8) row tiles per warp, at most 7 tiles per warp
+// (three accumulators per tile).  Cost in the units of pick_config: a 3M column tile costs about 0.78 of a 4M
+// one (3 of 4 DMMAs plus the shared per-k-tile overhead), the second barrier adds a little to the fixed part.
+bool pick_config3m(int n, int B, Config& cfg, double* cost_out) {
+    const int SMS = sm_count();
+    const int npad = round_up8(n);
+    if (npad > kMaxFusedNpad || n < 1) return false;
+    Geometry geo;
+    geo.n = n;
+    geo.npad = npad;
+    geo.KT = round_up16(n) / 4;
+    geo.RT = npad / 8;
+    if (geo.RT < 8) return false;  // small operators stay on the 4M kernel
+    const int MR = (geo.RT + 7) / 8;
+    // measured (profiles/probe/m3_check.py): 3M wins 15-25 % for one or two row tiles per warp; with three or
+    // four the narrow column tiles it is left with (7 accumulator tiles per warp at most) give the gain back
+    if (MR > 2) return false;
+    const int CT = (B + 7) / 8;
+    const int threads = 256;
+    constexpr double kFixed = 0.7, kTile = 0.78;
+    bool found = false;
+    double best = 0;
+    auto consider = [&](int NCW, bool split) {
+        Geometry g2 = geo;
+        g2.WR = 8;
+        g2.WC = 1;
+        g2.NCT = NCW;  // own tiles
+        const int MS = split ? MR / 2 : 0;
+        if (MR * NCW + MS > 7) return;
+        const size_t smem = (size_t)g2.KT * NCW * 32 * 24 + (split ? (size_t)2 * g2.KT * 32 * 24 : 0) +
+                            (size_t)(MR * NCW + MS) * 2 * threads * sizeof(double2) + 16;
+        if (smem > kSmemLimit) return;
+        int ctas;
+        double cost;
+        if (split) {
+            const int clusters = (CT + 2 * NCW) / (2 * NCW + 1);
+            const int slots = SMS / 2;
+            ctas = 2 * clusters;
+            cost = (double)((clusters + slots - 1) / slots) * (kFixed + kTile * (NCW + 0.5));
+        } else {
+            ctas = (CT + NCW - 1) / NCW;
+            cost = (double)((ctas + SMS - 1) / SMS) * (kFixed + kTile * NCW);
+        }
+        if (!found || cost < best) {
+            found = true;
+            best = cost;
+            cfg.geo = g2;
+            cfg.MR = MR;
+            cfg.NCW = NCW;
+            cfg.threads = threads;
+            cfg.smem = smem;
+            cfg.grid = ctas;
+            cfg.split = split;
+            cfg.m3 = true;
+        }
+    };
+    const char* nosplit = getenv("QDB_NO_SPLIT");
+    const bool allow_split = MR == 2 && SMS >= 2 && !(nosplit && nosplit[0] == '1');
+    for (int NCW = (MR == 1 ? 4 : 3); NCW >= 1; --NCW) {
+        consider(NCW, false);
+        if (allow_split) consider(NCW, true);
+    }
+    if (found && cost_out) *cost_out = best;
+    return found;
+}
+
+// Best tiling for the shared-signal solve: 3M when it is available and predicted faster (QDB_NO_3M=1 pins 4M).
+bool pick_config_shared(int n, int B, Config& cfg) {
+    double c4 = 0, c3 = 0;
+    Config cfg4, cfg3;
+    const bool ok4 = pick_config(n, B, 0, cfg4, &c4);
+    const char* no3 = getenv("QDB_NO_3M");
+    const bool ok3 = !(no3 && no3[0] == '1') && pick_config3m(n, B, cfg3, &c3);
+    if (ok3 && (!ok4 || c3 < c4)) {
+        cfg = cfg3;
+        return true;
+    }
+    if (ok4) cfg = cfg4;
+    return ok4;
 }
 
 template <int MR, int NCW>
 int launch_shared_t(const Config& cfg, int B, int S, const double2* gen, double h, double2* y, int ldy, cudaStream_t st) {
-    QDB_CUDA(cudaFuncSetAttribute(rk4_shared_kernel<MR, NCW, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-    rk4_shared_kernel<MR, NCW, false, 0, false><<<cfg.grid, cfg.threads, cfg.smem, st>>>(cfg.geo, B, S, gen, h, y, ldy);
+    QDB_CUDA(cudaFuncSetAttribute(rk4_shared_kernel<MR, NCW, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+    rk4_shared_kernel<MR, NCW, false, 0><<<cfg.grid, cfg.threads, cfg.smem, st>>>(cfg.geo, B, S, gen, h, y, ldy);
     QDB_LAUNCH_CHECK("rk4_shared_kernel");
     return QDB_OK;
 }
 
-template <int MR, int NCW, int SKT, bool M3>
+template <int MR, int NCW, int SKT>
 int launch_split_t(const Config& cfg, int B, int S, const double2* gen, double h, double2* y, int ldy, cudaStream_t st) {
-    auto kern = rk4_shared_kernel<MR, NCW, true, SKT, M3>;
+    auto kern = rk4_shared_kernel<MR, NCW, true, SKT>;
     QDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(cfg.grid);
@@ -819,6 +1228,27 @@ int launch_sweep_t(const Config& cfg, int K, int B, int S, const double2* stat, 
     return QDB_OK;
 }
 
+template <int MR, int NCW, bool SPLIT, int SKT>
+int launch_3m_t(const Config& cfg, int B, int S, const double2* gen, double h, double2* y, int ldy, cudaStream_t st) {
+    auto kern = rk4_shared3m_kernel<MR, NCW, SPLIT, SKT>;
+    QDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(cfg.grid);
+    lc.blockDim = dim3(cfg.threads);
+    lc.dynamicSmemBytes = cfg.smem;
+    lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = SPLIT ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    QDB_CUDA(cudaLaunchKernelEx(&lc, kern, cfg.geo, B, S, gen, h, y, ldy));
+    QDB_LAUNCH_CHECK("rk4_shared3m_kernel");
+    return QDB_OK;
+}
+
 #define QDB_DISPATCH(MRv, NCWv, CALL)                \
     if (cfg.MR == MRv && cfg.NCW == NCWv) return CALL
 
@@ -828,7 +1258,9 @@ bool rk4_fused_supported(int n) { return n >= 1 && round_up8(n) <= kMaxFusedNpad
 
 bool rk4_fused_tiling(int n, int B, int sweep_K, int* out) {
     Config cfg;
-    if (!pick_config(n, B, sweep_K, cfg)) return false;
+    const bool ok = sweep_K > 0 ? pick_config(n, B, sweep_K, cfg)
+                                : (sweep_K < 0 ? pick_config(n, B, 0, cfg) : pick_config_shared(n, B, cfg));
+    if (!ok) return false;
     out[0] = cfg.geo.WR;
     out[1] = cfg.geo.WC;
     out[2] = cfg.MR;
@@ -837,25 +1269,51 @@ bool rk4_fused_tiling(int n, int B, int sweep_K, int* out) {
     out[5] = cfg.grid;
     out[6] = cfg.threads;
     out[7] = (int)cfg.smem;
+    out[8] = cfg.m3 ? 1 : 0;
     return true;
 }
 
-int launch_rk4_fused_shared(int n, int B, int S, const double2* gen_table, double h, double2* y, int ldy, cudaStream_t st) {
+// table_layout: QDB_LAYOUT_PACKED -> 4M kernels, QDB_LAYOUT_PACKED3M -> 3M kernel (see rk4_fused_table_layout)
+int launch_rk4_fused_shared(int n, int B, int S, const double2* gen_table, int table_layout, double h, double2* y, int ldy,
+                            cudaStream_t st) {
     Config cfg;
-    if (!pick_config(n, B, 0, cfg)) {
-        set_error("rk4 fused: unsupported shape n=%d B=%d", n, B);
+    bool ok;
+    if (table_layout == QDB_LAYOUT_PACKED3M) {
+        ok = pick_config3m(n, B, cfg, nullptr);
+    } else {
+        ok = pick_config(n, B, 0, cfg);
+    }
+    if (!ok) {
+        set_error("rk4 fused: unsupported shape n=%d B=%d for table layout %d", n, B, table_layout);
         return QDB_E_UNSUPPORTED;
     }
 #define ARGS cfg, B, S, gen_table, h, y, ldy, st
+    if (cfg.m3) {
+        const bool static128 = cfg.geo.KT == 32 && cfg.geo.RT == 16 && cfg.geo.npad == 128;
+        if (cfg.split) {
+            if (static128) QDB_DISPATCH(2, 3, (launch_3m_t<2, 3, true, 32>(ARGS)));
+            QDB_DISPATCH(2, 1, (launch_3m_t<2, 1, true, 0>(ARGS)));
+            QDB_DISPATCH(2, 2, (launch_3m_t<2, 2, true, 0>(ARGS)));
+            QDB_DISPATCH(2, 3, (launch_3m_t<2, 3, true, 0>(ARGS)));
+        } else {
+            QDB_DISPATCH(1, 1, (launch_3m_t<1, 1, false, 0>(ARGS)));
+            QDB_DISPATCH(1, 2, (launch_3m_t<1, 2, false, 0>(ARGS)));
+            QDB_DISPATCH(1, 3, (launch_3m_t<1, 3, false, 0>(ARGS)));
+            QDB_DISPATCH(1, 4, (launch_3m_t<1, 4, false, 0>(ARGS)));
+            QDB_DISPATCH(2, 1, (launch_3m_t<2, 1, false, 0>(ARGS)));
+            QDB_DISPATCH(2, 2, (launch_3m_t<2, 2, false, 0>(ARGS)));
+            QDB_DISPATCH(2, 3, (launch_3m_t<2, 3, false, 0>(ARGS)));
+        }
+        set_error("rk4 fused 3M: no kernel for MR=%d NCW=%d split=%d", cfg.MR, cfg.NCW, (int)cfg.split);
+        return QDB_E_UNSUPPORTED;
+    }
     if (cfg.split) {
         // headline geometry (n = 121..128: 32 k-tiles, 16 row tiles) compiled with static geometry
         const bool static128 = cfg.geo.KT == 32 && cfg.geo.RT == 16 && cfg.geo.WR == 8 && cfg.geo.npad == 128;
-        const char* m3 = getenv("QDB_3M");
-        if (static128 && m3 && m3[0] == '1') QDB_DISPATCH(2, 3, (launch_split_t<2, 3, 32, true>(ARGS)));
-        if (static128) QDB_DISPATCH(2, 3, (launch_split_t<2, 3, 32, false>(ARGS)));
-        QDB_DISPATCH(2, 1, (launch_split_t<2, 1, 0, false>(ARGS)));
-        QDB_DISPATCH(2, 2, (launch_split_t<2, 2, 0, false>(ARGS)));
-        QDB_DISPATCH(2, 3, (launch_split_t<2, 3, 0, false>(ARGS)));
+        if (static128) QDB_DISPATCH(2, 3, (launch_split_t<2, 3, 32>(ARGS)));
+        QDB_DISPATCH(2, 1, (launch_split_t<2, 1, 0>(ARGS)));
+        QDB_DISPATCH(2, 2, (launch_split_t<2, 2, 0>(ARGS)));
+        QDB_DISPATCH(2, 3, (launch_split_t<2, 3, 0>(ARGS)));
     }
     QDB_DISPATCH(1, 1, (launch_shared_t<1, 1>(ARGS)));
     QDB_DISPATCH(1, 2, (launch_shared_t<1, 2>(ARGS)));
@@ -870,6 +1328,13 @@ int launch_rk4_fused_shared(int n, int B, int S, const double2* gen_table, doubl
 #undef ARGS
     set_error("rk4 fused: no kernel for MR=%d NCW=%d", cfg.MR, cfg.NCW);
     return QDB_E_UNSUPPORTED;
+}
+
+// table layout the shared-signal solve should be fed for this shape
+int rk4_fused_table_layout(int n, int B) {
+    Config cfg;
+    if (!pick_config_shared(n, B, cfg)) return QDB_LAYOUT_PACKED;
+    return cfg.m3 ? QDB_LAYOUT_PACKED3M : QDB_LAYOUT_PACKED;
 }
 
 int launch_rk4_fused_sweep(int n, int K, int B, int S, const double2* stat_packed, const double2* ops_packed,

@@ -171,13 +171,13 @@ def test_rk4_split_clusters_bit_identical(abi, n, B, S):
     y0 = dev(rng.standard_normal((n, B)) + 1j * rng.standard_normal((n, B)))
     old = os.environ.pop("QDB_NO_SPLIT", None)
     try:
-        tiling = abi.rk4_tiling(n, B)
+        tiling = abi.rk4_tiling(n, B, -1)  # the 4-product kernel a PACKED table runs on
         if n != 72:
-            assert tiling["split"] == 1, tiling
+            assert tiling["split"] == 1 and tiling["m3"] == 0, tiling
         y1 = y0.clone()
         abi.rk4_table_steps(n, packed, 1e-2, y1, S)
         os.environ["QDB_NO_SPLIT"] = "1"
-        assert abi.rk4_tiling(n, B)["split"] == 0
+        assert abi.rk4_tiling(n, B, -1)["split"] == 0
         y2 = y0.clone()
         abi.rk4_table_steps(n, packed, 1e-2, y2, S)
     finally:
@@ -199,6 +199,58 @@ def test_rk4_split_clusters_bit_identical(abi, n, B, S):
         y = y + (1.0 / 6) * h * (k1 + 2 * k2 + 2 * k3 + k4)
     err = torch.linalg.vector_norm(y1[:, cols] - y, dim=0).max().item()
     assert err < TOL_SOLVE
+
+
+@pytest.mark.parametrize("n,B,S", [
+    (128, 4096, 3),   # headline: static-geometry split kernel
+    (128, 4000, 2),   # ragged batch
+    (121, 3001, 2),   # same tiling, padded rows
+    (100, 2500, 2),   # dynamic geometry, split, rank 1 owns 5 of 8 shared row tiles
+    (128, 512, 2),    # whole-column CTAs, one column tile per warp
+    (64, 4096, 2),    # one row tile per warp
+    (72, 100, 2),     # 9 row tiles on 8 row warps
+    (57, 300, 2),     # smallest dimension the 3-product kernel takes
+])
+def test_rk4_three_product_kernel(abi, n, B, S):
+    """rk4_shared3m_kernel (3 real DMMAs per complex tile product, PACKED3M table) against the 4-product kernel
+    and a plain fp64 torch restatement of RK4.  3M changes rounding, not the algorithm: tolerance 1e-12 on the
+    column L2 error after S steps of a norm-10 generator."""
+    rng = np.random.default_rng(3 * n + B)
+    A = rng.standard_normal((2 * S + 1, n, n)) + 1j * rng.standard_normal((2 * S + 1, n, n))
+    table = dev((A - A.conj().transpose(0, 2, 1)) * (5.0 / np.sqrt(2 * n)))
+    packed = abi.pack_operators(table)
+    packed3 = abi.to_packed3m(packed)
+    y0 = dev(rng.standard_normal((n, B)) + 1j * rng.standard_normal((n, B)))
+    h = 1e-2
+    y3 = y0.clone()
+    abi.rk4_table_steps(n, packed3, h, y3, S, layout=abi.LAYOUT_PACKED3M)
+    y4 = y0.clone()
+    abi.rk4_table_steps(n, packed, h, y4, S, layout=abi.LAYOUT_PACKED)
+    scale = torch.linalg.vector_norm(y0, dim=0).max().item()
+    assert torch.linalg.vector_norm(y3 - y4, dim=0).max().item() < 1e-12 * scale
+    cols = torch.cat([torch.arange(min(16, B)), torch.arange(max(B - 8, 0), B)]).cuda()
+    y = y0[:, cols]
+    for s in range(S):
+        G0, G1, G2 = table[2 * s], table[2 * s + 1], table[2 * s + 2]
+        k1 = G0 @ y
+        k2 = G1 @ (y + 0.5 * h * k1)
+        k3 = G1 @ (y + 0.5 * h * k2)
+        k4 = G2 @ (y + h * k3)
+        y = y + (1.0 / 6) * h * (k1 + 2 * k2 + 2 * k3 + k4)
+    assert torch.linalg.vector_norm(y3[:, cols] - y, dim=0).max().item() < 1e-12 * scale
+
+
+def test_generator_packed3m_layout(abi):
+    rng = np.random.default_rng(11)
+    n, K, T = 100, 3, 4
+    ops = rng.standard_normal((K, n, n)) + 1j * rng.standard_normal((K, n, n))
+    stat = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    coeff, mu, times = rng.standard_normal((T, K)), rng.standard_normal(n), rng.uniform(0, 3, T)
+    pk_ops, pk_stat = abi.pack_operators(dev(ops)), abi.pack_operators(dev(stat[None]))[0]
+    a = abi.generator(n, pk_ops, pk_stat, dev(coeff), dev(mu), dev(times), layout=abi.LAYOUT_PACKED)
+    b = abi.generator(n, pk_ops, pk_stat, dev(coeff), dev(mu), dev(times), layout=abi.LAYOUT_PACKED3M)
+    assert b.shape == (T, abi.packed_elems(n) * 3 // 2)
+    assert torch.equal(b, abi.to_packed3m(a))
 
 
 @pytest.mark.parametrize("n,K,B,S,frame", [(32, 8, 48, 10, "full"), (5, 2, 3, 20, "diag"), (128, 8, 40, 3, "full"), (16, 2, 600, 4, "none")])
