@@ -184,6 +184,31 @@ int qdb_expm_steps_c128(int n, int K, int B, int S,
 int qdb_expm_c128(int n, const qdb_c128* A, int squarings, qdb_c128* out,
                   void* workspace, size_t ws_bytes, void* stream);
 
+/* f3 (and a6 on the device): coefficient table of K signal channels at T times.
+ *     out[t][j]    (B == 0: shared signals)   or   out[t][j][b]  (B > 0: one column per simulation)
+ *         = sum over terms i with chan[i] == j of  Re[ scale[i][b] * f_i(t) * exp(i (2 pi freq[i] t + phase[i])) ]
+ * f_i is piecewise constant: samples[samp_off[i] + b * samp_col_stride + idx], idx = (t - t0[i]) // dt[i] with
+ * NumPy's float floor division, zero outside [0, samp_len[i]) -- or constant (samp_len[i] == -1: the single
+ * sample at samp_off[i]).  samp_col_stride = 0 shares the samples between columns; scale may be NULL (= 1).
+ * chan, samp_off, samp_len have nterms entries; dt, t0, freq, phase have nterms entries, or [nterms][B] when
+ * params_per_col != 0 (frequency / phase / timing sweeps).  Everything lives on the device.
+ * Replaces SignalList.__call__ -> SignalSum.complex_value -> DiscreteSignal.envelope
+ * (signals/signals.py:801-803, 574-577, 296-311, 148-155) evaluated on the stage-time grid. */
+int qdb_signal_table_f64(int T, int K, int B, int nterms,
+                         const int* chan, const long long* samp_off, const int* samp_len,
+                         const double* dt, const double* t0, const double* freq, const double* phase,
+                         int params_per_col,
+                         const qdb_c128* samples, long long samp_col_stride, const qdb_c128* scale,
+                         const double* times, double* out, void* stream);
+
+/* f4: memory-slot outcome probabilities of a batch of final states (already in the measurement basis):
+ *     out[o][b] = sum_{i : outcome_of[i] == o} |y[i][b]|^2,  divided by sum_i |y[i][b]|^2 when normalize != 0.
+ * outcome_of (device, n ints in [0, n_out)) maps every basis state to its outcome bin; out is [n_out][B].
+ * Replaces Statevector.probabilities_dict + _get_memory_slot_probabilities + the normalisation of
+ * _get_experiment_result (backend/dynamics_backend.py:846-866, backend/backend_utils.py:106-147). */
+int qdb_outcome_probabilities_f64(int n, int B, int n_out, const qdb_c128* y, int ldy, const int* outcome_of,
+                                  int normalize, double* out, void* stream);
+
 /* Number of kernels this library has launched on the calling process since load (bench.py's
  * "gpu_launches" evidence). */
 unsigned long long qdb_launch_count(void);

@@ -546,3 +546,87 @@ def synthetic_lindblad(n, K, n_diss, B, seed):
     Y = rho.reshape(n * n, B, order="F")  # vec_F: row index i + k n
     sig = [(0.1 * (j + 1), 0.2 * j + 0.05, 0.3 * j) for j in range(K)]
     return H0, Hs, Ls, Y, sig
+
+
+# ----------------------------------------------------------------------------------------------
+# f4  final-state measurement: out of frame -> dressed basis -> normalise ->
+#     memory-slot outcome probabilities
+# ----------------------------------------------------------------------------------------------
+
+
+def dressed_state_decomposition(operator):
+    """eigh sorted by overlap with the elementary basis; backend/backend_utils.py:31-80."""
+    evals, evecs = np.linalg.eigh(np.array(operator))
+    dressed_evals = np.zeros_like(evals)
+    dressed_states = np.zeros_like(evecs)
+    found = []
+    for eigval, evec in zip(evals, evecs.transpose()):
+        position = int(np.argmax(np.abs(evec)))
+        if position in found:
+            raise ValueError("Dressed-state sorting failed due to non-unique np.argmax(np.abs(evec)).")
+        found.append(position)
+        dressed_states[:, position] = evec
+        dressed_evals[position] = eigval
+    return dressed_evals, dressed_states
+
+
+def subsystem_probabilities_dict(probs, dims, qargs):
+    """Restatement of qiskit.quantum_info Statevector.probabilities_dict(qargs) -- the absent third-party
+    dependency at this boundary (qiskit, unpinned in the reference's setup.py; algorithm of
+    QuantumState._subsystem_probabilities + _vector2dict): reshape |amplitude|^2 to reversed(dims), sum the
+    unmeasured subsystems, order the remaining axes so that qargs[0] is the LAST character of the key;
+    zero-probability outcomes are dropped.  Called from backend/dynamics_backend.py:862."""
+    dims = list(dims)
+    ndim = len(dims)
+    tens = np.reshape(np.asarray(probs, dtype=float), list(reversed(dims)))
+    qaxes = [ndim - 1 - q for q in reversed(qargs)]
+    sum_axis = tuple(i for i in range(ndim) if i not in qaxes)
+    if sum_axis:
+        tens = np.sum(tens, axis=sum_axis)
+    perm = np.argsort(np.argsort(qaxes))
+    tens = np.transpose(tens, axes=perm)
+    flat = np.reshape(tens, (tens.size,))
+    sub_dims = [dims[q] for q in qargs]
+    out = {}
+    for idx, p in enumerate(flat):
+        if p == 0:
+            continue
+        digits, rem = [], idx
+        for d in sub_dims:  # qargs[0] is the least significant digit
+            digits.append(str(rem % d))
+            rem //= d
+        out["".join(reversed(digits))] = float(p)
+    return out
+
+
+def memory_slot_probabilities(probability_dict, memory_slot_indices, num_memory_slots=None, max_outcome_value=None):
+    """backend/backend_utils.py:106-147."""
+    num_memory_slots = num_memory_slots or (max(memory_slot_indices) + 1)
+    out = {}
+    for level_str, prob in probability_dict.items():
+        result = ["0"] * num_memory_slots
+        for idx, level in zip(memory_slot_indices, reversed(level_str)):
+            if max_outcome_value and int(level) > max_outcome_value:
+                level = str(max_outcome_value)
+            result[-(idx + 1)] = level
+        key = "".join(result)
+        out[key] = out.get(key, 0.0) + prob
+    return out
+
+
+def final_state_memory_probabilities(y_frame, t, frame_operator, dressed_states, subsystem_dims, measurement_subsystems,
+                                     memory_slot_indices, num_memory_slots=None, max_outcome_value=None, normalize=True):
+    """One final state (standard basis, in the rotating frame) -> {memory-slot outcome: probability};
+    backend/dynamics_backend.py:846-866 for a Statevector."""
+    d, U = frame_decompose(frame_operator)
+    y = np.asarray(y_frame, dtype=complex)
+    if d is not None:
+        yfb = y if U is None else U.conj().T @ y
+        yfb = state_out_of_frame(d, t, yfb)
+        y = yfb if U is None else U @ yfb
+    y = dressed_states.conj().T @ y
+    if normalize:
+        y = y / np.linalg.norm(y)
+    probs = np.abs(y) ** 2
+    pd = subsystem_probabilities_dict(probs, subsystem_dims, measurement_subsystems)
+    return memory_slot_probabilities(pd, memory_slot_indices, num_memory_slots, max_outcome_value)

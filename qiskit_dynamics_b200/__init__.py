@@ -15,8 +15,10 @@ from .models import (RotatingFrame, GeneratorModel, HamiltonianModel, LindbladMo
                      LindbladCollection, VectorizedLindbladCollection)
 from .solvers import Solver, solve_lmde, solve_ode
 from . import distributed
+from . import measurement
+from .measurement import FinalStateMeasurement
 
-__all__ = ["QiskitError", "Signal", "DiscreteSignal", "SignalSum", "DiscreteSignalSum", "SignalList",
+__all__ = ["FinalStateMeasurement", "QiskitError", "Signal", "DiscreteSignal", "SignalSum", "DiscreteSignalSum", "SignalList",
            "RotatingFrame", "GeneratorModel", "HamiltonianModel", "LindbladModel", "OperatorCollection",
            "LindbladCollection", "VectorizedLindbladCollection", "Solver", "solve_lmde", "solve_ode",
            "asarray", "default_device", "set_default_device", "to_numpy", "distributed"]

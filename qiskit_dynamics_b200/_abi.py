@@ -51,6 +51,9 @@ SIGNATURES = {
     "qdb_rk4_table_layout": (_i, [_i, _i]),
     "qdb_table_entry_bytes": (_sz, [_i, _i]),
     "qdb_rk4_tiling": (_i, [_i, _i, _i, _vp]),
+    "qdb_signal_table_f64": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, ctypes.c_longlong, _vp, _vp, _vp,
+                                  _vp]),
+    "qdb_outcome_probabilities_f64": (_i, [_i, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "qdb_dmma_probe": (_i, [_vp, _i, _vp, _vp]),
     "qdb_expm_c128": (_i, [_i, _vp, _i, _vp, _vp, _sz, _vp]),
     "qdb_launch_count": (ctypes.c_ulonglong, []),
@@ -273,6 +276,37 @@ def rk4_table_steps(n, table, h, y, S, layout=LAYOUT_PACKED):
     _check(lib().qdb_rk4_table_steps_c128(n, B, S, _ptr(table, C, "table"), int(layout), float(h), _ptr(y, C, "y"), B,
                                           _stream()), "qdb_rk4_table_steps_c128")
     return y
+
+
+def signal_table(K, terms: dict, samples, times, B=0, col_stride=0, scale=None, out=None, params_per_col=False):
+    """Coefficient table (T, K) (B == 0) or (T, K, B) of K channels from flattened term arrays on the device.
+
+    ``terms``: dict of device tensors ``chan`` (int32), ``samp_off`` (int64), ``samp_len`` (int32), ``dt``, ``t0``,
+    ``freq``, ``phase`` (float64), each of length nterms; ``samples``: complex128 sample storage."""
+    T = int(times.shape[0])
+    nterms = int(terms["chan"].shape[0])
+    if out is None:
+        out = torch.empty((T, K) if B == 0 else (T, K, B), dtype=F, device=times.device)
+    I32, I64 = torch.int32, torch.int64
+    _check(lib().qdb_signal_table_f64(T, K, B, nterms, _ptr(terms["chan"], I32, "chan"), _ptr(terms["samp_off"], I64, "samp_off"),
+                                      _ptr(terms["samp_len"], I32, "samp_len"), _ptr(terms["dt"], F, "dt"),
+                                      _ptr(terms["t0"], F, "t0"), _ptr(terms["freq"], F, "freq"),
+                                      _ptr(terms["phase"], F, "phase"), int(bool(params_per_col)), _ptr(samples, C, "samples"),
+                                      int(col_stride),
+                                      _ptr(scale, C, "scale"), _ptr(times, F, "times"), _ptr(out, F, "out"), _stream()),
+           "qdb_signal_table_f64")
+    return out
+
+
+def outcome_probabilities(y, outcome_of, n_out: int, normalize: bool = True, out=None):
+    """(n_out, B) outcome probabilities of the columns of y (n, B); outcome_of: int32 (n,) bin of every basis state."""
+    n, B = y.shape
+    if out is None:
+        out = torch.empty((n_out, B), dtype=F, device=y.device)
+    _check(lib().qdb_outcome_probabilities_f64(n, B, int(n_out), _ptr(y, C, "y"), B, _ptr(outcome_of, torch.int32, "outcome_of"),
+                                               int(bool(normalize)), _ptr(out, F, "out"), _stream()),
+           "qdb_outcome_probabilities_f64")
+    return out
 
 
 def dmma_probe(iters: int = 20000, reps: int = 5) -> float:

@@ -35,10 +35,13 @@ class Signal:
                  name: Optional[str] = None):
         self._name = name
         self._is_constant = False
+        self._const_envelope = None  # numeric envelope (device-evaluable, see compile_signal_program)
         if callable(envelope):
             self._envelope = envelope
         else:
             const = np.asarray(envelope)
+            if const.ndim == 0:
+                self._const_envelope = complex(const)
             if np.all(np.asarray(carrier_freq) == 0.0):
                 self._is_constant = True
             self._envelope = lambda t, _c=const: _c * np.ones_like(t)
@@ -347,6 +350,117 @@ class SignalList(SignalCollection):
                     total = total + term(0.0)
             out.append(total)
         return np.asarray(out)
+
+
+# ---------------------------------------------------------------------------------------------
+# device form: flattened term arrays for qdb_signal_table_f64
+# ---------------------------------------------------------------------------------------------
+
+
+class SignalProgram:
+    """Flattened description of one SignalList -- or of B structurally identical SignalLists, one per
+    state column -- that the device evaluates on a time grid (``csrc/signals.cu``).
+
+    Terms are the elementary components of every channel in channel order: piecewise-constant
+    (:class:`DiscreteSignal`) or constant-envelope (:class:`Signal` with a numeric envelope) signals.  Arrays
+    (host, NumPy): ``chan`` (nterms,) int32; ``samp_len`` (nterms,) int32 (-1 = constant envelope);
+    ``samp_off`` (nterms,) int64; ``dt``, ``t0``, ``freq``, ``phase`` (nterms,) float64 -- or (nterms, B)
+    when they differ between columns; ``samples`` complex128, (S,) shared or (B, S) per column.
+    """
+
+    def __init__(self, num_channels, columns, chan, samp_len, samp_off, dt, t0, freq, phase, samples):
+        self.num_channels, self.columns = num_channels, columns
+        self.chan, self.samp_len, self.samp_off = chan, samp_len, samp_off
+        self.dt, self.t0, self.freq, self.phase = dt, t0, freq, phase
+        self.samples = samples
+        self._dev = None
+
+    @property
+    def params_per_column(self) -> bool:
+        return self.freq.ndim == 2
+
+    @property
+    def samples_per_column(self) -> bool:
+        return self.samples.ndim == 2
+
+    def to_device(self, device):
+        import torch
+
+        if self._dev is None or self._dev["device"] != device:
+            t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(device)  # noqa: E731
+            self._dev = {
+                "device": device,
+                "terms": {"chan": t(self.chan, np.int32), "samp_off": t(self.samp_off, np.int64),
+                          "samp_len": t(self.samp_len, np.int32), "dt": t(self.dt, np.float64), "t0": t(self.t0, np.float64),
+                          "freq": t(self.freq, np.float64), "phase": t(self.phase, np.float64)},
+                "samples": t(self.samples if self.samples.size else np.zeros(1, complex), np.complex128),
+            }
+        return self._dev
+
+    def table(self, times, device):
+        """(T, K) -- or (T, K, B) for a per-column program -- float64 device tensor."""
+        import torch
+
+        from . import _abi
+
+        d = self.to_device(device)
+        times_dev = times if isinstance(times, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(times, dtype=np.float64)).to(device)
+        stride = self.samples.shape[1] if self.samples_per_column else 0
+        return _abi.signal_table(self.num_channels, d["terms"], d["samples"], times_dev, B=self.columns, col_stride=stride,
+                                 params_per_col=self.params_per_column)
+
+
+def _term_descr(term):
+    """(samp_len, samples, dt, t0, freq, phase) of an elementary device-evaluable signal, else None."""
+    if isinstance(term, SignalSum):
+        return None
+    freq, phase = np.asarray(term.carrier_freq), np.asarray(term.phase)
+    if freq.ndim != 0 or phase.ndim != 0 or np.iscomplexobj(freq) or np.iscomplexobj(phase):
+        return None
+    if type(term) is DiscreteSignal:
+        samples = np.asarray(term.samples)
+        if samples.ndim != 1 or samples.dtype == object:
+            return None
+        return (samples.shape[0], samples.astype(complex), float(term.dt), float(term.start_time), float(freq), float(phase))
+    if type(term) is Signal and term._const_envelope is not None:
+        return (-1, np.asarray([term._const_envelope], dtype=complex), 1.0, 0.0, float(freq), float(phase))
+    return None
+
+
+def compile_signal_program(signal_lists) -> Optional[SignalProgram]:
+    """Device program of one SignalList, or of a list of SignalLists (sweep mode: one per column) that share
+    their structure (same channels, same kind and sample count of every term).  None when a term is an
+    arbitrary Python envelope -- those stay on the host path (:meth:`SignalList.table`)."""
+    single = isinstance(signal_lists, SignalList)
+    lists = [signal_lists] if single else list(signal_lists)
+    if not lists:
+        return None
+    per_col = []
+    for sl in lists:
+        descr = []
+        for j, entry in enumerate(sl.components):
+            for term in entry.components:
+                d = _term_descr(term)
+                if d is None:
+                    return None
+                descr.append((j,) + d)
+        per_col.append(descr)
+    ref = per_col[0]
+    sig = [(d[0], d[1]) for d in ref]
+    if any([(d[0], d[1]) for d in descr] != sig for descr in per_col[1:]):
+        return None
+    nterms, B = len(ref), len(lists)
+    chan = np.asarray([d[0] for d in ref], dtype=np.int32)
+    samp_len = np.asarray([d[1] for d in ref], dtype=np.int32)
+    counts = np.asarray([len(d[2]) for d in ref], dtype=np.int64)
+    samp_off = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int64) if nterms else np.zeros(0, np.int64)
+    params = np.asarray([[d[3:7] for d in descr] for descr in per_col], dtype=float).reshape(B, nterms, 4)
+    flat = [np.concatenate([d[2] for d in descr]) if nterms else np.zeros(0, complex) for descr in per_col]
+    shared_params = bool(np.all(params == params[:1]))
+    shared_samples = all(np.array_equal(f, flat[0]) for f in flat[1:])
+    pick = (lambda k: params[0, :, k].copy()) if shared_params else (lambda k: np.ascontiguousarray(params[:, :, k].T))
+    samples = flat[0] if shared_samples else np.stack(flat)
+    return SignalProgram(len(lists[0]), 0 if single else B, chan, samp_len, samp_off, pick(0), pick(1), pick(2), pick(3), samples)
 
 
 # ---------------------------------------------------------------------------------------------

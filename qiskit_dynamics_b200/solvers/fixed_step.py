@@ -97,10 +97,11 @@ def _columns(y0: torch.Tensor):
 
 def rk4_model_solve(model, t_span, y0_fb: torch.Tensor, max_dt, t_eval=None,
                     column_coefficients: Optional[Callable[[np.ndarray], np.ndarray]] = None,
-                    workspace_bytes: int = 1 << 30) -> OdeResult:
+                    workspace_bytes: int = 1 << 30, sweep_table_bytes: int = 1 << 30) -> OdeResult:
     """RK4 on a model generator, state already in the frame basis.
 
-    ``column_coefficients(times) -> (T, K, B)`` switches to sweep mode (per-column signal values).
+    ``column_coefficients(times) -> (T, K, B)`` (NumPy array or device tensor) switches to sweep mode
+    (per-column signal values).
     """
     coll = model._collection()
     n = coll.dim
@@ -121,20 +122,32 @@ def rk4_model_solve(model, t_span, y0_fb: torch.Tensor, max_dt, t_eval=None,
         S = int(S)
         times = stage_time_grid(t0, h, S)
         if column_coefficients is not None:
-            table = np.ascontiguousarray(column_coefficients(times), dtype=np.float64)
-            if table.shape != (times.shape[0], K, B):
-                raise QiskitError(f"per-column signal table has shape {table.shape}, expected {(times.shape[0], K, B)}")
-            coeff = asreal(table, y.device)
-            per_col = True
+            # sweep mode: the (T, K, B) table is built (host or device) and consumed in chunks of steps so that it
+            # never exceeds sweep_table_bytes of HBM, whatever the number of steps
+            per_step = 2 * K * B * 8
+            chunk = max(1, min(S, int(sweep_table_bytes // max(per_step, 1))))
+            for s0 in range(0, S, chunk):
+                Sc = min(chunk, S - s0)
+                tchunk = times[2 * s0: 2 * (s0 + Sc) + 1]
+                table = column_coefficients(tchunk)
+                if isinstance(table, torch.Tensor):
+                    coeff = table.to(device=y.device, dtype=torch.float64).contiguous()
+                else:
+                    coeff = asreal(np.ascontiguousarray(table, dtype=np.float64), y.device)
+                if tuple(coeff.shape) != (tchunk.shape[0], K, B):
+                    raise QiskitError(f"per-column signal table has shape {tuple(coeff.shape)}, expected {(tchunk.shape[0], K, B)}")
+                need = _abi.workspace_bytes(_abi.WS_RK4, n, K, B, Sc)
+                if ws is None or ws.numel() < need:
+                    ws = torch.empty(need, dtype=torch.uint8, device=y.device)
+                _abi.rk4_steps(n, ops, stat, ops_p, stat_p, coeff, mu, tchunk, float(h), y, Sc, per_col=True, workspace=ws)
         else:
             table = model._signal_table(times)
             coeff = None if table is None else asreal(table, y.device)
-            per_col = False
-        need = _abi.workspace_bytes(_abi.WS_RK4, n, K, B, S)
-        need = min(need, max(workspace_bytes, _abi.workspace_bytes(_abi.WS_RK4, n, K, B, 1)))
-        if ws is None or ws.numel() < need:
-            ws = torch.empty(need, dtype=torch.uint8, device=y.device)
-        _abi.rk4_steps(n, ops, stat, ops_p, stat_p, coeff, mu, times, float(h), y, S, per_col=per_col, workspace=ws)
+            need = _abi.workspace_bytes(_abi.WS_RK4, n, K, B, S)
+            need = min(need, max(workspace_bytes, _abi.workspace_bytes(_abi.WS_RK4, n, K, B, 1)))
+            if ws is None or ws.numel() < need:
+                ws = torch.empty(need, dtype=torch.uint8, device=y.device)
+            _abi.rk4_steps(n, ops, stat, ops_p, stat_p, coeff, mu, times, float(h), y, S, per_col=False, workspace=ws)
         ys.append(y.reshape(shape).clone())
     return trim_t_results(OdeResult(t=np.array(t_list), y=torch.stack(ys)), t_eval)
 

@@ -22,7 +22,7 @@ from scipy.integrate._ivp.ivp import OdeResult
 from ..arrays import asarray
 from ..exceptions import QiskitError
 from ..models import HamiltonianModel, LindbladModel, RotatingFrame
-from ..signals import Signal, SignalList
+from ..signals import Signal, SignalList, compile_signal_program
 from .fixed_step import rk4_model_solve
 from .solver_functions import (ODE_METHODS, is_lindblad_model_not_vectorized, is_lindblad_model_vectorized,
                                results_y_out_of_frame_basis, setup_generator_model_rhs_y0_in_frame_basis, solve_lmde)
@@ -118,7 +118,17 @@ class Solver:
             sig_lists.append(model.signals)
         self._set_new_signals(signals_list[0])
 
-        def column_coefficients(times: np.ndarray) -> np.ndarray:
+        # device route (row f3): when every term of every simulation is a sampled or constant-envelope signal
+        # and the simulations share their structure, one kernel builds the (T, K, B) table in HBM
+        if isinstance(model, LindbladModel):
+            flat_lists = [SignalList([s for part in sl if part is not None for s in part.components]) for sl in sig_lists]
+        else:
+            flat_lists = sig_lists
+        program = compile_signal_program(flat_lists)
+
+        def column_coefficients(times: np.ndarray):
+            if program is not None:
+                return program.table(times, Y0.device)
             cols = []
             for sl in sig_lists:
                 if isinstance(model, LindbladModel):

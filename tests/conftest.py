@@ -15,6 +15,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run with -m gpu on the B200 box)")
 
 
+MEASUREMENT_CASES = [
+    # (name, subsystem_dims, measurement_subsystems, memory_slot_indices, num_memory_slots, max_outcome_level)
+    ("two_transmons_both", [3, 3], [0, 1], [0, 1], None, 1),
+    ("two_transmons_q1_slot2", [3, 3], [1], [2], 3, None),
+    ("two_transmons_q0_levels", [3, 3], [0], [0], None, 2),
+    ("mixed_dims_swapped_slots", [2, 3, 2], [0, 2], [1, 0], None, 1),
+]  # same table as tests/golden/make_golden.py
+
+
 def load_golden(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"))
 

@@ -323,7 +323,73 @@ def gen_lindblad():
     save("lindblad", **out)
 
 
+# ---------------------------------------------------------------------------------------------
+MEASUREMENT_CASES = [
+    # (name, subsystem_dims, measurement_subsystems, memory_slot_indices, num_memory_slots, max_outcome_level)
+    ("two_transmons_both", [3, 3], [0, 1], [0, 1], None, 1),
+    ("two_transmons_q1_slot2", [3, 3], [1], [2], 3, None),
+    ("two_transmons_q0_levels", [3, 3], [0], [0], None, 2),
+    ("mixed_dims_swapped_slots", [2, 3, 2], [0, 2], [1, 0], None, 1),
+]
+
+
+def measurement_system(dims, seed):
+    """Duffing-like static Hamiltonian with weak exchange coupling (nearly diagonal, so that the dressed-state
+    sorting of backend_utils.py:31-80 is well defined), one drive operator, random final states."""
+    rng = np.random.default_rng(seed)
+    n = int(np.prod(dims))
+    levels = np.zeros((len(dims), n))
+    for i in range(n):
+        rem = i
+        for s, d in enumerate(dims):
+            levels[s, i] = rem % d
+            rem //= d
+    H0 = np.zeros((n, n), dtype=complex)
+    for s in range(len(dims)):
+        H0 += np.diag(2 * np.pi * ((4.8 + 0.31 * s) * levels[s] - 0.15 * levels[s] * (levels[s] - 1)))
+    A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    H0 = H0 + 0.02 * (A + A.conj().T)
+    Hd = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    Hd = (Hd + Hd.conj().T) / 2
+    B = 5
+    Y = rng.standard_normal((n, B)) + 1j * rng.standard_normal((n, B))
+    Y[:, 0] = 0.0
+    Y[0, 0] = 1.0  # one column: a basis state (many zero-probability outcomes)
+    return H0, Hd, Y
+
+
+def gen_measurement():
+    """Row f4.  Reference code executed: RotatingFrame.state_out_of_frame, _get_lab_frame_static_hamiltonian,
+    _get_dressed_state_decomposition, _get_memory_slot_probabilities (backend/backend_utils.py) in the order of
+    _get_experiment_result (backend/dynamics_backend.py:846-866).  Statevector.probabilities_dict belongs to the
+    absent qiskit package and is restated in oracle.numpy_oracle.subsystem_probabilities_dict."""
+    from qiskit_dynamics.backend import backend_utils as bu
+    out = {}
+    tf = 1.7
+    for ci, (name, dims, meas, slots, nslots, max_level) in enumerate(MEASUREMENT_CASES):
+        H0, Hd, Y = measurement_system(dims, 500 + ci)
+        model = HamiltonianModel(static_operator=H0, operators=[Hd], signals=[Signal(0.1, 4.8)], rotating_frame=H0)
+        lab_h = bu._get_lab_frame_static_hamiltonian(model)
+        evals, dressed = bu._get_dressed_state_decomposition(lab_h)
+        dicts = []
+        for b in range(Y.shape[1]):
+            yf = np.array(model.rotating_frame.state_out_of_frame(t=tf, y=Y[:, b]))
+            yf = dressed.conj().T @ yf
+            yf = yf / np.linalg.norm(yf)
+            pd = orc.subsystem_probabilities_dict(np.abs(yf) ** 2, dims, meas)
+            dicts.append(bu._get_memory_slot_probabilities(pd, slots, num_memory_slots=nslots, max_outcome_value=max_level))
+        labels = sorted(set().union(*[d.keys() for d in dicts]))
+        P = np.array([[d.get(lab, 0.0) for d in dicts] for lab in labels])
+        out[f"{name}_H0"], out[f"{name}_Hd"], out[f"{name}_Y"] = H0, Hd, Y
+        out[f"{name}_lab_h"], out[f"{name}_dressed_evals"], out[f"{name}_dressed_states"] = lab_h, evals, dressed
+        out[f"{name}_labels"] = np.array(labels)
+        out[f"{name}_probs"] = P
+    out["tf"] = np.array(tf)
+    save("measurement", **out)
+
+
 if __name__ == "__main__":
+    gen_measurement()
     gen_collection()
     gen_frame()
     gen_signals()

@@ -189,6 +189,84 @@ def test_model_construction_and_error_conventions(qd):
                          [t_span_to_list, _y0_to_list, _signals_to_list])
 
 
+def _npy_floor_divide(a, b):
+    """Python restatement of npy_floor_divide in csrc/signals.cu (NumPy's npy_divmod), same operation order."""
+    import math
+    if b == 0.0:
+        return math.copysign(math.inf, a) if a != 0 else math.nan
+    mod = math.fmod(a, b)
+    div = (a - mod) / b
+    if mod != 0.0 and ((b < 0.0) != (mod < 0.0)):
+        div -= 1.0
+    if div != 0.0:
+        fd = math.floor(div)
+        if div - fd > 0.5:
+            fd += 1.0
+        return fd
+    return math.copysign(0.0, a / b)
+
+
+def test_bin_index_rule_is_numpy_floor_division():
+    """The device bin selector restates NumPy's float floor division, which the reference uses
+    (signals/signals.py:304-308) and which differs from floor(a / b) on bin edges (1.0 // 0.1 == 9)."""
+    rng = np.random.default_rng(0)
+    assert np.float64(1.0) // np.float64(0.1) == 9.0 and np.floor(1.0 / 0.1) == 10.0
+    cases = [(1.0, 0.1), (0.3, 0.1), (0.7, 0.1), (-0.3, 0.1), (2.0, 0.25), (0.0, 0.1), (-0.0, 0.1), (1e-300, 0.1),
+             (5.0, -0.5), (-5.0, -0.5), (0.30000000000000004, 0.1)]
+    dts = [0.1, 0.2222222222222222, 1 / 4.5, 1e-3, 0.25, 3.0]
+    for dt in dts:  # accumulated stage times t <- t + h landing on bin edges
+        t = 0.0
+        for _ in range(200):
+            cases.append((t, dt))
+            cases.append((t + dt / 2, dt))
+            t = t + dt / 2
+    cases += [(float(a), float(b)) for a, b in zip(rng.uniform(-50, 50, 2000), rng.uniform(0.01, 3, 2000))]
+    for a, b in cases:
+        want = np.float64(a) // np.float64(b)
+        got = _npy_floor_divide(a, b)
+        assert got == want and np.signbit(got) == np.signbit(want), (a, b, got, want)
+
+
+def test_signal_program_compile(qd):
+    """Flattening of SignalLists into the device term arrays (row f3)."""
+    from qiskit_dynamics_b200.signals import compile_signal_program
+    sl = qd.SignalList([qd.Signal(0.3, 5.0, 0.1), qd.DiscreteSignal(0.1, np.arange(5) + 1j, carrier_freq=2.0) + 0.5, 1.0])
+    p = compile_signal_program(sl)
+    assert p.columns == 0 and p.num_channels == 3
+    assert list(p.chan) == [0, 1, 1, 2] and list(p.samp_len) == [-1, 5, -1, -1] and list(p.samp_off) == [0, 1, 6, 7]
+    np.testing.assert_array_equal(p.freq, [5.0, 2.0, 0.0, 0.0])
+    np.testing.assert_array_equal(p.samples, np.concatenate([[0.3], np.arange(5) + 1j, [0.5], [1.0]]))
+    # sweep: amplitude differs -> per-column samples, shared parameters
+    lists = [qd.SignalList([qd.Signal(0.3 * (b + 1), 5.0, 0.1), qd.DiscreteSignal(0.1, (np.arange(5) + 1j) * b, carrier_freq=2.0)])
+             for b in range(3)]
+    p = compile_signal_program(lists)
+    assert p.columns == 3 and not p.params_per_column and p.samples.shape == (3, 6)
+    # frequency sweep -> per-column parameters, shared samples
+    lists = [qd.SignalList([qd.Signal(0.3, 5.0 + b, 0.1)]) for b in range(4)]
+    p = compile_signal_program(lists)
+    assert p.params_per_column and p.freq.shape == (1, 4) and p.samples.shape == (1,)
+    # arbitrary Python envelopes and structure mismatches stay on the host path
+    assert compile_signal_program(qd.SignalList([qd.Signal(lambda t: t)])) is None
+    assert compile_signal_program([qd.SignalList([qd.Signal(1.0)]), qd.SignalList([qd.DiscreteSignal(0.1, [1.0])])]) is None
+
+
+def test_memory_slot_outcome_map_matches_oracle(qd):
+    """The product's basis-state -> outcome table (host set-up of row f4) against the oracle's dictionary
+    pipeline (pinned by the measurement fixtures) on every basis state."""
+    from conftest import MEASUREMENT_CASES
+    from oracle import numpy_oracle as orc
+    from qiskit_dynamics_b200.measurement import memory_slot_outcome_map
+    for name, dims, meas, slots, nslots, max_level in MEASUREMENT_CASES + [("wide", [2, 2, 3], [2, 0, 1], [0, 3, 1], 5, None)]:
+        labels, outcome_of = memory_slot_outcome_map(dims, meas, slots, nslots, max_level)
+        n = int(np.prod(dims))
+        assert outcome_of.shape == (n,) and outcome_of.dtype == np.int32 and labels == sorted(labels)
+        for i in range(n):
+            probs = np.zeros(n)
+            probs[i] = 1.0
+            d = orc.memory_slot_probabilities(orc.subsystem_probabilities_dict(probs, dims, meas), slots, nslots, max_level)
+            assert d == {labels[outcome_of[i]]: 1.0}, (name, i, d)
+
+
 def test_shard_bounds():
     from qiskit_dynamics_b200 import distributed as D
     for B in (1, 7, 512, 4096, 4097):

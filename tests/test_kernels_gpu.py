@@ -328,6 +328,44 @@ def test_expm_steps(abi):
     assert max_col_l2(yd.cpu().numpy(), y) < TOL_SOLVE
 
 
+def test_signal_table_device(abi):
+    """Row f3: qdb_signal_table_f64 against the host SignalList (pinned to the reference by the golden signal
+    fixtures).  Bin selection must be exact -- checked with samples that spell their own index, on stage-time
+    grids that land on bin edges -- values to 1e-14."""
+    import qiskit_dynamics_b200 as qd
+    from qiskit_dynamics_b200.signals import compile_signal_program
+    from qiskit_dynamics_b200.solvers import stage_time_grid
+    rng = np.random.default_rng(5)
+    for dt, h in ((0.1, 0.05), (1 / 4.5, 1 / 4.5), (0.25, 0.1), (0.2222222222222222, 0.1111111111111111)):
+        N = 37
+        times = np.concatenate([stage_time_grid(0.0, h, 90), [-0.3, -1e-18, N * dt, N * dt + 1.0, 0.7 - 3 * dt]])
+        # (1) index exactness: envelope value == bin index + 1, no carrier
+        ident = qd.SignalList([qd.DiscreteSignal(dt, np.arange(N) + 1.0), qd.DiscreteSignal(dt, np.arange(N) + 1.0, start_time=0.7)])
+        got = compile_signal_program(ident).table(times, "cuda").cpu().numpy()
+        assert np.array_equal(got, ident.table(times))
+        # (2) carriers, phases, complex samples, constant terms, sums inside one channel
+        sl = qd.SignalList([
+            qd.DiscreteSignal(dt, rng.standard_normal(N) + 1j * rng.standard_normal(N), carrier_freq=1.3, phase=0.4),
+            qd.DiscreteSignal(dt, rng.standard_normal(N), start_time=0.35, carrier_freq=-0.7) + qd.Signal(0.25, 2.0, -0.3) + 0.5,
+            qd.Signal(0.8 - 0.2j, 0.05, 1.0),
+            2.5,
+        ])
+        got = compile_signal_program(sl).table(times, "cuda").cpu().numpy()
+        np.testing.assert_allclose(got, sl.table(times), rtol=0, atol=1e-14)
+    # (3) sweep: per-column amplitudes (samples) and per-column carrier frequencies (parameters)
+    B, N, dt = 70, 20, 0.1
+    times = stage_time_grid(0.0, 0.05, 45)
+    base = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    lists = [qd.SignalList([qd.DiscreteSignal(dt, base * (0.5 + b / B), carrier_freq=1.0 + 0.01 * b, phase=0.1),
+                            qd.Signal(0.1 * (b + 1), 0.3, 0.0)]) for b in range(B)]
+    prog = compile_signal_program(lists)
+    assert prog.columns == B and prog.params_per_column and prog.samples_per_column
+    got = prog.table(times, "cuda").cpu().numpy()
+    want = np.stack([sl.table(times) for sl in lists], axis=-1)
+    assert got.shape == (times.shape[0], 2, B)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-14)
+
+
 def test_argument_errors(abi):
     y = torch.zeros((4, 2), dtype=torch.complex128, device="cuda")
     with pytest.raises(abi.QdbError):

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import numpy_oracle as orc
-from conftest import load_golden
+from conftest import MEASUREMENT_CASES, load_golden
 
 TOL = 1e-12
 
@@ -234,3 +234,25 @@ def test_lindblad():
     close(np.array([np.sum(np.abs(a)) for a in (H0, Hs, Ls, Y)] + [np.sum(a).real for a in (H0, Hs, Ls, Y)]), g["cfg3_check"], 1e-9)
     _, ys = orc.solve_vectorized_lindblad(H0, Hs, specs(sig), Ls, None, None, np.diag(H0).real, [0, 0.03], Y, 1e-2)
     close(ys[-1], g["cfg3_expm_y"], 1e-12)
+
+
+def test_measurement_post_processing():
+    """Row f4: dressed-state sorting, out-of-frame, normalisation and memory-slot probabilities against fixtures
+    produced by the reference's backend_utils functions."""
+    g = load_golden("measurement")
+    tf = float(g["tf"])
+    for name, dims, meas, slots, nslots, max_level in MEASUREMENT_CASES:
+        evals, dressed = orc.dressed_state_decomposition(g[f"{name}_lab_h"])
+        close(evals, g[f"{name}_dressed_evals"], 1e-10)
+        overlap = np.abs(np.sum(dressed.conj() * g[f"{name}_dressed_states"], axis=0))  # eigenvector phases are free
+        close(overlap, np.ones_like(overlap), 1e-10)
+        labels = [str(x) for x in g[f"{name}_labels"]]
+        Y = g[f"{name}_Y"]
+        for b in range(Y.shape[1]):
+            d = orc.final_state_memory_probabilities(Y[:, b], tf, g[f"{name}_H0"], g[f"{name}_dressed_states"], dims, meas,
+                                                     slots, nslots, max_level, normalize=True)
+            assert set(d) <= set(labels)
+            close(np.array([d.get(lab, 0.0) for lab in labels]), g[f"{name}_probs"][:, b])
+    # the reference's own example of the slot mapping (computed with backend_utils._get_memory_slot_probabilities)
+    assert orc.memory_slot_probabilities({"00": 0.1, "01": 0.2, "10": 0.3, "12": 0.4}, [0, 2], 3, 1) == \
+        {"000": 0.1, "001": 0.2, "100": 0.3, "101": 0.4}
