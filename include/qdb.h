@@ -191,7 +191,8 @@ int qdb_expm_c128(int n, const qdb_c128* A, int squarings, qdb_c128* out,
  * NumPy's float floor division, zero outside [0, samp_len[i]) -- or constant (samp_len[i] == -1: the single
  * sample at samp_off[i]).  samp_col_stride = 0 shares the samples between columns; scale may be NULL (= 1).
  * chan, samp_off, samp_len have nterms entries; dt, t0, freq, phase have nterms entries, or [nterms][B] when
- * params_per_col != 0 (frequency / phase / timing sweeps).  Everything lives on the device.
+ * params_per_col != 0 (frequency / phase / timing sweeps).  Everything lives on the device; times == NULL with
+ * T == 1 evaluates the single time t_scalar (one RHS call: no host-to-device copy at all).
  * Replaces SignalList.__call__ -> SignalSum.complex_value -> DiscreteSignal.envelope
  * (signals/signals.py:801-803, 574-577, 296-311, 148-155) evaluated on the stage-time grid. */
 int qdb_signal_table_f64(int T, int K, int B, int nterms,
@@ -199,7 +200,7 @@ int qdb_signal_table_f64(int T, int K, int B, int nterms,
                          const double* dt, const double* t0, const double* freq, const double* phase,
                          int params_per_col,
                          const qdb_c128* samples, long long samp_col_stride, const qdb_c128* scale,
-                         const double* times, double* out, void* stream);
+                         const double* times, double t_scalar, double* out, void* stream);
 
 /* f4: memory-slot outcome probabilities of a batch of final states (already in the measurement basis):
  *     out[o][b] = sum_{i : outcome_of[i] == o} |y[i][b]|^2,  divided by sum_i |y[i][b]|^2 when normalize != 0.

@@ -1,0 +1,80 @@
+"""Secondary configurations of BASELINE.json (cfg2, cfg3, cfg5-like) through the public API, device-resident inputs,
+CUDA-event timing, against the live DMMA peak.  One JSON line per configuration (sweep-mode
+throughput is reported beside the headline because the shared-signal shortcut does not exist there).
+
+    python profiles/probe/bench_configs.py [cfg2] [cfg3] [cfg5] [cfg4sweep] [rhs]
+"""
+import json, os, sys, time
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import qiskit_dynamics_b200 as qd
+from qiskit_dynamics_b200 import _abi as abi
+from qiskit_dynamics_b200.solvers import stage_time_grid
+from oracle import numpy_oracle as orc
+
+def dev(a): return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize(); best = 1e30
+    for _ in range(reps):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1))
+    return best
+which = set(sys.argv[1:]) or {"cfg2", "cfg3", "cfg5", "cfg4sweep", "rhs"}
+peak = abi.dmma_probe()
+
+def sweep(name, n, K, B, S, seed):
+    H0, Hs, Y, sig = orc.synthetic_schrodinger(n, K, 1, seed)
+    Gd, G, d, U = orc.generator_model_operators(H0, Hs, H0)
+    specs = [orc.SigSpec(*s) for s in sig]
+    h = 1e-3; times = stage_time_grid(0.0, h, S); base = orc.signal_list_values(specs, times)
+    amp = 0.5 + np.arange(B) / B
+    coeff = (dev(base)[:, :, None] * dev(amp)[None, None, :]).contiguous()
+    Gdv, Gdd = dev(G), dev(Gd); Gp, Gdp = abi.pack_operators(Gdv), abi.pack_operators(Gdd[None])[0]
+    mu = dev(-np.imag(d)); y0 = dev(np.repeat(U.conj().T @ Y, B, axis=1)); y = y0.clone()
+    def run():
+        y.copy_(y0); abi.rk4_steps(n, Gdv, Gdd, Gp, Gdp, coeff, mu, times, h, y, S, per_col=True)
+    ms = timeit(run)
+    alg = S * B * (4 * ((4 * K + 8) * n * n + 12 * n) + 28 * n)
+    exe = S * B * 4 * (K + 1) * 8 * n * n
+    print(json.dumps({"config": name, "kernel": "rk4_sweep_kernel", "n": n, "K": K, "B": B, "rk4_steps": S, "ms": ms,
+                      "us_per_step": ms * 1e3 / S, "state_rhs_per_s": 4 * S * B / ms * 1e3, "alg_tflops": alg / ms * 1e-9,
+                      "exec_tflops": exe / ms * 1e-9, "dmma_peak_tflops": peak, "alg_frac": alg / ms * 1e-9 / peak,
+                      "exec_frac": exe / ms * 1e-9 / peak, "tiling": abi.rk4_tiling(n, B, K),
+                      "unitarity_drift": float((torch.linalg.vector_norm(y, dim=0) - 1).abs().max())}), flush=True)
+
+if "cfg2" in which: sweep("cfg2: dim-32, 8 drive operators, batch-1024 amplitude sweep, RK4", 32, 8, 1024, 500, 2002)
+if "cfg5" in which: sweep("cfg5-like: dim-81 (4 three-level transmons), 8 channels, 8192 sweep points per GPU, RK4", 81, 8, 8192, 20, 2005)
+if "cfg4sweep" in which: sweep("cfg4 shape in sweep mode: dim-128, K=8, batch 4096", 128, 8, 4096, 20, 2004)
+
+if "cfg3" in which:
+    n, K, B = 27, 3, 4096
+    H0, Hs, Ls, Y, sig = orc.synthetic_lindblad(n, K, 6, B, 2003)
+    model = qd.LindbladModel(static_hamiltonian=H0, hamiltonian_operators=Hs, hamiltonian_signals=[qd.Signal(*s) for s in sig],
+                             static_dissipators=Ls, rotating_frame=np.diag(H0).real, vectorized=True)
+    y0 = qd.asarray(Y)
+    S = 4
+    def run(): return qd.solve_lmde(model, t_span=[0, S * 1e-2], y0=y0, method="scipy_expm", max_dt=1e-2)
+    ms = timeit(run, reps=3, warm=1)
+    m = n * n
+    apply_flops = S * 8 * m * m * B
+    print(json.dumps({"config": "cfg3: 3-transmon vectorised Lindblad dim 27 (729), 6 collapse ops, expm stepper, batch 4096",
+                      "n": m, "K": K, "B": B, "expm_steps": S, "ms": ms, "ms_per_step": ms / S, "steps_per_s": S / ms * 1e3,
+                      "column_steps_per_s": S * B / ms * 1e3, "apply_tflops_lower_bound": apply_flops / ms * 1e-9,
+                      "dmma_peak_tflops": peak}), flush=True)
+    A = torch.randn(m, m, dtype=torch.complex128, device="cuda"); A = (A - A.conj().T) * 0.01
+    Bm = torch.randn(m, B, dtype=torch.complex128, device="cuda"); C = torch.empty_like(Bm)
+    ms = timeit(lambda: abi.zgemm(A, Bm, out=C))
+    print(json.dumps({"kernel": "zgemm_kernel 729x4096x729", "ms": ms, "tflops": 8 * m * m * B / ms * 1e-9, "frac": 8 * m * m * B / ms * 1e-9 / peak}), flush=True)
+    ms = timeit(lambda: abi.zgemm(A, A))
+    print(json.dumps({"kernel": "zgemm_kernel 729^3", "ms": ms, "tflops": 8 * m ** 3 / ms * 1e-9, "frac": 8 * m ** 3 / ms * 1e-9 / peak}), flush=True)
+
+if "rhs" in which:
+    n, K, B = 128, 8, 4096
+    H0, Hs, Y, sig = orc.synthetic_schrodinger(n, K, B, 2004)
+    model = qd.HamiltonianModel(static_operator=H0, operators=Hs, signals=[qd.Signal(*s) for s in sig], rotating_frame=H0)
+    model.in_frame_basis = True
+    y = qd.asarray(Y)
+    ms = timeit(lambda: model(0.3, y), reps=20)
+    print(json.dumps({"config": "cfg4 single batched RHS call model(t, Y) (a4)", "ms": ms, "state_rhs_per_s": B / ms * 1e3,
+                      "tflops": B * (8 * n * n + 12 * n) / ms * 1e-9, "frac": B * (8 * n * n + 12 * n) / ms * 1e-9 / peak}), flush=True)

@@ -51,8 +51,8 @@ SIGNATURES = {
     "qdb_rk4_table_layout": (_i, [_i, _i]),
     "qdb_table_entry_bytes": (_sz, [_i, _i]),
     "qdb_rk4_tiling": (_i, [_i, _i, _i, _vp]),
-    "qdb_signal_table_f64": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, ctypes.c_longlong, _vp, _vp, _vp,
-                                  _vp]),
+    "qdb_signal_table_f64": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, ctypes.c_longlong, _vp, _vp, _d,
+                                  _vp, _vp]),
     "qdb_outcome_probabilities_f64": (_i, [_i, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "qdb_dmma_probe": (_i, [_vp, _i, _vp, _vp]),
     "qdb_expm_c128": (_i, [_i, _vp, _i, _vp, _vp, _sz, _vp]),
@@ -188,14 +188,23 @@ def zgemm(A, Bm, out=None, alpha=1.0 + 0j, beta=0.0 + 0j, colscale=None, pre=Non
     return out
 
 
+_rhs_ws_cache = {}
+
+
 def rhs(n, ops, stat, coeff, mu, t, y, per_col=False, out=None, workspace=None):
     """One fused RHS evaluation on y (n, B)."""
     K = 0 if ops is None else ops.shape[0]
     B = y.shape[1]
     if out is None:
         out = torch.empty_like(y)
-    need = workspace_bytes(WS_RHS, n, K, B)
-    if workspace is None or workspace.numel() < need:
+    if workspace is None:  # small (n^2 + 2n complex): keep one per (device, n) instead of allocating per call
+        key = (y.device, n)
+        workspace = _rhs_ws_cache.get(key)
+        if workspace is None:
+            workspace = torch.empty(workspace_bytes(WS_RHS, n, K, B), dtype=torch.uint8, device=y.device)
+            _rhs_ws_cache[key] = workspace
+    need = workspace.numel() if workspace.numel() >= (n * n + 2 * n + 64) * 16 else workspace_bytes(WS_RHS, n, K, B)
+    if workspace.numel() < need:
         workspace = torch.empty(need, dtype=torch.uint8, device=y.device)
     ldc = coeff.shape[-1] if (per_col and coeff is not None) else 0
     _check(lib().qdb_rhs_c128(n, K, B, _ptr(ops, C, "ops"), _ptr(stat, C, "stat"), _ptr(coeff, F, "coeff"),
@@ -279,21 +288,24 @@ def rk4_table_steps(n, table, h, y, S, layout=LAYOUT_PACKED):
 
 
 def signal_table(K, terms: dict, samples, times, B=0, col_stride=0, scale=None, out=None, params_per_col=False):
+    """``times``: float64 device tensor (T,), or a Python float (one time, no copy)."""
     """Coefficient table (T, K) (B == 0) or (T, K, B) of K channels from flattened term arrays on the device.
 
     ``terms``: dict of device tensors ``chan`` (int32), ``samp_off`` (int64), ``samp_len`` (int32), ``dt``, ``t0``,
     ``freq``, ``phase`` (float64), each of length nterms; ``samples``: complex128 sample storage."""
-    T = int(times.shape[0])
+    scalar = not isinstance(times, torch.Tensor)
+    T = 1 if scalar else int(times.shape[0])
     nterms = int(terms["chan"].shape[0])
     if out is None:
-        out = torch.empty((T, K) if B == 0 else (T, K, B), dtype=F, device=times.device)
+        out = torch.empty((T, K) if B == 0 else (T, K, B), dtype=F, device=samples.device)
     I32, I64 = torch.int32, torch.int64
     _check(lib().qdb_signal_table_f64(T, K, B, nterms, _ptr(terms["chan"], I32, "chan"), _ptr(terms["samp_off"], I64, "samp_off"),
                                       _ptr(terms["samp_len"], I32, "samp_len"), _ptr(terms["dt"], F, "dt"),
                                       _ptr(terms["t0"], F, "t0"), _ptr(terms["freq"], F, "freq"),
                                       _ptr(terms["phase"], F, "phase"), int(bool(params_per_col)), _ptr(samples, C, "samples"),
                                       int(col_stride),
-                                      _ptr(scale, C, "scale"), _ptr(times, F, "times"), _ptr(out, F, "out"), _stream()),
+                                      _ptr(scale, C, "scale"), None if scalar else _ptr(times, F, "times"),
+                                      float(times) if scalar else 0.0, _ptr(out, F, "out"), _stream()),
            "qdb_signal_table_f64")
     return out
 

@@ -39,8 +39,11 @@ def asarray(x, device=None) -> Optional[torch.Tensor]:
         return None
     device = default_device() if device is None else torch.device(device)
     if isinstance(x, torch.Tensor):
-        # resolve lazy conj/neg bits: raw device pointers cross the C-ABI
-        return x.to(device=device, dtype=CDTYPE).resolve_conj().resolve_neg().contiguous()
+        # resolve lazy conj/neg bits: raw device pointers cross the C-ABI.  A pinned host tensor is copied
+        # asynchronously on the current stream, so that the host goes on to build the step grid and the signal
+        # table while the state batch is in flight (every consumer is enqueued on the same stream).
+        nb = x.device.type == "cpu" and device.type == "cuda" and x.is_pinned()
+        return x.to(device=device, dtype=CDTYPE, non_blocking=nb).resolve_conj().resolve_neg().contiguous()
     if isinstance(x, (list, tuple)) and len(x) > 0 and isinstance(x[0], torch.Tensor):
         return torch.stack([asarray(e, device) for e in x]).contiguous()
     arr = np.asarray(x, dtype=complex) if not (isinstance(x, (list, tuple)) and len(x) and hasattr(x[0], "data") and not isinstance(x[0], np.ndarray)) \

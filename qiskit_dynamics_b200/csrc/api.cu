@@ -285,16 +285,17 @@ int qdb_rk4_table_steps_c128(int n, int B, int S, const qdb_c128* gen_table_pack
 int qdb_signal_table_f64(int T, int K, int B, int nterms, const int* chan, const long long* samp_off, const int* samp_len,
                          const double* dt, const double* t0, const double* freq, const double* phase, int params_per_col,
                          const qdb_c128* samples, long long samp_col_stride, const qdb_c128* scale, const double* times,
-                         double* out, void* stream) {
+                         double t_scalar, double* out, void* stream) {
     QDB_REQUIRE(T >= 0 && K >= 0 && B >= 0 && nterms >= 0, "qdb_signal_table_f64: bad T=%d K=%d B=%d nterms=%d", T, K, B, nterms);
     if (T == 0 || K == 0) return QDB_OK;
-    QDB_REQUIRE(times && out, "qdb_signal_table_f64: null times/out");
+    QDB_REQUIRE(out, "qdb_signal_table_f64: null out");
+    QDB_REQUIRE(times || T == 1, "qdb_signal_table_f64: times == NULL needs T == 1 (the time is t_scalar)");
     QDB_REQUIRE(nterms == 0 || (chan && samp_off && samp_len && dt && t0 && freq && phase && samples),
                 "qdb_signal_table_f64: null term array");
     QDB_REQUIRE(samp_col_stride >= 0, "qdb_signal_table_f64: negative column stride");
     QDB_REQUIRE(B > 0 || (!params_per_col && samp_col_stride == 0), "qdb_signal_table_f64: per-column inputs need B > 0");
     return launch_signal_table(T, K, B, nterms, chan, samp_off, samp_len, dt, t0, freq, phase, params_per_col, D2(samples), samp_col_stride,
-                               D2(scale), times, out, (cudaStream_t)stream);
+                               D2(scale), times, t_scalar, out, (cudaStream_t)stream);
 }
 
 int qdb_outcome_probabilities_f64(int n, int B, int n_out, const qdb_c128* y, int ldy, const int* outcome_of, int normalize,

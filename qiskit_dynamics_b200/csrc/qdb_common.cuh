@@ -119,7 +119,7 @@ int launch_rk4_fused_sweep(int n, int K, int B, int S, const double2* stat_packe
 int launch_signal_table(int T, int K, int B, int nterms, const int* chan, const long long* samp_off,
                         const int* samp_len, const double* dt, const double* t0, const double* freq,
                         const double* phase, int params_per_col, const double2* samples, long long col_stride,
-                        const double2* scale, const double* times, double* out, cudaStream_t st);
+                        const double2* scale, const double* times, double t_scalar, double* out, cudaStream_t st);
 int launch_outcome_probabilities(int n, int B, int n_out, const double2* y, int ldy, const int* outcome_of,
                                  int normalize, double* out, cudaStream_t st);
 int launch_axpby(size_t count, double2* dst, const double2* x, double a, const double2* y, double b,

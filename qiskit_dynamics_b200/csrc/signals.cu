@@ -47,12 +47,13 @@ struct SignalTerms {
 __global__ void __launch_bounds__(256) signal_table_kernel(int T, int K, int B, int nterms, SignalTerms tm,
                                                             const double2* __restrict__ samples, long long col_stride,
                                                             const double2* __restrict__ scale /*[nterms][B] or null*/,
-                                                            const double* __restrict__ times, double* __restrict__ out) {
+                                                            const double* __restrict__ times, double t_scalar,
+                                                            double* __restrict__ out) {
     const int ncol = B > 0 ? B : 1;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int t_idx = blockIdx.y;
     if (b >= ncol) return;
-    const double t = times[t_idx];
+    const double t = times ? times[t_idx] : t_scalar;
     double* o = out + ((size_t)t_idx * K) * ncol + b;
     for (int j = 0; j < K; ++j) o[(size_t)j * ncol] = 0.0;
     for (int i = 0; i < nterms; ++i) {
@@ -83,13 +84,13 @@ __global__ void __launch_bounds__(256) signal_table_kernel(int T, int K, int B, 
 
 int launch_signal_table(int T, int K, int B, int nterms, const int* chan, const long long* samp_off, const int* samp_len,
                         const double* dt, const double* t0, const double* freq, const double* phase, int params_per_col,
-                        const double2* samples, long long col_stride, const double2* scale, const double* times, double* out,
-                        cudaStream_t st) {
+                        const double2* samples, long long col_stride, const double2* scale, const double* times,
+                        double t_scalar, double* out, cudaStream_t st) {
     SignalTerms tm{chan, samp_off, samp_len, dt, t0, freq, phase, params_per_col};
     const int ncol = B > 0 ? B : 1;
     const int threads = ncol >= 256 ? 256 : (ncol >= 64 ? 64 : 32);
     dim3 grid((unsigned)((ncol + threads - 1) / threads), (unsigned)T);
-    signal_table_kernel<<<grid, threads, 0, st>>>(T, K, B, nterms, tm, samples, col_stride, scale, times, out);
+    signal_table_kernel<<<grid, threads, 0, st>>>(T, K, B, nterms, tm, samples, col_stride, scale, times, t_scalar, out);
     QDB_LAUNCH_CHECK("signal_table_kernel");
     return QDB_OK;
 }

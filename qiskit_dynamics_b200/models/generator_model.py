@@ -18,7 +18,7 @@ import torch
 from .. import _abi
 from ..arrays import asarray, asreal
 from ..exceptions import QiskitError
-from ..signals import Signal, SignalList
+from ..signals import Signal, SignalList, compile_signal_program
 from .operator_collections import OperatorCollection, _as_columns
 from .rotating_frame import RotatingFrame
 
@@ -141,6 +141,7 @@ class GeneratorModel(BaseGeneratorModel):
 
     @signals.setter
     def signals(self, signals: Union[SignalList, List[Signal], None]):
+        self._signal_program = False  # not compiled yet (None = compiled, not device-evaluable)
         if signals is None:
             self._signals = None
             return
@@ -167,6 +168,15 @@ class GeneratorModel(BaseGeneratorModel):
             return None
         self._require_signals()
         return self._signals.table(times)
+
+    def _device_coefficients(self, time, device):
+        """(1, K) signal values at one time, evaluated on the device when every term is a sampled or
+        constant-envelope signal (no host NumPy, no host-to-device copy); else None."""
+        if getattr(self, "_signal_program", False) is False:
+            self._signal_program = compile_signal_program(self._signals) if self._signals is not None else None
+        if self._signal_program is None or np.ndim(time) != 0:
+            return None
+        return self._signal_program.table(float(time), device)
 
     def _require_signals(self):
         if self._signals is None and self._operator_collection.operators is not None:
@@ -195,8 +205,10 @@ class GeneratorModel(BaseGeneratorModel):
         y2, restore = _as_columns(asarray(y))
         if y2.shape[0] != coll.dim:
             raise QiskitError(f"state has leading dimension {y2.shape[0]}, model dimension is {coll.dim}.")
-        sig = _signal_values(self._signals, time)
-        coeff = None if sig is None else asreal(sig, y2.device)
+        coeff = self._device_coefficients(time, y2.device)
+        if coeff is None:
+            sig = _signal_values(self._signals, time)
+            coeff = None if sig is None else asreal(sig, y2.device)
         if not self._in_frame_basis:
             y2 = self.rotating_frame.state_into_frame_basis(y2)
         out = _abi.rhs(coll.dim, coll.operators, coll.static_operator, coeff, self._frame_freqs(), float(time), y2)

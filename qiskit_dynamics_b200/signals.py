@@ -398,13 +398,16 @@ class SignalProgram:
         return self._dev
 
     def table(self, times, device):
-        """(T, K) -- or (T, K, B) for a per-column program -- float64 device tensor."""
+        """(T, K) -- or (T, K, B) for a per-column program -- float64 device tensor; a Python float gives T = 1."""
         import torch
 
         from . import _abi
 
         d = self.to_device(device)
-        times_dev = times if isinstance(times, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(times, dtype=np.float64)).to(device)
+        if np.ndim(times) == 0 and not isinstance(times, torch.Tensor):
+            times_dev = float(times)  # one time: passed by value
+        else:
+            times_dev = times if isinstance(times, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(times, dtype=np.float64)).to(device)
         stride = self.samples.shape[1] if self.samples_per_column else 0
         return _abi.signal_table(self.num_channels, d["terms"], d["samples"], times_dev, B=self.columns, col_stride=stride,
                                  params_per_col=self.params_per_column)
