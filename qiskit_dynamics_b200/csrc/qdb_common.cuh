@@ -122,6 +122,10 @@ int launch_signal_table(int T, int K, int B, int nterms, const int* chan, const 
                         const double2* scale, const double* times, double t_scalar, double* out, cudaStream_t st);
 int launch_outcome_probabilities(int n, int B, int n_out, const double2* y, int ldy, const int* outcome_of,
                                  int normalize, double* out, cudaStream_t st);
+bool rk4_sweep_small_supported(int n, int K, bool has_static);
+int launch_rk4_sweep_small(int n, int K, int B, int S, const double2* stat, const double2* ops, const double* coeff,
+                           int ldc, const double* mu, const double* times, double h, double2* y, int ldy,
+                           cudaStream_t st);
 int launch_axpby(size_t count, double2* dst, const double2* x, double a, const double2* y, double b,
                  cudaStream_t st);
 }  // namespace qdb

@@ -33,6 +33,7 @@
 #include <type_traits>
 
 #include "qdb_common.cuh"
+#include "rk4_device.cuh"
 
 namespace qdb {
 
@@ -47,11 +48,6 @@ struct Geometry {
 };
 
 // position of state element (row tile rt, row-in-tile g, column tile ct, column-in-tile cin) in the
-// B-fragment-ordered stage buffer: k-tile = 2 rt + g/4, fragment lane L = g%4 + 4 cin (bits: k0 k1 c0 c1 c2).
-// A 16 B shared access is served per quarter warp (8 lanes -> 8 distinct 16 B bank groups = slot mod 8):
-//   fragment load : the 8 lanes vary (k0, k1, c0);  epilogue store (C-fragment order, fixed i): (k0, c1, c2).
-// slot = L ^ ((L >> 2) & 6) sends (k0, k1^c1, c0^c2) to the bank bits: distinct in both cases.
-__device__ __forceinline__ int frag_swizzle(int L) { return L ^ ((L >> 2) & 6); }
 __device__ __forceinline__ int yin_pos(int NCT, int rt, int g, int ct, int cin) {
     const int kt = 2 * rt + (g >> 2);
     const int lane_b = (g & 3) + 4 * cin;
@@ -192,19 +188,6 @@ __device__ __forceinline__ void st_async_peer(const double2* p, const uint64_t* 
                  "d"(v.y), "r"(rb)
                  : "memory");
 }
-
-// RK4 stage combine shared by both kernels.  k-sum weights 1,2,2,1; next-input step h/2, h/2, h;
-// final update y + ((1/6) h) * ksum  (reference: fixed_step_solvers.py:60-73).
-struct StageCoef {
-    bool last;
-    double keep, wk, astep;
-    __device__ __forceinline__ StageCoef(int stage, double h) {
-        last = (stage == 3);
-        keep = stage == 0 ? 0.0 : 1.0;
-        wk = (stage == 1 || stage == 2) ? 2.0 : 1.0;
-        astep = stage < 2 ? 0.5 * h : (stage == 2 ? h : (1.0 / 6) * h);
-    }
-};
 
 // ------------------------------------------------------------------------------------------------
 // shared-signal mode
@@ -859,7 +842,11 @@ rk4_sweep_kernel(Geometry geo, int K, int B, int S, const double2* __restrict__ 
 
     const int has_static = stat != nullptr ? 1 : 0;
     const int J = K + has_static;  // operator passes per k-tile; pass 0 = static operator if present
-    const int total = KT * J;      // multiple of RING because KT is
+    // k-tiles that hold data: ceil(n / 4) <= KT.  The pass list (kt, j) is padded to a multiple of RING with passes
+    // over k-tile KTE, which exists and is all zero whenever KTE < KT (and KTE == KT makes KTE * J a multiple
+    // of RING already) -- n = 81 runs 21 k-tiles instead of the 24 the fragment ring is padded to.
+    const int KTE = (n + 3) >> 2;
+    const int total = (KTE * J + RING - 1) / RING * RING;
 
     size_t aoff[MR];
 #pragma unroll
@@ -871,13 +858,23 @@ rk4_sweep_kernel(Geometry geo, int K, int B, int S, const double2* __restrict__ 
 
     // ring primed with the first RING-1 (kt, j) passes; (pk, pj) = next pass to prefetch
     double2 ring[RING][MR];
-    int pk = 0, pj = 0;
+    int pk = 0, pj = 0, pit = 0;  // pit = index of the next prefetched pass within the stage
+    auto advance_prefetch = [&]() {
+        if (++pit == total) {
+            pit = 0;
+            pk = 0;
+            pj = 0;
+        } else if (++pj == J) {
+            pj = 0;
+            ++pk;
+        }
+    };
 #pragma unroll
     for (int u = 0; u < RING - 1; ++u) {
         const double2* src = a_src(pk, pj);
 #pragma unroll
         for (int m = 0; m < MR; ++m) ring[u][m] = __ldg(src + aoff[m]);
-        if (++pj == J) { pj = 0; if (++pk == KT) pk = 0; }
+        advance_prefetch();
     }
 
     int cur = 0;
@@ -907,7 +904,7 @@ rk4_sweep_kernel(Geometry geo, int K, int B, int S, const double2* __restrict__ 
                     const double2* src = a_src(pk, pj);
 #pragma unroll
                     for (int m = 0; m < MR; ++m) ring[(u + RING - 1) % RING][m] = __ldg(src + aoff[m]);
-                    if (++pj == J) { pj = 0; if (++pk == KT) pk = 0; }
+                    advance_prefetch();
                 }
                 if (j == 0) {
 #pragma unroll
@@ -941,21 +938,25 @@ rk4_sweep_kernel(Geometry geo, int K, int B, int S, const double2* __restrict__ 
         const StageCoef sc(stage, h);
         const int ydst = (cur ^ 1) * yin_elems;
 #pragma unroll
-        for (int m = 0; m < MR; ++m)
+        for (int m = 0; m < MR; ++m) {
+            double2 yv[NCW][2];  // all y-slab loads of the row tile ahead of its stores (see rk4_shared_kernel)
+#pragma unroll
+            for (int c = 0; c < NCW; ++c)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) yv[c][i] = sm[yst_off + ((m * NCW + c) * 2 + i) * nthr + tid];
 #pragma unroll
             for (int c = 0; c < NCW; ++c)
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const double2 k = cmul_conj_a(ph[m], make_double2(acc.re(m, c, i), acc.im(m, c, i)));
-                    const int slab = yst_off + ((m * NCW + c) * 2 + i) * nthr + tid;
-                    const double2 yv = sm[slab];
                     kr[m][c][i] = sc.keep * kr[m][c][i] + sc.wk * k.x;
                     ki[m][c][i] = sc.keep * ki[m][c][i] + sc.wk * k.y;
                     const double v_r = sc.last ? kr[m][c][i] : k.x, v_i = sc.last ? ki[m][c][i] : k.y;
-                    const double2 nxt = make_double2(yv.x + sc.astep * v_r, yv.y + sc.astep * v_i);
-                    if (sc.last) sm[slab] = nxt;
+                    const double2 nxt = make_double2(yv[c][i].x + sc.astep * v_r, yv[c][i].y + sc.astep * v_i);
+                    if (sc.last) sm[yst_off + ((m * NCW + c) * 2 + i) * nthr + tid] = nxt;
                     if (mvalid[m]) sm[ydst + yin_pos(NCT, rt[m], g, wc * NCW + c, 2 * q + i)] = cmul(ph_next[m], nxt);
                 }
+        }
 #pragma unroll
         for (int m = 0; m < MR; ++m) ph[m] = ph_next[m];
         acc.zero();
@@ -1340,6 +1341,9 @@ int rk4_fused_table_layout(int n, int B) {
 int launch_rk4_fused_sweep(int n, int K, int B, int S, const double2* stat_packed, const double2* ops_packed,
                            const double* coeff, int ldc,
                            const double* mu, const double* times_dev, double h, double2* y, int ldy, cudaStream_t st) {
+    // small operators: operators resident in shared memory, pre-scaled stage vectors, operator sum split over warps
+    if (rk4_sweep_small_supported(n, K, stat_packed != nullptr))
+        return launch_rk4_sweep_small(n, K, B, S, stat_packed, ops_packed, coeff, ldc, mu, times_dev, h, y, ldy, st);
     Config cfg;
     if (!pick_config(n, B, K > 0 ? K : 1, cfg)) {
         set_error("rk4 sweep: unsupported shape n=%d B=%d K=%d", n, B, K);

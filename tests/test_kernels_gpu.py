@@ -253,7 +253,19 @@ def test_generator_packed3m_layout(abi):
     assert torch.equal(b, abi.to_packed3m(a))
 
 
-@pytest.mark.parametrize("n,K,B,S,frame", [(32, 8, 48, 10, "full"), (5, 2, 3, 20, "diag"), (128, 8, 40, 3, "full"), (16, 2, 600, 4, "none")])
+@pytest.mark.parametrize("n,K,B,S,frame", [
+    (32, 8, 48, 10, "full"),    # cfg2 shape: small-operator kernel, 4 row warps x 2 operator groups
+    (5, 2, 3, 20, "diag"),      # one row tile, partial octet
+    (128, 8, 40, 3, "full"),    # generic kernel
+    (16, 2, 600, 4, "none"),    # two row tiles, 75 CTAs
+    (27, 3, 20, 6, "full"),     # padded rows inside 4 row tiles
+    (17, 5, 9, 5, "diag"),      # 3 row tiles, k padded to 32
+    (8, 1, 10, 8, "none"),      # single operator group
+    (12, 16, 5, 3, "full"),     # most operators the small kernel takes
+    (24, 17, 4, 2, "full"),     # one more: generic kernel
+    (81, 8, 24, 3, "full"),     # cfg5 dimension: 21 data k-tiles of 24 (padded pass list)
+    (50, 3, 16, 3, "diag"),     # 13 data k-tiles of 16
+])
 def test_rk4_fused_sweep(abi, n, K, B, S, frame):
     Gd, G, d, mu, y, specs = model_inputs(n, K, B, 99 + n, frame)
     t0, h = 0.0, 1e-3 if n >= 32 else 0.01
