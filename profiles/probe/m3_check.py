@@ -36,7 +36,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
                       "us_per_step": best * 1e3 / S, "alg_tflops": flops / best * 1e-9}))
 else:
     import torch
-    for n, B, S in ((128, 4096, 100), (128, 4096, 1000), (128, 512, 100), (64, 4096, 100), (100, 4096, 100), (200, 4096, 50), (128, 8192, 50)):
+    shapes = ((128, 4096, 100), (128, 4096, 1000), (128, 512, 100), (64, 4096, 100), (100, 4096, 100), (200, 4096, 50), (128, 8192, 50))
+    if len(sys.argv) > 1 and sys.argv[1] == "small":
+        shapes = ((128, 512, 200), (128, 256, 200), (100, 512, 200), (128, 64, 200))
+    for n, B, S in shapes:
         for m3 in ("0", "1"):
             env = dict(os.environ, QDB_3M=m3)
             r = subprocess.run([sys.executable, __file__, "child", str(n), str(B), str(S)], env=env, capture_output=True, text=True)

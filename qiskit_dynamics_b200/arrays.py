@@ -32,6 +32,17 @@ def default_device() -> torch.device:
     return torch.device("cpu")
 
 
+_pending_copies = []
+
+
+def wait_pending_copies() -> None:
+    """Block until every asynchronous pinned-host -> device copy issued by :func:`asarray` has completed.  The
+    solve entry points call this before returning, so a caller may overwrite its pinned input buffer as soon as
+    the solve call is back (the copy is long finished by then; the wait costs nothing)."""
+    while _pending_copies:
+        _pending_copies.pop().synchronize()
+
+
 def asarray(x, device=None) -> Optional[torch.Tensor]:
     """Anything array-like (numpy, nested lists, objects with __array__/.data, tensors) ->
     contiguous complex128 tensor on the compute device.  None passes through."""
@@ -43,7 +54,12 @@ def asarray(x, device=None) -> Optional[torch.Tensor]:
         # asynchronously on the current stream, so that the host goes on to build the step grid and the signal
         # table while the state batch is in flight (every consumer is enqueued on the same stream).
         nb = x.device.type == "cpu" and device.type == "cuda" and x.is_pinned()
-        return x.to(device=device, dtype=CDTYPE, non_blocking=nb).resolve_conj().resolve_neg().contiguous()
+        out = x.to(device=device, dtype=CDTYPE, non_blocking=nb).resolve_conj().resolve_neg().contiguous()
+        if nb:  # the caller's buffer must not be reused before the copy has landed: see wait_pending_copies
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(device))
+            _pending_copies.append(ev)
+        return out
     if isinstance(x, (list, tuple)) and len(x) > 0 and isinstance(x[0], torch.Tensor):
         return torch.stack([asarray(e, device) for e in x]).contiguous()
     arr = np.asarray(x, dtype=complex) if not (isinstance(x, (list, tuple)) and len(x) and hasattr(x[0], "data") and not isinstance(x[0], np.ndarray)) \

@@ -122,7 +122,7 @@ struct Frag3 {
     double s;   // re + im
 };
 template <int MR, int NCW, int MS, bool SPLIT>
-__device__ __forceinline__ void mma_block3(Accum<MR, NCW, true>& acc, Accum<MS, 1, true>& accs, const Frag3 (&a)[MR],
+__device__ __forceinline__ void mma_block3(Accum<MR, (NCW > 0 ? NCW : 1), true>& acc, Accum<MS, 1, true>& accs, const Frag3 (&a)[MR],
                                            const Frag3 (&a_s)[MS], const Frag3 (&b)[NCW + (SPLIT ? 1 : 0)]) {
 #pragma unroll
     for (int m = 0; m < MR; ++m)
@@ -483,9 +483,16 @@ rk4_shared3m_kernel(Geometry geo_rt, int B, int S, const double2* __restrict__ g
     static_assert(!SPLIT || MR % 2 == 0, "split mode halves the row tiles of the shared octet");
     typename std::conditional<(SKT > 0), StaticGeo3<MR, NCW, SPLIT, SKT>, Geometry>::type geo;
     if constexpr (SKT > 0) geo.n = geo_rt.n; else geo = geo_rt;
+    static_assert(NCW > 0 || SPLIT, "a CTA without own column tiles only exists in split mode");
     constexpr int MS = SPLIT ? MR / 2 : 1;
     constexpr int NB = NCW + (SPLIT ? 1 : 0);
     constexpr int SLOTS = (MR * NCW + (SPLIT ? MS : 0)) * 2;
+    // NCW == 0: pure row split -- the cluster owns ONE column octet, each CTA half of its rows (small batches:
+    // 64 octets keep 128 SMs busy instead of 64).  Only this rank's row tiles of A are streamed then, and the k-tiles
+    // are so short (3 DMMAs per warp) that the fragment ring is deepened to stay ahead of the L2 latency.
+    constexpr int NC1 = NCW > 0 ? NCW : 1;             // array extents
+    constexpr int MA = NCW > 0 ? MR : MS;              // row tiles of A a warp loads
+    constexpr int RG = (NCW == 0 && SKT > 0 && SKT % 8 == 0) ? 8 : RING;
     extern __shared__ __align__(16) double2 sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
@@ -570,11 +577,11 @@ rk4_shared3m_kernel(Geometry geo_rt, int B, int S, const double2* __restrict__ g
             }
     }
 
-    Accum<MR, NCW, true> acc;
+    Accum<MR, NC1, true> acc;
     acc.zero();
     Accum<MS, 1, true> accs;
     accs.zero();
-    double kr[MR][NCW][2], ki[MR][NCW][2];
+    double kr[MR][NC1][2], ki[MR][NC1][2];
 #pragma unroll
     for (int m = 0; m < MR; ++m)
 #pragma unroll
@@ -583,17 +590,20 @@ rk4_shared3m_kernel(Geometry geo_rt, int B, int S, const double2* __restrict__ g
 #pragma unroll
     for (int mm = 0; mm < MS; ++mm) ksr[mm][0] = ksr[mm][1] = ksi[mm][0] = ksi[mm][1] = 0.0;
 
-    size_t aoff[MR];
+    size_t aoff[MA];
 #pragma unroll
-    for (int m = 0; m < MR; ++m) aoff[m] = (size_t)rtl[m] * KT * 32 + lane;
+    for (int m = 0; m < MA; ++m) {
+        const int tile = NCW > 0 ? rtl[m] : (svalid[m % MS] ? rts[m % MS] : geo.RT - 1);
+        aoff[m] = (size_t)tile * KT * 32 + lane;
+    }
     // entry e: complex plane at gen + e * (3/2) entry_elems, sum plane right behind it
     const size_t entry_stride = entry_elems + entry_elems / 2;  // in double2 units (entry_elems is even)
 
-    Frag3 ring[RING][MR];
+    Frag3 ring[RG][MA];
 #pragma unroll
-    for (int u = 0; u < RING - 1; ++u)
+    for (int u = 0; u < RG - 1; ++u)
 #pragma unroll
-        for (int m = 0; m < MR; ++m) {
+        for (int m = 0; m < MA; ++m) {
             ring[u][m].c = ldg_stream(gen + aoff[m] + (size_t)u * 32);
             ring[u][m].s = ldg_stream_f64(reinterpret_cast<const double*>(gen + entry_elems) + aoff[m] + (size_t)u * 32);
         }
@@ -641,19 +651,19 @@ rk4_shared3m_kernel(Geometry geo_rt, int B, int S, const double2* __restrict__ g
         }
 
 #pragma unroll 1
-        for (int kt0 = 0; kt0 < KT; kt0 += RING) {
+        for (int kt0 = 0; kt0 < KT; kt0 += RG) {
 #pragma unroll
-            for (int u = 0; u < RING; ++u) {
+            for (int u = 0; u < RG; ++u) {
                 const int kt = kt0 + u;
                 {
-                    const int ktn = kt + RING - 1;
+                    const int ktn = kt + RG - 1;
                     const double2* ebase = ktn < KT ? gcur : gnxt;  // entry the fragment comes from
                     const size_t koff = (size_t)(ktn < KT ? ktn : ktn - KT) * 32;
                     const double* sbase = reinterpret_cast<const double*>(ebase + entry_elems);
 #pragma unroll
-                    for (int m = 0; m < MR; ++m) {
-                        ring[(u + RING - 1) % RING][m].c = ldg_stream(ebase + koff + aoff[m]);
-                        ring[(u + RING - 1) % RING][m].s = ldg_stream_f64(sbase + koff + aoff[m]);
+                    for (int m = 0; m < MA; ++m) {
+                        ring[(u + RG - 1) % RG][m].c = ldg_stream(ebase + koff + aoff[m]);
+                        ring[(u + RG - 1) % RG][m].s = ldg_stream_f64(sbase + koff + aoff[m]);
                     }
                 }
                 {
@@ -669,11 +679,18 @@ rk4_shared3m_kernel(Geometry geo_rt, int B, int S, const double2* __restrict__ g
                     }
                 }
                 Frag3 a_s[MS];
-                if constexpr (SPLIT) {
+                if constexpr (NCW == 0) {
+                    Frag3 a_none[MR];  // no own tiles: never read
 #pragma unroll
-                    for (int mm = 0; mm < MS; ++mm) a_s[mm] = rank ? ring[u][MS + mm] : ring[u][mm];
+                    for (int mm = 0; mm < MS; ++mm) a_s[mm] = ring[u][mm];
+                    mma_block3<MR, NCW, MS, SPLIT>(acc, accs, a_none, a_s, bfrag[u & 1]);
+                } else {
+                    if constexpr (SPLIT) {
+#pragma unroll
+                        for (int mm = 0; mm < MS; ++mm) a_s[mm] = rank ? ring[u][MS + mm] : ring[u][mm];
+                    }
+                    mma_block3<MR, NCW, MS, SPLIT>(acc, accs, ring[u], a_s, bfrag[u & 1]);
                 }
-                mma_block3<MR, NCW, MS, SPLIT>(acc, accs, ring[u], a_s, bfrag[u & 1]);
             }
         }
 
@@ -708,10 +725,10 @@ rk4_shared3m_kernel(Geometry geo_rt, int B, int S, const double2* __restrict__ g
         }
         // own tiles: combine into registers first (the accumulators die here), then wait until every warp has
         // finished reading the single-buffered stage planes, then overwrite them
-        double2 nx[MR][NCW][2];
+        double2 nx[MR][NC1][2];
 #pragma unroll
         for (int m = 0; m < MR; ++m) {
-            double2 yv[NCW][2];
+            double2 yv[NC1][2];
 #pragma unroll
             for (int c = 0; c < NCW; ++c)
 #pragma unroll
@@ -1172,6 +1189,7 @@ bool pick_config3m(int n, int B, Config& cfg, double* cost_out) {
         consider(NCW, false);
         if (allow_split) consider(NCW, true);
     }
+    if (allow_split) consider(0, true);  // pure row split: one octet per cluster (small batches)
     if (found && cost_out) *cost_out = best;
     return found;
 }
@@ -1293,6 +1311,8 @@ int launch_rk4_fused_shared(int n, int B, int S, const double2* gen_table, int t
         const bool static128 = cfg.geo.KT == 32 && cfg.geo.RT == 16 && cfg.geo.npad == 128;
         if (cfg.split) {
             if (static128) QDB_DISPATCH(2, 3, (launch_3m_t<2, 3, true, 32>(ARGS)));
+            if (static128) QDB_DISPATCH(2, 0, (launch_3m_t<2, 0, true, 32>(ARGS)));
+            QDB_DISPATCH(2, 0, (launch_3m_t<2, 0, true, 0>(ARGS)));
             QDB_DISPATCH(2, 1, (launch_3m_t<2, 1, true, 0>(ARGS)));
             QDB_DISPATCH(2, 2, (launch_3m_t<2, 2, true, 0>(ARGS)));
             QDB_DISPATCH(2, 3, (launch_3m_t<2, 3, true, 0>(ARGS)));

@@ -16,7 +16,7 @@ import torch
 from scipy.integrate._ivp.ivp import OdeResult
 
 from .. import _abi
-from ..arrays import asarray
+from ..arrays import asarray, wait_pending_copies
 from ..exceptions import QiskitError
 from ..models import BaseGeneratorModel, GeneratorModel, LindbladModel
 from .fixed_step import RK4_solver, expm_model_solve, rk4_model_solve, scipy_expm_solver
@@ -104,6 +104,7 @@ def solve_ode(rhs: Union[Callable, BaseGeneratorModel], t_span, y0, method="RK4"
             results.y = results_y_out_of_frame_basis(rhs, results.y, y0.ndim)
     finally:
         rhs.in_frame_basis = was_in_frame_basis
+        wait_pending_copies()
     return results
 
 
@@ -136,4 +137,5 @@ def solve_lmde(generator: Union[Callable, BaseGeneratorModel], t_span, y0, metho
             results.y = results_y_out_of_frame_basis(generator, results.y, y0.ndim)
     finally:
         generator.in_frame_basis = was_in_frame_basis
+        wait_pending_copies()
     return results

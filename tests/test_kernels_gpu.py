@@ -206,7 +206,10 @@ def test_rk4_split_clusters_bit_identical(abi, n, B, S):
     (128, 4000, 2),   # ragged batch
     (121, 3001, 2),   # same tiling, padded rows
     (100, 2500, 2),   # dynamic geometry, split, rank 1 owns 5 of 8 shared row tiles
-    (128, 512, 2),    # whole-column CTAs, one column tile per warp
+    (128, 512, 2),    # pure row split: one octet per 2-CTA cluster, deep fragment ring (static geometry)
+    (100, 300, 2),    # pure row split, dynamic geometry, rank 1 owns 5 of 8 row tiles
+    (128, 5, 3),      # a single partial octet
+    (128, 1024, 2),   # whole-column CTAs, one column tile per warp
     (64, 4096, 2),    # one row tile per warp
     (72, 100, 2),     # 9 row tiles on 8 row warps
     (57, 300, 2),     # smallest dimension the 3-product kernel takes
