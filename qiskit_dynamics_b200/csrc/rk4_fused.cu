@@ -159,26 +159,6 @@ __device__ __forceinline__ unsigned cluster_ctarank() {
 __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// mbarrier plumbing for the per-stage DSMEM exchange: the producer's st.async carries its own completion
-// (complete_tx on the CONSUMER's mbarrier), so no cluster-wide barrier or memory fence sits in the stage loop.
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(a), "r"(parity)
-        : "memory");
-}
 // 16 B into the peer CTA's shared memory at the offset of local pointer p, completing on the peer's copy of bar
 __device__ __forceinline__ void st_async_peer(const double2* p, const uint64_t* bar, unsigned peer, double2 v) {
     uint32_t rp, rb;

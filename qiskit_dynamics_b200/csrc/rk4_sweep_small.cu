@@ -7,7 +7,8 @@
 // SM a single column octet, i.e. four warps (ncu: tensor pipe 27 %, 'wait' + 'selected' 68 % of the stall samples).
 // This kernel restructures the same arithmetic for that regime:
 //   * all K+1 operators are staged ONCE per launch into shared memory in DMMA A-fragment order (147 KiB at
-//     n = 32, K = 8) -- the A operand is an LDS.128 at an immediate offset;
+//     n = 32, K = 8) by TMA bulk copies (cp.async.bulk -> one mbarrier) -- the A operand is an LDS.128 at an
+//     immediate offset;
 //   * per-column signal values scale the STAGE VECTOR, not the fragment: the epilogue writes K+1 scaled copies
 //     z_j = c_j[col] * u (one per operator; 36 KiB) so that the k loop is LDS + DMMA only -- the generic kernel
 //     re-scales every B fragment once per row warp with DMULs that compete with the DMMAs for the fp64 pipe;
@@ -48,12 +49,21 @@ rk4_sweep_small_kernel(int n, int K, int B, int S, const double2* __restrict__ s
     const bool framed = (mu != nullptr);
     const bool owner = (js == 0);              // owner warps hold y / k-sum and run the epilogue
 
-    // ---- stage the operators (static first) ----
-    for (int idx = tid; idx < J * ENTRY; idx += NTHR) {
-        const int j = idx / ENTRY, e = idx - j * ENTRY;
-        ops_s[idx] = (has_static && j == 0) ? stat[e] : ops[(size_t)(j - has_static) * ENTRY + e];
+    // ---- stage the operators (static first): one TMA bulk copy per operator, all counted on one mbarrier ----
+    uint64_t* tma_bar = reinterpret_cast<uint64_t*>(part + (JS - 1) * RT * 64);
+    if (tid == 0) {
+        mbar_init(tma_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int idx = tid; idx < J * KT * 32; idx += NTHR) z[idx] = make_double2(0.0, 0.0);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(tma_bar, (unsigned)(J * ENTRY * sizeof(double2)));
+        for (int j = 0; j < J; ++j)
+            tma_bulk_g2s(ops_s + (size_t)j * ENTRY, (has_static && j == 0) ? stat : ops + (size_t)(j - has_static) * ENTRY,
+                         (unsigned)(ENTRY * sizeof(double2)), tma_bar);
+    }
+    for (int idx = tid; idx < J * KT * 32; idx += NTHR) z[idx] = make_double2(0.0, 0.0);  // overlaps the copies
+    mbar_wait(tma_bar, 0);
     __syncthreads();
 
     // ---- this thread's two state elements: row 8 rt + g, columns col0 + 2q + i ----
@@ -201,7 +211,8 @@ bool pick_small(int n, int K, bool has_static, SmallCfg& c) {
     const int J = K + (has_static ? 1 : 0);
     int JS = RT <= 2 ? 4 : 2;
     while (JS > J) JS /= 2;
-    const size_t smem = ((size_t)J * 32 * RT * KT + (size_t)J * KT * 32 + (size_t)(JS - 1) * RT * 64) * sizeof(double2);
+    const size_t smem = ((size_t)J * 32 * RT * KT + (size_t)J * KT * 32 + (size_t)(JS - 1) * RT * 64) * sizeof(double2) +
+                        16 /*mbarrier*/;
     if (smem > 227 * 1024) return false;
     c.RT = RT;
     c.JS = JS;

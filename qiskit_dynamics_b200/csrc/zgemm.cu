@@ -1,23 +1,28 @@
 // General complex128 GEMM on the fp64 tensor pipe (DMMA m8n8k4), with the fused pro/epilogues of
 // the hot path.
 //
-// CTA tile 64 x 64, k-chunk 16, 8 warps as 4 (rows) x 2 (cols); each warp owns a 16 x 32 complex
-// tile = 2 x 4 DMMA tiles, i.e. 32 real DMMAs per k4-step fed by 2 + 4 LDS.128 -- the DMMA pipe
-// (16 issue cycles per DMMA per SM sub-partition) is the bound, not shared memory.
+// CTA tile 64 x BN (BN = 64 or 32), k-chunk 16, 8 warps as 4 (rows) x 2 (cols); each warp owns a 16 x BN/2
+// complex tile = 2 x BN/16 DMMA tiles, i.e. 32 (16) real DMMAs per k4-step fed by 2 + 4 (2 + 2) LDS.128 -- the
+// DMMA pipe (16 issue cycles per DMMA per SM sub-partition) is the bound, not shared memory.
 // Operand tiles are staged with a 3-deep cp.async ring; rows are padded so that every fragment
 // load is bank-conflict free (A stride = 64 mod 128 B, B stride = 32 mod 128 B).
+// Two CTAs fit an SM: the narrow tile is chosen when the 64 x 64 grid would leave half of those 296 slots
+// empty (the 729^3 products of the vectorised-Lindblad expm: 144 CTAs -> 276).
 #include "qdb_common.cuh"
 
 namespace qdb {
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16, STAGES = 3;
+constexpr int BM = 64, BK = 16, STAGES = 3;
 constexpr int A_LD = BK + 4;   // complex elements per smem row of A  (320 B)
-constexpr int B_LD = BN + 2;   // complex elements per smem row of B  (1056 B)
 constexpr int A_TILE = BM * A_LD;
-constexpr int B_TILE = BK * B_LD;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * (A_TILE + B_TILE) * sizeof(double2);
+template <int BN>
+struct TileB {
+    static constexpr int LD = BN + 2;  // complex elements per smem row of B  (1056 B / 544 B: 32 mod 128 B)
+    static constexpr int TILE = BK * LD;
+    static constexpr size_t SMEM = (size_t)STAGES * (A_TILE + TILE) * sizeof(double2);
+};
 
 struct EpiStd {
     double2* C;
@@ -63,10 +68,12 @@ __device__ __forceinline__ void epilogue(const EpiRk4& e, int r, int c, double2 
     e.acc[i] = a;
 }
 
-template <typename Epi>
+template <typename Epi, int BN>
 __global__ void __launch_bounds__(256) zgemm_kernel(int M, int N, int Kd, const double2* __restrict__ A, int lda,
                                                      const double2* __restrict__ Bm, int ldb,
                                                      const double2* __restrict__ pre, Epi epi) {
+    constexpr int B_LD = TileB<BN>::LD, B_TILE = TileB<BN>::TILE;
+    constexpr int NC = BN / 16;  // column tiles per warp
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* sA = reinterpret_cast<double2*>(smem_raw);
     double2* sB = sA + STAGES * A_TILE;
@@ -99,11 +106,11 @@ __global__ void __launch_bounds__(256) zgemm_kernel(int M, int N, int Kd, const 
         }
     };
 
-    double cr[2][4][2], ci[2][4][2];
+    double cr[2][NC][2], ci[2][NC][2];
 #pragma unroll
     for (int m = 0; m < 2; ++m)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) cr[m][c][0] = cr[m][c][1] = ci[m][c][0] = ci[m][c][1] = 0.0;
+        for (int c = 0; c < NC; ++c) cr[m][c][0] = cr[m][c][1] = ci[m][c][0] = ci[m][c][1] = 0.0;
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
@@ -120,14 +127,14 @@ __global__ void __launch_bounds__(256) zgemm_kernel(int M, int N, int Kd, const 
             cp_async_commit();
         }
         const double2* a_s = sA + (kt % STAGES) * A_TILE + (wm * 16 + g) * A_LD + q;
-        const double2* b_s = sB + (kt % STAGES) * B_TILE + q * B_LD + wn * 32 + g;
+        const double2* b_s = sB + (kt % STAGES) * B_TILE + q * B_LD + wn * (BN / 2) + g;
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
-            double2 a[2], b[4];
+            double2 a[2], b[NC];
 #pragma unroll
             for (int m = 0; m < 2; ++m) a[m] = a_s[m * 8 * A_LD + kk * 4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) b[c] = b_s[kk * 4 * B_LD + c * 8];
+            for (int c = 0; c < NC; ++c) b[c] = b_s[kk * 4 * B_LD + c * 8];
             if (pre != nullptr) {
                 const int k = kt * BK + kk * 4 + q;
                 const double2 p = k < Kd ? pre[k] : make_double2(0.0, 0.0);
@@ -140,14 +147,14 @@ __global__ void __launch_bounds__(256) zgemm_kernel(int M, int N, int Kd, const 
 #pragma unroll
             for (int m = 0; m < 2; ++m)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < NC; ++c) {
                     dmma(cr[m][c][0], cr[m][c][1], a[m].x, b[c].x);
                     dmma(ci[m][c][0], ci[m][c][1], a[m].x, b[c].y);
                 }
 #pragma unroll
             for (int m = 0; m < 2; ++m)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < NC; ++c) {
                     dmma(cr[m][c][0], cr[m][c][1], nai[m], b[c].y);
                     dmma(ci[m][c][0], ci[m][c][1], a[m].y, b[c].x);
                 }
@@ -160,27 +167,46 @@ __global__ void __launch_bounds__(256) zgemm_kernel(int M, int N, int Kd, const 
         const int r = m0 + wm * 16 + m * 8 + g;
         if (r >= M) continue;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < NC; ++c)
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                const int col = n0 + wn * 32 + c * 8 + 2 * q + i;
+                const int col = n0 + wn * (BN / 2) + c * 8 + 2 * q + i;
                 if (col < N) epilogue(epi, r, col, make_double2(cr[m][c][i], ci[m][c][i]));
             }
     }
 }
 
-template <typename Epi>
-int launch(int M, int N, int Kd, const double2* A, int lda, const double2* B, int ldb, const double2* pre,
-           const Epi& epi, cudaStream_t st) {
+int sm_count_zg() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0, v = 0;
+        sms = (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+               v > 0) ? v : 148;
+    }
+    return sms;
+}
+
+template <typename Epi, int BN>
+int launch_bn(int M, int N, int Kd, const double2* A, int lda, const double2* B, int ldb, const double2* pre,
+              const Epi& epi, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        QDB_CUDA(cudaFuncSetAttribute(zgemm_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        QDB_CUDA(cudaFuncSetAttribute(zgemm_kernel<Epi, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileB<BN>::SMEM));
         configured = true;
     }
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-    zgemm_kernel<Epi><<<grid, 256, SMEM_BYTES, st>>>(M, N, Kd, A, lda, B, ldb, pre, epi);
+    zgemm_kernel<Epi, BN><<<grid, 256, TileB<BN>::SMEM, st>>>(M, N, Kd, A, lda, B, ldb, pre, epi);
     QDB_LAUNCH_CHECK("zgemm_kernel");
     return QDB_OK;
+}
+
+template <typename Epi>
+int launch(int M, int N, int Kd, const double2* A, int lda, const double2* B, int ldb, const double2* pre,
+           const Epi& epi, cudaStream_t st) {
+    // 64 x 64 tiles unless they would fill fewer than the 2 CTA slots per SM
+    const long ctas64 = (long)((N + 63) / 64) * ((M + BM - 1) / BM);
+    if (ctas64 < 2L * sm_count_zg() && N > 32) return launch_bn<Epi, 32>(M, N, Kd, A, lda, B, ldb, pre, epi, st);
+    return launch_bn<Epi, 64>(M, N, Kd, A, lda, B, ldb, pre, epi, st);
 }
 
 }  // namespace

@@ -95,6 +95,42 @@ def test_full_size_independent_paths_agree(qd, headline):
     assert torch.equal(y4, y1)
 
 
+def test_cfg2_full_size_sweep_paths_agree(qd):
+    """cfg2 at full size (dim 32, 8 drive operators, 1024-point amplitude sweep, 1000 RK4 steps): the small-operator
+    sweep kernel against the generic sweep kernel (independent code: operators in shared memory + pre-scaled planes
+    vs streamed operators + per-fragment scaling), unitarity, and -- for the columns whose amplitude scale is 1 --
+    against the shared-signal kernels."""
+    import os
+    abi = qd._abi
+    from qiskit_dynamics_b200.solvers import stage_time_grid
+    n, K, B, S, h = 32, 8, 1024, 1000, 1e-3
+    H0, Hs, Y, sig = orc.synthetic_schrodinger(n, K, 1, 2002)
+    m = qd.HamiltonianModel(static_operator=H0, operators=Hs, signals=[qd.Signal(*s) for s in sig], rotating_frame=H0)
+    coll, mu = m._collection(), m._frame_freqs()
+    ops_p, stat_p = coll.packed()
+    times = stage_time_grid(0.0, h, S)
+    base = torch.from_numpy(m._signal_table(times)).cuda()
+    amp = torch.from_numpy(0.5 + np.arange(B) / B).cuda()
+    amp[7] = 1.0
+    amp[B - 3] = 1.0
+    coeff = (base[:, :, None] * amp[None, None, :]).contiguous()
+    y0 = m.rotating_frame.state_into_frame_basis(qd.asarray(np.repeat(Y, B, axis=1)))
+    assert abi.rk4_tiling(n, B, K)  # shape is served by the on-chip path
+    y_small = y0.clone()
+    abi.rk4_steps(n, coll.operators, coll.static_operator, ops_p, stat_p, coeff, mu, times, h, y_small, S, per_col=True)
+    os.environ["QDB_NO_SMALL_SWEEP"] = "1"
+    try:
+        y_gen = y0.clone()
+        abi.rk4_steps(n, coll.operators, coll.static_operator, ops_p, stat_p, coeff, mu, times, h, y_gen, S, per_col=True)
+    finally:
+        os.environ.pop("QDB_NO_SMALL_SWEEP", None)
+    assert col_err(y_small, y_gen) < 1e-12
+    assert float((torch.linalg.vector_norm(y_small, dim=0) - 1).abs().max()) < 1e-11
+    y_sh = y0[:, :8].clone()
+    abi.rk4_steps(n, coll.operators, coll.static_operator, ops_p, stat_p, base.contiguous(), mu, times, h, y_sh, S)
+    assert col_err(y_small[:, [7, B - 3]], y_sh[:, :2]) < 1e-12
+
+
 def test_vectorized_lindblad_full_dimension_properties(qd):
     """cfg3 dimension (n=27 -> 729), expm stepper: trace preservation and Hermiticity of rho."""
     n, K, B = 27, 3, 64
