@@ -587,6 +587,13 @@ rk4_shared3m_kernel(Geometry geo_rt, int B, int S, const double2* __restrict__ g
             ring[u][m].c = ldg_stream(gen + aoff[m] + (size_t)u * 32);
             ring[u][m].s = ldg_stream_f64(reinterpret_cast<const double*>(gen + entry_elems) + aoff[m] + (size_t)u * 32);
         }
+    const double2* pc[MA];  // running prefetch pointers: next fragment of the complex / sum plane
+    const double* ps[MA];
+#pragma unroll
+    for (int m = 0; m < MA; ++m) {
+        pc[m] = gen + aoff[m] + (RG - 1) * 32;
+        ps[m] = reinterpret_cast<const double*>(gen + entry_elems) + aoff[m] + (RG - 1) * 32;
+    }
 
     int cur = 0;
     unsigned tx_bytes = 0;
@@ -611,7 +618,6 @@ rk4_shared3m_kernel(Geometry geo_rt, int B, int S, const double2* __restrict__ g
         const int entry = 2 * step + (stage == 0 ? 0 : (stage == 3 ? 2 : 1));
         const int nstage = (stage + 1) & 3, nstep = step + (stage == 3 ? 1 : 0);
         const int nentry = (sidx + 1 < total_stages) ? 2 * nstep + (nstage == 0 ? 0 : (nstage == 3 ? 2 : 1)) : entry;
-        const double2* gcur = gen + (size_t)entry * entry_stride;
         const double2* gnxt = gen + (size_t)nentry * entry_stride;
         const double2* bc = own_c + ct0 * 32 + swl;
         const double* bs = own_s + ct0 * 32 + swl;
@@ -630,32 +636,43 @@ rk4_shared3m_kernel(Geometry geo_rt, int B, int S, const double2* __restrict__ g
             bfrag[0][NCW].s = shs[0];
         }
 
-#pragma unroll 1
-        for (int kt0 = 0; kt0 < KT; kt0 += RG) {
+        // k loop in blocks of RG k-tiles.  The fragment ring runs RG-1 k-tiles ahead through running pointers
+        // (pc / ps: next fragment of the complex / sum plane); only the LAST block of a stage crosses into the next
+        // table entry, so it is peeled and the steady blocks carry no entry-selection arithmetic at all.
+        const double2* nc = gnxt;                                                // next entry, complex plane
+        const double* ns = reinterpret_cast<const double*>(gnxt + entry_elems);  // next entry, sum plane
+        auto k_block = [&](auto last_tag, int kt0) {
+            constexpr bool LAST = decltype(last_tag)::value;
+            const double2* bck = bc + (size_t)kt0 * NCO * 32;
+            const double* bsk = bs + (size_t)kt0 * NCO * 32;
+            const double2* shck = shc + kt0 * 32;
+            const double* shsk = shs + kt0 * 32;
 #pragma unroll
             for (int u = 0; u < RG; ++u) {
-                const int kt = kt0 + u;
-                {
-                    const int ktn = kt + RG - 1;
-                    const double2* ebase = ktn < KT ? gcur : gnxt;  // entry the fragment comes from
-                    const size_t koff = (size_t)(ktn < KT ? ktn : ktn - KT) * 32;
-                    const double* sbase = reinterpret_cast<const double*>(ebase + entry_elems);
+                if (!LAST || u == 0) {  // fragment kt + RG-1 of this entry
 #pragma unroll
                     for (int m = 0; m < MA; ++m) {
-                        ring[(u + RG - 1) % RG][m].c = ldg_stream(ebase + koff + aoff[m]);
-                        ring[(u + RG - 1) % RG][m].s = ldg_stream_f64(sbase + koff + aoff[m]);
+                        ring[(u + RG - 1) % RG][m].c = ldg_stream(pc[m]);
+                        ring[(u + RG - 1) % RG][m].s = ldg_stream_f64(ps[m]);
+                        pc[m] += 32;
+                        ps[m] += 32;
+                    }
+                } else {  // fragments 0 .. RG-2 of the next entry
+#pragma unroll
+                    for (int m = 0; m < MA; ++m) {
+                        ring[(u + RG - 1) % RG][m].c = ldg_stream(nc + aoff[m] + (u - 1) * 32);
+                        ring[(u + RG - 1) % RG][m].s = ldg_stream_f64(ns + aoff[m] + (u - 1) * 32);
                     }
                 }
-                {
-                    const int ktb = min(kt + 1, KT - 1);
+                if (!LAST || u + 1 < RG) {  // B fragments of k-tile kt + 1 (none after the last k-tile of the stage)
 #pragma unroll
                     for (int c = 0; c < NCW; ++c) {
-                        bfrag[(u + 1) & 1][c].c = bc[(ktb * NCO + c) * 32];
-                        bfrag[(u + 1) & 1][c].s = bs[(ktb * NCO + c) * 32];
+                        bfrag[(u + 1) & 1][c].c = bck[((u + 1) * NCO + c) * 32];
+                        bfrag[(u + 1) & 1][c].s = bsk[((u + 1) * NCO + c) * 32];
                     }
                     if constexpr (SPLIT) {
-                        bfrag[(u + 1) & 1][NCW].c = shc[ktb * 32];
-                        bfrag[(u + 1) & 1][NCW].s = shs[ktb * 32];
+                        bfrag[(u + 1) & 1][NCW].c = shck[(u + 1) * 32];
+                        bfrag[(u + 1) & 1][NCW].s = shsk[(u + 1) * 32];
                     }
                 }
                 Frag3 a_s[MS];
@@ -672,6 +689,14 @@ rk4_shared3m_kernel(Geometry geo_rt, int B, int S, const double2* __restrict__ g
                     mma_block3<MR, NCW, MS, SPLIT>(acc, accs, ring[u], a_s, bfrag[u & 1]);
                 }
             }
+        };
+#pragma unroll 1
+        for (int kt0 = 0; kt0 < KT - RG; kt0 += RG) k_block(std::false_type{}, kt0);
+        k_block(std::true_type{}, KT - RG);
+#pragma unroll
+        for (int m = 0; m < MA; ++m) {  // the ring now holds fragments 0 .. RG-2 of the next entry
+            pc[m] = nc + aoff[m] + (RG - 1) * 32;
+            ps[m] = ns + aoff[m] + (RG - 1) * 32;
         }
 
         // ---- epilogue ----
