@@ -43,6 +43,34 @@ def wait_pending_copies() -> None:
         _pending_copies.pop().synchronize()
 
 
+_pinned_staging = {}
+_staging_event = {}
+
+
+def stage_to_device(values: np.ndarray, device) -> torch.Tensor:
+    """Small float64 host array -> device through a cached pinned staging buffer, without blocking the host
+    (``torch.from_numpy(x).to(device)`` from pageable memory synchronises the stream).  The buffer is reused by the
+    next call, which is safe because the solve entry points wait for the copy event before they return."""
+    device = torch.device(device)
+    values = np.ascontiguousarray(values, dtype=np.float64).reshape(-1)
+    if device.type != "cuda":
+        return torch.from_numpy(values.copy()).to(device)
+    prev = _staging_event.get(device)  # the staging buffer may still be the source of the previous grid's copy
+    if prev is not None:
+        prev.synchronize()
+    buf = _pinned_staging.get(device)
+    if buf is None or buf.numel() < values.size:
+        buf = torch.empty(max(values.size, 4096), dtype=torch.float64).pin_memory()
+        _pinned_staging[device] = buf
+    buf[: values.size].copy_(torch.from_numpy(values))
+    out = buf[: values.size].to(device, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(device))
+    _staging_event[device] = ev
+    _pending_copies.append(ev)
+    return out
+
+
 def asarray(x, device=None) -> Optional[torch.Tensor]:
     """Anything array-like (numpy, nested lists, objects with __array__/.data, tensors) ->
     contiguous complex128 tensor on the compute device.  None passes through."""

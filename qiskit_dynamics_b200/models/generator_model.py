@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from .. import _abi
-from ..arrays import asarray, asreal
+from ..arrays import asarray, asreal, stage_to_device
 from ..exceptions import QiskitError
 from ..signals import Signal, SignalList, compile_signal_program
 from .operator_collections import OperatorCollection, _as_columns
@@ -169,14 +169,31 @@ class GeneratorModel(BaseGeneratorModel):
         self._require_signals()
         return self._signals.table(times)
 
+    def _program(self):
+        """Device program of the current signals (compiled once per assignment), or None when a term is an
+        arbitrary Python envelope."""
+        if getattr(self, "_signal_program", False) is False:
+            self._signal_program = compile_signal_program(self._signals) if self._signals is not None else None
+        return self._signal_program
+
     def _device_coefficients(self, time, device):
         """(1, K) signal values at one time, evaluated on the device when every term is a sampled or
         constant-envelope signal (no host NumPy, no host-to-device copy); else None."""
-        if getattr(self, "_signal_program", False) is False:
-            self._signal_program = compile_signal_program(self._signals) if self._signals is not None else None
-        if self._signal_program is None or np.ndim(time) != 0:
+        prog = self._program()
+        if prog is None or np.ndim(time) != 0:
             return None
-        return self._signal_program.table(float(time), device)
+        return prog.table(float(time), device)
+
+    def _signal_table_device(self, times: np.ndarray, device):
+        """(T, K) table on a time grid built by the device signal kernel (row f3), or None: the host then falls
+        back to :meth:`_signal_table`.  The grid goes up through a pinned staging buffer, asynchronously, so that
+        the generator and stepper launches are enqueued while the state batch is still in flight."""
+        if self._operator_collection.operators is None:
+            return None
+        prog = self._program()
+        if prog is None:
+            return None
+        return prog.table(stage_to_device(times, device), device)
 
     def _require_signals(self):
         if self._signals is None and self._operator_collection.operators is not None:

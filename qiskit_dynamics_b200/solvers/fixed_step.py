@@ -141,8 +141,10 @@ def rk4_model_solve(model, t_span, y0_fb: torch.Tensor, max_dt, t_eval=None,
                     ws = torch.empty(need, dtype=torch.uint8, device=y.device)
                 _abi.rk4_steps(n, ops, stat, ops_p, stat_p, coeff, mu, tchunk, float(h), y, Sc, per_col=True, workspace=ws)
         else:
-            table = model._signal_table(times)
-            coeff = None if table is None else asreal(table, y.device)
+            coeff = model._signal_table_device(times, y.device) if hasattr(model, "_signal_table_device") else None
+            if coeff is None:  # arbitrary Python envelopes: one vectorised host evaluation
+                table = model._signal_table(times)
+                coeff = None if table is None else asreal(table, y.device)
             need = _abi.workspace_bytes(_abi.WS_RK4, n, K, B, S)
             need = min(need, max(workspace_bytes, _abi.workspace_bytes(_abi.WS_RK4, n, K, B, 1)))
             if ws is None or ws.numel() < need:
