@@ -55,6 +55,7 @@ typedef struct { double re, im; } qdb_c128;
 #define QDB_WS_RHS 0
 #define QDB_WS_RK4 1
 #define QDB_WS_EXPM 2
+#define QDB_WS_MAGNUS 3
 
 const char* qdb_last_error_string(void);
 int qdb_version(void);
@@ -178,6 +179,33 @@ int qdb_expm_steps_c128(int n, int K, int B, int S,
                         const double* times_mid_host, const int* squarings_host, double h,
                         qdb_c128* y, int ldy,
                         void* workspace, size_t ws_bytes, void* stream);
+
+/* a9 at Magnus orders 1, 2 and 3: S steps  y <- expm(Omega_s) y, where Omega_s is the truncated Magnus
+ * exponent of the step built from the generator at the order's Gauss-Legendre nodes:
+ *   order 1: Omega = h G(t + h/2)
+ *   order 2: Omega = h (g1 + g2)/2 + (sqrt(3)/12) h^2 [g2, g1],            nodes t + (1/2 -+ sqrt(3)/6) h
+ *   order 3: a1 = h g2, a2 = (sqrt(15)/3) h (g3 - g1), a3 = (10/3) h (g3 - 2 g2 + g1),
+ *            Omega = a1 + a3/12 + [-20 a1 - a3 + [a1,a2], a2 + [2 a3 + [a1,a2], a1]/60]/240,
+ *                                                                          nodes t + (1/2 -+ sqrt(15)/10) h, t + h/2
+ * (generator_kernel at the nodes, commutators as pairs of DMMA GEMMs, then the same Taylor
+ * scaling-and-squaring propagator and apply GEMM as qdb_expm_steps_c128).
+ *   times_host     : HOST [S][magnus_order] node times;  coeff : device [S][magnus_order][K] signal values there
+ *   squarings_host : HOST [S], from a norm bound on Omega_s
+ *   workspace      : qdb_workspace_bytes(QDB_WS_MAGNUS, n, K, B, S)
+ * Replaces get_exponential_take_step(magnus_order) + scipy.linalg.expm inside scipy_expm_solver
+ * (solvers/fixed_step_solvers.py:80-108, 327-401). */
+int qdb_magnus_steps_c128(int n, int K, int B, int S, int magnus_order,
+                          const qdb_c128* ops_rm, const qdb_c128* stat_rm,
+                          const double* coeff, const double* mu,
+                          const double* times_host, const int* squarings_host, double h,
+                          qdb_c128* y, int ldy,
+                          void* workspace, size_t ws_bytes, void* stream);
+
+/* The Magnus exponent alone: out = scale * Omega(h) from g = [magnus_order][n][n] row-major generators at the
+ * nodes (for generators that are arbitrary host callables: the callable protocol of scipy_expm_solver,
+ * solvers/fixed_step_solvers.py:80-108).  workspace: 0 / n^2 / 7 n^2 complex numbers for order 1 / 2 / 3. */
+int qdb_magnus_terms_c128(int n, int magnus_order, const qdb_c128* g, double h, double scale, qdb_c128* out,
+                          void* workspace, size_t ws_bytes, void* stream);
 
 /* Matrix exponential of one (n x n) row-major matrix with `squarings` halvings (building block
  * of qdb_expm_steps_c128, exported for parity tests against scipy.linalg.expm). */

@@ -399,6 +399,62 @@ def expm_step(generator: Callable, t, y, h):
     return _scipy_expm(generator(t + (h / 2)) * h) @ y
 
 
+def matrix_commutator(m1, m2):
+    """solvers/fixed_step_solvers.py:314-324."""
+    return m1 @ m2 - m2 @ m1
+
+
+def magnus_propagator(generator: Callable, t0, h, magnus_order: int = 1, expm_func=None):
+    """The one-step propagator of get_exponential_take_step for Magnus orders 1, 2 and 3
+    (Gauss-Legendre nodes and the commutator-free-of-derivatives forms);
+    solvers/fixed_step_solvers.py:327-395."""
+    expm_func = _scipy_expm if expm_func is None else expm_func
+    if magnus_order == 1:
+        return expm_func(generator(t0 + (h / 2)) * h)
+    if magnus_order == 2:
+        c1 = 0.5 - np.sqrt(3) / 6
+        c2 = 0.5 + np.sqrt(3) / 6
+        p2 = np.sqrt(3) / 12
+        g1 = generator(t0 + c1 * h)
+        g2 = generator(t0 + c2 * h)
+        return expm_func(h * (g1 + g2) / 2 + p2 * (h**2) * matrix_commutator(g2, g1))
+    if magnus_order == 3:
+        d1 = 0.5 - np.sqrt(15) / 10
+        d2 = 0.5
+        d3 = 0.5 + np.sqrt(15) / 10
+        c0 = np.sqrt(15) / 3
+        c1 = 10.0 / 3
+        g1 = generator(t0 + d1 * h)
+        g2 = generator(t0 + d2 * h)
+        g3 = generator(t0 + d3 * h)
+        a1 = h * g2
+        a2 = c0 * h * (g3 - g1)
+        a3 = c1 * h * (g3 - 2 * g2 + g1)
+        comm1 = matrix_commutator(a1, a2)
+        comm2 = matrix_commutator(2 * a3 + comm1, a1) / 60
+        return expm_func(a1 + (a3 / 12) + matrix_commutator(-20 * a1 - a3 + comm1, a2 + comm2) / 240)
+    raise ValueError("Only magnus_order 1, 2, and 3 are supported.")
+
+
+def magnus_step(magnus_order: int):
+    """take_step(generator, t0, y, h) = propagator @ y; solvers/fixed_step_solvers.py:397-401."""
+    def take_step(generator, t0, y, h):
+        return magnus_propagator(generator, t0, h, magnus_order) @ y
+    return take_step
+
+
+def magnus_node_offsets(magnus_order: int) -> np.ndarray:
+    """Generator evaluation points of one step as fractions of h (solvers/fixed_step_solvers.py:346,350-351,
+    367-369); the host code under test builds its time tables from the same expressions."""
+    if magnus_order == 1:
+        return np.array([0.5])
+    if magnus_order == 2:
+        return np.array([0.5 - np.sqrt(3) / 6, 0.5 + np.sqrt(3) / 6])
+    if magnus_order == 3:
+        return np.array([0.5 - np.sqrt(15) / 10, 0.5, 0.5 + np.sqrt(15) / 10])
+    raise ValueError("Only magnus_order 1, 2, and 3 are supported.")
+
+
 def fixed_step_solve(take_step, fn, t_span, y0, max_dt, t_eval=None):
     """solvers/fixed_step_solvers.py:441-459; returns (t, ys) with endpoints trimmed when
     t_eval is given (solvers/solver_utils.py:112-119)."""
@@ -434,7 +490,7 @@ def stage_time_grid(t0, h, n_steps):
 
 
 def solve_hamiltonian(static_operator, operators, specs, frame_operator, t_span, y0, max_dt,
-                      method="RK4", t_eval=None, hamiltonian=True):
+                      method="RK4", t_eval=None, hamiltonian=True, magnus_order=1):
     """solve_lmde(HamiltonianModel/GeneratorModel, method in {"RK4","scipy_expm"}) for a model
     given out of the frame basis; solvers/solver_functions.py:315-327,342-371,396-448."""
     Gd, G, d, U = generator_model_operators(static_operator, operators, frame_operator, hamiltonian)
@@ -444,7 +500,8 @@ def solve_hamiltonian(static_operator, operators, specs, frame_operator, t_span,
         t, ys = fixed_step_solve(rk4_step, lambda t, y: model_rhs(t, y, specs, G, Gd, d),
                                  t_span, yfb, max_dt, t_eval)
     elif method == "scipy_expm":
-        t, ys = fixed_step_solve(expm_step, lambda t: model_generator(t, specs, G, Gd, d),
+        step = expm_step if magnus_order == 1 else magnus_step(magnus_order)
+        t, ys = fixed_step_solve(step, lambda t: model_generator(t, specs, G, Gd, d),
                                  t_span, yfb, max_dt, t_eval)
     else:
         raise ValueError(method)
@@ -459,7 +516,7 @@ def solve_hamiltonian(static_operator, operators, specs, frame_operator, t_span,
 def solve_vectorized_lindblad(static_hamiltonian, hamiltonian_operators, ham_specs,
                               static_dissipators, dissipator_operators, dis_specs,
                               frame_operator, t_span, y0, max_dt, method="scipy_expm",
-                              t_eval=None):
+                              t_eval=None, magnus_order=1):
     """solve_lmde(LindbladModel(vectorized=True)); y0 is vec_F(rho) of shape (n^2,) or (n^2,B);
     lindblad_model.py:436-538, solver_functions.py:397-399,436-441."""
     Hd, Hops, Ds, Do, d, U = lindblad_model_operators(static_hamiltonian, hamiltonian_operators,
@@ -485,7 +542,7 @@ def solve_vectorized_lindblad(static_hamiltonian, hamiltonian_operators, ham_spe
     y0 = np.asarray(y0, dtype=complex)
     VU = None if U is None else np.kron(U.conj(), U)
     yfb = y0 if VU is None else VU.conj().T @ y0
-    step = rk4_step if method == "RK4" else expm_step
+    step = rk4_step if method == "RK4" else (expm_step if magnus_order == 1 else magnus_step(magnus_order))
     fn = rhs if method == "RK4" else generator
     t, ys = fixed_step_solve(step, fn, t_span, yfb, max_dt, t_eval)
     if VU is not None:

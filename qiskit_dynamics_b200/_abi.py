@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libqdb.so")
 LAYOUT_ROWMAJOR = 0
 LAYOUT_PACKED = 1
 LAYOUT_PACKED3M = 2
-WS_RHS, WS_RK4, WS_EXPM = 0, 1, 2
+WS_RHS, WS_RK4, WS_EXPM, WS_MAGNUS = 0, 1, 2, 3
 
 
 class QdbError(RuntimeError):
@@ -56,6 +56,8 @@ SIGNATURES = {
     "qdb_outcome_probabilities_f64": (_i, [_i, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "qdb_dmma_probe": (_i, [_vp, _i, _vp, _vp]),
     "qdb_expm_c128": (_i, [_i, _vp, _i, _vp, _vp, _sz, _vp]),
+    "qdb_magnus_steps_c128": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _i, _vp, _sz, _vp]),
+    "qdb_magnus_terms_c128": (_i, [_i, _i, _vp, _d, _d, _vp, _vp, _sz, _vp]),
     "qdb_launch_count": (ctypes.c_ulonglong, []),
 }
 
@@ -250,6 +252,38 @@ def expm_steps(n, ops_rm, stat_rm, coeff, mu, times_mid_host: np.ndarray, squari
                                      ctypes.c_void_p(workspace.data_ptr()), workspace.numel(), _stream()),
            "qdb_expm_steps_c128")
     return y
+
+
+def magnus_steps(n, ops_rm, stat_rm, coeff, mu, times_host: np.ndarray, squarings_host: np.ndarray, h, y, S, magnus_order,
+                 workspace=None):
+    """S exponential steps at Magnus order 1, 2 or 3; times_host (S, order) node times, coeff (S, order, K)."""
+    K = 0 if ops_rm is None else ops_rm.shape[0]
+    B = y.shape[1]
+    times_host = np.ascontiguousarray(times_host, dtype=np.float64)
+    squarings_host = np.ascontiguousarray(squarings_host, dtype=np.int32)
+    if times_host.size != S * magnus_order or squarings_host.size != S:
+        raise QdbError(f"magnus_steps: {times_host.size} node times / {squarings_host.size} squarings for S={S}, "
+                       f"order {magnus_order}")
+    need = workspace_bytes(WS_MAGNUS, n, K, B, S)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=y.device)
+    _check(lib().qdb_magnus_steps_c128(n, K, B, S, int(magnus_order), _ptr(ops_rm, C, "ops_rm"), _ptr(stat_rm, C, "stat_rm"),
+                                       _ptr(coeff, F, "coeff"), _ptr(mu, F, "mu"),
+                                       times_host.ctypes.data_as(ctypes.c_void_p),
+                                       squarings_host.ctypes.data_as(ctypes.c_void_p), float(h), _ptr(y, C, "y"), B,
+                                       ctypes.c_void_p(workspace.data_ptr()), workspace.numel(), _stream()),
+           "qdb_magnus_steps_c128")
+    return y
+
+
+def magnus_terms(g: torch.Tensor, h: float, magnus_order: int, scale: float = 1.0):
+    """scale * Omega(h) from the generators at the nodes, g of shape (order, n, n)."""
+    n = g.shape[-1]
+    out = torch.empty((n, n), dtype=C, device=g.device)
+    ws = torch.empty(max(1, 7 * n * n * 16), dtype=torch.uint8, device=g.device)
+    _check(lib().qdb_magnus_terms_c128(n, int(magnus_order), _ptr(g, C, "g"), float(h), float(scale), _ptr(out, C, "out"),
+                                       ctypes.c_void_p(ws.data_ptr()), ws.numel(), _stream()), "qdb_magnus_terms_c128")
+    return out
 
 
 def expm(A: torch.Tensor, squarings: int, out=None):

@@ -72,6 +72,8 @@ size_t qdb_workspace_bytes(int kind, int n, int K, int B, int S) {
             return 3 * align_up(n2) + 3 * align_up(yb) + align_up(3 * sizeof(double));
         case QDB_WS_EXPM:
             return 7 * align_up(n2) + align_up(yb);
+        case QDB_WS_MAGNUS:  // + node generators (3), Magnus temporaries (7), node times [3 S]
+            return 17 * align_up(n2) + align_up(yb) + align_up((size_t)3 * S * sizeof(double));
         default:
             return 0;
     }
@@ -378,6 +380,80 @@ int qdb_expm_steps_c128(int n, int K, int B, int S, const qdb_c128* ops_rm, cons
         ynext = t;
     }
     if (ycur != D2(y)) QDB_CUDA(cudaMemcpyAsync(y, ycur, (size_t)n * B * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+    return QDB_OK;
+}
+
+int qdb_magnus_terms_c128(int n, int magnus_order, const qdb_c128* g, double h, double scale, qdb_c128* out, void* workspace,
+                          size_t ws_bytes, void* stream) {
+    QDB_REQUIRE(n >= 1, "qdb_magnus_terms_c128: bad n=%d", n);
+    QDB_REQUIRE(magnus_order >= 1 && magnus_order <= 3, "qdb_magnus_terms_c128: Only magnus_order 1, 2, and 3 are supported (got %d)",
+                magnus_order);
+    QDB_REQUIRE(g && out, "qdb_magnus_terms_c128: null pointer");
+    const size_t need = (size_t)(magnus_order == 1 ? 0 : magnus_order == 2 ? 1 : 7) * n * n * sizeof(double2);
+    if (need > 0 && (!workspace || ws_bytes < need)) {
+        set_error("qdb_magnus_terms_c128: workspace too small (%zu < %zu)", ws_bytes, need);
+        return QDB_E_WORKSPACE;
+    }
+    return magnus_terms(n, magnus_order, D2(g), h, scale, D2(out), (double2*)workspace, (cudaStream_t)stream);
+}
+
+int qdb_magnus_steps_c128(int n, int K, int B, int S, int magnus_order, const qdb_c128* ops_rm, const qdb_c128* stat_rm,
+                          const double* coeff, const double* mu, const double* times_host, const int* squarings_host, double h,
+                          qdb_c128* y, int ldy, void* workspace, size_t ws_bytes, void* stream) {
+    QDB_REQUIRE(n >= 1 && K >= 0 && B >= 0 && S >= 0, "qdb_magnus_steps_c128: bad n=%d K=%d B=%d S=%d", n, K, B, S);
+    QDB_REQUIRE(magnus_order >= 1 && magnus_order <= 3, "qdb_magnus_steps_c128: Only magnus_order 1, 2, and 3 are supported (got %d)",
+                magnus_order);
+    if (S == 0) return QDB_OK;
+    QDB_REQUIRE(stat_rm || (ops_rm && K > 0), "qdb_magnus_steps_c128: neither static operator nor operators given");
+    QDB_REQUIRE(K == 0 || coeff, "qdb_magnus_steps_c128: K=%d but no signal table", K);
+    QDB_REQUIRE(squarings_host, "qdb_magnus_steps_c128: squarings missing");
+    QDB_REQUIRE(!mu || times_host, "qdb_magnus_steps_c128: frame given without times");
+    QDB_REQUIRE(B == 0 || (y && ldy == B), "qdb_magnus_steps_c128: need y with ldy == B");
+    if (ws_bytes < qdb_workspace_bytes(QDB_WS_MAGNUS, n, K, B, S) || !workspace) {
+        set_error("qdb_magnus_steps_c128: workspace too small (%zu < %zu)", ws_bytes, qdb_workspace_bytes(QDB_WS_MAGNUS, n, K, B, S));
+        return QDB_E_WORKSPACE;
+    }
+    if (B == 0) return QDB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)workspace;
+    const size_t n2 = align_up((size_t)n * n * sizeof(double2));
+    const size_t nn = (size_t)n * n;
+    double2* As = (double2*)ws;
+    double2* P = (double2*)(ws + n2);
+    double2* core_ws = (double2*)(ws + 2 * n2);   // 5 n^2 (contiguous, unaligned stride)
+    double2* gnodes = (double2*)(ws + 7 * n2);    // 3 n^2: generator at the nodes of the step
+    double2* mag_ws = (double2*)(ws + 10 * n2);   // 7 n^2: commutator temporaries
+    double2* ytmp = (double2*)(ws + 17 * n2);
+    double* times_dev = (double*)(ws + 17 * n2 + align_up((size_t)n * B * sizeof(double2)));
+    const int Q = magnus_order;
+    if (mu) QDB_CUDA(cudaMemcpyAsync(times_dev, times_host, (size_t)S * Q * sizeof(double), cudaMemcpyHostToDevice, st));
+    double2* ycur = D2(y);
+    double2* ynext = ytmp;
+    const double2 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0);
+    int rc;
+    for (int s = 0; s < S; ++s) {
+        const int sq = squarings_host[s];
+        QDB_REQUIRE(sq >= 0 && sq < 64, "qdb_magnus_steps_c128: bad squarings[%d]=%d", s, sq);
+        const double sc = ldexp(1.0, -sq);
+        const double* cs = coeff ? coeff + (size_t)s * Q * K : nullptr;
+        if (Q == 1) {  // As = (h / 2^sq) G_frame(t_s + h/2) straight from the generator kernel
+            rc = launch_generator(n, K, 1, QDB_LAYOUT_ROWMAJOR, D2(ops_rm), D2(stat_rm), cs, 0, mu, mu ? times_dev + s : nullptr, 0.0,
+                                  sc * h, As, st);
+            if (rc != QDB_OK) return rc;
+        } else {
+            rc = launch_generator(n, K, Q, QDB_LAYOUT_ROWMAJOR, D2(ops_rm), D2(stat_rm), cs, 0, mu,
+                                  mu ? times_dev + (size_t)s * Q : nullptr, 0.0, 1.0, gnodes, st);
+            if (rc != QDB_OK) return rc;
+            if ((rc = magnus_terms(n, Q, gnodes, h, sc, As, mag_ws, st)) != QDB_OK) return rc;
+        }
+        if ((rc = expm_core(n, As, sq, P, core_ws, st)) != QDB_OK) return rc;
+        if ((rc = launch_zgemm(n, B, n, P, n, ycur, ldy, ynext, ldy, one, zero, nullptr, nullptr, nullptr, st)) != QDB_OK) return rc;
+        double2* t = ycur;
+        ycur = ynext;
+        ynext = t;
+    }
+    if (ycur != D2(y)) QDB_CUDA(cudaMemcpyAsync(y, ycur, (size_t)n * B * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+    (void)nn;
     return QDB_OK;
 }
 

@@ -53,6 +53,55 @@ int expm_core(int n, const double2* As, int squarings, double2* out, double2* ws
 }  // namespace qdb
 
 // ------------------------------------------------------------------------------------------------
+// Magnus exponents of orders 2 and 3 (SURVEY.md 8(a) row a9 beyond first order; replaces the
+// magnus_order == 2 / 3 branches of get_exponential_take_step, solvers/fixed_step_solvers.py:348-395).
+// g holds the generator at the Gauss-Legendre nodes of the step (contiguous, stride n*n, row-major);
+// out = scale * Omega(h).  Commutators are pairs of DMMA GEMMs (C = A B, then C -= B A), the linear
+// combinations run through poly_kernel.  ws: n^2 (order 2) / 7 n^2 (order 3) complex numbers.
+// ------------------------------------------------------------------------------------------------
+namespace qdb {
+
+int magnus_terms(int n, int order, const double2* g, double h, double scale, double2* out, double2* ws, cudaStream_t st) {
+    const size_t e = (size_t)n * n;
+    const double2 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0), minus = make_double2(-1.0, 0.0);
+    int rc;
+#define COMMUTATOR(Cp, Ap, Bp)                                                                                          \
+    if ((rc = launch_zgemm(n, n, n, Ap, n, Bp, n, Cp, n, one, zero, nullptr, nullptr, nullptr, st)) != QDB_OK) return rc; \
+    if ((rc = launch_zgemm(n, n, n, Bp, n, Ap, n, Cp, n, minus, one, nullptr, nullptr, nullptr, st)) != QDB_OK) return rc
+    if (order == 1) return launch_poly(n, 0.0, scale * h, g, 0.0, nullptr, 0.0, nullptr, 0.0, nullptr, out, st);
+    if (order == 2) {
+        // Omega = h (g1 + g2) / 2 + (sqrt(3) / 12) h^2 [g2, g1]
+        const double2 *g1 = g, *g2 = g + e;
+        double2* C = ws;
+        COMMUTATOR(C, g2, g1);
+        const double p2 = sqrt(3.0) / 12.0;
+        return launch_poly(n, 0.0, scale * h * 0.5, g1, scale * h * 0.5, g2, scale * p2 * h * h, C, 0.0, nullptr, out, st);
+    }
+    if (order == 3) {
+        const double2 *g1 = g, *g2 = g + e, *g3 = g + 2 * e;
+        double2 *a1 = ws, *a2 = ws + e, *a3 = ws + 2 * e, *c1 = ws + 3 * e, *X = ws + 4 * e, *Q = ws + 5 * e, *R = ws + 6 * e;
+        const double k0 = sqrt(15.0) / 3.0 * h, k1 = 10.0 / 3.0 * h;
+        // a1 = h g2, a2 = (sqrt(15)/3) h (g3 - g1), a3 = (10/3) h (g3 - 2 g2 + g1)
+        if ((rc = launch_poly(n, 0.0, h, g2, 0.0, nullptr, 0.0, nullptr, 0.0, nullptr, a1, st)) != QDB_OK) return rc;
+        if ((rc = launch_poly(n, 0.0, k0, g3, -k0, g1, 0.0, nullptr, 0.0, nullptr, a2, st)) != QDB_OK) return rc;
+        if ((rc = launch_poly(n, 0.0, k1, g3, -2.0 * k1, g2, k1, g1, 0.0, nullptr, a3, st)) != QDB_OK) return rc;
+        COMMUTATOR(c1, a1, a2);                                                             // comm1 = [a1, a2]
+        if ((rc = launch_poly(n, 0.0, 2.0, a3, 1.0, c1, 0.0, nullptr, 0.0, nullptr, X, st)) != QDB_OK) return rc;
+        COMMUTATOR(Q, X, a1);                                                               // 60 comm2 = [2 a3 + comm1, a1]
+        double2* L = X;                                                                     // X is free again
+        if ((rc = launch_poly(n, 0.0, -20.0, a1, -1.0, a3, 1.0, c1, 0.0, nullptr, L, st)) != QDB_OK) return rc;
+        if ((rc = launch_poly(n, 0.0, 1.0, a2, 1.0 / 60.0, Q, 0.0, nullptr, 0.0, nullptr, R, st)) != QDB_OK) return rc;
+        COMMUTATOR(Q, L, R);                                                                // [-20 a1 - a3 + comm1, a2 + comm2]
+        return launch_poly(n, 0.0, scale, a1, scale / 12.0, a3, scale / 240.0, Q, 0.0, nullptr, out, st);
+    }
+#undef COMMUTATOR
+    set_error("magnus_terms: order %d not in {1, 2, 3}", order);
+    return QDB_E_ARG;
+}
+
+}  // namespace qdb
+
+// ------------------------------------------------------------------------------------------------
 // fp64 tensor-pipe peak probe: every warp issues independent DMMA m8n8k4 chains from registers.
 // Used by bench.py as the live roofline denominator (MEASURED_PEAKS.json has no fp64 entry).
 // ------------------------------------------------------------------------------------------------

@@ -98,6 +98,8 @@ int launch_phase_vectors(int n, const double* mu, double t, double2* pre, double
 int launch_poly(int n, double c0, double c1, const double2* A1, double c2, const double2* A2, double c3,
                 const double2* A3, double c4, const double2* A4, double2* out, cudaStream_t st);
 int expm_core(int n, const double2* As, int squarings, double2* out, double2* ws /*5 n^2*/, cudaStream_t st);
+int magnus_terms(int n, int order, const double2* g /*[order][n][n]*/, double h, double scale, double2* out,
+                 double2* ws /*order 2: n^2, order 3: 7 n^2*/, cudaStream_t st);
 int launch_zgemm(int M, int N, int Kd, const double2* A, int lda, const double2* B, int ldb,
                  double2* C, int ldc, double2 alpha, double2 beta, const double* colscale,
                  const double2* pre, const double2* post, cudaStream_t st);

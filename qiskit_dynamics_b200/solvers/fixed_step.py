@@ -154,24 +154,53 @@ def rk4_model_solve(model, t_span, y0_fb: torch.Tensor, max_dt, t_eval=None,
     return trim_t_results(OdeResult(t=np.array(t_list), y=torch.stack(ys)), t_eval)
 
 
-def expm_squarings(model, coeff_table: Optional[np.ndarray], h: float) -> np.ndarray:
-    """Squarings per step from the bound ||h G(t)||_1 <= |h| (||G_d||_1 + sum |c_j| ||G_j||_1) (the
-    frame phases have modulus 1), so that no device->host norm read is needed inside the loop."""
+def magnus_nodes(magnus_order: int) -> np.ndarray:
+    """Generator evaluation points of one exponential step, as fractions of h: the midpoint (order 1) or the
+    2- / 3-point Gauss-Legendre nodes (fixed_step_solvers.py:346, 350-351, 367-369)."""
+    if magnus_order == 1:
+        return np.array([0.5])
+    if magnus_order == 2:
+        return np.array([0.5 - np.sqrt(3) / 6, 0.5 + np.sqrt(3) / 6])
+    if magnus_order == 3:
+        return np.array([0.5 - np.sqrt(15) / 10, 0.5, 0.5 + np.sqrt(15) / 10])
+    raise QiskitError("Only magnus_order 1, 2, and 3 are supported.")
+
+
+def magnus_norm_bound(b: np.ndarray, h: float, magnus_order: int) -> np.ndarray:
+    """Upper bound on ||Omega||_1 of a step from bounds ``b[..., q]`` on ||G(t_q)||_1 at its nodes
+    (sub-multiplicativity: ||[X, Y]|| <= 2 ||X|| ||Y||)."""
+    h = abs(float(h))
+    if magnus_order == 1:
+        return h * b[..., 0]
+    if magnus_order == 2:
+        return h * (b[..., 0] + b[..., 1]) / 2 + (np.sqrt(3) / 12) * h * h * 2 * b[..., 0] * b[..., 1]
+    a1 = h * b[..., 1]
+    a2 = (np.sqrt(15) / 3) * h * (b[..., 2] + b[..., 0])
+    a3 = (10.0 / 3) * h * (b[..., 2] + 2 * b[..., 1] + b[..., 0])
+    comm1 = 2 * a1 * a2
+    comm2 = 2 * (2 * a3 + comm1) * a1 / 60
+    return a1 + a3 / 12 + 2 * (20 * a1 + a3 + comm1) * (a2 + comm2) / 240
+
+
+def expm_squarings(model, coeff_table: Optional[np.ndarray], h: float, magnus_order: int = 1) -> np.ndarray:
+    """Squarings per step from the bound ||G(t)||_1 <= ||G_d||_1 + sum |c_j| ||G_j||_1 at every node (the frame
+    phases have modulus 1) pushed through the Magnus exponent, so that no device->host norm read is needed
+    inside the loop.  ``coeff_table``: (S * order, K) signal values at the node times, or None."""
     s_norm, o_norms = model._collection().norms1()
-    S = 1 if coeff_table is None else coeff_table.shape[0]
-    bound = np.full(S, s_norm, dtype=float)
+    rows = magnus_order if coeff_table is None else coeff_table.shape[0]
+    b = np.full(rows, s_norm, dtype=float)
     if coeff_table is not None and o_norms.size:
-        bound = bound + np.abs(coeff_table) @ o_norms
-    bound = np.abs(h) * bound
+        b = b + np.abs(coeff_table) @ o_norms
+    bound = magnus_norm_bound(b.reshape(-1, magnus_order), h, magnus_order)
     with np.errstate(divide="ignore"):
         sq = np.ceil(np.log2(np.maximum(bound, 1e-300) / EXPM_THETA))
     return np.maximum(sq, 0).astype(np.int32)
 
 
 def expm_model_solve(model, t_span, y0_fb: torch.Tensor, max_dt, t_eval=None, magnus_order: int = 1) -> OdeResult:
-    """y <- expm(h G(t + h/2)) y per step (Magnus order 1) on a model generator."""
-    if magnus_order != 1:
-        raise QiskitError("Only magnus_order 1 is implemented by the fused B200 exponential stepper.")
+    """y <- expm(Omega) y per step on a model generator, Omega the Magnus exponent of order 1, 2 or 3 built from
+    the generator at the step's nodes (order 1: h G(t + h/2))."""
+    nodes = magnus_nodes(magnus_order)
     coll = model._collection()
     n = coll.dim
     y, shape = _columns(y0_fb)
@@ -185,14 +214,26 @@ def expm_model_solve(model, t_span, y0_fb: torch.Tensor, max_dt, t_eval=None, ma
     for t0, h, S in zip(t_list, h_list, n_list):
         S = int(S)
         starts = stage_time_grid(t0, h, S)[0::2][:-1]
-        mids = starts + (h / 2)
-        table = model._signal_table(mids)
+        if magnus_order == 1:
+            times = (starts + (h / 2)).reshape(S, 1)
+        else:
+            times = starts[:, None] + nodes[None, :] * h  # t0 + c_q * h, the reference's expression
+        table = model._signal_table(times.reshape(-1))
         coeff = None if table is None else asreal(table, y.device)
-        sq = expm_squarings(model, table, float(h)) if table is not None else np.repeat(expm_squarings(model, None, float(h)), S)
-        need = _abi.workspace_bytes(_abi.WS_EXPM, n, coll.num_operators, y.shape[1])
-        if ws is None or ws.numel() < need:
-            ws = torch.empty(need, dtype=torch.uint8, device=y.device)
-        _abi.expm_steps(n, coll.operators, coll.static_operator, coeff, mu, mids, sq, float(h), y, S, workspace=ws)
+        sq = expm_squarings(model, table, float(h), magnus_order)
+        if table is None:
+            sq = np.repeat(sq, S)
+        if magnus_order == 1:
+            need = _abi.workspace_bytes(_abi.WS_EXPM, n, coll.num_operators, y.shape[1])
+            if ws is None or ws.numel() < need:
+                ws = torch.empty(need, dtype=torch.uint8, device=y.device)
+            _abi.expm_steps(n, coll.operators, coll.static_operator, coeff, mu, times.reshape(-1), sq, float(h), y, S, workspace=ws)
+        else:
+            need = _abi.workspace_bytes(_abi.WS_MAGNUS, n, coll.num_operators, y.shape[1], S)
+            if ws is None or ws.numel() < need:
+                ws = torch.empty(need, dtype=torch.uint8, device=y.device)
+            _abi.magnus_steps(n, coll.operators, coll.static_operator, coeff, mu, times, sq, float(h), y, S, magnus_order,
+                              workspace=ws)
         ys.append(y.reshape(shape).clone())
     return trim_t_results(OdeResult(t=np.array(t_list), y=torch.stack(ys)), t_eval)
 
@@ -232,13 +273,17 @@ def RK4_solver(rhs: Callable, t_span, y0, max_dt, t_eval=None) -> OdeResult:
 
 
 def scipy_expm_solver(generator: Callable, t_span, y0, max_dt, t_eval=None, magnus_order: int = 1) -> OdeResult:
-    """Exponential stepper for an arbitrary ``generator(t)`` returning an (n, n) device tensor; the
-    exponential itself is the device Taylor scaling-and-squaring (qdb_expm_c128)."""
-    if magnus_order != 1:
-        raise QiskitError("Only magnus_order 1 is implemented by the B200 exponential stepper.")
+    """Exponential stepper (Magnus order 1, 2 or 3) for an arbitrary ``generator(t)`` returning an (n, n) device
+    tensor; the Magnus exponent (qdb_magnus_terms_c128) and the exponential itself (qdb_expm_c128, Taylor
+    scaling-and-squaring) are built on the device."""
+    nodes = magnus_nodes(magnus_order)
 
     def take_step(gen, t, y, h):
-        A = (asarray(gen(t + (h / 2))) * h).contiguous()
+        if magnus_order == 1:
+            A = (asarray(gen(t + (h / 2))) * h).contiguous()
+        else:
+            g = torch.stack([asarray(gen(t + c * h)) for c in nodes]).contiguous()
+            A = _abi.magnus_terms(g, float(h), magnus_order)
         norm = float(torch.linalg.matrix_norm(A, 1))
         sq = max(0, int(np.ceil(np.log2(max(norm, 1e-300) / EXPM_THETA))))
         P = _abi.expm(A, sq)

@@ -323,6 +323,56 @@ def gen_lindblad():
     save("lindblad", **out)
 
 
+def gen_magnus():
+    """scipy_expm_solver at Magnus orders 2 and 3 (solvers/fixed_step_solvers.py:80-108, 327-401): Hamiltonian
+    model (no frame / full frame, matrix and vector y0, t_eval), a plain callable generator, and the small
+    vectorised Lindblad system in its three frames; step sizes large enough that the commutator terms matter."""
+    out = {}
+    n, K, B = 5, 2, 3
+    H0, Hs, Y, sig = orc.synthetic_schrodinger(n, K, B, 11)
+    out["h_check"] = checksum(H0, Hs, Y)
+    for order in (2, 3):
+        m = HamiltonianModel(static_operator=H0, operators=Hs, signals=sigs(sig))
+        out[f"h_noframe_o{order}"] = solve_lmde(m, t_span=[0, 0.5], y0=Y, method="scipy_expm", max_dt=0.05,
+                                                magnus_order=order).y[-1]
+        m = HamiltonianModel(static_operator=H0, operators=Hs, signals=sigs(sig), rotating_frame=H0)
+        out[f"h_full_o{order}"] = solve_lmde(m, t_span=[0, 0.5], y0=Y, method="scipy_expm", max_dt=0.05,
+                                             magnus_order=order).y[-1]
+        out[f"h_full_vec_o{order}"] = solve_lmde(m, t_span=[0, 0.5], y0=Y[:, 0], method="scipy_expm", max_dt=0.05,
+                                                 magnus_order=order).y[-1]
+        r = solve_lmde(m, t_span=[0.5, 0.0], y0=Y, method="scipy_expm", max_dt=0.04, magnus_order=order,
+                       t_eval=[0.5, 0.31, 0.1])
+        out[f"h_full_teval_back_o{order}"] = r.y
+        # plain callable generator (non-commuting at different times)
+        A = -1j * H0
+        Bm = -1j * Hs[0]
+        r = solve_lmde(lambda t: A * np.cos(t) + Bm * np.sin(2 * t), t_span=[0, 1.0], y0=np.eye(n, dtype=complex),
+                       method="scipy_expm", max_dt=0.1, magnus_order=order)
+        out[f"callable_o{order}"] = r.y[-1]
+    # 17-dimensional system: wider than one DMMA tile, not a multiple of 8
+    n, K, B = 17, 3, 6
+    H0, Hs, Y, sig = orc.synthetic_schrodinger(n, K, B, 41)
+    out["h17_check"] = checksum(H0, Hs, Y)
+    m = HamiltonianModel(static_operator=H0, operators=Hs, signals=sigs(sig), rotating_frame=H0)
+    for order in (2, 3):
+        out[f"h17_full_o{order}"] = solve_lmde(m, t_span=[0, 0.3], y0=Y, method="scipy_expm", max_dt=0.03,
+                                               magnus_order=order).y[-1]
+    # small vectorised Lindblad (the system of gen_lindblad)
+    n, K, B = 3, 2, 4
+    H0, Hs, Ls, Y, sig = orc.synthetic_lindblad(n, K, 4, B, 31)
+    Lstat, Ldyn = Ls[:2], Ls[2:] + 0.02j * Ls[:2]
+    dsig = [(0.3, 0.0, 0.0), (0.2, 0.11, 0.4)]
+    out["l_check"] = checksum(H0, Hs, Ls, Y)
+    for frame_name, frame in (("none", None), ("full", H0), ("diag", np.diag(H0).real)):
+        mv = LindbladModel(static_hamiltonian=H0, hamiltonian_operators=Hs, hamiltonian_signals=sigs(sig),
+                           static_dissipators=Lstat, dissipator_operators=Ldyn, dissipator_signals=sigs(dsig),
+                           rotating_frame=frame, vectorized=True)
+        for order in (2, 3):
+            out[f"l_{frame_name}_o{order}"] = solve_lmde(mv, t_span=[0, 0.5], y0=Y, method="scipy_expm", max_dt=0.05,
+                                                         magnus_order=order).y[-1]
+    save("magnus", **out)
+
+
 # ---------------------------------------------------------------------------------------------
 MEASUREMENT_CASES = [
     # (name, subsystem_dims, measurement_subsystems, memory_slot_indices, num_memory_slots, max_outcome_level)
@@ -389,6 +439,12 @@ def gen_measurement():
 
 
 if __name__ == "__main__":
+    only = set(sys.argv[1:])  # e.g. `make_golden.py magnus` regenerates one file
+    if only:
+        for name in only:
+            globals()["gen_" + name]()
+        raise SystemExit(0)
+    gen_magnus()
     gen_measurement()
     gen_collection()
     gen_frame()

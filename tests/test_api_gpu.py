@@ -377,3 +377,40 @@ def test_lindblad(qd):
     r = qd.solve_lmde(mv, t_span=[0, 0.03], y0=Y, method="scipy_expm", max_dt=1e-2)
     assert max_col_l2(npy(r.y[-1]), g["cfg3_expm_y"]) < TOL
     close(mv(0.013, Y), g["cfg3_rhs"])
+
+
+def test_magnus_orders_2_and_3(qd):
+    """scipy_expm at Magnus orders 2 and 3 (fixed_step_solvers.py:80-108, 327-401): model generators run
+    qdb_magnus_steps_c128, callables run qdb_magnus_terms_c128 + qdb_expm_c128; fixtures from the reference."""
+    g = load_golden("magnus")
+    H0, Hs, Y, sig = orc.synthetic_schrodinger(5, 2, 3, 11)
+    for order in (2, 3):
+        kw = dict(method="scipy_expm", magnus_order=order)
+        m = qd.HamiltonianModel(static_operator=H0, operators=Hs, signals=sigs(qd, sig))
+        close(qd.solve_lmde(m, t_span=[0, 0.5], y0=Y, max_dt=0.05, **kw).y[-1], g[f"h_noframe_o{order}"])
+        m = qd.HamiltonianModel(static_operator=H0, operators=Hs, signals=sigs(qd, sig), rotating_frame=H0)
+        close(qd.solve_lmde(m, t_span=[0, 0.5], y0=Y, max_dt=0.05, **kw).y[-1], g[f"h_full_o{order}"])
+        close(qd.solve_lmde(m, t_span=[0, 0.5], y0=Y[:, 0], max_dt=0.05, **kw).y[-1], g[f"h_full_vec_o{order}"])
+        r = qd.solve_lmde(m, t_span=[0.5, 0.0], y0=Y, max_dt=0.04, t_eval=[0.5, 0.31, 0.1], **kw)
+        close(r.y, g[f"h_full_teval_back_o{order}"])
+        A, Bm = qd.asarray(-1j * H0), qd.asarray(-1j * Hs[0])
+        r = qd.solve_lmde(lambda t: A * np.cos(t) + Bm * np.sin(2 * t), t_span=[0, 1.0], y0=np.eye(5, dtype=complex),
+                          max_dt=0.1, **kw)
+        close(r.y[-1], g[f"callable_o{order}"])
+    H0, Hs, Y, sig = orc.synthetic_schrodinger(17, 3, 6, 41)
+    m = qd.HamiltonianModel(static_operator=H0, operators=Hs, signals=sigs(qd, sig), rotating_frame=H0)
+    for order in (2, 3):
+        r = qd.solve_lmde(m, t_span=[0, 0.3], y0=Y, method="scipy_expm", max_dt=0.03, magnus_order=order)
+        assert max_col_l2(npy(r.y[-1]), g[f"h17_full_o{order}"]) < TOL
+    H0, Hs, Ls, Y, sig = orc.synthetic_lindblad(3, 2, 4, 4, 31)
+    Lstat, Ldyn = Ls[:2], Ls[2:] + 0.02j * Ls[:2]
+    dsig = [(0.3, 0.0, 0.0), (0.2, 0.11, 0.4)]
+    for frame_name, frame in (("none", None), ("full", H0), ("diag", np.diag(H0).real)):
+        mv = qd.LindbladModel(static_hamiltonian=H0, hamiltonian_operators=Hs, hamiltonian_signals=sigs(qd, sig),
+                              static_dissipators=Lstat, dissipator_operators=Ldyn, dissipator_signals=sigs(qd, dsig),
+                              rotating_frame=frame, vectorized=True)
+        for order in (2, 3):
+            r = qd.solve_lmde(mv, t_span=[0, 0.5], y0=Y, method="scipy_expm", max_dt=0.05, magnus_order=order)
+            close(r.y[-1], g[f"l_{frame_name}_o{order}"], 1e-9)
+    with pytest.raises(qd.QiskitError):
+        qd.solve_lmde(mv, t_span=[0, 0.5], y0=Y, method="scipy_expm", max_dt=0.05, magnus_order=4)

@@ -12,6 +12,7 @@ import pytest
 import torch
 
 from conftest import ROOT, load_golden
+from oracle import numpy_oracle as orc
 
 
 @pytest.fixture(scope="module")
@@ -49,6 +50,29 @@ def test_abi_argument_validation_without_gpu(qd):
     assert rc == -1 and b"sig_mode" in l.qdb_last_error_string()
     assert l.qdb_rk4_steps_c128(4, 1, 0, 3, None, None, None, None, None, 0, 0, None, None, 0.1, None, 0, None, 0, None) == 0  # empty batch
     assert l.qdb_expm_steps_c128(4, 0, 1, 0, None, None, None, None, None, None, 0.1, None, 1, None, 0, None) == 0  # zero steps
+    assert l.qdb_magnus_steps_c128(4, 0, 1, 0, 3, None, None, None, None, None, None, 0.1, None, 1, None, 0, None) == 0  # zero steps
+    rc = l.qdb_magnus_steps_c128(4, 0, 1, 2, 4, None, None, None, None, None, None, 0.1, None, 1, None, 0, None)
+    assert rc == -1 and b"Only magnus_order 1, 2, and 3" in l.qdb_last_error_string()
+    assert l.qdb_magnus_terms_c128(4, 0, None, 0.1, 1.0, None, None, 0, None) == -1
+    assert qd._abi.workspace_bytes(qd._abi.WS_MAGNUS, 8, 2, 4, 5) >= 17 * 64 * 16 + 8 * 4 * 16 + 15 * 8
+
+
+def test_magnus_host_tables():
+    """Node offsets, node-time tables and the norm bound that picks the squarings (host side of row a9)."""
+    from qiskit_dynamics_b200.solvers.fixed_step import magnus_nodes, magnus_norm_bound
+    from qiskit_dynamics_b200 import QiskitError
+    for order in (1, 2, 3):
+        assert np.array_equal(magnus_nodes(order), orc.magnus_node_offsets(order))  # same expressions as the reference
+    with pytest.raises(QiskitError, match="Only magnus_order 1, 2, and 3"):
+        magnus_nodes(0)
+    rng = np.random.default_rng(5)
+    for order in (1, 2, 3):
+        for _ in range(10):
+            gs = [rng.standard_normal((6, 6)) + 1j * rng.standard_normal((6, 6)) for _ in range(order)]
+            it = iter(gs)
+            omega = orc.magnus_propagator(lambda t: next(it), 0.0, -0.3, order, expm_func=lambda x: x)
+            b = np.array([[np.linalg.norm(g_, 1) for g_ in gs]])
+            assert np.linalg.norm(omega, 1) <= magnus_norm_bound(b, -0.3, order)[0] * (1 + 1e-12)
 
 
 def test_no_cpu_fallback(qd):

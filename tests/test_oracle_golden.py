@@ -256,3 +256,39 @@ def test_measurement_post_processing():
     # the reference's own example of the slot mapping (computed with backend_utils._get_memory_slot_probabilities)
     assert orc.memory_slot_probabilities({"00": 0.1, "01": 0.2, "10": 0.3, "12": 0.4}, [0, 2], 3, 1) == \
         {"000": 0.1, "001": 0.2, "100": 0.3, "101": 0.4}
+
+
+def test_magnus_orders():
+    """Row a9 beyond first order: scipy_expm_solver(magnus_order=2, 3) of the reference
+    (solvers/fixed_step_solvers.py:327-401) against the oracle's restatement."""
+    g = load_golden("magnus")
+    H0, Hs, Y, sig = orc.synthetic_schrodinger(5, 2, 3, 11)
+    close(np.array([np.sum(np.abs(a)) for a in (H0, Hs, Y)] + [np.sum(a).real for a in (H0, Hs, Y)]), g["h_check"], 1e-9)
+    sp = [orc.SigSpec(*s) for s in sig]
+    for order in (2, 3):
+        kw = dict(method="scipy_expm", magnus_order=order)
+        close(orc.solve_hamiltonian(H0, Hs, sp, None, [0, 0.5], Y, 0.05, **kw)[1][-1], g[f"h_noframe_o{order}"])
+        close(orc.solve_hamiltonian(H0, Hs, sp, H0, [0, 0.5], Y, 0.05, **kw)[1][-1], g[f"h_full_o{order}"], 1e-11)
+        close(orc.solve_hamiltonian(H0, Hs, sp, H0, [0, 0.5], Y[:, 0], 0.05, **kw)[1][-1], g[f"h_full_vec_o{order}"], 1e-11)
+        close(orc.solve_hamiltonian(H0, Hs, sp, H0, [0.5, 0.0], Y, 0.04, t_eval=[0.5, 0.31, 0.1], **kw)[1],
+              g[f"h_full_teval_back_o{order}"], 1e-11)
+        A, Bm = -1j * H0, -1j * Hs[0]
+        ys = orc.fixed_step_solve(orc.magnus_step(order), lambda t: A * np.cos(t) + Bm * np.sin(2 * t), [0, 1.0],
+                                  np.eye(5, dtype=complex), 0.1)[1]
+        close(ys[-1], g[f"callable_o{order}"])
+    # the orders differ from each other by far more than the tolerance (the fixtures do discriminate)
+    assert np.max(np.abs(g["h_full_o2"] - g["h_full_o3"])) > 1e-9
+    H0, Hs, Y, sig = orc.synthetic_schrodinger(17, 3, 6, 41)
+    sp = [orc.SigSpec(*s) for s in sig]
+    for order in (2, 3):
+        close(orc.solve_hamiltonian(H0, Hs, sp, H0, [0, 0.3], Y, 0.03, method="scipy_expm", magnus_order=order)[1][-1],
+              g[f"h17_full_o{order}"], 1e-11)
+    H0, Hs, Ls, Y, sig = orc.synthetic_lindblad(3, 2, 4, 4, 31)
+    Lstat, Ldyn = Ls[:2], Ls[2:] + 0.02j * Ls[:2]
+    sp = [orc.SigSpec(*s) for s in sig]
+    dsp = [orc.SigSpec(0.3, 0.0, 0.0), orc.SigSpec(0.2, 0.11, 0.4)]
+    for frame_name, frame in (("none", None), ("full", H0), ("diag", np.diag(H0).real)):
+        for order in (2, 3):
+            _, ys = orc.solve_vectorized_lindblad(H0, Hs, sp, Lstat, Ldyn, dsp, frame, [0, 0.5], Y, 0.05, "scipy_expm",
+                                                  magnus_order=order)
+            close(ys[-1], g[f"l_{frame_name}_o{order}"], 1e-11)

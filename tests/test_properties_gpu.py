@@ -202,3 +202,24 @@ def test_edge_cases(qd):
         k4 = f(times[2 * s + 2], yg + 1e-3 * k3, 0)
         yg = yg + (1.0 / 6) * 1e-3 * (k1 + 2 * k2 + 2 * k3 + k4)
     assert col_err(mm.rotating_frame.state_out_of_frame_basis(yg), rf) < 1e-12
+
+
+def test_magnus_convergence_orders(qd):
+    """The exponential stepper at Magnus order q converges like h^(2q): halving the step divides the error
+    by 4 / 16 / 64 (measured on the oracle for this system: 4.1 / 15.3 / 61.1 between h = 1/16 and 1/32)."""
+    n, K, B = 16, 3, 8
+    H0, Hs, Y, _ = orc.synthetic_schrodinger(n, K, B, 77)
+    sig = [qd.Signal(2.0 * (j + 1), 0.7 * j + 0.4, 0.3 * j) for j in range(K)]
+    m = qd.HamiltonianModel(static_operator=H0, operators=Hs, signals=sig, rotating_frame=H0)
+
+    def sol(h, order):
+        return qd.solve_lmde(m, t_span=[0, 1.0], y0=Y, method="scipy_expm", max_dt=h, magnus_order=order).y[-1]
+
+    ref = sol(1 / 512, 3)
+    for order, lo, hi in ((1, 3.5, 4.6), (2, 13.0, 18.0), (3, 50.0, 75.0)):
+        e1, e2 = col_err(sol(1 / 16, order), ref), col_err(sol(1 / 32, order), ref)
+        assert lo < e1 / e2 < hi, (order, e1, e2)
+    # every order keeps the flow unitary (the exponent is anti-Hermitian term by term)
+    for order in (2, 3):
+        norms = torch.linalg.vector_norm(sol(1 / 16, order), dim=0)
+        assert float((norms - 1).abs().max()) < 1e-12
