@@ -8,6 +8,8 @@
 // load is bank-conflict free (A stride = 64 mod 128 B, B stride = 32 mod 128 B).
 // Two CTAs fit an SM: the narrow tile is chosen when the 64 x 64 grid would leave half of those 296 slots
 // empty (the 729^3 products of the vectorised-Lindblad expm: 144 CTAs -> 276).
+#include <cstdlib>
+
 #include "qdb_common.cuh"
 
 namespace qdb {
@@ -176,6 +178,177 @@ __global__ void __launch_bounds__(256) zgemm_kernel(int M, int N, int Kd, const 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 3-product variant ("3M"): the DMMA issue rate is the roof of every fp64 GEMM here, and a complex tile
+// product needs only three real ones:  p1 += ar br,  p2 += ai bi,  p3 += (ar + ai)(br + bi);
+// re = p1 - p2, im = p3 - p1 - p2 formed once in the epilogue (the trick of rk4_shared3m_kernel, csrc/rk4_fused.cu).
+// A DADD inside the k loop runs on the same fp64 pipe as the DMMAs, so the (re + im) sums are formed ONCE per
+// element while the operand tiles pass through registers on their way to shared memory (global -> registers ->
+// shared, the `pre` phases of the A columns are applied there too) instead of once per fragment load (2x for A,
+// 4x for B).  The k loop is then 12 LDS + 24 DMMAs per k4-step and warp.
+//   CTA tile 64 x 64, k-chunk 16, 8 warps as 4 x 2, warp tile 16 x 32 (2 x 4 DMMA tiles, 3 accumulators each).
+//   Three shared-memory stages + one chunk in registers: chunk kt+2 is stored (and chunk kt+3 requested) in the
+//   middle of the DMMAs of chunk kt, one __syncthreads per chunk; fragment loads run one k4-step ahead of the DMMAs,
+//   across chunk boundaries (with one CTA per SM there are only two warps per sub-partition to hide a bubble).
+//   Per stage: A complex [64][20] double2, A sums [64][20] double, B complex [16][66] double2, B sums [16][68]
+//   double -- the row strides make every fragment load conflict free (128-bit loads per quarter warp: rows 2j and
+//   2j+1 sit 16 banks apart; 64-bit loads per half warp: four rows tile the 32 banks).
+// Error bound: normwise (a few ulp of |A||B|) instead of componentwise.
+// ------------------------------------------------------------------------------------------------
+constexpr int T_STAGES = 3;
+constexpr int TA_LD = 20, TAS_LD = 20, TB_LD = 66, TBS_LD = 68;
+constexpr size_t T_AC = (size_t)BM * TA_LD * sizeof(double2);    // 20480
+constexpr size_t T_AS = (size_t)BM * TAS_LD * sizeof(double);    // 10240
+constexpr size_t T_BC = (size_t)BK * TB_LD * sizeof(double2);    // 16896
+constexpr size_t T_BS = (size_t)BK * TBS_LD * sizeof(double);    //  8704
+constexpr size_t T_STAGE = T_AC + T_AS + T_BC + T_BS;            // 56320
+constexpr size_t T_SMEM = T_STAGES * T_STAGE;                    // 168960
+
+template <typename Epi>
+__global__ void __launch_bounds__(256, 1) zgemm3m_kernel(int M, int N, int Kd, const double2* __restrict__ A, int lda,
+                                                          const double2* __restrict__ Bm, int ldb,
+                                                          const double2* __restrict__ pre, Epi epi) {
+    constexpr int BN = 64;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2;  // 4 x 2 warps
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int numK = (Kd + BK - 1) / BK;
+
+    // staging map: A element (ar + 16 i, ac), B element (br + 4 i, bc), i < 4
+    const int ar = tid >> 4, ac = tid & 15, br = tid >> 6, bc = tid & 63;
+    double2 ra[4], rb[4], rp;
+    auto gload = [&](int kt) {
+        const int k0 = kt * BK;
+        const bool kok = k0 + ac < Kd;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = m0 + ar + 16 * i;
+            ra[i] = (kok && r < M) ? ldg_stream(A + (size_t)r * lda + k0 + ac) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = k0 + br + 4 * i;
+            rb[i] = (r < Kd && n0 + bc < N) ? ldg_stream(Bm + (size_t)r * ldb + n0 + bc) : make_double2(0.0, 0.0);
+        }
+        if (pre != nullptr) rp = kok ? pre[k0 + ac] : make_double2(0.0, 0.0);
+    };
+    auto sstore = [&](int slot) {
+        unsigned char* st = smem_raw + (size_t)slot * T_STAGE;
+        double2* a_c = reinterpret_cast<double2*>(st);
+        double* a_s = reinterpret_cast<double*>(st + T_AC);
+        double2* b_c = reinterpret_cast<double2*>(st + T_AC + T_AS);
+        double* b_s = reinterpret_cast<double*>(st + T_AC + T_AS + T_BC);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double2 v = ra[i];
+            if (pre != nullptr) v = cmul(v, rp);
+            a_c[(ar + 16 * i) * TA_LD + ac] = v;
+            a_s[(ar + 16 * i) * TAS_LD + ac] = v.x + v.y;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            b_c[(br + 4 * i) * TB_LD + bc] = rb[i];
+            b_s[(br + 4 * i) * TBS_LD + bc] = rb[i].x + rb[i].y;
+        }
+    };
+
+    double p[3][2][4][2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) p[a][m][c][0] = p[a][m][c][1] = 0.0;
+
+    // fragments of one k4-step: 6 LDS.128 + 6 LDS.64, consumed by 24 DMMAs
+    struct Frags {
+        double2 a[2], b[4];
+        double as[2], bs[4];
+    };
+    const int a_off = (wm * 16 + g) * TA_LD + q, as_off = (wm * 16 + g) * TAS_LD + q;
+    const int b_off = q * TB_LD + wn * 32 + g, bs_off = q * TBS_LD + wn * 32 + g;
+    auto load_frags = [&](int slot, int kk, Frags& f) {
+        const unsigned char* st = smem_raw + (size_t)slot * T_STAGE;
+        const double2* a_c = reinterpret_cast<const double2*>(st) + a_off + kk * 4;
+        const double* a_s = reinterpret_cast<const double*>(st + T_AC) + as_off + kk * 4;
+        const double2* b_c = reinterpret_cast<const double2*>(st + T_AC + T_AS) + b_off + kk * 4 * TB_LD;
+        const double* b_s = reinterpret_cast<const double*>(st + T_AC + T_AS + T_BC) + bs_off + kk * 4 * TBS_LD;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            f.a[m] = a_c[m * 8 * TA_LD];
+            f.as[m] = a_s[m * 8 * TAS_LD];
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            f.b[c] = b_c[c * 8];
+            f.bs[c] = b_s[c * 8];
+        }
+    };
+    auto mma = [&](const Frags& f) {
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dmma(p[0][m][c][0], p[0][m][c][1], f.a[m].x, f.b[c].x);
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dmma(p[1][m][c][0], p[1][m][c][1], f.a[m].y, f.b[c].y);
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dmma(p[2][m][c][0], p[2][m][c][1], f.as[m], f.bs[c]);
+    };
+
+    // Software pipeline: the fragments of k4-step i+1 are requested before the DMMAs of step i are issued -- across
+    // chunk boundaries too: chunk kt+1 was stored during iteration kt-1 and published by the barrier that ended it,
+    // so its first fragments can be fetched in the last k4-step of chunk kt, ahead of the barrier.  The barrier at
+    // the end of iteration kt publishes chunk kt+2 (stored in the middle of the iteration, while DMMAs are queued)
+    // and retires every read of stage kt % 3 before iteration kt+1 overwrites it with chunk kt+3.
+    gload(0);
+    sstore(0);
+    if (numK > 1) {
+        gload(1);
+        sstore(1);
+    }
+    if (numK > 2) gload(2);
+    __syncthreads();
+    Frags f0, f1;
+    load_frags(0, 0, f0);
+    int slot = 0;
+#pragma unroll 1
+    for (int kt = 0; kt < numK; ++kt) {
+        const int nslot = slot == T_STAGES - 1 ? 0 : slot + 1;
+        load_frags(slot, 1, f1);
+        mma(f0);
+        load_frags(slot, 2, f0);
+        if (kt + 2 < numK) sstore(nslot == T_STAGES - 1 ? 0 : nslot + 1);  // stage (kt + 2) % 3
+        mma(f1);
+        load_frags(slot, 3, f1);
+        if (kt + 3 < numK) gload(kt + 3);
+        mma(f0);
+        if (kt + 1 < numK) load_frags(nslot, 0, f0);
+        mma(f1);
+        __syncthreads();
+        slot = nslot;
+    }
+
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        const int r = m0 + wm * 16 + m * 8 + g;
+        if (r >= M) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int col = n0 + wn * 32 + c * 8 + 2 * q + i;
+                if (col < N)
+                    epilogue(epi, r, col, make_double2(p[0][m][c][i] - p[1][m][c][i], (p[2][m][c][i] - p[0][m][c][i]) - p[1][m][c][i]));
+            }
+    }
+}
+
 int sm_count_zg() {
     static int sms = 0;
     if (sms == 0) {
@@ -201,8 +374,33 @@ int launch_bn(int M, int N, int Kd, const double2* A, int lda, const double2* B,
 }
 
 template <typename Epi>
+int launch_3m(int M, int N, int Kd, const double2* A, int lda, const double2* B, int ldb, const double2* pre,
+              const Epi& epi, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        QDB_CUDA(cudaFuncSetAttribute(zgemm3m_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM));
+        configured = true;
+    }
+    dim3 grid((N + 63) / 64, (M + BM - 1) / BM);
+    zgemm3m_kernel<Epi><<<grid, 256, T_SMEM, st>>>(M, N, Kd, A, lda, B, ldb, pre, epi);
+    QDB_LAUNCH_CHECK("zgemm3m_kernel");
+    return QDB_OK;
+}
+
+// QDB_ZGEMM_4M=1 pins the 4-product kernel (bit-level reference of the 3-product one in the tests)
+bool zgemm_3m_enabled() {
+    const char* e = getenv("QDB_ZGEMM_4M");
+    return !(e && e[0] == '1');
+}
+
+template <typename Epi>
 int launch(int M, int N, int Kd, const double2* A, int lda, const double2* B, int ldb, const double2* pre,
            const Epi& epi, cudaStream_t st) {
+    // 3-product kernel (one CTA per SM) once its 64 x 64 grid fills at least half of the SMs and the k loop is long
+    // enough to amortise the three-stage fill; small products stay on the 4-product kernel (two CTAs per SM, narrow tiles)
+    const long tiles64 = (long)((N + 63) / 64) * ((M + BM - 1) / BM);
+    if (zgemm_3m_enabled() && 2 * tiles64 >= sm_count_zg() && Kd >= 64)
+        return launch_3m<Epi>(M, N, Kd, A, lda, B, ldb, pre, epi, st);
     // 64 x 64 tiles unless they would fill fewer than the 2 CTA slots per SM
     const long ctas64 = (long)((N + 63) / 64) * ((M + BM - 1) / BM);
     if (ctas64 < 2L * sm_count_zg() && N > 32) return launch_bn<Epi, 32>(M, N, Kd, A, lda, B, ldb, pre, epi, st);

@@ -75,7 +75,9 @@ def test_pack_and_generator(abi):
         np.testing.assert_allclose(outs, stat, rtol=0, atol=0)
 
 
-@pytest.mark.parametrize("M,N,Kd", [(1, 1, 1), (5, 3, 7), (64, 64, 16), (65, 67, 17), (128, 4096, 128), (729, 40, 729), (200, 130, 33)])
+@pytest.mark.parametrize("M,N,Kd", [(1, 1, 1), (5, 3, 7), (64, 64, 16), (65, 67, 17), (128, 4096, 128), (729, 40, 729), (200, 130, 33),
+                                    # 3-product kernel (>= 74 tiles of 64 x 64, k >= 64): full tiles, ragged edges in all three dimensions
+                                    (729, 729, 729), (200, 1500, 67), (321, 963, 130), (64, 4800, 64)])
 def test_zgemm(abi, M, N, Kd):
     rng = np.random.default_rng(M * 1000 + N)
     A = rng.standard_normal((M, Kd)) + 1j * rng.standard_normal((M, Kd))
@@ -92,6 +94,27 @@ def test_zgemm(abi, M, N, Kd):
     abi.zgemm(dev(A), dev(Bm), out=c, alpha=alpha, beta=beta, colscale=dev(cs), pre=dev(pre), post=dev(post))
     ref = beta * C0 + alpha * cs[None, :] * post[:, None] * (A @ (pre[:, None] * Bm))
     np.testing.assert_allclose(c.cpu().numpy(), ref, rtol=0, atol=TOL_OP * scale * 10)
+
+
+def test_zgemm_three_product_vs_four_product(abi, monkeypatch):
+    """The 3-product kernel changes rounding only: against the 4-product kernel (QDB_ZGEMM_4M=1) on the shapes of the
+    vectorised-Lindblad propagator (729^3) and its application (729 x 4096 x 729) the difference stays at a few
+    ulp of |A||B| (normwise bound), and both agree with NumPy."""
+    rng = np.random.default_rng(7)
+    for M, N, Kd in ((729, 729, 729), (729, 4096, 729), (128, 4096, 128)):
+        A = rng.standard_normal((M, Kd)) + 1j * rng.standard_normal((M, Kd))
+        Bm = rng.standard_normal((Kd, N)) + 1j * rng.standard_normal((Kd, N))
+        Ad, Bd = dev(A), dev(Bm)
+        before = abi.launch_count()
+        out3 = abi.zgemm(Ad, Bd).cpu().numpy()
+        monkeypatch.setenv("QDB_ZGEMM_4M", "1")
+        out4 = abi.zgemm(Ad, Bd).cpu().numpy()
+        monkeypatch.delenv("QDB_ZGEMM_4M")
+        assert abi.launch_count() - before == 2
+        bound = np.abs(A) @ np.abs(Bm)
+        assert np.max(np.abs(out3 - out4) / bound) < 16 * np.finfo(float).eps
+        assert np.max(np.abs(out3 - out4)) > 0  # two different kernels did run
+        np.testing.assert_allclose(out3, A @ Bm, rtol=0, atol=TOL_OP * np.sqrt(Kd) * 10)
 
 
 @pytest.mark.parametrize("n,K,B,frame", [(8, 3, 5, "full"), (5, 2, 3, "diag"), (5, 2, 1, "none"), (128, 8, 64, "full"), (32, 8, 40, "full")])
@@ -295,8 +318,9 @@ def test_rk4_fused_sweep(abi, n, K, B, S, frame):
     assert max_col_l2(yd.cpu().numpy()[:, :4], ref2[:, :4]) < TOL_SOLVE
 
 
-def test_rk4_generic_large_n(abi):
-    n, K, B, S = 264, 2, 24, 3
+@pytest.mark.parametrize("B,S", [(24, 3), (2048, 2)])  # 4-product GEMM stages / 3-product GEMM stages (160 tiles)
+def test_rk4_generic_large_n(abi, B, S):
+    n, K = 264, 2
     Gd, G, d, mu, y, specs = model_inputs(n, K, B, 5, "full")
     t0, h = 0.0, 1e-3
     times = orc.stage_time_grid(t0, h, S)
