@@ -37,10 +37,12 @@ def sweep(name, n, K, B, S, seed):
     ms = timeit(run)
     alg = S * B * (4 * ((4 * K + 8) * n * n + 12 * n) + 28 * n)
     exe = S * B * 4 * (K + 1) * 8 * n * n
-    print(json.dumps({"config": name, "kernel": "rk4_sweep_kernel", "n": n, "K": K, "B": B, "rk4_steps": S, "ms": ms,
+    tiling = abi.rk4_tiling(n, B, K)
+    kernel = "rk4_sweepf_kernel" if tiling["m3"] == 2 else ("rk4_sweep_small_kernel" if n <= 32 and K <= 16 else "rk4_sweep_kernel")
+    print(json.dumps({"config": name, "kernel": kernel, "sweep_kernel_env": os.environ.get("QDB_SWEEP_KERNEL", "auto"), "n": n, "K": K, "B": B, "rk4_steps": S, "ms": ms,
                       "us_per_step": ms * 1e3 / S, "state_rhs_per_s": 4 * S * B / ms * 1e3, "alg_tflops": alg / ms * 1e-9,
                       "exec_tflops": exe / ms * 1e-9, "dmma_peak_tflops": peak, "alg_frac": alg / ms * 1e-9 / peak,
-                      "exec_frac": exe / ms * 1e-9 / peak, "tiling": abi.rk4_tiling(n, B, K),
+                      "exec_frac": exe / ms * 1e-9 / peak, "tiling": tiling,
                       "unitarity_drift": float((torch.linalg.vector_norm(y, dim=0) - 1).abs().max())}), flush=True)
 
 if "cfg2" in which: sweep("cfg2: dim-32, 8 drive operators, batch-1024 amplitude sweep, RK4", 32, 8, 1024, 500, 2002)

@@ -67,8 +67,14 @@ size_t qdb_workspace_bytes(int kind, int n, int K, int B, int S) {
         case QDB_WS_RHS:
             return align_up(n2) + 2 * align_up((size_t)n * sizeof(double2));
         case QDB_WS_RK4:
-            if (rk4_fused_supported(n))
-                return align_up((size_t)(2 * S + 1) * np2) + align_up((size_t)(2 * S + 1) * sizeof(double));
+            if (rk4_fused_supported(n)) {
+                // shared signals: generator table + stage times; per-column signals: stage times + the formed-sweep
+                // operator copy (the caller does not say which mode it will ask for: the larger of the two)
+                const size_t shared = align_up((size_t)(2 * S + 1) * np2) + align_up((size_t)(2 * S + 1) * sizeof(double));
+                const size_t sweep = align_up((size_t)(2 * S + 1) * sizeof(double)) +
+                                     (rk4_sweepf_supported(n, K) ? align_up(rk4_sweepf_workspace_bytes(n, K)) : 0);
+                return shared > sweep ? shared : sweep;
+            }
             return 3 * align_up(n2) + 3 * align_up(yb) + align_up(3 * sizeof(double));
         case QDB_WS_EXPM:
             return 7 * align_up(n2) + align_up(yb);
@@ -199,7 +205,11 @@ int qdb_rk4_steps_c128(int n, int K, int B, int S, const qdb_c128* ops_rm, const
             }
             double* times_dev = (double*)ws;
             if (mu) QDB_CUDA(cudaMemcpyAsync(times_dev, times_host, (size_t)(2 * S + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
-            return launch_rk4_fused_sweep(n, K, B, S, D2(stat_packed), D2(ops_packed), coeff, ldc, mu, times_dev, h, D2(y), ldy, st);
+            // the formed-generator kernel needs room for its operator copy behind the stage times; without it the
+            // operator-pass kernels run
+            void* fws = nullptr;
+            if (rk4_sweepf_supported(n, K) && ws_bytes >= need + align_up(rk4_sweepf_workspace_bytes(n, K))) fws = ws + need;
+            return launch_rk4_fused_sweep(n, K, B, S, D2(stat_packed), D2(ops_packed), coeff, ldc, mu, times_dev, h, D2(y), ldy, fws, st);
         }
         // shared signals: chunk the step loop so that the generator table fits the workspace
         const int table_layout = rk4_fused_table_layout(n, B);

@@ -117,7 +117,14 @@ int rk4_fused_table_layout(int n, int B);
 int launch_rk4_fused_sweep(int n, int K, int B, int S, const double2* stat_packed /*or null*/,
                            const double2* ops_packed /*[K]*/, const double* coeff, int ldc,
                            const double* mu, const double* times_dev,
-                           double h, double2* y, int ldy, cudaStream_t st);
+                           double h, double2* y, int ldy, void* ws /*rk4_sweepf_workspace_bytes*/, cudaStream_t st);
+// formed-generator sweep kernel (rk4_sweepf.cu): 3 <= K <= 8
+bool rk4_sweepf_supported(int n, int K);
+bool rk4_sweepf_selected(int n, int K, bool small_kernel_available);
+size_t rk4_sweepf_workspace_bytes(int n, int K);
+bool rk4_sweepf_tiling(int n, int B, int K, int* out);
+int launch_rk4_sweepf(int n, int K, int B, int S, const double2* stat_packed, const double2* ops_packed, const double* coeff,
+                      int ldc, const double* mu, const double* times_dev, double h, double2* y, int ldy, void* ws, cudaStream_t st);
 int launch_signal_table(int T, int K, int B, int nterms, const int* chan, const long long* samp_off,
                         const int* samp_len, const double* dt, const double* t0, const double* freq,
                         const double* phase, int params_per_col, const double2* samples, long long col_stride,

@@ -1,0 +1,456 @@
+// Fused RK4 in sweep mode (per-column signal values) with the generator FORMED per column on the tensor pipe
+// (SURVEY.md 8(a) rows a1 + a2 + a3 + a7 per column; the reference's order of operations: G_b = G_d + sum_j c_jb G_j,
+// then G_b y_b -- models/operator_collections.py:101-134).
+//
+// Why.  rk4_sweep_kernel computes sum_j G_j (c_jb y_b): K+1 complex operator passes, 4 (K+1) fp64 FMAs per generator
+// element and column.  The fp64 tensor pipe and the fp64 FMA pipe of sm_100 are ONE pipe (profiles/r01_l_fp64_probe2.jsonl:
+// any mix of DMMA and DFMA issues 16 FMA per clock and sub-partition), so what counts is the FMA total -- and forming
+// G_b first needs only 2 K + 4: the coefficients are real, so a generator element costs 2 K FMAs, and its use 4.
+//   * formation = a DMMA whose k dimension is the OPERATOR index: A = 8 generator elements (rows 8 rt + g of column c)
+//     x 4 operators, B = 4 operators x 8 columns of the batch (the signal values of the stage, held in registers),
+//     C = the static operator broadcast over the columns, D = Re (or Im) of G_b[8 rt + g][c] for 8 columns.
+//     K <= 4: one DMMA per part, K <= 8: two.
+//   * D arrives in exactly the accumulator layout (lane 4 g + q: row g, columns 2 q, 2 q + 1), so the product with
+//     y_b[c] is four DFMAs per column on registers; the state row c is a 32 B broadcast load from shared memory.
+// Per generator element and column: 2 Kpad + 4 FMAs (20 at K = 8) against 36 -- the algorithmic count of SURVEY 8(d).
+//
+// A CTA owns 8 NCT whole columns for the entire launch (as in rk4_fused.cu).  Operators stream L2 -> registers in
+// fragment order (layout below, built per call by pack_sweepf_kernel) through a two-deep register ring, one matrix
+// column ahead; the stage vector lives in shared memory as [row][column] (row stride 8 NCT + 1 complex numbers: the
+// epilogue's two-row stores fall into disjoint banks), single buffered between two barriers per stage; y and the RK4
+// k-sum sit in thread-private shared-memory slabs.  Frame phases: on the stage-vector rows when written, on the
+// result rows when read (as rk4_sweep_kernel).
+//
+// Operator layout ("formed-sweep"): opsf[((rt * C2 + c) * KS + ks) * 32 + 4 g + q] = ops[4 ks + q][8 rt + g][c],
+// statf[(rt * C2 + c) * 8 + g] = stat[8 rt + g][c]; zero outside the matrix; C2 = n rounded up to even.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "qdb_common.cuh"
+#include "rk4_device.cuh"
+
+namespace qdb {
+
+namespace {
+
+struct FGeo {
+    int n, npad, C2, RT;
+    int WR, WC, NCT;
+};
+
+// D = A B + C with C = (c, c) kept intact (the static operator is reused for every column tile)
+__device__ __forceinline__ void dmma_from(double& d0, double& d1, double a, double b, double c) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+        : "=d"(d0), "=d"(d1)
+        : "d"(a), "d"(b), "d"(c), "d"(c));
+}
+
+__global__ void pack_sweepf_kernel(int n, int K, int KS, int C2, int RT, const double2* __restrict__ ops_packed,
+                                   const double2* __restrict__ stat_packed, double2* __restrict__ opsf,
+                                   double2* __restrict__ statf) {
+    const int kpad = round_up16(n);
+    const size_t per_op = (size_t)round_up8(n) * kpad;
+    const size_t nops = (size_t)RT * C2 * KS * 32;
+    const size_t nstat = (size_t)RT * C2 * 8;
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < nops) {
+        const int lane = (int)(e & 31);
+        size_t t = e >> 5;
+        const int ks = (int)(t % KS);
+        t /= KS;
+        const int c = (int)(t % C2), rt = (int)(t / C2);
+        const int j = 4 * ks + (lane & 3), r = 8 * rt + (lane >> 2);
+        double2 v = make_double2(0.0, 0.0);
+        if (j < K && r < n && c < n) v = ops_packed[(size_t)j * per_op + packed_index(kpad, r, c)];
+        opsf[e] = v;
+    } else if (e < nops + nstat && statf != nullptr) {
+        const size_t s = e - nops;
+        const int gg = (int)(s & 7);
+        const size_t t = s >> 3;
+        const int c = (int)(t % C2), rt = (int)(t / C2);
+        const int r = 8 * rt + gg;
+        double2 v = make_double2(0.0, 0.0);
+        if (stat_packed != nullptr && r < n && c < n) v = stat_packed[packed_index(kpad, r, c)];
+        statf[s] = v;
+    }
+}
+
+template <int MR, int NCW, int KS>
+__global__ void __launch_bounds__(256, 1)
+rk4_sweepf_kernel(FGeo geo, int K, int B, int S, const double2* __restrict__ statf /*or null*/,
+                  const double2* __restrict__ opsf, const double* __restrict__ coeff /*[2S+1][K][ldc]*/, int ldc,
+                  const double* __restrict__ mu, const double* __restrict__ times /*[2S+1]*/, double h,
+                  double2* __restrict__ y, int ldy) {
+    extern __shared__ __align__(16) double2 sm[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int wr = warp % geo.WR, wc = warp / geo.WR;
+    const int n = geo.n, C2 = geo.C2, NCT = geo.NCT;
+    const int nthr = blockDim.x;
+    const int ncols = 8 * NCT, LD = ncols + 1;
+    double2* ys = sm;                                   // [npad][LD] stage vector, pre-phased
+    double2* yslab = sm + (size_t)geo.npad * LD;        // [MR*NCW*2][nthr]
+    double2* kslab = yslab + (size_t)MR * NCW * 2 * nthr;
+    const int col0 = blockIdx.x * ncols;
+    const int lc0 = 8 * wc * NCW;  // first local column of this warp
+    const bool framed = (mu != nullptr);
+    const bool has_stat = (statf != nullptr);
+
+    int rt[MR], rtl[MR];
+    bool mvalid[MR];
+    double mu_row[MR];
+#pragma unroll
+    for (int m = 0; m < MR; ++m) {
+        rt[m] = wr + geo.WR * m;
+        mvalid[m] = rt[m] < geo.RT;
+        rtl[m] = mvalid[m] ? rt[m] : geo.RT - 1;
+        const int row = 8 * rt[m] + g;
+        mu_row[m] = (framed && mvalid[m] && row < n) ? mu[row] : 0.0;
+    }
+    double2 ph[MR];
+    {
+        const double t0 = framed ? times[0] : 0.0;
+#pragma unroll
+        for (int m = 0; m < MR; ++m) ph[m] = framed ? frame_phase(mu_row[m], t0) : make_double2(1.0, 0.0);
+    }
+
+    for (int i = tid; i < geo.npad * LD; i += nthr) ys[i] = make_double2(0.0, 0.0);
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < MR; ++m)
+#pragma unroll
+        for (int c = 0; c < NCW; ++c)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int row = 8 * rt[m] + g;
+                const int lc = lc0 + 8 * c + 2 * q + i;
+                double2 v = make_double2(0.0, 0.0);
+                if (mvalid[m] && row < n && col0 + lc < B) v = y[(size_t)row * ldy + col0 + lc];
+                yslab[((m * NCW + c) * 2 + i) * nthr + tid] = v;
+                if (mvalid[m]) ys[row * LD + lc] = cmul(ph[m], v);
+            }
+
+    double ar[MR][NCW][2], ai[MR][NCW][2];  // G_b y accumulators (C-fragment layout)
+#pragma unroll
+    for (int m = 0; m < MR; ++m)
+#pragma unroll
+        for (int c = 0; c < NCW; ++c) ar[m][c][0] = ar[m][c][1] = ai[m][c][0] = ai[m][c][1] = 0.0;
+
+    // operator stream: per matrix column c and row tile, KS fragments of 32 complex numbers + 8 static entries
+    const double2* pa[MR];
+    const double2* ps[MR];
+#pragma unroll
+    for (int m = 0; m < MR; ++m) {
+        pa[m] = opsf + (size_t)rtl[m] * C2 * KS * 32 + lane;
+        ps[m] = has_stat ? statf + (size_t)rtl[m] * C2 * 8 + g : nullptr;
+    }
+    double2 ring[2][MR][KS], rs[2][MR];
+    auto fetch = [&](int c, double2 (&dst)[MR][KS], double2 (&dsts)[MR]) {
+#pragma unroll
+        for (int m = 0; m < MR; ++m) {
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) dst[m][ks] = __ldg(pa[m] + ((size_t)c * KS + ks) * 32);
+            dsts[m] = has_stat ? __ldg(ps[m] + (size_t)c * 8) : make_double2(0.0, 0.0);
+        }
+    };
+    fetch(0, ring[0], rs[0]);
+
+    // signal values of a stage in DMMA B-fragment order: lane (g, q) holds c[4 ks + q][column 8 ct + g]
+    auto load_coef = [&](int entry, double (&cf)[NCW][KS]) {
+#pragma unroll
+        for (int c = 0; c < NCW; ++c)
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const int j = 4 * ks + q, col = col0 + lc0 + 8 * c + g;
+                cf[c][ks] = (j < K && col < B) ? coeff[((size_t)entry * K + j) * ldc + col] : 0.0;
+            }
+    };
+    double cf[NCW][KS], cfn[NCW][KS];
+    load_coef(0, cf);
+    __syncthreads();
+
+    // one matrix column: form G_b[rows of this warp][c] for the warp's columns, multiply with y_b[c]
+    auto column = [&](int c, const double2 (&A)[MR][KS], const double2 (&As)[MR]) {
+        double2 yv[NCW][2];
+#pragma unroll
+        for (int ct = 0; ct < NCW; ++ct)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) yv[ct][i] = ys[c * LD + lc0 + 8 * ct + 2 * q + i];
+        double gr[2][NCW][2], gi[2][NCW][2];
+        auto form = [&](int m, int slot) {
+#pragma unroll
+            for (int ct = 0; ct < NCW; ++ct) {
+                dmma_from(gr[slot][ct][0], gr[slot][ct][1], A[m][0].x, cf[ct][0], As[m].x);
+                dmma_from(gi[slot][ct][0], gi[slot][ct][1], A[m][0].y, cf[ct][0], As[m].y);
+            }
+#pragma unroll
+            for (int ks = 1; ks < KS; ++ks)
+#pragma unroll
+                for (int ct = 0; ct < NCW; ++ct) {
+                    dmma(gr[slot][ct][0], gr[slot][ct][1], A[m][ks].x, cf[ct][ks]);
+                    dmma(gi[slot][ct][0], gi[slot][ct][1], A[m][ks].y, cf[ct][ks]);
+                }
+        };
+        form(0, 0);
+#pragma unroll
+        for (int m = 0; m < MR; ++m) {
+            if (m + 1 < MR) form(m + 1, (m + 1) & 1);  // next row tile's DMMAs are queued before this tile's DFMAs wait
+            const int s = m & 1;
+#pragma unroll
+            for (int ct = 0; ct < NCW; ++ct)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    ar[m][ct][i] = fma(gr[s][ct][i], yv[ct][i].x, ar[m][ct][i]);
+                    ai[m][ct][i] = fma(gr[s][ct][i], yv[ct][i].y, ai[m][ct][i]);
+                    ar[m][ct][i] = fma(-gi[s][ct][i], yv[ct][i].y, ar[m][ct][i]);
+                    ai[m][ct][i] = fma(gi[s][ct][i], yv[ct][i].x, ai[m][ct][i]);
+                }
+        }
+    };
+
+    const int total_stages = 4 * S;
+#pragma unroll 1
+    for (int sidx = 0; sidx < total_stages; ++sidx) {
+        const int step = sidx >> 2, stage = sidx & 3;
+        const int entry = 2 * step + (stage == 0 ? 0 : (stage == 3 ? 2 : 1));
+        const int nstage = (stage + 1) & 3, nstep = step + (stage == 3 ? 1 : 0);
+        const int next_entry = (sidx + 1 < total_stages) ? 2 * nstep + (nstage == 0 ? 0 : (nstage == 3 ? 2 : 1)) : entry;
+        load_coef(next_entry, cfn);  // lands during the column loop
+
+#pragma unroll 1
+        for (int c = 0; c < C2; c += 2) {
+            fetch(c + 1, ring[1], rs[1]);
+            column(c, ring[0], rs[0]);
+            fetch(c + 2 < C2 ? c + 2 : 0, ring[0], rs[0]);  // wraps: the operators are time independent
+            column(c + 1, ring[1], rs[1]);
+        }
+
+        // ---- epilogue: post-phase conj(p(t_stage)) on k, RK4 combine, pre-phase p(t_next) on the next stage input ----
+        double2 ph_next[MR];
+        {
+            const double tn = framed ? times[next_entry] : 0.0;
+#pragma unroll
+            for (int m = 0; m < MR; ++m) ph_next[m] = (framed && next_entry != entry) ? frame_phase(mu_row[m], tn) : ph[m];
+        }
+        const StageCoef sc(stage, h);
+#pragma unroll
+        for (int m = 0; m < MR; ++m)
+#pragma unroll
+            for (int ct = 0; ct < NCW; ++ct)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int slot = ((m * NCW + ct) * 2 + i) * nthr + tid;
+                    const double2 k = cmul_conj_a(ph[m], make_double2(ar[m][ct][i], ai[m][ct][i]));
+                    double2 ks = stage == 0 ? make_double2(0.0, 0.0) : kslab[slot];
+                    ks.x = sc.keep * ks.x + sc.wk * k.x;
+                    ks.y = sc.keep * ks.y + sc.wk * k.y;
+                    const double v_r = sc.last ? ks.x : k.x, v_i = sc.last ? ks.y : k.y;
+                    const double2 yv = yslab[slot];
+                    const double2 nxt = make_double2(yv.x + sc.astep * v_r, yv.y + sc.astep * v_i);
+                    if (sc.last) yslab[slot] = nxt; else kslab[slot] = ks;
+                    const double2 pn = cmul(ph_next[m], nxt);
+                    ar[m][ct][i] = pn.x;  // parked in the accumulator registers until every warp has left the column loop
+                    ai[m][ct][i] = pn.y;
+                }
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < MR; ++m)
+#pragma unroll
+            for (int ct = 0; ct < NCW; ++ct)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    if (mvalid[m]) ys[(8 * rt[m] + g) * LD + lc0 + 8 * ct + 2 * q + i] = make_double2(ar[m][ct][i], ai[m][ct][i]);
+                    ar[m][ct][i] = 0.0;
+                    ai[m][ct][i] = 0.0;
+                }
+#pragma unroll
+        for (int m = 0; m < MR; ++m) ph[m] = ph_next[m];
+#pragma unroll
+        for (int ct = 0; ct < NCW; ++ct)
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) cf[ct][ks] = cfn[ct][ks];
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int m = 0; m < MR; ++m)
+#pragma unroll
+        for (int c = 0; c < NCW; ++c)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int row = 8 * rt[m] + g;
+                const int col = col0 + lc0 + 8 * c + 2 * q + i;
+                if (mvalid[m] && row < n && col < B) y[(size_t)row * ldy + col] = yslab[((m * NCW + c) * 2 + i) * nthr + tid];
+            }
+}
+
+struct FConfig {
+    FGeo geo;
+    int MR, NCW, KS, threads, grid;
+    size_t smem;
+};
+
+constexpr size_t kSmemLimitF = 227 * 1024;
+
+int sm_count_f() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0, v = 0;
+        sms = (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+               v > 0) ? v : 148;
+    }
+    return sms;
+}
+
+bool pick_sweepf(int n, int B, int K, FConfig& cfg) {
+    if (n < 1 || round_up8(n) > 256 || K < 1 || K > 8) return false;
+    const int SMS = sm_count_f();
+    FGeo geo;
+    geo.n = n;
+    geo.npad = round_up8(n);
+    geo.C2 = (n + 1) & ~1;
+    geo.RT = geo.npad / 8;
+    const int CT = (B + 7) / 8;
+    int WR, WC, MR;
+    if (geo.RT >= 8) {
+        WR = 8;
+        WC = 1;
+        MR = (geo.RT + 7) / 8;
+        const int MR4 = (geo.RT + 3) / 4;
+        if (MR4 <= 4 && MR4 * 4 < MR * 8) {  // fewer idle row slots with 4 row warps x 2 column warps
+            WR = 4;
+            WC = 2;
+            MR = MR4;
+        }
+    } else {
+        WR = 1;
+        while (WR < geo.RT) WR *= 2;
+        MR = 1;
+        WC = 8 / WR;
+    }
+    if (const char* force = getenv("QDB_FORCE_SWEEPF")) {  // "WR,WC,MR" (profiling only)
+        int fwr, fwc, fmr;
+        if (sscanf(force, "%d,%d,%d", &fwr, &fwc, &fmr) == 3 && fwr * fmr >= geo.RT && fwr * fwc <= 8 && fmr >= 1 && fmr <= 4) {
+            WR = fwr;
+            WC = fwc;
+            MR = fmr;
+        }
+    }
+    static const int ncw_opts[5][3] = {{0, 0, 0}, {4, 2, 1}, {3, 2, 1}, {2, 1, 0}, {1, 0, 0}};
+    bool found = false;
+    double best = 0;
+    // fewer column warps when the batch is too small to give every SM a CTA
+    for (int wc = WC; wc >= 1; wc /= 2) {
+        for (int o = 0; o < 3; ++o) {
+            const int NCW = ncw_opts[MR][o];
+            if (NCW == 0) continue;
+            const int NCT = NCW * wc, threads = 32 * WR * wc;
+            const size_t smem = ((size_t)geo.npad * (8 * NCT + 1) + (size_t)2 * MR * NCW * 2 * threads) * sizeof(double2);
+            if (smem > kSmemLimitF) continue;
+            const int ctas = (CT + NCT - 1) / NCT;
+            // busiest SM: waves x (fixed per-stage part + pipe time of its column tiles).  A sub-partition with two warps
+            // keeps the fp64 pipe full; a lone warp (128-thread CTAs) reaches about 0.65 of it but leaves twice as many
+            // CTAs for a batch that cannot fill the chip.
+            const double wps = threads / 128.0;
+            const double cost = (double)((ctas + SMS - 1) / SMS) * (0.5 + NCW * wps / (wps >= 2.0 ? 1.0 : 0.65));
+            if (!found || cost < best - 1e-9) {
+                found = true;
+                best = cost;
+                cfg.geo = geo;
+                cfg.geo.WR = WR;
+                cfg.geo.WC = wc;
+                cfg.geo.NCT = NCT;
+                cfg.MR = MR;
+                cfg.NCW = NCW;
+                cfg.KS = (K + 3) / 4;
+                cfg.threads = threads;
+                cfg.grid = ctas;
+                cfg.smem = smem;
+            }
+        }
+    }
+    return found;
+}
+
+template <int MR, int NCW, int KS>
+int launch_sweepf_t(const FConfig& cfg, int K, int B, int S, const double2* statf, const double2* opsf, const double* coeff, int ldc,
+                    const double* mu, const double* times, double h, double2* y, int ldy, cudaStream_t st) {
+    QDB_CUDA(cudaFuncSetAttribute(rk4_sweepf_kernel<MR, NCW, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+    rk4_sweepf_kernel<MR, NCW, KS><<<cfg.grid, cfg.threads, cfg.smem, st>>>(cfg.geo, K, B, S, statf, opsf, coeff, ldc, mu, times, h, y, ldy);
+    QDB_LAUNCH_CHECK("rk4_sweepf_kernel");
+    return QDB_OK;
+}
+
+}  // namespace
+
+// 0 = automatic, 1 = legacy kernels only (QDB_SWEEP_KERNEL=legacy), 2 = formed-generator kernel wherever it exists
+// (QDB_SWEEP_KERNEL=formed; the automatic choice keeps the shared-memory-resident kernel for n <= 32)
+static int sweep_kernel_mode() {
+    const char* e = getenv("QDB_SWEEP_KERNEL");
+    if (e && strcmp(e, "legacy") == 0) return 1;
+    if (e && strcmp(e, "formed") == 0) return 2;
+    return 0;
+}
+
+bool rk4_sweepf_supported(int n, int K) { return n >= 1 && round_up8(n) <= 256 && K >= 3 && K <= 8; }
+
+bool rk4_sweepf_selected(int n, int K, bool small_kernel_available) {
+    const int mode = sweep_kernel_mode();
+    if (mode == 1 || !rk4_sweepf_supported(n, K)) return false;
+    return mode == 2 || !small_kernel_available;
+}
+
+size_t rk4_sweepf_workspace_bytes(int n, int K) {
+    const size_t RT = round_up8(n) / 8, C2 = (n + 1) & ~1, KS = (K + 3) / 4;
+    return (RT * C2 * KS * 32 + RT * C2 * 8) * sizeof(double2);
+}
+
+bool rk4_sweepf_tiling(int n, int B, int K, int* out) {
+    FConfig cfg;
+    if (!pick_sweepf(n, B, K, cfg)) return false;
+    out[0] = cfg.geo.WR;
+    out[1] = cfg.geo.WC;
+    out[2] = cfg.MR;
+    out[3] = cfg.NCW;
+    out[4] = 0;
+    out[5] = cfg.grid;
+    out[6] = cfg.threads;
+    out[7] = (int)cfg.smem;
+    out[8] = 2;  // 2 = formed-generator sweep kernel
+    return true;
+}
+
+int launch_rk4_sweepf(int n, int K, int B, int S, const double2* stat_packed, const double2* ops_packed, const double* coeff,
+                      int ldc, const double* mu, const double* times_dev, double h, double2* y, int ldy, void* ws, cudaStream_t st) {
+    FConfig cfg;
+    if (!pick_sweepf(n, B, K, cfg)) {
+        set_error("rk4 formed sweep: unsupported shape n=%d B=%d K=%d", n, B, K);
+        return QDB_E_UNSUPPORTED;
+    }
+    const size_t nops = (size_t)cfg.geo.RT * cfg.geo.C2 * cfg.KS * 32, nstat = (size_t)cfg.geo.RT * cfg.geo.C2 * 8;
+    double2* opsf = (double2*)ws;
+    double2* statf = stat_packed ? opsf + nops : nullptr;
+    const size_t total = nops + (stat_packed ? nstat : 0);
+    pack_sweepf_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n, K, cfg.KS, cfg.geo.C2, cfg.geo.RT, ops_packed, stat_packed, opsf, statf);
+    QDB_LAUNCH_CHECK("pack_sweepf_kernel");
+#define QDB_F(mr, ncw)                                                                                                     \
+    if (cfg.MR == mr && cfg.NCW == ncw) {                                                                                  \
+        if (cfg.KS == 1) return launch_sweepf_t<mr, ncw, 1>(cfg, K, B, S, statf, opsf, coeff, ldc, mu, times_dev, h, y, ldy, st); \
+        return launch_sweepf_t<mr, ncw, 2>(cfg, K, B, S, statf, opsf, coeff, ldc, mu, times_dev, h, y, ldy, st);           \
+    }
+    QDB_F(1, 1)
+    QDB_F(1, 2)
+    QDB_F(1, 4)
+    QDB_F(2, 1)
+    QDB_F(2, 2)
+    QDB_F(2, 3)
+    QDB_F(3, 1)
+    QDB_F(3, 2)
+    QDB_F(4, 1)
+#undef QDB_F
+    set_error("rk4 formed sweep: no kernel for MR=%d NCW=%d", cfg.MR, cfg.NCW);
+    return QDB_E_UNSUPPORTED;
+}
+
+}  // namespace qdb

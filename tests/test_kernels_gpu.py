@@ -318,6 +318,65 @@ def test_rk4_fused_sweep(abi, n, K, B, S, frame):
     assert max_col_l2(yd.cpu().numpy()[:, :4], ref2[:, :4]) < TOL_SOLVE
 
 
+@pytest.mark.parametrize("kernel", ["formed", "legacy"])
+@pytest.mark.parametrize("n,K,B,S,frame", [
+    (32, 8, 48, 6, "full"),     # cfg2 shape: 4 row warps, two DMMA k-steps over the operator index
+    (81, 8, 40, 3, "full"),     # cfg5 dimension: odd n (matrix columns padded to 82), 11 row tiles on 4 x 3 slots
+    (128, 8, 72, 3, "full"),    # cfg4 shape in sweep mode: 8 row warps x 2 row tiles, ragged last CTA
+    (5, 3, 3, 10, "diag"),      # one row tile, one k-step, partial octet
+    (17, 5, 9, 5, "diag"),      # K padded 5 -> 8
+    (50, 4, 16, 3, "none"),     # exactly one k-step, no frame
+    (27, 6, 20, 4, "full"),
+    (200, 3, 12, 2, "full"),    # 25 row tiles: 8 row warps x 4 row tiles
+    (16, 7, 600, 3, "none"),    # many CTAs of a small system
+])
+def test_rk4_sweep_kernel_variants(abi, monkeypatch, kernel, n, K, B, S, frame):
+    """Both sweep-kernel families on the same inputs: the formed-generator kernel (DMMA over the operator index + DFMA
+    product, rk4_sweepf.cu) and the operator-pass kernels (rk4_sweep_kernel / rk4_sweep_small_kernel), pinned through
+    QDB_SWEEP_KERNEL, each against the oracle's per-column solves; with and without a static operator."""
+    monkeypatch.setenv("QDB_SWEEP_KERNEL", kernel)
+    assert abi.rk4_tiling(n, B, K)["m3"] == (2 if kernel == "formed" else 0)
+    Gd, G, d, mu, y, specs = model_inputs(n, K, B, 77 + n, frame)
+    t0, h = 0.0, 1e-3 if n >= 32 else 0.01
+    times = orc.stage_time_grid(t0, h, S)
+    base = orc.signal_list_values(specs, times)
+    amp = 0.5 + np.arange(B) / B
+    coeff = base[:, :, None] * amp[None, None, :]
+    nref = min(B, 24)
+    cols = np.unique(np.concatenate([np.arange(min(B, 12)), np.arange(B - min(B, 12), B)]))[:nref]
+    Gdev, Gd_dev = dev(G), dev(Gd)
+    for static in (True, False):
+        ref = {}
+        for b in cols:
+            sp = [orc.SigSpec(s.envelope * amp[b], s.carrier_freq, s.phase) for s in specs]
+            ref[b] = _oracle_rk4(Gd if static else None, G, d, sp, y[:, b], t0, h, S)
+        yd = dev(y)
+        abi.rk4_steps(n, Gdev, Gd_dev if static else None, abi.pack_operators(Gdev),
+                      abi.pack_operators(Gd_dev[None])[0] if static else None, dev(coeff), None if mu is None else dev(mu),
+                      times, h, yd, S, per_col=True)
+        out = yd.cpu().numpy()
+        assert max(np.linalg.norm(out[:, b] - ref[b]) for b in cols) < TOL_SOLVE
+        assert np.all(np.isfinite(out))
+
+
+def test_rk4_sweep_kernels_agree_full_batch(abi, monkeypatch):
+    """cfg5-like batch (n=81, K=8, 2048 columns: 64 CTAs): every column of the formed-generator kernel against the
+    operator-pass kernel -- two different summation orders of the same per-column solve."""
+    n, K, B, S = 81, 8, 2048, 2
+    Gd, G, d, mu, y, specs = model_inputs(n, K, B, 5, "full")
+    times = orc.stage_time_grid(0.0, 1e-3, S)
+    coeff = orc.signal_list_values(specs, times)[:, :, None] * (0.5 + np.arange(B) / B)[None, None, :]
+    args = (n, dev(G), dev(Gd), abi.pack_operators(dev(G)), abi.pack_operators(dev(Gd)[None])[0], dev(coeff), dev(mu), times, 1e-3)
+    outs = {}
+    for kernel in ("formed", "legacy"):
+        monkeypatch.setenv("QDB_SWEEP_KERNEL", kernel)
+        yd = dev(y)
+        abi.rk4_steps(*args, yd, S, per_col=True)
+        outs[kernel] = yd.cpu().numpy()
+    assert max_col_l2(outs["formed"], outs["legacy"]) < 1e-13
+    assert np.max(np.abs(outs["formed"] - outs["legacy"])) > 0
+
+
 @pytest.mark.parametrize("B,S", [(24, 3), (2048, 2)])  # 4-product GEMM stages / 3-product GEMM stages (160 tiles)
 def test_rk4_generic_large_n(abi, B, S):
     n, K = 264, 2
