@@ -46,8 +46,21 @@ def flops_per_column_step(n):
 
 
 def workload(n, K, B, seed):
-    from oracle import numpy_oracle as orc  # synthetic-input generator shared with the tests
-    H0, Hs, Y, sig = orc.synthetic_schrodinger(n, K, B, seed)
+    """Synthetic cfg4 inputs: H0 = 5 herm(n), H_j = herm(n) with herm = (A + A^dag) / (2 sqrt n),
+    unit-norm complex-normal state columns, signals (0.1 (j+1), 0.2 j + 0.05, 0.3 j).  Written out here so that the
+    B200 arm never imports oracle/ (test infrastructure); tests/test_host_cpu.py checks it draws the same numbers
+    as the generator the parity tests use."""
+    rng = np.random.default_rng(seed)
+
+    def herm():
+        a = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        return (a + a.conj().T) / (2 * np.sqrt(n))
+
+    H0 = 5 * herm()
+    Hs = np.array([herm() for _ in range(K)])
+    Y = rng.standard_normal((n, B)) + 1j * rng.standard_normal((n, B))
+    Y = Y / np.linalg.norm(Y, axis=0, keepdims=True)
+    sig = [(0.1 * (j + 1), 0.2 * j + 0.05, 0.3 * j) for j in range(K)]
     return H0, Hs, Y, sig
 
 

@@ -128,6 +128,11 @@ int qdb_rhs_c128(int n, int K, int B,
  *            per column (sweep).
  *   ops_packed / stat_packed : QDB_LAYOUT_PACKED (sig_mode 1 and the on-chip path), plus the
  *            row-major copies ops_rm / stat_rm used when n is too large for the on-chip path.
+ *   workspace : qdb_workspace_bytes(QDB_WS_RK4, n, K, B, S) covers either mode.  sig_mode 0 chunks the
+ *            step loop when the generator table does not fit a smaller workspace.  sig_mode 1 with
+ *            3 <= K <= 8 forms the per-column generator on the tensor pipe (rk4_sweepf_kernel) when the
+ *            workspace has room for its operator copy behind the stage times, and runs the
+ *            operator-pass kernels otherwise (and for other K).
  * Replaces RK4_solver.take_step + the fixed_step_solver_template loop
  * (solvers/fixed_step_solvers.py:43-77,441-454) applied to GeneratorModel.evaluate_rhs. */
 int qdb_rk4_steps_c128(int n, int K, int B, int S,
@@ -157,7 +162,7 @@ size_t qdb_table_entry_bytes(int n, int layout);
  * the per-column kernel.
  * out[0..7] = {warps along rows, warps along columns, row tiles per warp, own column tiles per warp,
  * split (1 = 2-CTA clusters sharing one column octet through DSMEM), CTAs, threads per CTA,
- * dynamic shared memory bytes, 3M (1 = three-product complex tiles)}.  Returns QDB_E_UNSUPPORTED when n is
+ * dynamic shared memory bytes, 3M (1 = three-product complex tiles; 2 = formed-generator sweep kernel)}.  Returns QDB_E_UNSUPPORTED when n is
  * outside the on-chip path. */
 int qdb_rk4_tiling(int n, int B, int sweep_K, int* out /* host, 9 ints */);
 

@@ -36,8 +36,10 @@ def sweep(name, n, K, B, S, seed):
         y.copy_(y0); abi.rk4_steps(n, Gdv, Gdd, Gp, Gdp, coeff, mu, times, h, y, S, per_col=True)
     ms = timeit(run)
     alg = S * B * (4 * ((4 * K + 8) * n * n + 12 * n) + 28 * n)
-    exe = S * B * 4 * (K + 1) * 8 * n * n
     tiling = abi.rk4_tiling(n, B, K)
+    # executed flops: operator-pass kernels run K+1 complex passes (8 flops per element each); the formed-generator
+    # kernel runs 2 Kpad FMAs to form an element and 4 to use it, i.e. (4 Kpad + 8) n^2 flops = the algorithmic count
+    exe = S * B * 4 * ((4 * ((K + 3) // 4 * 4) + 8) if tiling["m3"] == 2 else (K + 1) * 8) * n * n
     kernel = "rk4_sweepf_kernel" if tiling["m3"] == 2 else ("rk4_sweep_small_kernel" if n <= 32 and K <= 16 else "rk4_sweep_kernel")
     print(json.dumps({"config": name, "kernel": kernel, "sweep_kernel_env": os.environ.get("QDB_SWEEP_KERNEL", "auto"), "n": n, "K": K, "B": B, "rk4_steps": S, "ms": ms,
                       "us_per_step": ms * 1e3 / S, "state_rhs_per_s": 4 * S * B / ms * 1e3, "alg_tflops": alg / ms * 1e-9,

@@ -22,7 +22,10 @@
 // result rows when read (as rk4_sweep_kernel).
 //
 // Operator layout ("formed-sweep"): opsf[((rt * C2 + c) * KS + ks) * 32 + 4 g + q] = ops[4 ks + q][8 rt + g][c],
-// statf[(rt * C2 + c) * 8 + g] = stat[8 rt + g][c]; zero outside the matrix; C2 = n rounded up to even.
+// statf[((rt * C2 + c) * 8 + g) * 2 + {0, 1}] = (re, re), (im, im) of stat[8 rt + g][c] -- stored duplicated because the
+// DMMA C operand is a register PAIR (both columns of the lane get the same static element): loaded this way it is
+// usable as it arrives, instead of four register moves in front of every formation DMMA (ncu, first version: 80 moves per
+// two matrix columns, on the issue path of the DMMAs).  Zero outside the matrix; C2 = n rounded up to even.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -39,11 +42,11 @@ struct FGeo {
     int WR, WC, NCT;
 };
 
-// D = A B + C with C = (c, c) kept intact (the static operator is reused for every column tile)
-__device__ __forceinline__ void dmma_from(double& d0, double& d1, double a, double b, double c) {
+// D = A B + C with C kept intact (the static operator pair is reused for every column tile)
+__device__ __forceinline__ void dmma_from(double& d0, double& d1, double a, double b, double2 c) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
         : "=d"(d0), "=d"(d1)
-        : "d"(a), "d"(b), "d"(c), "d"(c));
+        : "d"(a), "d"(b), "d"(c.x), "d"(c.y));
 }
 
 __global__ void pack_sweepf_kernel(int n, int K, int KS, int C2, int RT, const double2* __restrict__ ops_packed,
@@ -72,7 +75,8 @@ __global__ void pack_sweepf_kernel(int n, int K, int KS, int C2, int RT, const d
         const int r = 8 * rt + gg;
         double2 v = make_double2(0.0, 0.0);
         if (stat_packed != nullptr && r < n && c < n) v = stat_packed[packed_index(kpad, r, c)];
-        statf[s] = v;
+        statf[2 * s] = make_double2(v.x, v.x);
+        statf[2 * s + 1] = make_double2(v.y, v.y);
     }
 }
 
@@ -143,15 +147,16 @@ rk4_sweepf_kernel(FGeo geo, int K, int B, int S, const double2* __restrict__ sta
 #pragma unroll
     for (int m = 0; m < MR; ++m) {
         pa[m] = opsf + (size_t)rtl[m] * C2 * KS * 32 + lane;
-        ps[m] = has_stat ? statf + (size_t)rtl[m] * C2 * 8 + g : nullptr;
+        ps[m] = has_stat ? statf + ((size_t)rtl[m] * C2 * 8 + g) * 2 : nullptr;
     }
-    double2 ring[2][MR][KS], rs[2][MR];
-    auto fetch = [&](int c, double2 (&dst)[MR][KS], double2 (&dsts)[MR]) {
+    double2 ring[2][MR][KS], rs[2][MR][2];
+    auto fetch = [&](int c, double2 (&dst)[MR][KS], double2 (&dsts)[MR][2]) {
 #pragma unroll
         for (int m = 0; m < MR; ++m) {
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) dst[m][ks] = __ldg(pa[m] + ((size_t)c * KS + ks) * 32);
-            dsts[m] = has_stat ? __ldg(ps[m] + (size_t)c * 8) : make_double2(0.0, 0.0);
+            dsts[m][0] = has_stat ? __ldg(ps[m] + (size_t)c * 16) : make_double2(0.0, 0.0);
+            dsts[m][1] = has_stat ? __ldg(ps[m] + (size_t)c * 16 + 1) : make_double2(0.0, 0.0);
         }
     };
     fetch(0, ring[0], rs[0]);
@@ -171,7 +176,7 @@ rk4_sweepf_kernel(FGeo geo, int K, int B, int S, const double2* __restrict__ sta
     __syncthreads();
 
     // one matrix column: form G_b[rows of this warp][c] for the warp's columns, multiply with y_b[c]
-    auto column = [&](int c, const double2 (&A)[MR][KS], const double2 (&As)[MR]) {
+    auto column = [&](int c, const double2 (&A)[MR][KS], const double2 (&As)[MR][2]) {
         double2 yv[NCW][2];
 #pragma unroll
         for (int ct = 0; ct < NCW; ++ct)
@@ -181,8 +186,8 @@ rk4_sweepf_kernel(FGeo geo, int K, int B, int S, const double2* __restrict__ sta
         auto form = [&](int m, int slot) {
 #pragma unroll
             for (int ct = 0; ct < NCW; ++ct) {
-                dmma_from(gr[slot][ct][0], gr[slot][ct][1], A[m][0].x, cf[ct][0], As[m].x);
-                dmma_from(gi[slot][ct][0], gi[slot][ct][1], A[m][0].y, cf[ct][0], As[m].y);
+                dmma_from(gr[slot][ct][0], gr[slot][ct][1], A[m][0].x, cf[ct][0], As[m][0]);
+                dmma_from(gi[slot][ct][0], gi[slot][ct][1], A[m][0].y, cf[ct][0], As[m][1]);
             }
 #pragma unroll
             for (int ks = 1; ks < KS; ++ks)
@@ -197,12 +202,18 @@ rk4_sweepf_kernel(FGeo geo, int K, int B, int S, const double2* __restrict__ sta
         for (int m = 0; m < MR; ++m) {
             if (m + 1 < MR) form(m + 1, (m + 1) & 1);  // next row tile's DMMAs are queued before this tile's DFMAs wait
             const int s = m & 1;
+            // two passes over the tile's elements so that no DFMA follows the one it depends on
 #pragma unroll
             for (int ct = 0; ct < NCW; ++ct)
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     ar[m][ct][i] = fma(gr[s][ct][i], yv[ct][i].x, ar[m][ct][i]);
                     ai[m][ct][i] = fma(gr[s][ct][i], yv[ct][i].y, ai[m][ct][i]);
+                }
+#pragma unroll
+            for (int ct = 0; ct < NCW; ++ct)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
                     ar[m][ct][i] = fma(-gi[s][ct][i], yv[ct][i].y, ar[m][ct][i]);
                     ai[m][ct][i] = fma(gi[s][ct][i], yv[ct][i].x, ai[m][ct][i]);
                 }
@@ -403,7 +414,7 @@ bool rk4_sweepf_selected(int n, int K, bool small_kernel_available) {
 
 size_t rk4_sweepf_workspace_bytes(int n, int K) {
     const size_t RT = round_up8(n) / 8, C2 = (n + 1) & ~1, KS = (K + 3) / 4;
-    return (RT * C2 * KS * 32 + RT * C2 * 8) * sizeof(double2);
+    return (RT * C2 * KS * 32 + RT * C2 * 16) * sizeof(double2);
 }
 
 bool rk4_sweepf_tiling(int n, int B, int K, int* out) {
@@ -428,7 +439,7 @@ int launch_rk4_sweepf(int n, int K, int B, int S, const double2* stat_packed, co
         set_error("rk4 formed sweep: unsupported shape n=%d B=%d K=%d", n, B, K);
         return QDB_E_UNSUPPORTED;
     }
-    const size_t nops = (size_t)cfg.geo.RT * cfg.geo.C2 * cfg.KS * 32, nstat = (size_t)cfg.geo.RT * cfg.geo.C2 * 8;
+    const size_t nops = (size_t)cfg.geo.RT * cfg.geo.C2 * cfg.KS * 32, nstat = (size_t)cfg.geo.RT * cfg.geo.C2 * 8;  // static entries (2 double2 each)
     double2* opsf = (double2*)ws;
     double2* statf = stat_packed ? opsf + nops : nullptr;
     const size_t total = nops + (stat_packed ? nstat : 0);

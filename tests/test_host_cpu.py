@@ -311,3 +311,15 @@ def test_gloo_world_size_2_gather():
                          cwd=ROOT, env=env, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "GLOO_OK rank=0" in res.stdout and "GLOO_OK rank=1" in res.stdout
+
+
+def test_bench_workload_matches_the_test_generator():
+    """bench.py builds its inputs without importing oracle/; they must be the numbers the parity tests use."""
+    sys.path.insert(0, ROOT)
+    import bench
+    for a, b in zip(bench.workload(16, 3, 5, 2004), orc.synthetic_schrodinger(16, 3, 5, 2004)):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    head = src[:src.index("def cpu_reference_rate")]
+    assert "oracle" not in head.replace("oracle/", "").replace("oracle port", "").replace("(oracle)", ""), \
+        "the B200 arm of bench.py must not import the oracle"
