@@ -73,3 +73,65 @@ def solve_lmde_sharded(generator, t_span, y0: torch.Tensor, gather: bool = True,
     if gather:
         res.y = all_gather_columns(res.y, B)
     return res
+
+
+def shard_list(items: List, rank: Optional[int] = None, world_size: Optional[int] = None) -> List:
+    """This rank's contiguous block of a list of simulations (same split as :func:`shard_bounds`)."""
+    lo, hi = shard_bounds(len(items), rank, world_size)
+    return list(items[lo:hi])
+
+
+def solver_solve_sharded(solver, t_span, y0, signals: List, measurement=None, gather: bool = True, **kwargs):
+    """``Solver.solve`` for a LIST of simulations -- a parameter sweep (BASELINE.json configs[4]: 65 536 points over the
+    8 GPUs of a box) -- with the list split into contiguous blocks over the ranks.
+
+    Every rank runs its block through ``solver.solve`` (one sweep-mode launch per block when the simulations qualify,
+    solvers/solver_classes.py:556-590 semantics otherwise); nothing is exchanged while stepping.  Afterwards ONE
+    all-gather moves either the final states ``(n, N)`` or, when ``measurement`` (a
+    :class:`~qiskit_dynamics_b200.measurement.FinalStateMeasurement`) is given, the memory-slot outcome probabilities
+    ``(n_out, N)`` -- the "final observables" of the north star.
+
+    ``signals`` is the list of per-simulation signal specifications; ``y0`` is one initial state shared by all
+    simulations or a list with one per simulation.  Returns ``(local_results, gathered)``: this rank's list of
+    ``OdeResult`` and the gathered table (``None`` when ``gather`` is false; this rank's block when not distributed).
+    """
+    nsim = len(signals)
+    local_signals = shard_list(signals)
+    if isinstance(y0, list):
+        if len(y0) != nsim:
+            raise ValueError(f"y0 lists {len(y0)} initial states for {nsim} simulations")
+        local_y0 = shard_list(y0)
+    else:
+        local_y0 = y0
+    if not local_signals:  # more ranks than simulations: this rank idles but still joins the collective
+        local_results = []
+    else:
+        local_results = solver.solve(t_span=t_span, y0=local_y0, signals=local_signals, **kwargs)
+        if not isinstance(local_results, list):
+            local_results = [local_results]
+    if not gather:
+        return local_results, None
+    if local_results:
+        finals = torch.stack([r.y[-1] for r in local_results], dim=-1)  # (n, n_local)
+        t_final = float(local_results[0].t[-1])
+        table = measurement.probabilities(t_final, finals) if measurement is not None else finals
+    else:
+        table = None
+    rank, w = world()
+    if w > 1:
+        # ranks without simulations need the table's row count and dtype to take part in the gather
+        rows = torch.tensor([0 if table is None else table.shape[0], 0 if table is None else int(table.is_complex())],
+                            dtype=torch.int64, device=_collective_device(table))
+        dist.all_reduce(rows, op=dist.ReduceOp.MAX)
+        if table is None:
+            table = torch.zeros((int(rows[0]), 0), dtype=torch.complex128 if int(rows[1]) else torch.float64,
+                                device=rows.device)
+    return local_results, (all_gather_columns(table, nsim) if table is not None else None)
+
+
+def _collective_device(t: Optional[torch.Tensor]) -> torch.device:
+    if t is not None:
+        return t.device
+    if dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")

@@ -414,3 +414,20 @@ def test_magnus_orders_2_and_3(qd):
             close(r.y[-1], g[f"l_{frame_name}_o{order}"], 1e-9)
     with pytest.raises(qd.QiskitError):
         qd.solve_lmde(mv, t_span=[0, 0.5], y0=Y, method="scipy_expm", max_dt=0.05, magnus_order=4)
+
+
+def test_nccl_sharded_sweep(qd):
+    """Row (e) for the sweep path: a list of simulations split over 2 GPUs (one process each, NCCL), one gather of the
+    final observables, equal to the single-GPU sweep.  Needs two devices (the 1-GPU box skips it; log of a 2-GPU run:
+    profiles/r01_r_nccl_sharded_sweep.log)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29641", os.path.join(root, "tests", "_nccl_worker.py")],
+                         cwd=root, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "NCCL_OK rank=0" in res.stdout and "NCCL_OK rank=1" in res.stdout
