@@ -130,7 +130,7 @@ int qdb_rhs_c128(int n, int K, int B,
  *            row-major copies ops_rm / stat_rm used when n is too large for the on-chip path.
  *   workspace : qdb_workspace_bytes(QDB_WS_RK4, n, K, B, S) covers either mode.  sig_mode 0 chunks the
  *            step loop when the generator table does not fit a smaller workspace.  sig_mode 1 with
- *            3 <= K <= 8 forms the per-column generator on the tensor pipe (rk4_sweepf_kernel) when the
+ *            3 <= K <= 16 forms the per-column generator on the tensor pipe (rk4_sweepf_kernel) when the
  *            workspace has room for its operator copy behind the stage times, and runs the
  *            operator-pass kernels otherwise (and for other K).
  * Replaces RK4_solver.take_step + the fixed_step_solver_template loop

@@ -9,14 +9,14 @@
 //   * formation = a DMMA whose k dimension is the OPERATOR index: A = 8 generator elements (rows 8 rt + g of column c)
 //     x 4 operators, B = 4 operators x 8 columns of the batch (the signal values of the stage, held in registers),
 //     C = the static operator broadcast over the columns, D = Re (or Im) of G_b[8 rt + g][c] for 8 columns.
-//     K <= 4: one DMMA per part, K <= 8: two.
+//     K <= 4: one DMMA per part, K <= 8: two, ... K <= 16: four (template parameter KS).
 //   * D arrives in exactly the accumulator layout (lane 4 g + q: row g, columns 2 q, 2 q + 1), so the product with
 //     y_b[c] is four DFMAs per column on registers; the state row c is a 32 B broadcast load from shared memory.
 // Per generator element and column: 2 Kpad + 4 FMAs (20 at K = 8) against 36 -- the algorithmic count of SURVEY 8(d).
 //
 // A CTA owns 8 NCT whole columns for the entire launch (as in rk4_fused.cu).  Operators stream L2 -> registers in
-// fragment order (layout below, built per call by pack_sweepf_kernel) through a two-deep register ring, one matrix
-// column ahead; the stage vector lives in shared memory as [row][column] (row stride 8 NCT + 1 complex numbers: the
+// fragment order (layout below, built per call by pack_sweepf_kernel) through a register ring of 2 (4 for small
+// warp tiles) matrix columns, each slot refilled as soon as its column is consumed; the stage vector lives in shared memory as [row][column] (row stride 8 NCT + 1 complex numbers: the
 // epilogue's two-row stores fall into disjoint banks), single buffered between two barriers per stage; y and the RK4
 // k-sum sit in thread-private shared-memory slabs.  Frame phases: on the stage-vector rows when written, on the
 // result rows when read (as rk4_sweep_kernel).
@@ -79,6 +79,13 @@ __global__ void pack_sweepf_kernel(int n, int K, int KS, int C2, int RT, const d
         statf[2 * s + 1] = make_double2(v.y, v.y);
     }
 }
+
+// columns of the generator in flight per warp: small warp tiles (one or two DMMA tiles) have too few independent
+// DMMA -> DFMA chains per matrix column to cover their latency with the one or two warps a sub-partition holds
+template <int MR, int NCW>
+struct ColumnsInFlight {
+    static constexpr int value = (MR * NCW <= 2) ? 4 : 2;  // cfg2 (one tile per warp): 15.8 / 10.4 / 11.6 us per step with 2 / 4 / 8
+};
 
 template <int MR, int NCW, int KS>
 __global__ void __launch_bounds__(256, 1)
@@ -149,7 +156,8 @@ rk4_sweepf_kernel(FGeo geo, int K, int B, int S, const double2* __restrict__ sta
         pa[m] = opsf + (size_t)rtl[m] * C2 * KS * 32 + lane;
         ps[m] = has_stat ? statf + ((size_t)rtl[m] * C2 * 8 + g) * 2 : nullptr;
     }
-    double2 ring[2][MR][KS], rs[2][MR][2];
+    constexpr int CU = ColumnsInFlight<MR, NCW>::value;
+    double2 ring[CU][MR][KS], rs[CU][MR][2];
     auto fetch = [&](int c, double2 (&dst)[MR][KS], double2 (&dsts)[MR][2]) {
 #pragma unroll
         for (int m = 0; m < MR; ++m) {
@@ -159,7 +167,8 @@ rk4_sweepf_kernel(FGeo geo, int K, int B, int S, const double2* __restrict__ sta
             dsts[m][1] = has_stat ? __ldg(ps[m] + (size_t)c * 16 + 1) : make_double2(0.0, 0.0);
         }
     };
-    fetch(0, ring[0], rs[0]);
+#pragma unroll
+    for (int i = 0; i < (CU == 2 ? 1 : CU); ++i) fetch(i, ring[i], rs[i]);
 
     // signal values of a stage in DMMA B-fragment order: lane (g, q) holds c[4 ks + q][column 8 ct + g]
     auto load_coef = [&](int entry, double (&cf)[NCW][KS]) {
@@ -229,12 +238,24 @@ rk4_sweepf_kernel(FGeo geo, int K, int B, int S, const double2* __restrict__ sta
         const int next_entry = (sidx + 1 < total_stages) ? 2 * nstep + (nstage == 0 ? 0 : (nstage == 3 ? 2 : 1)) : entry;
         load_coef(next_entry, cfn);  // lands during the column loop
 
+        if constexpr (CU == 2) {
 #pragma unroll 1
-        for (int c = 0; c < C2; c += 2) {
-            fetch(c + 1, ring[1], rs[1]);
-            column(c, ring[0], rs[0]);
-            fetch(c + 2 < C2 ? c + 2 : 0, ring[0], rs[0]);  // wraps: the operators are time independent
-            column(c + 1, ring[1], rs[1]);
+            for (int c = 0; c < C2; c += 2) {
+                fetch(c + 1, ring[1], rs[1]);
+                column(c, ring[0], rs[0]);
+                fetch(c + 2 < C2 ? c + 2 : 0, ring[0], rs[0]);  // wraps: the operators are time independent
+                column(c + 1, ring[1], rs[1]);
+            }
+        } else {
+#pragma unroll 1
+            for (int c = 0; c < C2; c += CU) {
+#pragma unroll
+                for (int i = 0; i < CU; ++i) {
+                    column(c + i, ring[i], rs[i]);
+                    const int nxt = c + CU + i;  // refill the slot CU - 1 columns ahead (wraps around)
+                    fetch(nxt < C2 ? nxt : nxt - C2, ring[i], rs[i]);
+                }
+            }
         }
 
         // ---- epilogue: post-phase conj(p(t_stage)) on k, RK4 combine, pre-phase p(t_next) on the next stage input ----
@@ -315,12 +336,12 @@ int sm_count_f() {
 }
 
 bool pick_sweepf(int n, int B, int K, FConfig& cfg) {
-    if (n < 1 || round_up8(n) > 256 || K < 1 || K > 8) return false;
+    if (n < 1 || round_up8(n) > 256 || K < 1 || K > 16) return false;
     const int SMS = sm_count_f();
     FGeo geo;
     geo.n = n;
     geo.npad = round_up8(n);
-    geo.C2 = (n + 1) & ~1;
+    geo.C2 = 0;  // set with the tiling: n rounded up to the columns in flight
     geo.RT = geo.npad / 8;
     const int CT = (B + 7) / 8;
     int WR, WC, MR;
@@ -372,6 +393,10 @@ bool pick_sweepf(int n, int B, int K, FConfig& cfg) {
                 cfg.geo.WR = WR;
                 cfg.geo.WC = wc;
                 cfg.geo.NCT = NCT;
+                {
+                    const int cu = (MR * NCW <= 2) ? 4 : 2;  // ColumnsInFlight<MR, NCW>
+                    cfg.geo.C2 = (n + cu - 1) / cu * cu;
+                }
                 cfg.MR = MR;
                 cfg.NCW = NCW;
                 cfg.KS = (K + 3) / 4;
@@ -396,7 +421,7 @@ int launch_sweepf_t(const FConfig& cfg, int K, int B, int S, const double2* stat
 }  // namespace
 
 // 0 = automatic, 1 = legacy kernels only (QDB_SWEEP_KERNEL=legacy), 2 = formed-generator kernel wherever it exists
-// (QDB_SWEEP_KERNEL=formed; the automatic choice keeps the shared-memory-resident kernel for n <= 32)
+// (QDB_SWEEP_KERNEL=formed: also for K = 1, 2, where the automatic choice keeps the operator-pass kernels)
 static int sweep_kernel_mode() {
     const char* e = getenv("QDB_SWEEP_KERNEL");
     if (e && strcmp(e, "legacy") == 0) return 1;
@@ -404,16 +429,21 @@ static int sweep_kernel_mode() {
     return 0;
 }
 
-bool rk4_sweepf_supported(int n, int K) { return n >= 1 && round_up8(n) <= 256 && K >= 3 && K <= 8; }
+bool rk4_sweepf_supported(int n, int K) { return n >= 1 && round_up8(n) <= 256 && K >= 1 && K <= 16; }
 
 bool rk4_sweepf_selected(int n, int K, bool small_kernel_available) {
     const int mode = sweep_kernel_mode();
     if (mode == 1 || !rk4_sweepf_supported(n, K)) return false;
-    return mode == 2 || !small_kernel_available;
+    if (mode == 2) return true;
+    // K <= 2: the operator-pass kernels need fewer FMAs (4 (K + 1) <= 2 Kpad + 4) and measure 1.0-1.7x faster
+    // (profiles/r01_t_sweep_formed_vs_legacy_K.jsonl); 3 <= K <= 16: the formed-generator kernel, 1.2-4.9x faster at
+    // every size tried, shared-memory-resident small systems included (r01_t_sweep_formed_vs_legacy_small.jsonl)
+    (void)small_kernel_available;
+    return K >= 3;
 }
 
 size_t rk4_sweepf_workspace_bytes(int n, int K) {
-    const size_t RT = round_up8(n) / 8, C2 = (n + 1) & ~1, KS = (K + 3) / 4;
+    const size_t RT = round_up8(n) / 8, C2 = (n + 7) & ~7 /* the largest of the paddings */, KS = (K + 3) / 4;
     return (RT * C2 * KS * 32 + RT * C2 * 16) * sizeof(double2);
 }
 
@@ -448,7 +478,9 @@ int launch_rk4_sweepf(int n, int K, int B, int S, const double2* stat_packed, co
 #define QDB_F(mr, ncw)                                                                                                     \
     if (cfg.MR == mr && cfg.NCW == ncw) {                                                                                  \
         if (cfg.KS == 1) return launch_sweepf_t<mr, ncw, 1>(cfg, K, B, S, statf, opsf, coeff, ldc, mu, times_dev, h, y, ldy, st); \
-        return launch_sweepf_t<mr, ncw, 2>(cfg, K, B, S, statf, opsf, coeff, ldc, mu, times_dev, h, y, ldy, st);           \
+        if (cfg.KS == 2) return launch_sweepf_t<mr, ncw, 2>(cfg, K, B, S, statf, opsf, coeff, ldc, mu, times_dev, h, y, ldy, st); \
+        if (cfg.KS == 3) return launch_sweepf_t<mr, ncw, 3>(cfg, K, B, S, statf, opsf, coeff, ldc, mu, times_dev, h, y, ldy, st); \
+        return launch_sweepf_t<mr, ncw, 4>(cfg, K, B, S, statf, opsf, coeff, ldc, mu, times_dev, h, y, ldy, st);           \
     }
     QDB_F(1, 1)
     QDB_F(1, 2)

@@ -329,6 +329,11 @@ def test_rk4_fused_sweep(abi, n, K, B, S, frame):
     (27, 6, 20, 4, "full"),
     (200, 3, 12, 2, "full"),    # 25 row tiles: 8 row warps x 4 row tiles
     (16, 7, 600, 3, "none"),    # many CTAs of a small system
+    (12, 16, 5, 3, "full"),     # four DMMA k-steps over the operator index
+    (24, 11, 7, 3, "diag"),     # three k-steps, K padded 11 -> 12
+    (81, 12, 16, 2, "none"),    # three k-steps at the cfg5 dimension (largest register footprint)
+    (9, 2, 20, 5, "diag"),      # K < 3: formed only when pinned
+    (40, 1, 10, 4, "full"),
 ])
 def test_rk4_sweep_kernel_variants(abi, monkeypatch, kernel, n, K, B, S, frame):
     """Both sweep-kernel families on the same inputs: the formed-generator kernel (DMMA over the operator index + DFMA
