@@ -40,6 +40,7 @@ namespace {
 struct FGeo {
     int n, npad, C2, RT;
     int WR, WC, NCT;
+    int WK;  // warp groups that share the matrix columns (1, or 2 when the batch cannot fill the chip)
 };
 
 // D = A B + C with C kept intact (the static operator pair is reused for every column tile)
@@ -87,7 +88,7 @@ struct ColumnsInFlight {
     static constexpr int value = (MR * NCW <= 2) ? 4 : 2;  // cfg2 (one tile per warp): 15.8 / 10.4 / 11.6 us per step with 2 / 4 / 8
 };
 
-template <int MR, int NCW, int KS>
+template <int MR, int NCW, int KS, bool KSPLIT>
 __global__ void __launch_bounds__(256, 1)
 rk4_sweepf_kernel(FGeo geo, int K, int B, int S, const double2* __restrict__ statf /*or null*/,
                   const double2* __restrict__ opsf, const double* __restrict__ coeff /*[2S+1][K][ldc]*/, int ldc,
@@ -96,13 +97,21 @@ rk4_sweepf_kernel(FGeo geo, int K, int B, int S, const double2* __restrict__ sta
     extern __shared__ __align__(16) double2 sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
-    const int wr = warp % geo.WR, wc = warp / geo.WR;
+    // warp = wr + WR (wc + WC wk): group wk works on its share of the matrix columns for the same rows and batch columns;
+    // group 0 owns the state (slabs, epilogue), the others hand their partial sums over through shared memory
+    const int wgrp = geo.WR * geo.WC;
+    const int wk = KSPLIT ? warp / wgrp : 0, w0 = warp - wk * wgrp;
+    const int wr = w0 % geo.WR, wc = w0 / geo.WR;
     const int n = geo.n, C2 = geo.C2, NCT = geo.NCT;
-    const int nthr = blockDim.x;
+    const int nthr_all = blockDim.x;
+    const int nthr = 32 * wgrp;          // threads of one group: the stride of the thread-private slabs
+    const int tid0 = tid - wk * nthr;    // index within the group
+    const bool owner = KSPLIT ? (wk == 0) : true;
     const int ncols = 8 * NCT, LD = ncols + 1;
     double2* ys = sm;                                   // [npad][LD] stage vector, pre-phased
     double2* yslab = sm + (size_t)geo.npad * LD;        // [MR*NCW*2][nthr]
     double2* kslab = yslab + (size_t)MR * NCW * 2 * nthr;
+    double2* red = kslab + (size_t)MR * NCW * 2 * nthr;  // [MR*NCW*2][nthr], only when WK == 2
     const int col0 = blockIdx.x * ncols;
     const int lc0 = 8 * wc * NCW;  // first local column of this warp
     const bool framed = (mu != nullptr);
@@ -126,8 +135,9 @@ rk4_sweepf_kernel(FGeo geo, int K, int B, int S, const double2* __restrict__ sta
         for (int m = 0; m < MR; ++m) ph[m] = framed ? frame_phase(mu_row[m], t0) : make_double2(1.0, 0.0);
     }
 
-    for (int i = tid; i < geo.npad * LD; i += nthr) ys[i] = make_double2(0.0, 0.0);
+    for (int i = tid; i < geo.npad * LD; i += nthr_all) ys[i] = make_double2(0.0, 0.0);
     __syncthreads();
+    if (owner) {
 #pragma unroll
     for (int m = 0; m < MR; ++m)
 #pragma unroll
@@ -138,9 +148,10 @@ rk4_sweepf_kernel(FGeo geo, int K, int B, int S, const double2* __restrict__ sta
                 const int lc = lc0 + 8 * c + 2 * q + i;
                 double2 v = make_double2(0.0, 0.0);
                 if (mvalid[m] && row < n && col0 + lc < B) v = y[(size_t)row * ldy + col0 + lc];
-                yslab[((m * NCW + c) * 2 + i) * nthr + tid] = v;
+                yslab[((m * NCW + c) * 2 + i) * nthr + tid0] = v;
                 if (mvalid[m]) ys[row * LD + lc] = cmul(ph[m], v);
             }
+    }
 
     double ar[MR][NCW][2], ai[MR][NCW][2];  // G_b y accumulators (C-fragment layout)
 #pragma unroll
@@ -167,8 +178,9 @@ rk4_sweepf_kernel(FGeo geo, int K, int B, int S, const double2* __restrict__ sta
             dsts[m][1] = has_stat ? __ldg(ps[m] + (size_t)c * 16 + 1) : make_double2(0.0, 0.0);
         }
     };
+    const int cspan = KSPLIT ? C2 / 2 : C2, cb = wk * cspan, ce = cb + cspan;  // this group's matrix columns
 #pragma unroll
-    for (int i = 0; i < (CU == 2 ? 1 : CU); ++i) fetch(i, ring[i], rs[i]);
+    for (int i = 0; i < (CU == 2 ? 1 : CU); ++i) fetch(cb + i, ring[i], rs[i]);
 
     // signal values of a stage in DMMA B-fragment order: lane (g, q) holds c[4 ks + q][column 8 ct + g]
     auto load_coef = [&](int entry, double (&cf)[NCW][KS]) {
@@ -237,54 +249,90 @@ rk4_sweepf_kernel(FGeo geo, int K, int B, int S, const double2* __restrict__ sta
         const int nstage = (stage + 1) & 3, nstep = step + (stage == 3 ? 1 : 0);
         const int next_entry = (sidx + 1 < total_stages) ? 2 * nstep + (nstage == 0 ? 0 : (nstage == 3 ? 2 : 1)) : entry;
         load_coef(next_entry, cfn);  // lands during the column loop
+        // frame phases of the next stage time, computed in front of the epilogue (in-order warps cannot run them "under" the
+        // column loop, and large tiles have no registers to carry them across it)
+        constexpr bool kEarlyPhases = false;  // tried for small tiles: the sincos in front of the loop costs more than it hides (cfg2 10.4 -> 11.6 us/step)
+        double2 ph_next[MR];
+        auto next_phases = [&]() {
+            const double tn = framed ? times[next_entry] : 0.0;
+#pragma unroll
+            for (int m = 0; m < MR; ++m) ph_next[m] = (framed && next_entry != entry) ? frame_phase(mu_row[m], tn) : ph[m];
+        };
+        if constexpr (kEarlyPhases) next_phases();
 
         if constexpr (CU == 2) {
 #pragma unroll 1
-            for (int c = 0; c < C2; c += 2) {
+            for (int c = cb; c < ce; c += 2) {
                 fetch(c + 1, ring[1], rs[1]);
                 column(c, ring[0], rs[0]);
-                fetch(c + 2 < C2 ? c + 2 : 0, ring[0], rs[0]);  // wraps: the operators are time independent
+                fetch(c + 2 < ce ? c + 2 : cb, ring[0], rs[0]);  // wraps: the operators are time independent
                 column(c + 1, ring[1], rs[1]);
             }
         } else {
 #pragma unroll 1
-            for (int c = 0; c < C2; c += CU) {
+            for (int c = cb; c < ce; c += CU) {
 #pragma unroll
                 for (int i = 0; i < CU; ++i) {
                     column(c + i, ring[i], rs[i]);
                     const int nxt = c + CU + i;  // refill the slot CU - 1 columns ahead (wraps around)
-                    fetch(nxt < C2 ? nxt : nxt - C2, ring[i], rs[i]);
+                    fetch(nxt < ce ? nxt : nxt - cspan, ring[i], rs[i]);
                 }
             }
         }
 
-        // ---- epilogue: post-phase conj(p(t_stage)) on k, RK4 combine, pre-phase p(t_next) on the next stage input ----
-        double2 ph_next[MR];
-        {
-            const double tn = framed ? times[next_entry] : 0.0;
+        // ---- partial sums of the other warp group (matrix columns split over two groups) ----
+        if constexpr (KSPLIT) {
+            if (!owner) {
 #pragma unroll
-            for (int m = 0; m < MR; ++m) ph_next[m] = (framed && next_entry != entry) ? frame_phase(mu_row[m], tn) : ph[m];
+                for (int m = 0; m < MR; ++m)
+#pragma unroll
+                    for (int ct = 0; ct < NCW; ++ct)
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            red[((m * NCW + ct) * 2 + i) * nthr + tid0] = make_double2(ar[m][ct][i], ai[m][ct][i]);
+                            ar[m][ct][i] = 0.0;
+                            ai[m][ct][i] = 0.0;
+                        }
+            }
+            __syncthreads();
+            if (owner) {
+#pragma unroll
+                for (int m = 0; m < MR; ++m)
+#pragma unroll
+                    for (int ct = 0; ct < NCW; ++ct)
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const double2 p = red[((m * NCW + ct) * 2 + i) * nthr + tid0];
+                            ar[m][ct][i] += p.x;
+                            ai[m][ct][i] += p.y;
+                        }
+            }
         }
+
+        // ---- epilogue: post-phase conj(p(t_stage)) on k, RK4 combine, pre-phase p(t_next) on the next stage input ----
+        if constexpr (!kEarlyPhases) next_phases();
         const StageCoef sc(stage, h);
+        if (owner) {
 #pragma unroll
-        for (int m = 0; m < MR; ++m)
+            for (int m = 0; m < MR; ++m)
 #pragma unroll
-            for (int ct = 0; ct < NCW; ++ct)
+                for (int ct = 0; ct < NCW; ++ct)
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int slot = ((m * NCW + ct) * 2 + i) * nthr + tid;
-                    const double2 k = cmul_conj_a(ph[m], make_double2(ar[m][ct][i], ai[m][ct][i]));
-                    double2 ks = stage == 0 ? make_double2(0.0, 0.0) : kslab[slot];
-                    ks.x = sc.keep * ks.x + sc.wk * k.x;
-                    ks.y = sc.keep * ks.y + sc.wk * k.y;
-                    const double v_r = sc.last ? ks.x : k.x, v_i = sc.last ? ks.y : k.y;
-                    const double2 yv = yslab[slot];
-                    const double2 nxt = make_double2(yv.x + sc.astep * v_r, yv.y + sc.astep * v_i);
-                    if (sc.last) yslab[slot] = nxt; else kslab[slot] = ks;
-                    const double2 pn = cmul(ph_next[m], nxt);
-                    ar[m][ct][i] = pn.x;  // parked in the accumulator registers until every warp has left the column loop
-                    ai[m][ct][i] = pn.y;
-                }
+                    for (int i = 0; i < 2; ++i) {
+                        const int slot = ((m * NCW + ct) * 2 + i) * nthr + tid0;
+                        const double2 k = cmul_conj_a(ph[m], make_double2(ar[m][ct][i], ai[m][ct][i]));
+                        double2 ks = stage == 0 ? make_double2(0.0, 0.0) : kslab[slot];
+                        ks.x = sc.keep * ks.x + sc.wk * k.x;
+                        ks.y = sc.keep * ks.y + sc.wk * k.y;
+                        const double v_r = sc.last ? ks.x : k.x, v_i = sc.last ? ks.y : k.y;
+                        const double2 yv = yslab[slot];
+                        const double2 nxt = make_double2(yv.x + sc.astep * v_r, yv.y + sc.astep * v_i);
+                        if (sc.last) yslab[slot] = nxt; else kslab[slot] = ks;
+                        const double2 pn = cmul(ph_next[m], nxt);
+                        ar[m][ct][i] = pn.x;  // parked in the accumulator registers until every warp has left the column loop
+                        ai[m][ct][i] = pn.y;
+                    }
+        }
         __syncthreads();
 #pragma unroll
         for (int m = 0; m < MR; ++m)
@@ -292,7 +340,7 @@ rk4_sweepf_kernel(FGeo geo, int K, int B, int S, const double2* __restrict__ sta
             for (int ct = 0; ct < NCW; ++ct)
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    if (mvalid[m]) ys[(8 * rt[m] + g) * LD + lc0 + 8 * ct + 2 * q + i] = make_double2(ar[m][ct][i], ai[m][ct][i]);
+                    if (owner && mvalid[m]) ys[(8 * rt[m] + g) * LD + lc0 + 8 * ct + 2 * q + i] = make_double2(ar[m][ct][i], ai[m][ct][i]);
                     ar[m][ct][i] = 0.0;
                     ai[m][ct][i] = 0.0;
                 }
@@ -313,7 +361,7 @@ rk4_sweepf_kernel(FGeo geo, int K, int B, int S, const double2* __restrict__ sta
             for (int i = 0; i < 2; ++i) {
                 const int row = 8 * rt[m] + g;
                 const int col = col0 + lc0 + 8 * c + 2 * q + i;
-                if (mvalid[m] && row < n && col < B) y[(size_t)row * ldy + col] = yslab[((m * NCW + c) * 2 + i) * nthr + tid];
+                if (owner && mvalid[m] && row < n && col < B) y[(size_t)row * ldy + col] = yslab[((m * NCW + c) * 2 + i) * nthr + tid0];
             }
 }
 
@@ -372,20 +420,26 @@ bool pick_sweepf(int n, int B, int K, FConfig& cfg) {
     static const int ncw_opts[5][3] = {{0, 0, 0}, {4, 2, 1}, {3, 2, 1}, {2, 1, 0}, {1, 0, 0}};
     bool found = false;
     double best = 0;
-    // fewer column warps when the batch is too small to give every SM a CTA
+    // fewer column warps when the batch is too small to give every SM a CTA; CTAs that end up with at most four warps
+    // then split the matrix columns over two warp groups (WK = 2) so that every sub-partition still holds two warps
+    const char* nok = getenv("QDB_SWEEPF_NO_KSPLIT");
+    const bool ksplit_ok = !(nok && nok[0] == '1');
     for (int wc = WC; wc >= 1; wc /= 2) {
         for (int o = 0; o < 3; ++o) {
             const int NCW = ncw_opts[MR][o];
             if (NCW == 0) continue;
-            const int NCT = NCW * wc, threads = 32 * WR * wc;
-            const size_t smem = ((size_t)geo.npad * (8 * NCT + 1) + (size_t)2 * MR * NCW * 2 * threads) * sizeof(double2);
-            if (smem > kSmemLimitF) continue;
+            const int NCT = NCW * wc, threads0 = 32 * WR * wc;
             const int ctas = (CT + NCT - 1) / NCT;
+            const int cu = (MR * NCW <= 2) ? 4 : 2;  // ColumnsInFlight<MR, NCW>
+            const int WK = (ksplit_ok && MR * NCW <= 4 && threads0 <= 128 && ctas <= SMS && n >= 2 * cu) ? 2 : 1;
+            const int threads = threads0 * WK;
+            const size_t smem = ((size_t)geo.npad * (8 * NCT + 1) + (size_t)(WK == 2 ? 3 : 2) * MR * NCW * 2 * threads0) * sizeof(double2);
+            if (smem > kSmemLimitF) continue;
             // busiest SM: waves x (fixed per-stage part + pipe time of its column tiles).  A sub-partition with two warps
             // keeps the fp64 pipe full; a lone warp (128-thread CTAs) reaches about 0.65 of it but leaves twice as many
             // CTAs for a batch that cannot fill the chip.
             const double wps = threads / 128.0;
-            const double cost = (double)((ctas + SMS - 1) / SMS) * (0.5 + NCW * wps / (wps >= 2.0 ? 1.0 : 0.65));
+            const double cost = (double)((ctas + SMS - 1) / SMS) * (0.5 + NCW * (threads0 / 128.0) / (wps >= 2.0 ? 1.0 : 0.65));
             if (!found || cost < best - 1e-9) {
                 found = true;
                 best = cost;
@@ -393,10 +447,8 @@ bool pick_sweepf(int n, int B, int K, FConfig& cfg) {
                 cfg.geo.WR = WR;
                 cfg.geo.WC = wc;
                 cfg.geo.NCT = NCT;
-                {
-                    const int cu = (MR * NCW <= 2) ? 4 : 2;  // ColumnsInFlight<MR, NCW>
-                    cfg.geo.C2 = (n + cu - 1) / cu * cu;
-                }
+                cfg.geo.WK = WK;
+                cfg.geo.C2 = (n + cu * WK - 1) / (cu * WK) * (cu * WK);
                 cfg.MR = MR;
                 cfg.NCW = NCW;
                 cfg.KS = (K + 3) / 4;
@@ -409,13 +461,23 @@ bool pick_sweepf(int n, int B, int K, FConfig& cfg) {
     return found;
 }
 
+template <int MR, int NCW, int KS, bool KSPLIT>
+int launch_sweepf_k(const FConfig& cfg, int K, int B, int S, const double2* statf, const double2* opsf, const double* coeff, int ldc,
+                    const double* mu, const double* times, double h, double2* y, int ldy, cudaStream_t st) {
+    QDB_CUDA(cudaFuncSetAttribute(rk4_sweepf_kernel<MR, NCW, KS, KSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+    rk4_sweepf_kernel<MR, NCW, KS, KSPLIT><<<cfg.grid, cfg.threads, cfg.smem, st>>>(cfg.geo, K, B, S, statf, opsf, coeff, ldc, mu, times, h, y, ldy);
+    QDB_LAUNCH_CHECK("rk4_sweepf_kernel");
+    return QDB_OK;
+}
+
 template <int MR, int NCW, int KS>
 int launch_sweepf_t(const FConfig& cfg, int K, int B, int S, const double2* statf, const double2* opsf, const double* coeff, int ldc,
                     const double* mu, const double* times, double h, double2* y, int ldy, cudaStream_t st) {
-    QDB_CUDA(cudaFuncSetAttribute(rk4_sweepf_kernel<MR, NCW, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-    rk4_sweepf_kernel<MR, NCW, KS><<<cfg.grid, cfg.threads, cfg.smem, st>>>(cfg.geo, K, B, S, statf, opsf, coeff, ldc, mu, times, h, y, ldy);
-    QDB_LAUNCH_CHECK("rk4_sweepf_kernel");
-    return QDB_OK;
+    // the matrix-column split exists for CTAs of at most four warps per group: tiles of up to MR x NCW = 4 x 1
+    if constexpr (MR * NCW <= 4) {
+        if (cfg.geo.WK == 2) return launch_sweepf_k<MR, NCW, KS, true>(cfg, K, B, S, statf, opsf, coeff, ldc, mu, times, h, y, ldy, st);
+    }
+    return launch_sweepf_k<MR, NCW, KS, false>(cfg, K, B, S, statf, opsf, coeff, ldc, mu, times, h, y, ldy, st);
 }
 
 }  // namespace
@@ -443,7 +505,7 @@ bool rk4_sweepf_selected(int n, int K, bool small_kernel_available) {
 }
 
 size_t rk4_sweepf_workspace_bytes(int n, int K) {
-    const size_t RT = round_up8(n) / 8, C2 = (n + 7) & ~7 /* the largest of the paddings */, KS = (K + 3) / 4;
+    const size_t RT = round_up8(n) / 8, C2 = (n + 7) & ~7 /* the largest of the paddings (4 columns in flight x 2 warp groups) */, KS = (K + 3) / 4;
     return (RT * C2 * KS * 32 + RT * C2 * 16) * sizeof(double2);
 }
 
@@ -451,7 +513,7 @@ bool rk4_sweepf_tiling(int n, int B, int K, int* out) {
     FConfig cfg;
     if (!pick_sweepf(n, B, K, cfg)) return false;
     out[0] = cfg.geo.WR;
-    out[1] = cfg.geo.WC;
+    out[1] = cfg.geo.WC * cfg.geo.WK;  // column warps x warp groups sharing the matrix columns
     out[2] = cfg.MR;
     out[3] = cfg.NCW;
     out[4] = 0;
