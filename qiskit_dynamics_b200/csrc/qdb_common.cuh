@@ -118,9 +118,9 @@ int launch_rk4_fused_sweep(int n, int K, int B, int S, const double2* stat_packe
                            const double2* ops_packed /*[K]*/, const double* coeff, int ldc,
                            const double* mu, const double* times_dev,
                            double h, double2* y, int ldy, void* ws /*rk4_sweepf_workspace_bytes*/, cudaStream_t st);
-// formed-generator sweep kernel (rk4_sweepf.cu): 1 <= K <= 16, chosen automatically for K >= 3
+// formed-generator sweep kernel (rk4_sweepf.cu): 1 <= K <= 16; chosen automatically for K >= 3, and for K <= 2 on large batches
 bool rk4_sweepf_supported(int n, int K);
-bool rk4_sweepf_selected(int n, int K, bool small_kernel_available);
+bool rk4_sweepf_selected(int n, int K, int B, bool small_kernel_available);
 size_t rk4_sweepf_workspace_bytes(int n, int K);
 bool rk4_sweepf_tiling(int n, int B, int K, int* out);
 int launch_rk4_sweepf(int n, int K, int B, int S, const double2* stat_packed, const double2* ops_packed, const double* coeff,

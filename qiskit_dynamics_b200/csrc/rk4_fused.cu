@@ -1281,7 +1281,7 @@ int launch_3m_t(const Config& cfg, int B, int S, const double2* gen, double h, d
 bool rk4_fused_supported(int n) { return n >= 1 && round_up8(n) <= kMaxFusedNpad; }
 
 bool rk4_fused_tiling(int n, int B, int sweep_K, int* out) {
-    if (sweep_K > 0 && rk4_sweepf_selected(n, sweep_K, rk4_sweep_small_supported(n, sweep_K, true)))
+    if (sweep_K > 0 && rk4_sweepf_selected(n, sweep_K, B, rk4_sweep_small_supported(n, sweep_K, true)))
         return rk4_sweepf_tiling(n, B, sweep_K, out);
     Config cfg;
     const bool ok = sweep_K > 0 ? pick_config(n, B, sweep_K, cfg)
@@ -1370,7 +1370,7 @@ int launch_rk4_fused_sweep(int n, int K, int B, int S, const double2* stat_packe
                            const double* mu, const double* times_dev, double h, double2* y, int ldy, void* ws, cudaStream_t st) {
     // K >= 3: generator formed per column on the tensor pipe (2 Kpad + 4 FMAs per element instead of 4 (K + 1))
     const bool small_ok = rk4_sweep_small_supported(n, K, stat_packed != nullptr);
-    if (ws != nullptr && rk4_sweepf_selected(n, K, small_ok))
+    if (ws != nullptr && rk4_sweepf_selected(n, K, B, small_ok))
         return launch_rk4_sweepf(n, K, B, S, stat_packed, ops_packed, coeff, ldc, mu, times_dev, h, y, ldy, ws, st);
     // small operators: operators resident in shared memory, pre-scaled stage vectors, operator sum split over warps
     if (small_ok)

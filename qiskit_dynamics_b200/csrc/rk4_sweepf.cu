@@ -13,6 +13,9 @@
 //   * D arrives in exactly the accumulator layout (lane 4 g + q: row g, columns 2 q, 2 q + 1), so the product with
 //     y_b[c] is four DFMAs per column on registers; the state row c is a 32 B broadcast load from shared memory.
 // Per generator element and column: 2 Kpad + 4 FMAs (20 at K = 8) against 36 -- the algorithmic count of SURVEY 8(d).
+//   * K <= 2 (KS = -K): a DMMA would waste three quarters (half) of its k dimension, so the formation runs on DFMAs as
+//     well -- 2 K + 4 FMAs against the 4 (K + 1) of the operator-pass kernels.  Operators are then stored like the static
+//     operator (8 entries per row tile and matrix column), the signal values per lane are those of its two columns.
 //
 // A CTA owns 8 NCT whole columns for the entire launch (as in rk4_fused.cu).  Operators stream L2 -> registers in
 // fragment order (layout below, built per call by pack_sweepf_kernel) through a register ring of 2 (4 for small
@@ -22,6 +25,7 @@
 // result rows when read (as rk4_sweep_kernel).
 //
 // Operator layout ("formed-sweep"): opsf[((rt * C2 + c) * KS + ks) * 32 + 4 g + q] = ops[4 ks + q][8 rt + g][c],
+// (K <= 2: opsf[((rt * C2 + c) * K + j) * 8 + g] = ops[j][8 rt + g][c]);
 // statf[((rt * C2 + c) * 8 + g) * 2 + {0, 1}] = (re, re), (im, im) of stat[8 rt + g][c] -- stored duplicated because the
 // DMMA C operand is a register PAIR (both columns of the lane get the same static element): loaded this way it is
 // usable as it arrives, instead of four register moves in front of every formation DMMA (ncu, first version: 80 moves per
@@ -29,6 +33,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "qdb_common.cuh"
 #include "rk4_device.cuh"
@@ -55,10 +60,20 @@ __global__ void pack_sweepf_kernel(int n, int K, int KS, int C2, int RT, const d
                                    double2* __restrict__ statf) {
     const int kpad = round_up16(n);
     const size_t per_op = (size_t)round_up8(n) * kpad;
-    const size_t nops = (size_t)RT * C2 * KS * 32;
+    const size_t nops = KS > 0 ? (size_t)RT * C2 * KS * 32 : (size_t)RT * C2 * K * 8;
     const size_t nstat = (size_t)RT * C2 * 8;
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < nops) {
+    if (e < nops && KS < 0) {  // FMA formation: [rt][c][j][g]
+        const int gg = (int)(e & 7);
+        size_t t = e >> 3;
+        const int j = (int)(t % K);
+        t /= K;
+        const int c = (int)(t % C2), rt = (int)(t / C2);
+        const int r = 8 * rt + gg;
+        double2 v = make_double2(0.0, 0.0);
+        if (r < n && c < n) v = ops_packed[(size_t)j * per_op + packed_index(kpad, r, c)];
+        opsf[e] = v;
+    } else if (e < nops) {
         const int lane = (int)(e & 31);
         size_t t = e >> 5;
         const int ks = (int)(t % KS);
@@ -159,21 +174,26 @@ rk4_sweepf_kernel(FGeo geo, int K, int B, int S, const double2* __restrict__ sta
 #pragma unroll
         for (int c = 0; c < NCW; ++c) ar[m][c][0] = ar[m][c][1] = ai[m][c][0] = ai[m][c][1] = 0.0;
 
-    // operator stream: per matrix column c and row tile, KS fragments of 32 complex numbers + 8 static entries
+    // operator stream: per matrix column c and row tile, KS fragments of 32 complex numbers (K <= 2: K x 8 entries)
+    // + 8 static entries
+    constexpr bool FMAF = (KS < 0);       // formation on the FMA pipe
+    constexpr int NF = FMAF ? -KS : KS;   // fragments (DMMA k-steps), or operators, per matrix column and row tile
+    constexpr int FSTRIDE = FMAF ? 8 : 32;
+    using CoefT = typename std::conditional<FMAF, double2, double>::type;
     const double2* pa[MR];
     const double2* ps[MR];
 #pragma unroll
     for (int m = 0; m < MR; ++m) {
-        pa[m] = opsf + (size_t)rtl[m] * C2 * KS * 32 + lane;
+        pa[m] = opsf + (size_t)rtl[m] * C2 * NF * FSTRIDE + (FMAF ? g : lane);
         ps[m] = has_stat ? statf + ((size_t)rtl[m] * C2 * 8 + g) * 2 : nullptr;
     }
     constexpr int CU = ColumnsInFlight<MR, NCW>::value;
-    double2 ring[CU][MR][KS], rs[CU][MR][2];
-    auto fetch = [&](int c, double2 (&dst)[MR][KS], double2 (&dsts)[MR][2]) {
+    double2 ring[CU][MR][NF], rs[CU][MR][2];
+    auto fetch = [&](int c, double2 (&dst)[MR][NF], double2 (&dsts)[MR][2]) {
 #pragma unroll
         for (int m = 0; m < MR; ++m) {
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) dst[m][ks] = __ldg(pa[m] + ((size_t)c * KS + ks) * 32);
+            for (int ks = 0; ks < NF; ++ks) dst[m][ks] = __ldg(pa[m] + ((size_t)c * NF + ks) * FSTRIDE);
             dsts[m][0] = has_stat ? __ldg(ps[m] + (size_t)c * 16) : make_double2(0.0, 0.0);
             dsts[m][1] = has_stat ? __ldg(ps[m] + (size_t)c * 16 + 1) : make_double2(0.0, 0.0);
         }
@@ -183,21 +203,28 @@ rk4_sweepf_kernel(FGeo geo, int K, int B, int S, const double2* __restrict__ sta
     for (int i = 0; i < (CU == 2 ? 1 : CU); ++i) fetch(cb + i, ring[i], rs[i]);
 
     // signal values of a stage in DMMA B-fragment order: lane (g, q) holds c[4 ks + q][column 8 ct + g]
-    auto load_coef = [&](int entry, double (&cf)[NCW][KS]) {
+    // (FMA formation: c[j][columns 8 ct + 2 q, + 1], the two columns the lane accumulates)
+    auto load_coef = [&](int entry, CoefT (&cf)[NCW][NF]) {
 #pragma unroll
         for (int c = 0; c < NCW; ++c)
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-                const int j = 4 * ks + q, col = col0 + lc0 + 8 * c + g;
-                cf[c][ks] = (j < K && col < B) ? coeff[((size_t)entry * K + j) * ldc + col] : 0.0;
+            for (int ks = 0; ks < NF; ++ks) {
+                if constexpr (FMAF) {
+                    const int col = col0 + lc0 + 8 * c + 2 * q;
+                    const double* src = coeff + ((size_t)entry * K + ks) * ldc + col;
+                    cf[c][ks] = make_double2(col < B ? src[0] : 0.0, col + 1 < B ? src[1] : 0.0);
+                } else {
+                    const int j = 4 * ks + q, col = col0 + lc0 + 8 * c + g;
+                    cf[c][ks] = (j < K && col < B) ? coeff[((size_t)entry * K + j) * ldc + col] : 0.0;
+                }
             }
     };
-    double cf[NCW][KS], cfn[NCW][KS];
+    CoefT cf[NCW][NF], cfn[NCW][NF];
     load_coef(0, cf);
     __syncthreads();
 
     // one matrix column: form G_b[rows of this warp][c] for the warp's columns, multiply with y_b[c]
-    auto column = [&](int c, const double2 (&A)[MR][KS], const double2 (&As)[MR][2]) {
+    auto column = [&](int c, const double2 (&A)[MR][NF], const double2 (&As)[MR][2]) {
         double2 yv[NCW][2];
 #pragma unroll
         for (int ct = 0; ct < NCW; ++ct)
@@ -205,18 +232,37 @@ rk4_sweepf_kernel(FGeo geo, int K, int B, int S, const double2* __restrict__ sta
             for (int i = 0; i < 2; ++i) yv[ct][i] = ys[c * LD + lc0 + 8 * ct + 2 * q + i];
         double gr[2][NCW][2], gi[2][NCW][2];
         auto form = [&](int m, int slot) {
-#pragma unroll
-            for (int ct = 0; ct < NCW; ++ct) {
-                dmma_from(gr[slot][ct][0], gr[slot][ct][1], A[m][0].x, cf[ct][0], As[m][0]);
-                dmma_from(gi[slot][ct][0], gi[slot][ct][1], A[m][0].y, cf[ct][0], As[m][1]);
-            }
-#pragma unroll
-            for (int ks = 1; ks < KS; ++ks)
+            if constexpr (FMAF) {
 #pragma unroll
                 for (int ct = 0; ct < NCW; ++ct) {
-                    dmma(gr[slot][ct][0], gr[slot][ct][1], A[m][ks].x, cf[ct][ks]);
-                    dmma(gi[slot][ct][0], gi[slot][ct][1], A[m][ks].y, cf[ct][ks]);
+                    gr[slot][ct][0] = fma(cf[ct][0].x, A[m][0].x, As[m][0].x);
+                    gr[slot][ct][1] = fma(cf[ct][0].y, A[m][0].x, As[m][0].x);
+                    gi[slot][ct][0] = fma(cf[ct][0].x, A[m][0].y, As[m][1].x);
+                    gi[slot][ct][1] = fma(cf[ct][0].y, A[m][0].y, As[m][1].x);
                 }
+#pragma unroll
+                for (int j = 1; j < NF; ++j)
+#pragma unroll
+                    for (int ct = 0; ct < NCW; ++ct) {
+                        gr[slot][ct][0] = fma(cf[ct][j].x, A[m][j].x, gr[slot][ct][0]);
+                        gr[slot][ct][1] = fma(cf[ct][j].y, A[m][j].x, gr[slot][ct][1]);
+                        gi[slot][ct][0] = fma(cf[ct][j].x, A[m][j].y, gi[slot][ct][0]);
+                        gi[slot][ct][1] = fma(cf[ct][j].y, A[m][j].y, gi[slot][ct][1]);
+                    }
+            } else {
+#pragma unroll
+                for (int ct = 0; ct < NCW; ++ct) {
+                    dmma_from(gr[slot][ct][0], gr[slot][ct][1], A[m][0].x, cf[ct][0], As[m][0]);
+                    dmma_from(gi[slot][ct][0], gi[slot][ct][1], A[m][0].y, cf[ct][0], As[m][1]);
+                }
+#pragma unroll
+                for (int ks = 1; ks < NF; ++ks)
+#pragma unroll
+                    for (int ct = 0; ct < NCW; ++ct) {
+                        dmma(gr[slot][ct][0], gr[slot][ct][1], A[m][ks].x, cf[ct][ks]);
+                        dmma(gi[slot][ct][0], gi[slot][ct][1], A[m][ks].y, cf[ct][ks]);
+                    }
+            }
         };
         form(0, 0);
 #pragma unroll
@@ -349,7 +395,7 @@ rk4_sweepf_kernel(FGeo geo, int K, int B, int S, const double2* __restrict__ sta
 #pragma unroll
         for (int ct = 0; ct < NCW; ++ct)
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) cf[ct][ks] = cfn[ct][ks];
+            for (int ks = 0; ks < NF; ++ks) cf[ct][ks] = cfn[ct][ks];
         __syncthreads();
     }
 
@@ -451,7 +497,7 @@ bool pick_sweepf(int n, int B, int K, FConfig& cfg) {
                 cfg.geo.C2 = (n + cu * WK - 1) / (cu * WK) * (cu * WK);
                 cfg.MR = MR;
                 cfg.NCW = NCW;
-                cfg.KS = (K + 3) / 4;
+                cfg.KS = K <= 2 ? -K : (K + 3) / 4;  // K <= 2: formation on the FMA pipe
                 cfg.threads = threads;
                 cfg.grid = ctas;
                 cfg.smem = smem;
@@ -493,15 +539,19 @@ static int sweep_kernel_mode() {
 
 bool rk4_sweepf_supported(int n, int K) { return n >= 1 && round_up8(n) <= 256 && K >= 1 && K <= 16; }
 
-bool rk4_sweepf_selected(int n, int K, bool small_kernel_available) {
+bool rk4_sweepf_selected(int n, int K, int B, bool small_kernel_available) {
     const int mode = sweep_kernel_mode();
     if (mode == 1 || !rk4_sweepf_supported(n, K)) return false;
     if (mode == 2) return true;
-    // K <= 2: the operator-pass kernels need fewer FMAs (4 (K + 1) <= 2 Kpad + 4) and measure 1.0-1.7x faster
-    // (profiles/r01_t_sweep_formed_vs_legacy_K.jsonl); 3 <= K <= 16: the formed-generator kernel, 1.2-4.9x faster at
-    // every size tried, shared-memory-resident small systems included (r01_t_sweep_formed_vs_legacy_small.jsonl)
     (void)small_kernel_available;
-    return K >= 3;
+    // 3 <= K <= 16: the formed-generator kernel is 1.02-4.9x faster at every size tried, shared-memory-resident small
+    // systems included (profiles/r01_t_sweep_formed_vs_legacy_small.jsonl, ..._K.jsonl).
+    if (K >= 3) return true;
+    // K <= 2 (formation on the FMA pipe, 2 K + 4 against 4 (K + 1) FMAs): 1.07-1.85x faster once the batch is more than
+    // one wave of column octets, except K = 1 at large n (n=128: 0.90x); below one wave the operator-pass kernels win
+    // (n=32, B=1024: 0.72x) -- profiles/r01_z_sweep_formed_vs_legacy_K12.jsonl
+    const int octets = (B + 7) / 8;
+    return octets > sm_count_f() && (K == 2 || n < 100);
 }
 
 size_t rk4_sweepf_workspace_bytes(int n, int K) {
@@ -531,7 +581,7 @@ int launch_rk4_sweepf(int n, int K, int B, int S, const double2* stat_packed, co
         set_error("rk4 formed sweep: unsupported shape n=%d B=%d K=%d", n, B, K);
         return QDB_E_UNSUPPORTED;
     }
-    const size_t nops = (size_t)cfg.geo.RT * cfg.geo.C2 * cfg.KS * 32, nstat = (size_t)cfg.geo.RT * cfg.geo.C2 * 8;  // static entries (2 double2 each)
+    const size_t nops = cfg.KS > 0 ? (size_t)cfg.geo.RT * cfg.geo.C2 * cfg.KS * 32 : (size_t)cfg.geo.RT * cfg.geo.C2 * K * 8, nstat = (size_t)cfg.geo.RT * cfg.geo.C2 * 8;  // static entries (2 double2 each)
     double2* opsf = (double2*)ws;
     double2* statf = stat_packed ? opsf + nops : nullptr;
     const size_t total = nops + (stat_packed ? nstat : 0);
@@ -539,6 +589,8 @@ int launch_rk4_sweepf(int n, int K, int B, int S, const double2* stat_packed, co
     QDB_LAUNCH_CHECK("pack_sweepf_kernel");
 #define QDB_F(mr, ncw)                                                                                                     \
     if (cfg.MR == mr && cfg.NCW == ncw) {                                                                                  \
+        if (cfg.KS == -1) return launch_sweepf_t<mr, ncw, -1>(cfg, K, B, S, statf, opsf, coeff, ldc, mu, times_dev, h, y, ldy, st); \
+        if (cfg.KS == -2) return launch_sweepf_t<mr, ncw, -2>(cfg, K, B, S, statf, opsf, coeff, ldc, mu, times_dev, h, y, ldy, st); \
         if (cfg.KS == 1) return launch_sweepf_t<mr, ncw, 1>(cfg, K, B, S, statf, opsf, coeff, ldc, mu, times_dev, h, y, ldy, st); \
         if (cfg.KS == 2) return launch_sweepf_t<mr, ncw, 2>(cfg, K, B, S, statf, opsf, coeff, ldc, mu, times_dev, h, y, ldy, st); \
         if (cfg.KS == 3) return launch_sweepf_t<mr, ncw, 3>(cfg, K, B, S, statf, opsf, coeff, ldc, mu, times_dev, h, y, ldy, st); \
