@@ -12,6 +12,7 @@ namespace qdb {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 void count_launch(int n = 1);
+int sm_count();  // SMs of the current device (148 on B200 when the query fails), per-device cached
 
 #define QDB_CUDA(call)                                        \
     do {                                                      \

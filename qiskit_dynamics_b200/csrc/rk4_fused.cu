@@ -1014,19 +1014,6 @@ struct Config {
 constexpr int kMaxFusedNpad = 256;
 constexpr size_t kSmemLimit = 227 * 1024;
 
-int sm_count() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
-            sms = v;
-        else
-            sms = 148;  // B200
-    }
-    return sms;
-}
-
 bool pick_config(int n, int B, int K_sweep /*0 for shared*/, Config& cfg, double* cost_out = nullptr) {
     const int SMS = sm_count();
     const int npad = round_up8(n);

@@ -419,19 +419,9 @@ struct FConfig {
 
 constexpr size_t kSmemLimitF = 227 * 1024;
 
-int sm_count_f() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0, v = 0;
-        sms = (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
-               v > 0) ? v : 148;
-    }
-    return sms;
-}
-
 bool pick_sweepf(int n, int B, int K, FConfig& cfg) {
     if (n < 1 || round_up8(n) > 256 || K < 1 || K > 16) return false;
-    const int SMS = sm_count_f();
+    const int SMS = sm_count();
     FGeo geo;
     geo.n = n;
     geo.npad = round_up8(n);
@@ -551,7 +541,7 @@ bool rk4_sweepf_selected(int n, int K, int B, bool small_kernel_available) {
     // one wave of column octets, except K = 1 at large n (n=128: 0.90x); below one wave the operator-pass kernels win
     // (n=32, B=1024: 0.72x) -- profiles/r01_z_sweep_formed_vs_legacy_K12.jsonl
     const int octets = (B + 7) / 8;
-    return octets > sm_count_f() && (K == 2 || n < 100);
+    return octets > sm_count() && (K == 2 || n < 100);
 }
 
 size_t rk4_sweepf_workspace_bytes(int n, int K) {

@@ -349,24 +349,11 @@ __global__ void __launch_bounds__(256, 1) zgemm3m_kernel(int M, int N, int Kd, c
     }
 }
 
-int sm_count_zg() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0, v = 0;
-        sms = (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
-               v > 0) ? v : 148;
-    }
-    return sms;
-}
-
 template <typename Epi, int BN>
 int launch_bn(int M, int N, int Kd, const double2* A, int lda, const double2* B, int ldb, const double2* pre,
               const Epi& epi, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        QDB_CUDA(cudaFuncSetAttribute(zgemm_kernel<Epi, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileB<BN>::SMEM));
-        configured = true;
-    }
+    // per launch, not cached: the attribute belongs to the current device, and one process may drive several
+    QDB_CUDA(cudaFuncSetAttribute(zgemm_kernel<Epi, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileB<BN>::SMEM));
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
     zgemm_kernel<Epi, BN><<<grid, 256, TileB<BN>::SMEM, st>>>(M, N, Kd, A, lda, B, ldb, pre, epi);
     QDB_LAUNCH_CHECK("zgemm_kernel");
@@ -376,11 +363,7 @@ int launch_bn(int M, int N, int Kd, const double2* A, int lda, const double2* B,
 template <typename Epi>
 int launch_3m(int M, int N, int Kd, const double2* A, int lda, const double2* B, int ldb, const double2* pre,
               const Epi& epi, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        QDB_CUDA(cudaFuncSetAttribute(zgemm3m_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM));
-        configured = true;
-    }
+    QDB_CUDA(cudaFuncSetAttribute(zgemm3m_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM));
     dim3 grid((N + 63) / 64, (M + BM - 1) / BM);
     zgemm3m_kernel<Epi><<<grid, 256, T_SMEM, st>>>(M, N, Kd, A, lda, B, ldb, pre, epi);
     QDB_LAUNCH_CHECK("zgemm3m_kernel");
@@ -399,11 +382,11 @@ int launch(int M, int N, int Kd, const double2* A, int lda, const double2* B, in
     // 3-product kernel (one CTA per SM) once its 64 x 64 grid fills at least half of the SMs and the k loop is long
     // enough to amortise the three-stage fill; small products stay on the 4-product kernel (two CTAs per SM, narrow tiles)
     const long tiles64 = (long)((N + 63) / 64) * ((M + BM - 1) / BM);
-    if (zgemm_3m_enabled() && 2 * tiles64 >= sm_count_zg() && Kd >= 64)
+    if (zgemm_3m_enabled() && 2 * tiles64 >= sm_count() && Kd >= 64)
         return launch_3m<Epi>(M, N, Kd, A, lda, B, ldb, pre, epi, st);
     // 64 x 64 tiles unless they would fill fewer than the 2 CTA slots per SM
     const long ctas64 = (long)((N + 63) / 64) * ((M + BM - 1) / BM);
-    if (ctas64 < 2L * sm_count_zg() && N > 32) return launch_bn<Epi, 32>(M, N, Kd, A, lda, B, ldb, pre, epi, st);
+    if (ctas64 < 2L * sm_count() && N > 32) return launch_bn<Epi, 32>(M, N, Kd, A, lda, B, ldb, pre, epi, st);
     return launch_bn<Epi, 64>(M, N, Kd, A, lda, B, ldb, pre, epi, st);
 }
 

@@ -22,7 +22,7 @@ from scipy.integrate._ivp.ivp import OdeResult
 from ..arrays import asarray
 from ..exceptions import QiskitError
 from ..models import HamiltonianModel, LindbladModel, RotatingFrame
-from ..signals import Signal, SignalList, compile_signal_program
+from ..signals import Signal, SignalList, SignalSum, compile_signal_program
 from .fixed_step import rk4_model_solve
 from .solver_functions import (ODE_METHODS, is_lindblad_model_not_vectorized, is_lindblad_model_vectorized,
                                results_y_out_of_frame_basis, setup_generator_model_rhs_y0_in_frame_basis, solve_lmde)
@@ -102,8 +102,16 @@ class Solver:
         spans = np.asarray(t_span_list, dtype=float)
         if not np.all(spans == spans[0]):
             return None
-        y0s = [validate_and_format_initial_state(y, model) for y in y0_list]
-        if any(y.ndim != 1 for y in y0s):
+        # one conversion (and host-to-device copy) per DISTINCT initial state: a single y0 shared by a large sweep arrives
+        # here repeated once per simulation
+        converted = {}
+        y0s = []
+        for y in y0_list:
+            key = id(y)
+            if key not in converted:
+                converted[key] = validate_and_format_initial_state(y, model)
+            y0s.append(converted[key])
+        if any(y.ndim != 1 for y in converted.values()):
             return None
         t_eval = kwargs.get("t_eval", None)
         max_dt = kwargs["max_dt"]
@@ -111,20 +119,30 @@ class Solver:
         if extra:
             return None
 
-        # per-simulation SignalLists (validated by the model's own setter)
-        sig_lists = []
-        for signals in signals_list:
-            self._set_new_signals(signals)
-            sig_lists.append(model.signals)
-        self._set_new_signals(signals_list[0])
-
         # device route (row f3): when every term of every simulation is a sampled or constant-envelope signal
-        # and the simulations share their structure, one kernel builds the (T, K, B) table in HBM
-        if isinstance(model, LindbladModel):
-            flat_lists = [SignalList([s for part in sl if part is not None for s in part.components]) for sl in sig_lists]
-        else:
-            flat_lists = sig_lists
-        program = compile_signal_program(flat_lists)
+        # and the simulations share their structure, one kernel builds the (T, K, B) table in HBM.
+        # Fast path for large sweeps of a Hamiltonian model: plain lists of elementary signals are compiled as they
+        # are (length-checked here), without a SignalList -- one DiscreteSignalSum per channel -- per simulation.
+        program, sig_lists = None, None
+        K = model._collection().num_operators
+        if isinstance(model, HamiltonianModel) and all(
+                isinstance(sl, list) and len(sl) == K and all(isinstance(x, Signal) and not isinstance(x, SignalSum) for x in sl)
+                for sl in signals_list):
+            program = compile_signal_program(signals_list)
+            if program is not None:
+                self._set_new_signals(signals_list[0])
+        if program is None:
+            # per-simulation SignalLists (validated by the model's own setter)
+            sig_lists = []
+            for signals in signals_list:
+                self._set_new_signals(signals)
+                sig_lists.append(model.signals)
+            self._set_new_signals(signals_list[0])
+            if isinstance(model, LindbladModel):
+                flat_lists = [SignalList([s for part in sl if part is not None for s in part.components]) for sl in sig_lists]
+            else:
+                flat_lists = sig_lists
+            program = compile_signal_program(flat_lists)
 
         def column_coefficients(times: np.ndarray):
             if program is not None:
@@ -138,7 +156,10 @@ class Solver:
                     cols.append(sl.table(times))
             return np.stack(cols, axis=-1)  # (T, K, B)
 
-        Y0 = torch.stack(y0s, dim=1).contiguous()  # (n, B): one column per simulation
+        if len(converted) == 1:
+            Y0 = y0s[0].reshape(-1, 1).expand(-1, nsim).contiguous()  # (n, B): the shared state in every column
+        else:
+            Y0 = torch.stack(y0s, dim=1).contiguous()  # (n, B): one column per simulation
         _, _, y0_fb, was = setup_generator_model_rhs_y0_in_frame_basis(model, Y0)
         try:
             res = rk4_model_solve(model, spans[0], y0_fb, max_dt, t_eval=t_eval, column_coefficients=column_coefficients)
@@ -146,7 +167,8 @@ class Solver:
                 res.y = results_y_out_of_frame_basis(model, res.y, 2)
         finally:
             model.in_frame_basis = was
-        return [OdeResult(t=res.t, y=res.y[:, :, b].contiguous()) for b in range(nsim)]
+        per_sim = res.y.permute(2, 0, 1).contiguous()  # one transpose; per_sim[b] is the contiguous (T, n) result of simulation b
+        return [OdeResult(t=res.t, y=per_sim[b]) for b in range(nsim)]
 
 
 # ---------------------------------------------------------------------------------------------

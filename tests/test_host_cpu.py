@@ -323,3 +323,22 @@ def test_bench_workload_matches_the_test_generator():
     head = src[:src.index("def cpu_reference_rate")]
     assert "oracle" not in head.replace("oracle/", "").replace("oracle port", "").replace("(oracle)", ""), \
         "the B200 arm of bench.py must not import the oracle"
+
+
+def test_signal_program_from_plain_lists(qd):
+    """Large sweeps hand Solver.solve plain lists of elementary signals; compiling them directly must give the same
+    device program as the SignalList route (which wraps every channel of every simulation into a SignalSum)."""
+    from qiskit_dynamics_b200.signals import SignalList, compile_signal_program
+    rng = np.random.default_rng(3)
+    lists = [[qd.DiscreteSignal(dt=0.2, samples=rng.standard_normal(6) + 1j * rng.standard_normal(6), start_time=0.1 * (j % 2),
+                                carrier_freq=1.0 + j, phase=0.3 * b) for j in range(3)] for b in range(7)]
+    fast, slow = compile_signal_program(lists), compile_signal_program([SignalList(l) for l in lists])
+    for name in ("chan", "samp_len", "samp_off", "dt", "t0", "freq", "phase", "samples"):
+        assert np.array_equal(getattr(fast, name), getattr(slow, name)), name
+    assert (fast.num_channels, fast.columns) == (slow.num_channels, slow.columns) == (3, 7)
+    const = [[qd.Signal(0.3 * (b + 1), 1.0 + j, 0.1) for j in range(2)] for b in range(4)]
+    fast, slow = compile_signal_program(const), compile_signal_program([SignalList(l) for l in const])
+    for name in ("chan", "samp_len", "samp_off", "dt", "t0", "freq", "phase", "samples"):
+        assert np.array_equal(getattr(fast, name), getattr(slow, name)), name
+    assert compile_signal_program([[qd.Signal(lambda t: t, 1.0)]]) is None      # Python envelope: host path
+    assert compile_signal_program([[qd.Signal(1.0)], [qd.DiscreteSignal(0.1, [1.0, 2.0])]]) is None  # structure differs
