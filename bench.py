@@ -18,6 +18,7 @@ A "step" is one pass of the hot path over one batch: a fused solve of RK4_STEPS 
            tensor pipe: algorithmic flops per launch / its mean CUDA-event duration, over the
            live-measured DMMA peak (MEASURED_PEAKS.json has no fp64 entry; datasheet 37-40 TF).
   cpu_baseline : the oracle port of the reference's NumPy path (same BLAS calls) on the host cores.
+  sweep_mode : per-column-signal RK4 (cfg2, cfg5-like) beside the headline, device-resident (rank 0, untimed region).
 """
 import argparse
 import json
@@ -328,6 +329,46 @@ def run_b200(args):
     kernel_name = (f"{'rk4_shared3m_kernel' if tiling['m3'] else 'rk4_shared_kernel'}<{tiling['row_tiles_per_warp']},"
                    f"{tiling['col_tiles_per_warp']},{'split' if tiling['split'] else 'whole'}>")
 
+    # ---------------- sweep mode beside the headline (the shared-signal shortcut does not exist there) ----------------
+    def sweep_rate(n2, K2, B2, S2, seed2):
+        """Device-resident per-column-signal RK4 (cfg2 / cfg5-like): state-RHS/s and algorithmic fraction of the roof."""
+        H0s, Hss, Ys, sigs = workload(n2, K2, 1, seed2)
+        m2 = qd.HamiltonianModel(static_operator=H0s, operators=Hss, signals=[qd.Signal(a_, nu_, ph_) for a_, nu_, ph_ in sigs],
+                                 rotating_frame=H0s)
+        c2 = m2._collection()
+        p_ops, p_stat = c2.packed()
+        t2 = stage_time_grid(0.0, MAX_DT, S2)
+        base = torch.from_numpy(m2._signal_table(t2)).to(dev)
+        amp = 0.5 + torch.arange(B2, dtype=torch.float64, device=dev) / B2
+        coeff2 = (base[:, :, None] * amp[None, None, :]).contiguous()  # (T, K, B): amplitude sweep
+        y2_0 = m2.rotating_frame.state_into_frame_basis(qd.asarray(np.repeat(Ys, B2, axis=1)))
+        y2 = y2_0.clone()
+
+        def run():
+            y2.copy_(y2_0)
+            abi.rk4_steps(n2, c2.operators, c2.static_operator, p_ops, p_stat, coeff2, m2._frame_freqs(), t2, MAX_DT, y2, S2,
+                          per_col=True)
+        best = float("inf")
+        for it in range(5):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            run()
+            a1.record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                best = min(best, a0.elapsed_time(a1))
+        alg = S2 * B2 * (4 * ((4 * K2 + 8) * n2 * n2 + 12 * n2) + 28 * n2)
+        tl = abi.rk4_tiling(n2, B2, K2)
+        return {"n": n2, "K": K2, "batch": B2, "rk4_steps": S2, "us_per_rk4_step": best * 1e3 / S2,
+                "state_rhs_per_s": 4.0 * S2 * B2 / (best * 1e-3), "alg_tflops": alg / best * 1e-9,
+                "kernel": "rk4_sweepf_kernel" if tl["m3"] == 2 else "rk4_sweep_kernel"}
+
+    sweep_mode = None
+    if rank == 0:
+        sweep_mode = {"cfg2": sweep_rate(32, 8, 1024, 500, 2002), "cfg5_like": sweep_rate(81, 8, 8192, 20, 2005),
+                      "note": "per-column signal values (parameter sweeps), device-resident, best of 3 after 2 warm-ups; "
+                              "algorithmic flops per RHS = (4K+8) n^2 + 12 n (SURVEY 8(d))"}
+
     # parity spot check of the timed configuration (not timed): norm preservation of the unitary flow
     norms = torch.linalg.vector_norm(y_work, dim=0)
     norm_dev = float((norms - 1.0).abs().max().item())
@@ -335,6 +376,8 @@ def run_b200(args):
     if rank == 0:
         threads = cpu_threads()
         cpu_rate, cpu_sec = cpu_reference_rate(n, K, B, steps=2, warmup=1, rk4_steps=CPU_BASELINE_RK4_STEPS)
+        for cfg_ in ("cfg2", "cfg5_like"):
+            sweep_mode[cfg_]["alg_frac"] = sweep_mode[cfg_]["alg_tflops"] / peak_tf
         line = {
             "metric": "rhs_evals_per_sec", "value": value, "unit": "state-RHS/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
@@ -359,6 +402,7 @@ def run_b200(args):
                          if tiling["m3"] else "achieved = algorithmic = executed flops",
                          "peak_source": "live DMMA m8n8k4 issue-rate probe (qdb_dmma_probe); MEASURED_PEAKS.json has no "
                                         "fp64 entry; B200 datasheet fp64 tensor 37-40 TFLOP/s"},
+            "sweep_mode": sweep_mode,
             "cpu_baseline": {"value": cpu_rate, "unit": "state-RHS/s", "cores": threads, "kind": "port",
                              "sample": f"{CPU_BASELINE_RK4_STEPS} RK4 steps (one full bench step) of the same n={n}, K={K}, "
                                        f"B={B} batch x 2 repeats after 1 warm-up ({cpu_sec:.2f} s each), NumPy/OpenBLAS "
