@@ -56,6 +56,7 @@ typedef struct { double re, im; } qdb_c128;
 #define QDB_WS_RK4 1
 #define QDB_WS_EXPM 2
 #define QDB_WS_MAGNUS 3
+#define QDB_WS_PROP 4
 
 const char* qdb_last_error_string(void);
 int qdb_version(void);
@@ -211,6 +212,24 @@ int qdb_magnus_steps_c128(int n, int K, int B, int S, int magnus_order,
  * solvers/fixed_step_solvers.py:80-108).  workspace: 0 / n^2 / 7 n^2 complex numbers for order 1 / 2 / 3. */
 int qdb_magnus_terms_c128(int n, int magnus_order, const qdb_c128* g, double h, double scale, qdb_c128* out,
                           void* workspace, size_t ws_bytes, void* stream);
+
+/* Time-parallel LMDE stepping: the product  P_total = P_{S-1} ... P_1 P_0  of the S one-step propagators of an
+ * interval, built side by side (the step index is the batch dimension of the DMMA GEMM launches) and multiplied
+ * pairwise; the caller applies it to the state batch with one qdb_zgemm_c128.
+ *   kind 0      : RK4 propagator  1 + (h/6)(k1 + 2 k2 + 2 k3 + k4)  (generator at t, t + h/2, t + h:
+ *                 times_host [S][3], coeff [S][3][K])
+ *   kind 1,2,3  : expm of the Magnus exponent of that order (times_host [S][kind], coeff [S][kind][K],
+ *                 squarings_host [S]; see qdb_magnus_steps_c128)
+ *   workspace   : qdb_workspace_bytes(QDB_WS_PROP, n, K, 0, S) holds all S steps at once; with less (at least the
+ *                 S = 1 size) the steps are processed in chunks.
+ * Replaces jax_RK4_parallel_solver / jax_expm_parallel_solver and their vmap + associative_scan template
+ * (solvers/fixed_step_solvers.py:206-244, 279-311, 524-613), which the reference offers on JAX only. */
+int qdb_step_propagators_c128(int n, int K, int S, int kind,
+                              const qdb_c128* ops_rm, const qdb_c128* stat_rm,
+                              const double* coeff, const double* mu,
+                              const double* times_host, const int* squarings_host, double h,
+                              qdb_c128* P_total,
+                              void* workspace, size_t ws_bytes, void* stream);
 
 /* Matrix exponential of one (n x n) row-major matrix with `squarings` halvings (building block
  * of qdb_expm_steps_c128, exported for parity tests against scipy.linalg.expm). */

@@ -474,6 +474,56 @@ def fixed_step_solve(take_step, fn, t_span, y0, max_dt, t_eval=None):
     return t_list, ys
 
 
+def rk4_step_propagator(generator: Callable, t, h):
+    """take_step of jax_RK4_parallel_solver (solvers/fixed_step_solvers.py:225-237): the RK4 step as a matrix."""
+    ident = np.eye(np.asarray(generator(t)).shape[-1], dtype=complex)
+    h2 = 0.5 * h
+    gh2 = generator(t + h2)
+    k1 = generator(t)
+    k2 = gh2 @ (ident + h2 * k1)
+    k3 = gh2 @ (ident + h2 * k2)
+    k4 = generator(t + h) @ (ident + h * k3)
+    return ident + (1.0 / 6) * h * (k1 + 2 * k2 + 2 * k3 + k4)
+
+
+def parallel_solve(step_propagator: Callable, generator: Callable, t_span, y0, max_dt, t_eval=None):
+    """fixed_step_lmde_solver_parallel_template_jax (solvers/fixed_step_solvers.py:524-613) without JAX: step times
+    t + h * arange(n) per interval (not accumulated), one propagator per step, cumulative products (later steps on the
+    left), results at the interval ends = cumulative propagator applied to y0.  step_propagator(generator, t, h)."""
+    y0 = np.asarray(y0, dtype=complex)
+    t_list, h_list, n_list = fixed_step_sizes(t_span, t_eval, max_dt)
+    ys = [y0]
+    total = None
+    for t, h, n in zip(t_list, h_list, n_list):
+        for ts in t + h * np.arange(n):
+            P = step_propagator(generator, ts, h)
+            total = P if total is None else P @ total
+        ys.append(total @ y0)
+    ys = np.asarray(ys)
+    if t_eval is not None:
+        return t_list[1:-1], ys[1:-1]
+    return t_list, ys
+
+
+def solve_hamiltonian_parallel(static_operator, operators, specs, frame_operator, t_span, y0, max_dt, kind="RK4",
+                               magnus_order=1, t_eval=None, hamiltonian=True):
+    """solve_lmde(model, method="jax_RK4_parallel" | "jax_expm_parallel") restated on NumPy (the reference runs these
+    on JAX only, which is absent here: this restatement is pinned only through its agreement with the sequential
+    solvers, which are pinned by the fixtures -- same propagators, associativity of the matrix product)."""
+    Gd, G, d, U = generator_model_operators(static_operator, operators, frame_operator, hamiltonian)
+    y0 = np.asarray(y0, dtype=complex)
+    yfb = y0 if U is None else U.conj().T @ y0
+    gen = lambda t: model_generator(t, specs, G, Gd, d)  # noqa: E731
+    if kind == "RK4":
+        step = rk4_step_propagator
+    else:
+        step = lambda g, t, h: magnus_propagator(g, t, h, magnus_order)  # noqa: E731
+    t, ys = parallel_solve(step, gen, t_span, yfb, max_dt, t_eval)
+    if U is not None:
+        ys = (U @ ys.T).T if y0.ndim == 1 else U @ ys
+    return t, ys
+
+
 def stage_time_grid(t0, h, n_steps):
     """The 2S+1 stage times the template visits for one interval, with the same accumulation as
     the loop above (t <- t + h; midpoints t + 0.5 h): [t_0, t_0+h/2, t_1, t_1+h/2, ..., t_S]."""

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libqdb.so")
 LAYOUT_ROWMAJOR = 0
 LAYOUT_PACKED = 1
 LAYOUT_PACKED3M = 2
-WS_RHS, WS_RK4, WS_EXPM, WS_MAGNUS = 0, 1, 2, 3
+WS_RHS, WS_RK4, WS_EXPM, WS_MAGNUS, WS_PROP = 0, 1, 2, 3, 4
 
 
 class QdbError(RuntimeError):
@@ -58,6 +58,7 @@ SIGNATURES = {
     "qdb_expm_c128": (_i, [_i, _vp, _i, _vp, _vp, _sz, _vp]),
     "qdb_magnus_steps_c128": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _i, _vp, _sz, _vp]),
     "qdb_magnus_terms_c128": (_i, [_i, _i, _vp, _d, _d, _vp, _vp, _sz, _vp]),
+    "qdb_step_propagators_c128": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _vp, _sz, _vp]),
     "qdb_launch_count": (ctypes.c_ulonglong, []),
 }
 
@@ -274,6 +275,32 @@ def magnus_steps(n, ops_rm, stat_rm, coeff, mu, times_host: np.ndarray, squaring
                                        ctypes.c_void_p(workspace.data_ptr()), workspace.numel(), _stream()),
            "qdb_magnus_steps_c128")
     return y
+
+
+def step_propagators(n, ops_rm, stat_rm, coeff, mu, times_host: np.ndarray, squarings_host, h, S, kind, max_ws_bytes=1 << 31,
+                     out=None):
+    """Product of the S one-step propagators of an interval (kind 0: RK4, 1..3: expm at that Magnus order)."""
+    K = 0 if ops_rm is None else ops_rm.shape[0]
+    dev = (ops_rm if ops_rm is not None else stat_rm).device
+    Q = 3 if kind == 0 else kind
+    times_host = np.ascontiguousarray(times_host, dtype=np.float64)
+    if times_host.size != S * Q:
+        raise QdbError(f"step_propagators: {times_host.size} node times for S={S} steps of {Q} nodes")
+    sq_ptr = None
+    if kind != 0:
+        squarings_host = np.ascontiguousarray(squarings_host, dtype=np.int32)
+        if squarings_host.size != S:
+            raise QdbError(f"step_propagators: {squarings_host.size} squarings for S={S}")
+        sq_ptr = squarings_host.ctypes.data_as(ctypes.c_void_p)
+    need = min(workspace_bytes(WS_PROP, n, K, 0, S), max(max_ws_bytes, workspace_bytes(WS_PROP, n, K, 0, 1)))
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    if out is None:
+        out = torch.empty((n, n), dtype=C, device=dev)
+    _check(lib().qdb_step_propagators_c128(n, K, S, int(kind), _ptr(ops_rm, C, "ops_rm"), _ptr(stat_rm, C, "stat_rm"),
+                                           _ptr(coeff, F, "coeff"), _ptr(mu, F, "mu"),
+                                           times_host.ctypes.data_as(ctypes.c_void_p), sq_ptr, float(h), _ptr(out, C, "P_total"),
+                                           ctypes.c_void_p(ws.data_ptr()), ws.numel(), _stream()), "qdb_step_propagators_c128")
+    return out
 
 
 def magnus_terms(g: torch.Tensor, h: float, magnus_order: int, scale: float = 1.0):

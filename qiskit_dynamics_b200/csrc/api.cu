@@ -90,6 +90,8 @@ size_t qdb_workspace_bytes(int kind, int n, int K, int B, int S) {
             return 3 * align_up(n2) + 3 * align_up(yb) + align_up(3 * sizeof(double));
         case QDB_WS_EXPM:
             return 7 * align_up(n2) + align_up(yb);
+        case QDB_WS_PROP:
+            return propagator_workspace_bytes(n, S);
         case QDB_WS_MAGNUS:  // + node generators (3), Magnus temporaries (7), node times [3 S]
             return 17 * align_up(n2) + align_up(yb) + align_up((size_t)3 * S * sizeof(double));
         default:
@@ -477,6 +479,20 @@ int qdb_magnus_steps_c128(int n, int K, int B, int S, int magnus_order, const qd
     if (ycur != D2(y)) QDB_CUDA(cudaMemcpyAsync(y, ycur, (size_t)n * B * sizeof(double2), cudaMemcpyDeviceToDevice, st));
     (void)nn;
     return QDB_OK;
+}
+
+int qdb_step_propagators_c128(int n, int K, int S, int kind, const qdb_c128* ops_rm, const qdb_c128* stat_rm, const double* coeff,
+                              const double* mu, const double* times_host, const int* squarings_host, double h, qdb_c128* P_total,
+                              void* workspace, size_t ws_bytes, void* stream) {
+    QDB_REQUIRE(n >= 1 && K >= 0 && S >= 1, "qdb_step_propagators_c128: bad n=%d K=%d S=%d", n, K, S);
+    QDB_REQUIRE(kind >= 0 && kind <= 3, "qdb_step_propagators_c128: kind %d not in {0 (RK4), 1, 2, 3 (Magnus order)}", kind);
+    QDB_REQUIRE(stat_rm || (ops_rm && K > 0), "qdb_step_propagators_c128: neither static operator nor operators given");
+    QDB_REQUIRE(K == 0 || coeff, "qdb_step_propagators_c128: K=%d but no signal table", K);
+    QDB_REQUIRE(kind == 0 || squarings_host, "qdb_step_propagators_c128: squarings missing");
+    QDB_REQUIRE(!mu || times_host, "qdb_step_propagators_c128: frame given without times");
+    QDB_REQUIRE(P_total && workspace, "qdb_step_propagators_c128: null pointer");
+    return step_propagator_product(n, K, S, kind, D2(ops_rm), D2(stat_rm), coeff, mu, times_host, squarings_host, h, D2(P_total),
+                                   workspace, ws_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,167 @@
+// Time-parallel fixed-step solvers for LMDEs (the reference's jax_RK4_parallel_solver / jax_expm_parallel_solver,
+// solvers/fixed_step_solvers.py:206-244, 279-311, and their template :524-613): every step has a propagator that does
+// not depend on the state,
+//     RK4 :  P = 1 + (h/6)(k1 + 2 k2 + 2 k3 + k4),  k1 = G(t), k2 = G(t+h/2)(1 + h/2 k1), k3 = G(t+h/2)(1 + h/2 k2),
+//            k4 = G(t+h)(1 + h k3)
+//     expm:  P = expm(Omega)  (Magnus order 1, 2 or 3, see expm.cu)
+// so all S propagators of an interval are built side by side and multiplied together pairwise,
+//     P_total = P_{S-1} ... P_1 P_0,
+// and the state batch is touched once per interval.  The reference does this with jax.vmap + associative_scan; here the
+// step dimension is the batch dimension (grid.z) of one DMMA GEMM launch per RK4 stage and per level of the product
+// tree -- S products of 128^3 fill the chip where a single one occupies four CTAs.  For n x n generators and B columns
+// a step costs 4 (8 n^3) flops instead of 4 (8 n^2 B): the shared-signal shortcut of SURVEY 8(d) (32x fewer flops at
+// n = 128, B = 4096), offered under the reference's own method names; it does not exist for per-column signals.
+#include "qdb_common.cuh"
+
+namespace qdb {
+
+namespace {
+
+// P[s] = 1 + (1/6) h (k1 + 2 k2 + 2 k3 + k4), k1 = G[3 s]  (evaluation order of fixed_step_solvers.py:237)
+__global__ void rk4_prop_combine_kernel(int n, size_t nn, size_t total, double h, const double2* __restrict__ G,
+                                        const double2* __restrict__ K2, const double2* __restrict__ K3,
+                                        const double2* __restrict__ K4, double2* __restrict__ P) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const size_t s = idx / nn, e = idx - s * nn;
+    const int r = (int)(e / n), c = (int)(e - (size_t)r * n);
+    const double2 k1 = G[3 * s * nn + e], k2 = K2[idx], k3 = K3[idx], k4 = K4[idx];
+    const double f = (1.0 / 6) * h;
+    double2 v = make_double2(f * (k1.x + 2 * k2.x + 2 * k3.x + k4.x), f * (k1.y + 2 * k2.y + 2 * k3.y + k4.y));
+    if (r == c) v.x += 1.0;
+    P[idx] = v;
+}
+
+inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+// gather every third matrix of G (offset `which`) into a dense [S][nn] array
+int gather_third(size_t nn, int S, const double2* G, int which, double2* dst, cudaStream_t st) {
+    QDB_CUDA(cudaMemcpy2DAsync(dst, nn * sizeof(double2), G + (size_t)which * nn, 3 * nn * sizeof(double2), nn * sizeof(double2),
+                               (size_t)S, cudaMemcpyDeviceToDevice, st));
+    return QDB_OK;
+}
+
+// RK4 step propagators of S steps from G = [S][3][n][n] (generator at t, t + h/2, t + h): four launches over all steps
+int rk4_step_propagators(int n, int S, const double2* G, double h, double2* K2, double2* K3, double2* K4, double2* P,
+                         cudaStream_t st) {
+    const size_t nn = (size_t)n * n;
+    const double2 one = make_double2(1.0, 0.0);
+    int rc;
+    // k2 = Gm + (h/2) Gm k1
+    if ((rc = gather_third(nn, S, G, 1, K2, st)) != QDB_OK) return rc;
+    if ((rc = launch_zgemm_batched(n, n, n, G + nn, n, 3 * (long long)nn, G, n, 3 * (long long)nn, K2, n, (long long)nn,
+                                   make_double2(0.5 * h, 0.0), one, S, st)) != QDB_OK) return rc;
+    // k3 = Gm + (h/2) Gm k2
+    if ((rc = gather_third(nn, S, G, 1, K3, st)) != QDB_OK) return rc;
+    if ((rc = launch_zgemm_batched(n, n, n, G + nn, n, 3 * (long long)nn, K2, n, (long long)nn, K3, n, (long long)nn,
+                                   make_double2(0.5 * h, 0.0), one, S, st)) != QDB_OK) return rc;
+    // k4 = G1 + h G1 k3
+    if ((rc = gather_third(nn, S, G, 2, K4, st)) != QDB_OK) return rc;
+    if ((rc = launch_zgemm_batched(n, n, n, G + 2 * nn, n, 3 * (long long)nn, K3, n, (long long)nn, K4, n, (long long)nn,
+                                   make_double2(h, 0.0), one, S, st)) != QDB_OK) return rc;
+    const size_t total = (size_t)S * nn;
+    rk4_prop_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n, nn, total, h, G, K2, K3, K4, P);
+    QDB_LAUNCH_CHECK("rk4_prop_combine_kernel");
+    return QDB_OK;
+}
+
+// out = P[count-1] ... P[1] P[0]; P is overwritten, tmp holds ceil(count / 2) matrices.  One batched GEMM per level.
+int product_tree(int n, int count, double2* P, double2* tmp, double2* out, cudaStream_t st) {
+    const size_t nn = (size_t)n * n;
+    double2 *cur = P, *other = tmp;
+    int m = count, rc;
+    while (m > 1) {
+        const int pairs = m / 2;
+        if ((rc = launch_zgemm_batched(n, n, n, cur + nn, n, 2 * (long long)nn, cur, n, 2 * (long long)nn, other, n, (long long)nn,
+                                       make_double2(1.0, 0.0), make_double2(0.0, 0.0), pairs, st)) != QDB_OK) return rc;
+        if (m & 1)
+            QDB_CUDA(cudaMemcpyAsync(other + (size_t)pairs * nn, cur + (size_t)(m - 1) * nn, nn * sizeof(double2),
+                                     cudaMemcpyDeviceToDevice, st));
+        double2* t = cur;
+        cur = other;
+        other = t;
+        m = pairs + (m & 1);
+    }
+    QDB_CUDA(cudaMemcpyAsync(out, cur, nn * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+    return QDB_OK;
+}
+
+}  // namespace
+
+size_t propagator_workspace_bytes(int n, int S) {
+    const size_t nn = align256((size_t)n * n * sizeof(double2));
+    if (S < 1) S = 1;
+    // RK4: G [3 S] + K2, K3, K4 [S each] + P [S] + tree [ceil(S/2)]; expm: 16 scratch matrices + P + tree; both: two
+    // accumulators and the node times
+    const size_t per_step = 7 * nn + (nn + 1) / 2;
+    return (size_t)S * per_step + 20 * nn + align256((size_t)3 * S * sizeof(double));
+}
+
+// kind 0: RK4 (times/coeff [S][3]); kind 1..3: exponential of the Magnus exponent of that order (times/coeff [S][kind])
+int step_propagator_product(int n, int K, int S, int kind, const double2* ops_rm, const double2* stat_rm, const double* coeff,
+                            const double* mu, const double* times_host, const int* squarings_host, double h, double2* P_total,
+                            void* workspace, size_t ws_bytes, cudaStream_t st) {
+    const size_t nn = (size_t)n * n, nnb = align256(nn * sizeof(double2));
+    // largest chunk of steps that fits the workspace
+    int Sc = S;
+    while (Sc > 1 && propagator_workspace_bytes(n, Sc) > ws_bytes) Sc = (Sc + 1) / 2;
+    if (propagator_workspace_bytes(n, Sc) > ws_bytes) {
+        set_error("qdb_step_propagators_c128: workspace too small (%zu < %zu)", ws_bytes, propagator_workspace_bytes(n, 1));
+        return QDB_E_WORKSPACE;
+    }
+    const int Q = kind == 0 ? 3 : kind;  // generator evaluations per step
+    char* ws = (char*)workspace;
+    double2* acc_a = (double2*)ws;                      // running product
+    double2* acc_b = (double2*)(ws + nnb);              // chunk product / swap
+    double2* scratch = (double2*)(ws + 2 * nnb);        // 18 matrices: expm As, core (5), node generators (3), Magnus (7), spare
+    double2* P = (double2*)(ws + 20 * nnb);             // [Sc]
+    double2* tree = P + (size_t)Sc * nn;                // [ceil(Sc/2)]
+    double2* big = tree + (size_t)((Sc + 1) / 2) * nn;  // RK4: G [3 Sc], K2, K3, K4 [Sc each]
+    double* times_dev = (double*)(ws + propagator_workspace_bytes(n, Sc) - align256((size_t)3 * Sc * sizeof(double)));
+    const double2 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0);
+    int rc;
+    bool first = true;
+    for (int s0 = 0; s0 < S; s0 += Sc) {
+        const int Sn = S - s0 < Sc ? S - s0 : Sc;
+        const double* cs = coeff ? coeff + (size_t)s0 * Q * K : nullptr;
+        if (mu) QDB_CUDA(cudaMemcpyAsync(times_dev, times_host + (size_t)s0 * Q, (size_t)Sn * Q * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (kind == 0) {
+            double2 *G = big, *K2 = big + (size_t)3 * Sn * nn, *K3 = K2 + (size_t)Sn * nn, *K4 = K3 + (size_t)Sn * nn;
+            rc = launch_generator(n, K, 3 * Sn, QDB_LAYOUT_ROWMAJOR, ops_rm, stat_rm, cs, 0, mu, mu ? times_dev : nullptr, 0.0, 1.0, G, st);
+            if (rc != QDB_OK) return rc;
+            if ((rc = rk4_step_propagators(n, Sn, G, h, K2, K3, K4, P, st)) != QDB_OK) return rc;
+        } else {
+            double2 *As = scratch, *core_ws = scratch + nn, *gnodes = scratch + 6 * nn, *mag_ws = scratch + 9 * nn;
+            for (int s = 0; s < Sn; ++s) {
+                const int sq = squarings_host[s0 + s];
+                if (sq < 0 || sq >= 64) {
+                    set_error("qdb_step_propagators_c128: bad squarings[%d]=%d", s0 + s, sq);
+                    return QDB_E_ARG;
+                }
+                const double sc = ldexp(1.0, -sq);
+                const double* c1 = cs ? cs + (size_t)s * Q * K : nullptr;
+                if (Q == 1) {
+                    rc = launch_generator(n, K, 1, QDB_LAYOUT_ROWMAJOR, ops_rm, stat_rm, c1, 0, mu, mu ? times_dev + s : nullptr, 0.0, sc * h, As, st);
+                    if (rc != QDB_OK) return rc;
+                } else {
+                    rc = launch_generator(n, K, Q, QDB_LAYOUT_ROWMAJOR, ops_rm, stat_rm, c1, 0, mu, mu ? times_dev + (size_t)s * Q : nullptr, 0.0,
+                                          1.0, gnodes, st);
+                    if (rc != QDB_OK) return rc;
+                    if ((rc = magnus_terms(n, Q, gnodes, h, sc, As, mag_ws, st)) != QDB_OK) return rc;
+                }
+                if ((rc = expm_core(n, As, sq, P + (size_t)s * nn, core_ws, st)) != QDB_OK) return rc;
+            }
+        }
+        double2* dst = first ? acc_a : acc_b;
+        if ((rc = product_tree(n, Sn, P, tree, dst, st)) != QDB_OK) return rc;
+        if (!first) {  // total <- chunk * total
+            if ((rc = launch_zgemm(n, n, n, acc_b, n, acc_a, n, scratch, n, one, zero, nullptr, nullptr, nullptr, st)) != QDB_OK) return rc;
+            QDB_CUDA(cudaMemcpyAsync(acc_a, scratch, nn * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+        }
+        first = false;
+    }
+    QDB_CUDA(cudaMemcpyAsync(P_total, acc_a, nn * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+    return QDB_OK;
+}
+
+}  // namespace qdb

@@ -104,12 +104,20 @@ int magnus_terms(int n, int order, const double2* g /*[order][n][n]*/, double h,
 int launch_zgemm(int M, int N, int Kd, const double2* A, int lda, const double2* B, int ldb,
                  double2* C, int ldc, double2 alpha, double2 beta, const double* colscale,
                  const double2* pre, const double2* post, cudaStream_t st);
+int launch_zgemm_batched(int M, int N, int Kd, const double2* A, int lda, long long sA, const double2* B, int ldb,
+                         long long sB, double2* C, int ldc, long long sC, double2 alpha, double2 beta, int count,
+                         cudaStream_t st);
 // two-output RK4 stage epilogue variant (generic large-n path):
 //   k = G * yin ;  yout = ybase + a_next * k ;  acc = (first ? 0 : acc) + w * k
 int launch_zgemm_rk4stage(int n, int B, const double2* G, const double2* yin, int ldy,
                           const double2* ybase, double2* yout, double2* acc, double a_next, double w,
                           int first, cudaStream_t st);
 int launch_dmma_probe(double* sink, int iters, int* grid_out, cudaStream_t st);
+// time-parallel solvers (propagator.cu)
+size_t propagator_workspace_bytes(int n, int S);
+int step_propagator_product(int n, int K, int S, int kind, const double2* ops_rm, const double2* stat_rm, const double* coeff,
+                            const double* mu, const double* times_host, const int* squarings_host, double h, double2* P_total,
+                            void* workspace, size_t ws_bytes, cudaStream_t st);
 bool rk4_fused_supported(int n);
 bool rk4_fused_tiling(int n, int B, int sweep_K, int* out);
 int launch_rk4_fused_shared(int n, int B, int S, const double2* gen_table, int table_layout, double h,

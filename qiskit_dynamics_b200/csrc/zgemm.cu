@@ -32,6 +32,8 @@ struct EpiStd {
     double2 alpha, beta;
     const double* colscale;
     const double2* post;
+    long long sC;  // batch stride of C (elements); 0 for a single product
+    __device__ __forceinline__ void shift(unsigned z) { C += (size_t)z * (size_t)sC; }
 };
 
 struct EpiRk4 {
@@ -41,6 +43,12 @@ struct EpiRk4 {
     int ld;
     double a_next, w;
     int first;
+    __device__ __forceinline__ void shift(unsigned) {}
+};
+
+// batched products (grid.z): operand strides in elements, 0 = shared by every product of the batch
+struct BatchStride {
+    long long sA, sB;
 };
 
 __device__ __forceinline__ void epilogue(const EpiStd& e, int r, int c, double2 v) {
@@ -71,9 +79,12 @@ __device__ __forceinline__ void epilogue(const EpiRk4& e, int r, int c, double2 
 }
 
 template <typename Epi, int BN>
-__global__ void __launch_bounds__(256) zgemm_kernel(int M, int N, int Kd, const double2* __restrict__ A, int lda,
-                                                     const double2* __restrict__ Bm, int ldb,
-                                                     const double2* __restrict__ pre, Epi epi) {
+__global__ void __launch_bounds__(256) zgemm_kernel(int M, int N, int Kd, const double2* __restrict__ A0, int lda,
+                                                     const double2* __restrict__ Bm0, int ldb,
+                                                     const double2* __restrict__ pre, Epi epi, BatchStride bs) {
+    const double2* __restrict__ A = A0 + (size_t)blockIdx.z * (size_t)bs.sA;
+    const double2* __restrict__ Bm = Bm0 + (size_t)blockIdx.z * (size_t)bs.sB;
+    epi.shift(blockIdx.z);
     constexpr int B_LD = TileB<BN>::LD, B_TILE = TileB<BN>::TILE;
     constexpr int NC = BN / 16;  // column tiles per warp
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -205,9 +216,12 @@ constexpr size_t T_STAGE = T_AC + T_AS + T_BC + T_BS;            // 56320
 constexpr size_t T_SMEM = T_STAGES * T_STAGE;                    // 168960
 
 template <typename Epi>
-__global__ void __launch_bounds__(256, 1) zgemm3m_kernel(int M, int N, int Kd, const double2* __restrict__ A, int lda,
-                                                          const double2* __restrict__ Bm, int ldb,
-                                                          const double2* __restrict__ pre, Epi epi) {
+__global__ void __launch_bounds__(256, 1) zgemm3m_kernel(int M, int N, int Kd, const double2* __restrict__ A0, int lda,
+                                                          const double2* __restrict__ Bm0, int ldb,
+                                                          const double2* __restrict__ pre, Epi epi, BatchStride bs) {
+    const double2* __restrict__ A = A0 + (size_t)blockIdx.z * (size_t)bs.sA;
+    const double2* __restrict__ Bm = Bm0 + (size_t)blockIdx.z * (size_t)bs.sB;
+    epi.shift(blockIdx.z);
     constexpr int BN = 64;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -351,21 +365,21 @@ __global__ void __launch_bounds__(256, 1) zgemm3m_kernel(int M, int N, int Kd, c
 
 template <typename Epi, int BN>
 int launch_bn(int M, int N, int Kd, const double2* A, int lda, const double2* B, int ldb, const double2* pre,
-              const Epi& epi, cudaStream_t st) {
+              const Epi& epi, BatchStride bs, int count, cudaStream_t st) {
     // per launch, not cached: the attribute belongs to the current device, and one process may drive several
     QDB_CUDA(cudaFuncSetAttribute(zgemm_kernel<Epi, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileB<BN>::SMEM));
-    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-    zgemm_kernel<Epi, BN><<<grid, 256, TileB<BN>::SMEM, st>>>(M, N, Kd, A, lda, B, ldb, pre, epi);
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, count);
+    zgemm_kernel<Epi, BN><<<grid, 256, TileB<BN>::SMEM, st>>>(M, N, Kd, A, lda, B, ldb, pre, epi, bs);
     QDB_LAUNCH_CHECK("zgemm_kernel");
     return QDB_OK;
 }
 
 template <typename Epi>
 int launch_3m(int M, int N, int Kd, const double2* A, int lda, const double2* B, int ldb, const double2* pre,
-              const Epi& epi, cudaStream_t st) {
+              const Epi& epi, BatchStride bs, int count, cudaStream_t st) {
     QDB_CUDA(cudaFuncSetAttribute(zgemm3m_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM));
-    dim3 grid((N + 63) / 64, (M + BM - 1) / BM);
-    zgemm3m_kernel<Epi><<<grid, 256, T_SMEM, st>>>(M, N, Kd, A, lda, B, ldb, pre, epi);
+    dim3 grid((N + 63) / 64, (M + BM - 1) / BM, count);
+    zgemm3m_kernel<Epi><<<grid, 256, T_SMEM, st>>>(M, N, Kd, A, lda, B, ldb, pre, epi, bs);
     QDB_LAUNCH_CHECK("zgemm3m_kernel");
     return QDB_OK;
 }
@@ -378,16 +392,16 @@ bool zgemm_3m_enabled() {
 
 template <typename Epi>
 int launch(int M, int N, int Kd, const double2* A, int lda, const double2* B, int ldb, const double2* pre,
-           const Epi& epi, cudaStream_t st) {
-    // 3-product kernel (one CTA per SM) once its 64 x 64 grid fills at least half of the SMs and the k loop is long
-    // enough to amortise the three-stage fill; small products stay on the 4-product kernel (two CTAs per SM, narrow tiles)
-    const long tiles64 = (long)((N + 63) / 64) * ((M + BM - 1) / BM);
+           const Epi& epi, cudaStream_t st, BatchStride bs = BatchStride{0, 0}, int count = 1) {
+    // 3-product kernel (one CTA per SM) once its 64 x 64 grid (times the batch) fills at least half of the SMs and the
+    // k loop is long enough to amortise the three-stage fill; small products stay on the 4-product kernel (two CTAs
+    // per SM, narrow tiles)
+    const long tiles64 = (long)((N + 63) / 64) * ((M + BM - 1) / BM) * count;
     if (zgemm_3m_enabled() && 2 * tiles64 >= sm_count() && Kd >= 64)
-        return launch_3m<Epi>(M, N, Kd, A, lda, B, ldb, pre, epi, st);
+        return launch_3m<Epi>(M, N, Kd, A, lda, B, ldb, pre, epi, bs, count, st);
     // 64 x 64 tiles unless they would fill fewer than the 2 CTA slots per SM
-    const long ctas64 = (long)((N + 63) / 64) * ((M + BM - 1) / BM);
-    if (ctas64 < 2L * sm_count() && N > 32) return launch_bn<Epi, 32>(M, N, Kd, A, lda, B, ldb, pre, epi, st);
-    return launch_bn<Epi, 64>(M, N, Kd, A, lda, B, ldb, pre, epi, st);
+    if (tiles64 < 2L * sm_count() && N > 32) return launch_bn<Epi, 32>(M, N, Kd, A, lda, B, ldb, pre, epi, bs, count, st);
+    return launch_bn<Epi, 64>(M, N, Kd, A, lda, B, ldb, pre, epi, bs, count, st);
 }
 
 }  // namespace
@@ -396,8 +410,24 @@ int launch_zgemm(int M, int N, int Kd, const double2* A, int lda, const double2*
                  double2 alpha, double2 beta, const double* colscale, const double2* pre, const double2* post,
                  cudaStream_t st) {
     if (M == 0 || N == 0) return QDB_OK;
-    EpiStd e{C, ldc, alpha, beta, colscale, post};
+    EpiStd e{C, ldc, alpha, beta, colscale, post, 0};
     return launch(M, N, Kd, A, lda, B, ldb, pre, e, st);
+}
+
+// count independent products C_z = alpha A_z B_z + beta C_z, z < count, operands sA / sB / sC elements apart (grid.z; a
+// stride of 0 shares the operand).  One launch fills the chip with products that are far too small to do so alone:
+// the step propagators of the time-parallel solvers (propagator.cu).
+int launch_zgemm_batched(int M, int N, int Kd, const double2* A, int lda, long long sA, const double2* B, int ldb, long long sB,
+                         double2* C, int ldc, long long sC, double2 alpha, double2 beta, int count, cudaStream_t st) {
+    if (M == 0 || N == 0 || count == 0) return QDB_OK;
+    for (int z0 = 0; z0 < count; z0 += 65535) {  // grid.z limit
+        const int c = count - z0 < 65535 ? count - z0 : 65535;
+        EpiStd e{C + (size_t)z0 * sC, ldc, alpha, beta, nullptr, nullptr, sC};
+        const int rc = launch(M, N, Kd, A + (size_t)z0 * sA, lda, B + (size_t)z0 * sB, ldb, (const double2*)nullptr, e, st,
+                              BatchStride{sA, sB}, c);
+        if (rc != QDB_OK) return rc;
+    }
+    return QDB_OK;
 }
 
 int launch_zgemm_rk4stage(int n, int B, const double2* G, const double2* yin, int ldy, const double2* ybase,

@@ -1,10 +1,12 @@
 """solve_ode / solve_lmde: the method-string dispatch of the reference
 (solvers/solver_functions.py:129-373) with the fixed-step methods served by the fused kernels.
 
-Supported ``method`` strings: ``"RK4"`` (and its JAX alias ``"jax_RK4"``) and ``"scipy_expm"``
-(aliases ``"jax_expm"``, ``"expm"``).  The reference's adaptive SciPy/JAX/diffrax integrators,
-Lanczos and the time-parallel JAX variants are a different algorithm family and outside this
-build: asking for them raises ``QiskitError``.
+Supported ``method`` strings: ``"RK4"`` (and its JAX alias ``"jax_RK4"``), ``"scipy_expm"`` (aliases
+``"jax_expm"``, ``"expm"``; ``magnus_order`` 1, 2, 3) and the time-parallel LMDE solvers
+``"jax_RK4_parallel"`` / ``"jax_expm_parallel"`` (propagators of all steps built side by side, then
+multiplied; model generators only).  The reference's adaptive SciPy/JAX/diffrax integrators and Lanczos
+are a different algorithm family and outside this build: asking for
+them raises ``QiskitError``.
 """
 
 from __future__ import annotations
@@ -19,12 +21,12 @@ from .. import _abi
 from ..arrays import asarray, wait_pending_copies
 from ..exceptions import QiskitError
 from ..models import BaseGeneratorModel, GeneratorModel, LindbladModel
-from .fixed_step import RK4_solver, expm_model_solve, rk4_model_solve, scipy_expm_solver
+from .fixed_step import RK4_solver, expm_model_solve, parallel_model_solve, rk4_model_solve, scipy_expm_solver
 
 ODE_METHODS = ["RK4", "jax_RK4"]
-LMDE_METHODS = ["scipy_expm", "jax_expm", "expm"]
-_REFERENCE_ONLY = ["RK45", "RK23", "BDF", "DOP853", "Radau", "LSODA", "jax_odeint", "lanczos_diag",
-                   "jax_lanczos_diag", "jax_expm_parallel", "jax_RK4_parallel"]
+LMDE_METHODS = ["scipy_expm", "jax_expm", "expm", "jax_RK4_parallel", "jax_expm_parallel"]
+PARALLEL_METHODS = {"jax_RK4_parallel": "RK4", "jax_expm_parallel": "expm"}
+_REFERENCE_ONLY = ["RK45", "RK23", "BDF", "DOP853", "Radau", "LSODA", "jax_odeint", "lanczos_diag", "jax_lanczos_diag"]
 
 
 def _unsupported(method, who: str):
@@ -125,14 +127,22 @@ def solve_lmde(generator: Union[Callable, BaseGeneratorModel], t_span, y0, metho
     if is_lindblad_model_not_vectorized(generator):
         raise QiskitError("LMDE-specific methods with LindbladModel requires setting a vectorized=True.")
     if "max_dt" not in kwargs:
-        raise QiskitError("fixed-step method scipy_expm requires max_dt.")
+        raise QiskitError(f"fixed-step method {method} requires max_dt.")
     y0 = asarray(y0)
+    if method in PARALLEL_METHODS and not isinstance(generator, BaseGeneratorModel):
+        raise QiskitError(f"Method {method} needs a model generator (GeneratorModel, HamiltonianModel or a vectorized "
+                          "LindbladModel): the step propagators are built from its operators on the device.")
     if not isinstance(generator, BaseGeneratorModel):
         return scipy_expm_solver(generator, t_span, y0, t_eval=t_eval, **kwargs)
 
     _, _, y0_fb, was_in_frame_basis = setup_generator_model_rhs_y0_in_frame_basis(generator, y0)
     try:
-        results = expm_model_solve(generator, t_span, y0_fb, t_eval=t_eval, **kwargs)
+        if method in PARALLEL_METHODS:
+            if PARALLEL_METHODS[method] == "RK4" and "magnus_order" in kwargs:
+                raise QiskitError("magnus_order is an option of the exponential solvers only.")
+            results = parallel_model_solve(generator, t_span, y0_fb, t_eval=t_eval, kind=PARALLEL_METHODS[method], **kwargs)
+        else:
+            results = expm_model_solve(generator, t_span, y0_fb, t_eval=t_eval, **kwargs)
         if not was_in_frame_basis:
             results.y = results_y_out_of_frame_basis(generator, results.y, y0.ndim)
     finally:

@@ -431,3 +431,41 @@ def test_nccl_sharded_sweep(qd):
                          cwd=root, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "NCCL_OK rank=0" in res.stdout and "NCCL_OK rank=1" in res.stdout
+
+
+def test_time_parallel_methods(qd):
+    """jax_RK4_parallel / jax_expm_parallel (fixed_step_solvers.py:206-244, 279-311, 524-613): step propagators built side
+    by side and multiplied.  Against the oracle's NumPy restatement of the parallel template, and against the sequential
+    solvers (same propagators; associativity of the product) -- the reference itself runs these on JAX only."""
+    H0, Hs, Y, sig = orc.synthetic_schrodinger(17, 3, 6, 41)
+    sp = [orc.SigSpec(*s) for s in sig]
+    for frame in (None, H0, np.diag(H0).real):
+        m = qd.HamiltonianModel(static_operator=H0, operators=Hs, signals=sigs(qd, sig), rotating_frame=frame)
+        r = qd.solve_lmde(m, t_span=[0, 0.3], y0=Y, method="jax_RK4_parallel", max_dt=0.01)
+        _, yo = orc.solve_hamiltonian_parallel(H0, Hs, sp, frame, [0, 0.3], Y, 0.01, kind="RK4")
+        assert tuple(r.y.shape) == yo.shape and max_col_l2(npy(r.y[-1]), yo[-1]) < TOL
+        seq = qd.solve_lmde(m, t_span=[0, 0.3], y0=Y, method="RK4", max_dt=0.01)
+        assert max_col_l2(npy(r.y[-1]), npy(seq.y[-1])) < TOL
+        for order in (1, 2, 3):
+            te = [0.0, 0.11, 0.3] if order == 2 else None
+            r = qd.solve_lmde(m, t_span=[0, 0.3], y0=Y, method="jax_expm_parallel", max_dt=0.03, magnus_order=order, t_eval=te)
+            to, yo = orc.solve_hamiltonian_parallel(H0, Hs, sp, frame, [0, 0.3], Y, 0.03, kind="expm", magnus_order=order, t_eval=te)
+            assert np.array_equal(np.asarray(r.t), np.asarray(to))
+            assert max(max_col_l2(npy(r.y[i]), yo[i]) for i in range(yo.shape[0])) < TOL
+    # odd step counts, a single step, backwards, vector y0, chunked workspace (7 steps per chunk at most)
+    m = qd.HamiltonianModel(static_operator=H0, operators=Hs, signals=sigs(qd, sig), rotating_frame=H0)
+    for S, kw in ((1, {}), (5, {}), (37, {}), (37, dict(workspace_bytes=1))):
+        r = qd.solve_lmde(m, t_span=[0.2, 0.0], y0=Y[:, 0], method="jax_RK4_parallel", max_dt=0.2 / S * (1 + 1e-12), **kw)
+        _, yo = orc.solve_hamiltonian_parallel(H0, Hs, sp, H0, [0.2, 0.0], Y[:, 0], 0.2 / S * (1 + 1e-12), kind="RK4")
+        assert max_col_l2(npy(r.y[-1]), yo[-1]) < TOL, S
+    # vectorised Lindblad: the parallel exponential solver equals the sequential one
+    H0, Hs, Ls, Yl, sig = orc.synthetic_lindblad(3, 2, 4, 5, 31)
+    mv = qd.LindbladModel(static_hamiltonian=H0, hamiltonian_operators=Hs, hamiltonian_signals=sigs(qd, sig),
+                          static_dissipators=Ls, rotating_frame=np.diag(H0).real, vectorized=True)
+    a = qd.solve_lmde(mv, t_span=[0, 0.5], y0=Yl, method="jax_expm_parallel", max_dt=0.05, magnus_order=2)
+    b = qd.solve_lmde(mv, t_span=[0, 0.5], y0=Yl, method="scipy_expm", max_dt=0.05, magnus_order=2)
+    close(a.y[-1], b.y[-1], 1e-10)
+    with pytest.raises(qd.QiskitError):
+        qd.solve_lmde(lambda t: qd.asarray(H0), t_span=[0, 1], y0=Yl, method="jax_expm_parallel", max_dt=0.1)
+    with pytest.raises(qd.QiskitError):
+        qd.solve_lmde(mv, t_span=[0, 1], y0=Yl, method="jax_RK4_parallel")
