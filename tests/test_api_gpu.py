@@ -464,7 +464,7 @@ def test_time_parallel_methods(qd):
                           static_dissipators=Ls, rotating_frame=np.diag(H0).real, vectorized=True)
     a = qd.solve_lmde(mv, t_span=[0, 0.5], y0=Yl, method="jax_expm_parallel", max_dt=0.05, magnus_order=2)
     b = qd.solve_lmde(mv, t_span=[0, 0.5], y0=Yl, method="scipy_expm", max_dt=0.05, magnus_order=2)
-    close(a.y[-1], b.y[-1], 1e-10)
+    close(a.y[-1], npy(b.y[-1]), 1e-10)
     with pytest.raises(qd.QiskitError):
         qd.solve_lmde(lambda t: qd.asarray(H0), t_span=[0, 1], y0=Yl, method="jax_expm_parallel", max_dt=0.1)
     with pytest.raises(qd.QiskitError):
