@@ -32,7 +32,7 @@ _REFERENCE_ONLY = ["RK45", "RK23", "BDF", "DOP853", "Radau", "LSODA", "jax_odein
 def _unsupported(method, who: str):
     if method in _REFERENCE_ONLY:
         return QiskitError(
-            f"Method {method} is not part of the B200 build (fixed-step RK4 and scipy_expm only); "
+            f"Method {method} is not part of the B200 build (fixed-step RK4, scipy_expm and their time-parallel variants only); "
             f"it is not supported by {who}."
         )
     return QiskitError(f"Method {method} not supported by {who}.")
