@@ -27,6 +27,16 @@ print(json.dumps({"config": "cfg4: n=128, K=8, B=4096, 1000 RK4 steps, shared si
                   "time_parallel_ms": out["jax_RK4_parallel"], "speedup": out["RK4"] / out["jax_RK4_parallel"],
                   "max_col_diff": float(torch.linalg.vector_norm(out["RK4_y"] - out["jax_RK4_parallel_y"], dim=0).max())}), flush=True)
 
+out = {}
+for method in ("scipy_expm", "jax_expm_parallel"):
+    res = {}
+    def run(): res["y"] = qd.solve_lmde(m, t_span=[0, 0.2], y0=y0, method=method, max_dt=1e-3).y[-1]
+    out[method] = timeit(run); out[method + "_y"] = res["y"]
+print(json.dumps({"config": "cfg4 shape with the exponential stepper: n=128, B=4096, 200 expm steps (Magnus order 1)",
+                  "direct_ms": out["scipy_expm"], "time_parallel_ms": out["jax_expm_parallel"],
+                  "speedup": out["scipy_expm"] / out["jax_expm_parallel"],
+                  "max_col_diff": float(torch.linalg.vector_norm(out["scipy_expm_y"] - out["jax_expm_parallel_y"], dim=0).max())}), flush=True)
+
 n, K, B = 27, 3, 4096
 H0, Hs, Ls, Y, sig = orc.synthetic_lindblad(n, K, 6, B, 2003)
 mv = qd.LindbladModel(static_hamiltonian=H0, hamiltonian_operators=Hs, hamiltonian_signals=[qd.Signal(*s) for s in sig],
