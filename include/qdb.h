@@ -177,6 +177,10 @@ int qdb_dmma_probe(double* sink, int iters, double* flops_out, void* stream);
  *   times_mid_host : HOST [S] midpoints t_s + h/2;  coeff : device [S][K] at those midpoints
  *   squarings_host : HOST [S] number of squarings per step (chosen by the caller from a norm
  *                    bound so that no device->host sync is needed inside the loop)
+ *   workspace      : qdb_workspace_bytes(QDB_WS_EXPM, n, K, B, S).  With the S = 1 size the steps run one at a
+ *                    time; with more, the propagators of a chunk of steps are built side by side (one generator
+ *                    launch + one batched Taylor exponential, all steps of the chunk sharing the largest number
+ *                    of squarings) and then applied in order.
  * Replaces get_exponential_take_step(magnus_order=1) + scipy.linalg.expm
  * (solvers/fixed_step_solvers.py:343-346,400-401,104). */
 int qdb_expm_steps_c128(int n, int K, int B, int S,

@@ -243,9 +243,8 @@ def expm_steps(n, ops_rm, stat_rm, coeff, mu, times_mid_host: np.ndarray, squari
     B = y.shape[1]
     times_mid_host = np.ascontiguousarray(times_mid_host, dtype=np.float64)
     squarings_host = np.ascontiguousarray(squarings_host, dtype=np.int32)
-    need = workspace_bytes(WS_EXPM, n, K, B)
-    if workspace is None or workspace.numel() < need:
-        workspace = torch.empty(need, dtype=torch.uint8, device=y.device)
+    if workspace is None or workspace.numel() < workspace_bytes(WS_EXPM, n, K, B):
+        workspace = torch.empty(workspace_bytes(WS_EXPM, n, K, B, S), dtype=torch.uint8, device=y.device)
     _check(lib().qdb_expm_steps_c128(n, K, B, S, _ptr(ops_rm, C, "ops_rm"), _ptr(stat_rm, C, "stat_rm"),
                                      _ptr(coeff, F, "coeff"), _ptr(mu, F, "mu"),
                                      times_mid_host.ctypes.data_as(ctypes.c_void_p),

@@ -88,8 +88,16 @@ size_t qdb_workspace_bytes(int kind, int n, int K, int B, int S) {
                 return shared > sweep ? shared : sweep;
             }
             return 3 * align_up(n2) + 3 * align_up(yb) + align_up(3 * sizeof(double));
-        case QDB_WS_EXPM:
-            return 7 * align_up(n2) + align_up(yb);
+        case QDB_WS_EXPM: {
+            // S = 1: one step at a time.  S > 1: room to build the propagators of up to S steps side by side (batched
+            // Taylor exponentials) before they are applied one after the other -- capped at 1 GiB of matrices
+            const size_t per = 7 * align_up(n2);
+            size_t chunk = (size_t)S;
+            const size_t cap = ((size_t)1 << 30) / per;
+            if (chunk > cap) chunk = cap;
+            if (chunk < 1) chunk = 1;
+            return chunk * per + align_up(yb) + align_up((size_t)S * sizeof(double));
+        }
         case QDB_WS_PROP:
             return propagator_workspace_bytes(n, S);
         case QDB_WS_MAGNUS:  // + node generators (3), Magnus temporaries (7), node times [3 S]
@@ -382,14 +390,54 @@ int qdb_expm_steps_c128(int n, int K, int B, int S, const qdb_c128* ops_rm, cons
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
     const size_t n2 = align_up((size_t)n * n * sizeof(double2));
+    const double2 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0);
+    int rc;
+    // The propagators do not depend on the state: with room for several steps they are built side by side -- one
+    // generator launch and one batched Taylor exponential per chunk (a lone n = 128 product occupies four CTAs) -- and
+    // then applied one after the other.  All steps of a chunk share the largest number of squarings any of them needs.
+    {
+        const size_t fixed = align_up((size_t)n * B * sizeof(double2)) + align_up((size_t)S * sizeof(double));
+        const size_t room = ws_bytes > fixed ? (ws_bytes - fixed) / (7 * n2) : 0;
+        const int Sc = room > (size_t)S ? S : (int)room;
+        if (Sc >= 2) {
+            const size_t nn = (size_t)n * n;
+            double2* As = (double2*)ws;                       // [Sc]
+            double2* bws = As + (size_t)Sc * nn;              // [5 Sc]
+            double2* P = bws + (size_t)5 * Sc * nn;           // [Sc]
+            double2* ytmp = (double2*)(ws + (size_t)Sc * 7 * n2);
+            double* times_dev = (double*)((char*)ytmp + align_up((size_t)n * B * sizeof(double2)));
+            double2 *ycur = D2(y), *ynext = ytmp;
+            for (int s0 = 0; s0 < S; s0 += Sc) {
+                const int Sn = S - s0 < Sc ? S - s0 : Sc;
+                int sq = 0;
+                for (int s = 0; s < Sn; ++s) {
+                    const int v = squarings_host[s0 + s];
+                    QDB_REQUIRE(v >= 0 && v < 64, "qdb_expm_steps_c128: bad squarings[%d]=%d", s0 + s, v);
+                    sq = v > sq ? v : sq;
+                }
+                if (mu) QDB_CUDA(cudaMemcpyAsync(times_dev, times_mid_host + s0, (size_t)Sn * sizeof(double), cudaMemcpyHostToDevice, st));
+                rc = launch_generator(n, K, Sn, QDB_LAYOUT_ROWMAJOR, D2(ops_rm), D2(stat_rm), coeff ? coeff + (size_t)s0 * K : nullptr, 0,
+                                      mu, mu ? times_dev : nullptr, 0.0, ldexp(h, -sq), As, st);
+                if (rc != QDB_OK) return rc;
+                if ((rc = expm_core_batched(n, Sn, As, sq, P, bws, st)) != QDB_OK) return rc;
+                for (int s = 0; s < Sn; ++s) {
+                    rc = launch_zgemm(n, B, n, P + (size_t)s * nn, n, ycur, ldy, ynext, ldy, one, zero, nullptr, nullptr, nullptr, st);
+                    if (rc != QDB_OK) return rc;
+                    double2* t = ycur;
+                    ycur = ynext;
+                    ynext = t;
+                }
+            }
+            if (ycur != D2(y)) QDB_CUDA(cudaMemcpyAsync(y, ycur, (size_t)n * B * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+            return QDB_OK;
+        }
+    }
     double2* As = (double2*)ws;
     double2* P = (double2*)(ws + n2);
     double2* core_ws = (double2*)(ws + 2 * n2);  // 5 n^2 (contiguous, unaligned stride)
     double2* ytmp = (double2*)(ws + 7 * n2);
     double2* ycur = D2(y);
     double2* ynext = ytmp;
-    const double2 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0);
-    int rc;
     for (int s = 0; s < S; ++s) {
         const int sq = squarings_host[s];
         QDB_REQUIRE(sq >= 0 && sq < 64, "qdb_expm_steps_c128: bad squarings[%d]=%d", s, sq);

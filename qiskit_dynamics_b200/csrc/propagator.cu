@@ -35,62 +35,6 @@ __global__ void rk4_prop_combine_kernel(int n, size_t nn, size_t total, double h
 
 inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
-// out[z] = c0 1 + c1 A1[z] + c2 A2[z] + c3 A3[z] + c4 A4[z] for a batch of n x n matrices (null pointers are skipped)
-__global__ void poly_batched_kernel(int n, size_t nn, size_t total, double c0, double c1, const double2* __restrict__ A1, double c2,
-                                    const double2* __restrict__ A2, double c3, const double2* __restrict__ A3, double c4,
-                                    const double2* __restrict__ A4, double2* __restrict__ out) {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const size_t e = idx % nn;
-    const int r = (int)(e / n), c = (int)(e - (size_t)r * n);
-    double2 v = make_double2(r == c ? c0 : 0.0, 0.0);
-    if (A1) { const double2 a = A1[idx]; v.x = fma(c1, a.x, v.x); v.y = fma(c1, a.y, v.y); }
-    if (A2) { const double2 a = A2[idx]; v.x = fma(c2, a.x, v.x); v.y = fma(c2, a.y, v.y); }
-    if (A3) { const double2 a = A3[idx]; v.x = fma(c3, a.x, v.x); v.y = fma(c3, a.y, v.y); }
-    if (A4) { const double2 a = A4[idx]; v.x = fma(c4, a.x, v.x); v.y = fma(c4, a.y, v.y); }
-    out[idx] = v;
-}
-
-// expm of `count` matrices at once: the degree-16 Taylor / Paterson-Stockmeyer scheme of expm_core (expm.cu) with every
-// product a batched GEMM.  As [count][nn] is already scaled by 2^-squarings (one common count: the largest any step
-// needs); ws holds 5 count matrices; out [count][nn].
-int expm_core_batched(int n, int count, const double2* As, int squarings, double2* out, double2* ws, cudaStream_t st) {
-    const size_t nn = (size_t)n * n, tot = (size_t)count * nn;
-    const long long sn = (long long)nn;
-    double2 *A2 = ws, *A3 = ws + tot, *A4 = ws + 2 * tot, *T1 = ws + 3 * tot, *T2 = ws + 4 * tot;
-    const double2 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0);
-    double f[17];
-    f[0] = 1.0;
-    for (int k = 1; k <= 16; ++k) f[k] = f[k - 1] / k;
-    const unsigned blocks = (unsigned)((tot + 255) / 256);
-    int rc;
-#define BGEMM(Cp, Ap, Bp, beta) \
-    if ((rc = launch_zgemm_batched(n, n, n, Ap, n, sn, Bp, n, sn, Cp, n, sn, one, beta, count, st)) != QDB_OK) return rc
-#define BPOLY(c0, c1, c2, c3, c4, A4p, dst)                                                                  \
-    poly_batched_kernel<<<blocks, 256, 0, st>>>(n, nn, tot, c0, c1, As, c2, A2, c3, A3, c4, A4p, dst);         \
-    QDB_LAUNCH_CHECK("poly_batched_kernel")
-    BGEMM(A2, As, As, zero);
-    BGEMM(A3, A2, As, zero);
-    BGEMM(A4, A2, A2, zero);
-    BPOLY(f[12], f[13], f[14], f[15], f[16], A4, T1);                  // B3
-    BPOLY(f[8], f[9], f[10], f[11], 0.0, (const double2*)nullptr, T2);  // B2 = P2 + A4 B3
-    BGEMM(T2, A4, T1, one);
-    BPOLY(f[4], f[5], f[6], f[7], 0.0, (const double2*)nullptr, T1);    // B1 = P1 + A4 B2
-    BGEMM(T1, A4, T2, one);
-    double2* dst = squarings == 0 ? out : T2;
-    BPOLY(f[0], f[1], f[2], f[3], 0.0, (const double2*)nullptr, dst);   // B0 = P0 + A4 B1
-    BGEMM(dst, A4, T1, one);
-    double2* cur = dst;
-    for (int s = 0; s < squarings; ++s) {
-        double2* nxt = (s == squarings - 1) ? out : (cur == T2 ? T1 : T2);
-        BGEMM(nxt, cur, cur, zero);
-        cur = nxt;
-    }
-#undef BGEMM
-#undef BPOLY
-    return QDB_OK;
-}
-
 // gather every third matrix of G (offset `which`) into a dense [S][nn] array
 int gather_third(size_t nn, int S, const double2* G, int which, double2* dst, cudaStream_t st) {
     QDB_CUDA(cudaMemcpy2DAsync(dst, nn * sizeof(double2), G + (size_t)which * nn, 3 * nn * sizeof(double2), nn * sizeof(double2),
@@ -144,6 +88,62 @@ int product_tree(int n, int count, double2* P, double2* tmp, double2* out, cudaS
 }
 
 }  // namespace
+
+// out[z] = c0 1 + c1 A1[z] + c2 A2[z] + c3 A3[z] + c4 A4[z] for a batch of n x n matrices (null pointers are skipped)
+static __global__ void poly_batched_kernel(int n, size_t nn, size_t total, double c0, double c1, const double2* __restrict__ A1, double c2,
+                                    const double2* __restrict__ A2, double c3, const double2* __restrict__ A3, double c4,
+                                    const double2* __restrict__ A4, double2* __restrict__ out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const size_t e = idx % nn;
+    const int r = (int)(e / n), c = (int)(e - (size_t)r * n);
+    double2 v = make_double2(r == c ? c0 : 0.0, 0.0);
+    if (A1) { const double2 a = A1[idx]; v.x = fma(c1, a.x, v.x); v.y = fma(c1, a.y, v.y); }
+    if (A2) { const double2 a = A2[idx]; v.x = fma(c2, a.x, v.x); v.y = fma(c2, a.y, v.y); }
+    if (A3) { const double2 a = A3[idx]; v.x = fma(c3, a.x, v.x); v.y = fma(c3, a.y, v.y); }
+    if (A4) { const double2 a = A4[idx]; v.x = fma(c4, a.x, v.x); v.y = fma(c4, a.y, v.y); }
+    out[idx] = v;
+}
+
+// expm of `count` matrices at once: the degree-16 Taylor / Paterson-Stockmeyer scheme of expm_core (expm.cu) with every
+// product a batched GEMM.  As [count][nn] is already scaled by 2^-squarings (one common count: the largest any step
+// needs); ws holds 5 count matrices; out [count][nn].
+int expm_core_batched(int n, int count, const double2* As, int squarings, double2* out, double2* ws, cudaStream_t st) {
+    const size_t nn = (size_t)n * n, tot = (size_t)count * nn;
+    const long long sn = (long long)nn;
+    double2 *A2 = ws, *A3 = ws + tot, *A4 = ws + 2 * tot, *T1 = ws + 3 * tot, *T2 = ws + 4 * tot;
+    const double2 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0);
+    double f[17];
+    f[0] = 1.0;
+    for (int k = 1; k <= 16; ++k) f[k] = f[k - 1] / k;
+    const unsigned blocks = (unsigned)((tot + 255) / 256);
+    int rc;
+#define BGEMM(Cp, Ap, Bp, beta) \
+    if ((rc = launch_zgemm_batched(n, n, n, Ap, n, sn, Bp, n, sn, Cp, n, sn, one, beta, count, st)) != QDB_OK) return rc
+#define BPOLY(c0, c1, c2, c3, c4, A4p, dst)                                                                  \
+    poly_batched_kernel<<<blocks, 256, 0, st>>>(n, nn, tot, c0, c1, As, c2, A2, c3, A3, c4, A4p, dst);         \
+    QDB_LAUNCH_CHECK("poly_batched_kernel")
+    BGEMM(A2, As, As, zero);
+    BGEMM(A3, A2, As, zero);
+    BGEMM(A4, A2, A2, zero);
+    BPOLY(f[12], f[13], f[14], f[15], f[16], A4, T1);                  // B3
+    BPOLY(f[8], f[9], f[10], f[11], 0.0, (const double2*)nullptr, T2);  // B2 = P2 + A4 B3
+    BGEMM(T2, A4, T1, one);
+    BPOLY(f[4], f[5], f[6], f[7], 0.0, (const double2*)nullptr, T1);    // B1 = P1 + A4 B2
+    BGEMM(T1, A4, T2, one);
+    double2* dst = squarings == 0 ? out : T2;
+    BPOLY(f[0], f[1], f[2], f[3], 0.0, (const double2*)nullptr, dst);   // B0 = P0 + A4 B1
+    BGEMM(dst, A4, T1, one);
+    double2* cur = dst;
+    for (int s = 0; s < squarings; ++s) {
+        double2* nxt = (s == squarings - 1) ? out : (cur == T2 ? T1 : T2);
+        BGEMM(nxt, cur, cur, zero);
+        cur = nxt;
+    }
+#undef BGEMM
+#undef BPOLY
+    return QDB_OK;
+}
 
 size_t propagator_workspace_bytes(int n, int S) {
     const size_t nn = align256((size_t)n * n * sizeof(double2));

@@ -224,7 +224,7 @@ def expm_model_solve(model, t_span, y0_fb: torch.Tensor, max_dt, t_eval=None, ma
         if table is None:
             sq = np.repeat(sq, S)
         if magnus_order == 1:
-            need = _abi.workspace_bytes(_abi.WS_EXPM, n, coll.num_operators, y.shape[1])
+            need = _abi.workspace_bytes(_abi.WS_EXPM, n, coll.num_operators, y.shape[1], S)  # room for batched propagators
             if ws is None or ws.numel() < need:
                 ws = torch.empty(need, dtype=torch.uint8, device=y.device)
             _abi.expm_steps(n, coll.operators, coll.static_operator, coeff, mu, times.reshape(-1), sq, float(h), y, S, workspace=ws)

@@ -427,8 +427,17 @@ def test_expm_steps(abi):
     bound = abs(h) * (np.linalg.norm(Sst, 1) + np.abs(coeff) @ np.array([np.linalg.norm(o, 1) for o in ops]))
     sq = np.maximum(0, np.ceil(np.log2(np.maximum(bound, 1e-300) / 0.7))).astype(np.int32)
     yd = dev(Y)
-    abi.expm_steps(n * n, dev(ops), dev(Sst), dev(coeff), dev(mu), mids, sq, h, yd, S)
+    abi.expm_steps(n * n, dev(ops), dev(Sst), dev(coeff), dev(mu), mids, sq, h, yd, S)  # propagators of all steps batched
     assert max_col_l2(yd.cpu().numpy(), y) < TOL_SOLVE
+    # the one-step-at-a-time route (workspace of the S = 1 size) and a chunked one (3 steps per chunk)
+    m2 = n * n
+    for steps_of_room in (1, 3):
+        ws = torch.empty(abi.workspace_bytes(abi.WS_EXPM, m2, K, B, steps_of_room) + (S - steps_of_room) * 8 + 256,
+                         dtype=torch.uint8, device="cuda")
+        y2 = dev(Y)
+        abi.expm_steps(m2, dev(ops), dev(Sst), dev(coeff), dev(mu), mids, sq, h, y2, S, workspace=ws)
+        assert max_col_l2(y2.cpu().numpy(), y) < TOL_SOLVE
+        assert max_col_l2(y2.cpu().numpy(), yd.cpu().numpy()) < 1e-13
 
 
 def test_signal_table_device(abi):
