@@ -10,7 +10,11 @@ Parity status: PINNED.  `tests/test_oracle_golden.py` checks every function belo
 the fixtures in `tests/golden/*.npz`, which were produced by running the unmodified
 reference (qiskit-dynamics 0.6.0 @ 6b54df2f, NumPy path) through `oracle/ref_shim.py` with
 `tests/golden/make_golden.py`; when `/root/reference` is mounted the same test module also
-compares this oracle against the live reference.
+compares this oracle against the live reference.  One exception: the time-parallel template
+(`parallel_solve`, `rk4_step_propagator`) restates code the reference runs on JAX only, which is
+absent here, so no fixture exists for it; it is pinned INDIRECTLY -- the same step propagators in a
+different association order must reproduce the fixture-pinned sequential solvers
+(`test_parallel_template_agrees_with_sequential`, 1e-13).
 
 Third-party arithmetic at the boundary: NumPy/OpenBLAS (`tensordot`, `matmul`, ufuncs) and
 `scipy.linalg.expm` -- exactly the calls the reference makes, so that this port is also a

@@ -292,3 +292,25 @@ def test_magnus_orders():
             _, ys = orc.solve_vectorized_lindblad(H0, Hs, sp, Lstat, Ldyn, dsp, frame, [0, 0.5], Y, 0.05, "scipy_expm",
                                                   magnus_order=order)
             close(ys[-1], g[f"l_{frame_name}_o{order}"], 1e-11)
+
+
+def test_parallel_template_agrees_with_sequential():
+    """The NumPy restatement of the reference's JAX-only parallel template (fixed_step_solvers.py:206-244, 524-613) has no
+    fixture of its own: it must reproduce the sequential solvers, which are pinned above, from the same step propagators
+    (RK4 on a linear system IS its propagator; exponential steps at every Magnus order), and the golden RK4 / expm solves."""
+    g = load_golden("rk4_solves")
+    H0, Hs, Y, sp = g["odd_H0"], g["odd_Hs"], g["odd_Y"], specs(g["odd_sig"])
+    fr = np.diag(H0).real
+    close(orc.solve_hamiltonian_parallel(H0, Hs, sp, None, [0, 0.5], Y, 0.01, kind="RK4")[1][-1], g["odd_noframe_y"], 1e-12)
+    close(orc.solve_hamiltonian_parallel(H0, Hs, sp, fr, [0, 0.5], Y, 0.01, kind="RK4")[1][-1], g["odd_diagframe_y"], 1e-12)
+    close(orc.solve_hamiltonian_parallel(H0, Hs, sp, fr, [0, 0.5], Y, 0.01, kind="expm")[1][-1], g["odd_expm_y"], 1e-12)
+    close(orc.solve_hamiltonian_parallel(H0, Hs, sp, H0, [0, 0.5], Y, 0.01, kind="expm")[1][-1], g["odd_expm_fullframe_y"], 1e-11)
+    gm = load_golden("magnus")
+    H0, Hs, Y, sig = orc.synthetic_schrodinger(5, 2, 3, 11)
+    sp = [orc.SigSpec(*s) for s in sig]
+    for order in (2, 3):
+        close(orc.solve_hamiltonian_parallel(H0, Hs, sp, H0, [0, 0.5], Y, 0.05, kind="expm", magnus_order=order)[1][-1],
+              gm[f"h_full_o{order}"], 1e-11)
+        t, ys = orc.solve_hamiltonian_parallel(H0, Hs, sp, H0, [0.5, 0.0], Y, 0.04, kind="expm", magnus_order=order,
+                                               t_eval=[0.5, 0.31, 0.1])
+        close(ys, gm[f"h_full_teval_back_o{order}"], 1e-11)
