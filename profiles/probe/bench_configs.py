@@ -2,7 +2,7 @@
 CUDA-event timing, against the live DMMA peak.  One JSON line per configuration (sweep-mode
 throughput is reported beside the headline because the shared-signal shortcut does not exist there).
 
-    python profiles/probe/bench_configs.py [cfg2] [cfg3] [cfg5] [cfg4sweep] [rhs]
+    python profiles/probe/bench_configs.py [cfg1] [cfg2] [cfg3] [cfg5] [cfg4sweep] [rhs]
 """
 import json, os, sys, time
 import numpy as np, torch
@@ -20,7 +20,7 @@ def timeit(fn, reps=5, warm=2):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1))
     return best
-which = set(sys.argv[1:]) or {"cfg2", "cfg3", "cfg5", "cfg4sweep", "rhs"}
+which = set(sys.argv[1:]) or {"cfg1", "cfg2", "cfg3", "cfg5", "cfg4sweep", "rhs"}
 peak = abi.dmma_probe()
 
 def sweep(name, n, K, B, S, seed):
@@ -46,6 +46,28 @@ def sweep(name, n, K, B, S, seed):
                       "exec_tflops": exe / ms * 1e-9, "dmma_peak_tflops": peak, "alg_frac": alg / ms * 1e-9 / peak,
                       "exec_frac": exe / ms * 1e-9 / peak, "tiling": tiling,
                       "unitarity_drift": float((torch.linalg.vector_norm(y, dim=0) - 1).abs().max())}), flush=True)
+
+if "cfg1" in which:
+    # BASELINE configs[0]: 2-qubit HamiltonianModel, one Rabi drive, fixed-step RK4, T = 10, max_dt = 1e-3 (10 000 steps,
+    # ONE state): latency bound by construction -- one fused launch walks all steps; the time-parallel solver builds the
+    # 10 000 4 x 4 propagators in batched launches.  CPU figure: the oracle port (the reference's NumPy path) here.
+    X = np.array([[0, 1], [1, 0]], dtype=complex); Z = np.diag([1.0, -1.0]).astype(complex); I2 = np.eye(2, dtype=complex)
+    H0 = 2 * np.pi * 5 * (np.kron(Z, I2) + np.kron(I2, Z)) / 2; H1 = 2 * np.pi * 0.1 * np.kron(X, I2) / 2
+    y0 = np.array([1.0, 0, 0, 0], dtype=complex)
+    model = qd.HamiltonianModel(static_operator=H0, operators=[H1], signals=[qd.Signal(1.0, 5.0)], rotating_frame=H0)
+    yd = qd.asarray(y0)
+    res = {}
+    def run(method):
+        def f(): res[method] = qd.solve_lmde(model, t_span=[0, 10.0], y0=yd, method=method, max_dt=1e-3).y[-1]
+        return f
+    ms_direct = timeit(run("RK4"), reps=3, warm=1); ms_par = timeit(run("jax_RK4_parallel"), reps=3, warm=1)
+    t0 = time.perf_counter()
+    _, yo = orc.solve_hamiltonian(H0, [H1], [orc.SigSpec(1.0, 5.0)], H0, [0, 10.0], y0, 1e-3)
+    cpu_s = time.perf_counter() - t0
+    print(json.dumps({"config": "cfg1: 2-qubit HamiltonianModel, 1 Rabi drive, RK4, 10000 steps, one state", "fused_rk4_ms": ms_direct,
+                      "time_parallel_ms": ms_par, "numpy_port_cpu_ms": cpu_s * 1e3, "us_per_step_fused": ms_direct * 1e3 / 10000,
+                      "err_fused_vs_oracle": float(np.linalg.norm(res["RK4"].cpu().numpy() - yo[-1])),
+                      "err_parallel_vs_oracle": float(np.linalg.norm(res["jax_RK4_parallel"].cpu().numpy() - yo[-1]))}), flush=True)
 
 if "cfg2" in which: sweep("cfg2: dim-32, 8 drive operators, batch-1024 amplitude sweep, RK4", 32, 8, 1024, 500, 2002)
 if "cfg5" in which: sweep("cfg5-like: dim-81 (4 three-level transmons), 8 channels, 8192 sweep points per GPU, RK4", 81, 8, 8192, 20, 2005)
