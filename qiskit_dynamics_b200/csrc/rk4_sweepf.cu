@@ -18,18 +18,21 @@
 //     operator (8 entries per row tile and matrix column), the signal values per lane are those of its two columns.
 //
 // A CTA owns 8 NCT whole columns for the entire launch (as in rk4_fused.cu).  Operators stream L2 -> registers in
-// fragment order (layout below, built per call by pack_sweepf_kernel) through a register ring of 2 (4 for small
-// warp tiles) matrix columns, each slot refilled as soon as its column is consumed; the stage vector lives in shared memory as [row][column] (row stride 8 NCT + 1 complex numbers: the
-// epilogue's two-row stores fall into disjoint banks), single buffered between two barriers per stage; y and the RK4
-// k-sum sit in thread-private shared-memory slabs.  Frame phases: on the stage-vector rows when written, on the
-// result rows when read (as rk4_sweep_kernel).
+// fragment order (layout below, built per call by pack_sweepf_kernel) through a register ring of 2 matrix columns --
+// 4 for small warp tiles, which have too few independent DMMA -> DFMA chains per column -- each slot refilled as soon
+// as its column is consumed.  The stage vector lives in shared memory as [row][column] (row stride 8 NCT + 1 complex
+// numbers: the epilogue's two-row stores fall into disjoint banks), single buffered between two barriers per stage; y
+// and the RK4 k-sum sit in thread-private shared-memory slabs.  Frame phases: on the stage-vector rows when written,
+// on the result rows when read (as rk4_sweep_kernel).  When the batch cannot fill the chip, a second warp group
+// (KSPLIT) takes half of the matrix columns and hands its partial sums over through shared memory.
 //
 // Operator layout ("formed-sweep"): opsf[((rt * C2 + c) * KS + ks) * 32 + 4 g + q] = ops[4 ks + q][8 rt + g][c],
 // (K <= 2: opsf[((rt * C2 + c) * K + j) * 8 + g] = ops[j][8 rt + g][c]);
 // statf[((rt * C2 + c) * 8 + g) * 2 + {0, 1}] = (re, re), (im, im) of stat[8 rt + g][c] -- stored duplicated because the
 // DMMA C operand is a register PAIR (both columns of the lane get the same static element): loaded this way it is
 // usable as it arrives, instead of four register moves in front of every formation DMMA (ncu, first version: 80 moves per
-// two matrix columns, on the issue path of the DMMAs).  Zero outside the matrix; C2 = n rounded up to even.
+// two matrix columns, on the issue path of the DMMAs).  Zero outside the matrix; C2 = n rounded up to the matrix columns
+// in flight (times the warp groups that share them).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
