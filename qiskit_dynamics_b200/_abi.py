@@ -264,9 +264,9 @@ def magnus_steps(n, ops_rm, stat_rm, coeff, mu, times_host: np.ndarray, squaring
     if times_host.size != S * magnus_order or squarings_host.size != S:
         raise QdbError(f"magnus_steps: {times_host.size} node times / {squarings_host.size} squarings for S={S}, "
                        f"order {magnus_order}")
-    need = workspace_bytes(WS_MAGNUS, n, K, B, S)
-    if workspace is None or workspace.numel() < need:
-        workspace = torch.empty(need, dtype=torch.uint8, device=y.device)
+    # a caller's workspace is used as it is when it holds at least one step (the library then works in smaller chunks)
+    if workspace is None or workspace.numel() < workspace_bytes(WS_MAGNUS, n, K, B, 1) + 3 * S * 8 + 256:
+        workspace = torch.empty(workspace_bytes(WS_MAGNUS, n, K, B, S), dtype=torch.uint8, device=y.device)
     _check(lib().qdb_magnus_steps_c128(n, K, B, S, int(magnus_order), _ptr(ops_rm, C, "ops_rm"), _ptr(stat_rm, C, "stat_rm"),
                                        _ptr(coeff, F, "coeff"), _ptr(mu, F, "mu"),
                                        times_host.ctypes.data_as(ctypes.c_void_p),

@@ -100,8 +100,14 @@ size_t qdb_workspace_bytes(int kind, int n, int K, int B, int S) {
         }
         case QDB_WS_PROP:
             return propagator_workspace_bytes(n, S);
-        case QDB_WS_MAGNUS:  // + node generators (3), Magnus temporaries (7), node times [3 S]
-            return 17 * align_up(n2) + align_up(yb) + align_up((size_t)3 * S * sizeof(double));
+        case QDB_WS_MAGNUS: {  // per step of a chunk: node generators (3), Magnus temporaries (7), A, Taylor (5), P
+            const size_t per = 17 * align_up(n2);
+            size_t chunk = (size_t)S;
+            const size_t cap = ((size_t)1 << 30) / per;
+            if (chunk > cap) chunk = cap;
+            if (chunk < 1) chunk = 1;
+            return chunk * per + align_up(yb) + align_up((size_t)3 * S * sizeof(double));
+        }
         default:
             return 0;
     }
@@ -481,8 +487,11 @@ int qdb_magnus_steps_c128(int n, int K, int B, int S, int magnus_order, const qd
     QDB_REQUIRE(squarings_host, "qdb_magnus_steps_c128: squarings missing");
     QDB_REQUIRE(!mu || times_host, "qdb_magnus_steps_c128: frame given without times");
     QDB_REQUIRE(B == 0 || (y && ldy == B), "qdb_magnus_steps_c128: need y with ldy == B");
-    if (ws_bytes < qdb_workspace_bytes(QDB_WS_MAGNUS, n, K, B, S) || !workspace) {
-        set_error("qdb_magnus_steps_c128: workspace too small (%zu < %zu)", ws_bytes, qdb_workspace_bytes(QDB_WS_MAGNUS, n, K, B, S));
+    // smallest usable workspace: one step at a time (qdb_workspace_bytes gives room for a chunk of steps side by side)
+    const size_t min_need = 17 * align_up((size_t)n * n * sizeof(double2)) + align_up((size_t)n * B * sizeof(double2)) +
+                            align_up((size_t)3 * S * sizeof(double));
+    if (ws_bytes < min_need || !workspace) {
+        set_error("qdb_magnus_steps_c128: workspace too small (%zu < %zu)", ws_bytes, min_need);
         return QDB_E_WORKSPACE;
     }
     if (B == 0) return QDB_OK;
@@ -498,11 +507,52 @@ int qdb_magnus_steps_c128(int n, int K, int B, int S, int magnus_order, const qd
     double2* ytmp = (double2*)(ws + 17 * n2);
     double* times_dev = (double*)(ws + 17 * n2 + align_up((size_t)n * B * sizeof(double2)));
     const int Q = magnus_order;
+    const double2 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0);
+    int rc;
+    // With room for several steps, their exponents (node generators, commutators) and exponentials are built side by
+    // side in batched launches and then applied in order (see qdb_expm_steps_c128).
+    if (Q >= 2) {
+        const size_t fixed = align_up((size_t)n * B * sizeof(double2)) + align_up((size_t)3 * S * sizeof(double));
+        const size_t room = ws_bytes > fixed ? (ws_bytes - fixed) / (17 * n2) : 0;
+        const int Sc = room > (size_t)S ? S : (int)room;
+        if (Sc >= 2) {
+            double2* gn = (double2*)ws;                                   // [Sc][Q]
+            double2* mws = gn + (size_t)Sc * Q * nn;                      // [Sc] or [7 Sc]
+            double2* Asb = mws + (size_t)Sc * (Q == 2 ? 1 : 7) * nn;      // [Sc]
+            double2* bws = Asb + (size_t)Sc * nn;                         // [5 Sc]
+            double2* Pb = bws + (size_t)5 * Sc * nn;                      // [Sc]
+            double2* yt = (double2*)(ws + (size_t)Sc * 17 * n2);
+            double* tdev = (double*)((char*)yt + align_up((size_t)n * B * sizeof(double2)));
+            double2 *ycur = D2(y), *ynext = yt;
+            for (int s0 = 0; s0 < S; s0 += Sc) {
+                const int Sn = S - s0 < Sc ? S - s0 : Sc;
+                int sq = 0;
+                for (int s = 0; s < Sn; ++s) {
+                    const int v = squarings_host[s0 + s];
+                    QDB_REQUIRE(v >= 0 && v < 64, "qdb_magnus_steps_c128: bad squarings[%d]=%d", s0 + s, v);
+                    sq = v > sq ? v : sq;
+                }
+                if (mu) QDB_CUDA(cudaMemcpyAsync(tdev, times_host + (size_t)s0 * Q, (size_t)Sn * Q * sizeof(double), cudaMemcpyHostToDevice, st));
+                rc = launch_generator(n, K, Sn * Q, QDB_LAYOUT_ROWMAJOR, D2(ops_rm), D2(stat_rm), coeff ? coeff + (size_t)s0 * Q * K : nullptr,
+                                      0, mu, mu ? tdev : nullptr, 0.0, 1.0, gn, st);
+                if (rc != QDB_OK) return rc;
+                if ((rc = magnus_terms_batched(n, Q, Sn, gn, h, ldexp(1.0, -sq), Asb, mws, st)) != QDB_OK) return rc;
+                if ((rc = expm_core_batched(n, Sn, Asb, sq, Pb, bws, st)) != QDB_OK) return rc;
+                for (int s = 0; s < Sn; ++s) {
+                    rc = launch_zgemm(n, B, n, Pb + (size_t)s * nn, n, ycur, ldy, ynext, ldy, one, zero, nullptr, nullptr, nullptr, st);
+                    if (rc != QDB_OK) return rc;
+                    double2* t = ycur;
+                    ycur = ynext;
+                    ynext = t;
+                }
+            }
+            if (ycur != D2(y)) QDB_CUDA(cudaMemcpyAsync(y, ycur, (size_t)n * B * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+            return QDB_OK;
+        }
+    }
     if (mu) QDB_CUDA(cudaMemcpyAsync(times_dev, times_host, (size_t)S * Q * sizeof(double), cudaMemcpyHostToDevice, st));
     double2* ycur = D2(y);
     double2* ynext = ytmp;
-    const double2 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0);
-    int rc;
     for (int s = 0; s < S; ++s) {
         const int sq = squarings_host[s];
         QDB_REQUIRE(sq >= 0 && sq < 64, "qdb_magnus_steps_c128: bad squarings[%d]=%d", s, sq);
@@ -525,7 +575,6 @@ int qdb_magnus_steps_c128(int n, int K, int B, int S, int magnus_order, const qd
         ynext = t;
     }
     if (ycur != D2(y)) QDB_CUDA(cudaMemcpyAsync(y, ycur, (size_t)n * B * sizeof(double2), cudaMemcpyDeviceToDevice, st));
-    (void)nn;
     return QDB_OK;
 }
 

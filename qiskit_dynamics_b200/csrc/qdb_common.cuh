@@ -115,6 +115,8 @@ int launch_zgemm_rk4stage(int n, int B, const double2* G, const double2* yin, in
 int launch_dmma_probe(double* sink, int iters, int* grid_out, cudaStream_t st);
 // time-parallel solvers (propagator.cu)
 size_t propagator_workspace_bytes(int n, int S);
+int magnus_terms_batched(int n, int order, int count, const double2* g /*[count][order][n^2]*/, double h, double scale,
+                         double2* out /*[count][n^2]*/, double2* ws /*order 2: count n^2, order 3: 7 count n^2*/, cudaStream_t st);
 int expm_core_batched(int n, int count, const double2* As, int squarings, double2* out, double2* ws /*5 count n^2*/, cudaStream_t st);
 int step_propagator_product(int n, int K, int S, int kind, const double2* ops_rm, const double2* stat_rm, const double* coeff,
                             const double* mu, const double* times_host, const int* squarings_host, double h, double2* P_total,

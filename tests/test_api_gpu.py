@@ -414,6 +414,26 @@ def test_magnus_orders_2_and_3(qd):
             close(r.y[-1], g[f"l_{frame_name}_o{order}"], 1e-9)
     with pytest.raises(qd.QiskitError):
         qd.solve_lmde(mv, t_span=[0, 0.5], y0=Y, method="scipy_expm", max_dt=0.05, magnus_order=4)
+    # the C-ABI entry with room for one step at a time (step-by-step route) and for chunks of 3 steps (batched exponents,
+    # commutators and exponentials) gives the same states as the full-size workspace used above
+    abi = qd._abi
+    from qiskit_dynamics_b200.solvers.fixed_step import expm_squarings, magnus_nodes
+    from qiskit_dynamics_b200.arrays import asreal
+    mv.in_frame_basis = True
+    coll, n2, S, h = mv._collection(), 9, 10, 0.05
+    for order in (2, 3):
+        times = (h * np.arange(S))[:, None] + magnus_nodes(order)[None, :] * h
+        table = mv._signal_table(times.reshape(-1))
+        sq = expm_squarings(mv, table, h, order)
+        outs = []
+        for steps_of_room in (S, 1, 3):
+            nbytes = abi.workspace_bytes(abi.WS_MAGNUS, n2, coll.num_operators, Y.shape[1], steps_of_room) + 3 * S * 8 + 256
+            y = qd.asarray(Y).clone()
+            abi.magnus_steps(n2, coll.operators, coll.static_operator, asreal(table, y.device), mv._frame_freqs(), times, sq, h, y, S,
+                             order, workspace=torch.empty(nbytes, dtype=torch.uint8, device=y.device))
+            outs.append(npy(y))
+        assert max_col_l2(outs[1], outs[0]) < 1e-13 and max_col_l2(outs[2], outs[0]) < 1e-13
+    mv.in_frame_basis = False
 
 
 def test_nccl_sharded_sweep(qd):
