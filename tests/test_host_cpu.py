@@ -342,3 +342,13 @@ def test_signal_program_from_plain_lists(qd):
         assert np.array_equal(getattr(fast, name), getattr(slow, name)), name
     assert compile_signal_program([[qd.Signal(lambda t: t, 1.0)]]) is None      # Python envelope: host path
     assert compile_signal_program([[qd.Signal(1.0)], [qd.DiscreteSignal(0.1, [1.0, 2.0])]]) is None  # structure differs
+
+
+def test_integration_doc_matches_the_abi(qd):
+    """The ctypes stub shown in INTEGRATION.md lists the same number of arguments as the binding the package uses."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    found = dict(re.findall(r"_lib\.(qdb_[a-z0-9_]+)\.argtypes = \[([^\]]*)\]", text))
+    assert len(found) >= 10
+    for name, args in found.items():
+        assert name in qd._abi.SIGNATURES, name
+        assert len([a for a in args.split(",") if a.strip()]) == len(qd._abi.SIGNATURES[name][1]), name
