@@ -431,31 +431,36 @@ def _term_descr(term):
 
 
 def _compile_discrete_lists(lists) -> Optional[SignalProgram]:
-    """compile_signal_program for the shape large pulse sweeps have -- B plain lists of K DiscreteSignals, channel j
-    with the same sample count in every simulation, scalar carrier and phase -- written against the objects' fields
-    with preallocated arrays (a quarter of the host time of the general route); None when the input is anything else."""
+    """compile_signal_program for the shape large pulse sweeps have -- B plain lists of K DiscreteSignals with scalar
+    carrier and phase -- written against the objects' fields with preallocated arrays (a quarter of the host time of
+    the general route); None when the input is anything else.  Sample counts may differ between simulations (pulses of
+    different durations): channel j is padded with zeros to its longest simulation, which is what a DiscreteSignal
+    evaluates to past its end -- the padding to a common duration of the reference's batched schedule path
+    (solvers/solver_classes.py:607-660)."""
     B, first = len(lists), lists[0]
     K = len(first)
     if K == 0 or any(type(x) is not DiscreteSignal for x in first):
         return None
-    lens = [x._padded.shape[0] - 1 for x in first]
     if any(x._padded.ndim != 1 or x._padded.dtype == object for x in first):
         return None
+    lens = [0] * K
+    for sl in lists:
+        if len(sl) != K:
+            return None
+        for j, x in enumerate(sl):
+            if type(x) is not DiscreteSignal or x._padded.ndim != 1:
+                return None
+            if x._padded.shape[0] - 1 > lens[j]:
+                lens[j] = x._padded.shape[0] - 1
     offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-    samples = np.empty((B, int(offs[-1])), dtype=complex)
+    samples = np.zeros((B, int(offs[-1])), dtype=complex)
     params = np.empty((B, K, 4))
     try:
         for b, sl in enumerate(lists):
-            if len(sl) != K:
-                return None
             row, prm = samples[b], params[b]
             for j, x in enumerate(sl):
-                if type(x) is not DiscreteSignal:
-                    return None
                 pad = x._padded
-                if pad.ndim != 1 or pad.shape[0] - 1 != lens[j]:
-                    return None
-                row[offs[j]:offs[j + 1]] = pad[:-1]
+                row[offs[j]:offs[j] + pad.shape[0] - 1] = pad[:-1]
                 prm[j, 0], prm[j, 1], prm[j, 2], prm[j, 3] = x._dt, x._start_time, x._carrier_freq, x._phase
     except (TypeError, ValueError):  # array-valued or complex carrier / phase, object samples: the general route decides
         return None

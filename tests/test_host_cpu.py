@@ -352,3 +352,24 @@ def test_integration_doc_matches_the_abi(qd):
     for name, args in found.items():
         assert name in qd._abi.SIGNATURES, name
         assert len([a for a in args.split(",") if a.strip()]) == len(qd._abi.SIGNATURES[name][1]), name
+
+
+def test_signal_program_pads_ragged_pulse_sweeps(qd):
+    """Simulations whose pulses have different sample counts compile to the program of the explicitly zero-padded
+    signals (a DiscreteSignal is zero past its end), and evaluate like them on the host."""
+    from qiskit_dynamics_b200.signals import SignalList, compile_signal_program
+    rng = np.random.default_rng(8)
+    lens = [[5, 3], [2, 7], [5, 7], [1, 1]]
+    raw = [[rng.standard_normal(n_) + 1j * rng.standard_normal(n_) for n_ in row] for row in lens]
+    mk = lambda samples, j, b: qd.DiscreteSignal(dt=0.2, samples=samples, start_time=0.1 * j, carrier_freq=1.0 + j, phase=0.2 * b)  # noqa: E731
+    ragged = [[mk(raw[b][j], j, b) for j in range(2)] for b in range(4)]
+    target = [5, 7]
+    padded = [[mk(np.concatenate([raw[b][j], np.zeros(target[j] - len(raw[b][j]))]), j, b) for j in range(2)] for b in range(4)]
+    a, c = compile_signal_program(ragged), compile_signal_program(padded)
+    assert a is not None and c is not None
+    for name in ("chan", "samp_len", "samp_off", "dt", "t0", "freq", "phase", "samples"):
+        assert np.array_equal(getattr(a, name), getattr(c, name)), name
+    assert list(a.samp_len) == target
+    ts = np.linspace(-0.3, 2.5, 57)
+    for b in range(4):
+        assert np.array_equal(SignalList(ragged[b])(ts), SignalList(padded[b])(ts))
