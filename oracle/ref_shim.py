@@ -1,4 +1,4 @@
-"""Import shim: lets the UNMODIFIED reference at /root/reference import in this container.
+"""Import shim: lets the UNMODIFIED reference (baseline/_ref install, else /root/reference) import without its absent deps.
 
 TEST INFRASTRUCTURE ONLY (used by tests/golden/make_golden.py and by the optional
 oracle-vs-reference checks in tests/ when /root/reference is mounted).  It is never
@@ -132,12 +132,18 @@ for modname, setup in (("matplotlib", None), ("multiset", None)):
             p = types.ModuleType("matplotlib.pyplot"); p.axis = object; m.pyplot = p; sys.modules["matplotlib.pyplot"] = p
         else:
             m.Multiset = type("Multiset", (dict,), {}); m.FrozenMultiset = m.Multiset
-REFERENCE_ROOT = "/root/reference"
+import os as _os
+
+# Where the UNMODIFIED reference lives: the git-ignored pip install under baseline/_ref (made once with
+# `pip install --no-index --no-deps --target baseline/_ref <copy of /root/reference>`; it travels to the GPU box
+# with gpurun), else the read-only mount of the dev container.
+_REPO = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+_CANDIDATES = [_os.path.join(_REPO, "baseline", "_ref"), "/root/reference"]
+REFERENCE_ROOT = next((c for c in _CANDIDATES if _os.path.isdir(_os.path.join(c, "qiskit_dynamics"))), _CANDIDATES[-1])
 
 
 def reference_available() -> bool:
-    import os
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "qiskit_dynamics"))
+    return _os.path.isdir(_os.path.join(REFERENCE_ROOT, "qiskit_dynamics"))
 
 
 if reference_available() and REFERENCE_ROOT not in sys.path:

@@ -200,8 +200,8 @@ def rhs(n, ops, stat, coeff, mu, t, y, per_col=False, out=None, workspace=None):
     B = y.shape[1]
     if out is None:
         out = torch.empty_like(y)
-    if workspace is None:  # small (n^2 + 2n complex): keep one per (device, n) instead of allocating per call
-        key = (y.device, n)
+    if workspace is None:  # small (n^2 + 2n complex): keep one per (device, n, stream) instead of allocating per call
+        key = (y.device, n, torch.cuda.current_stream(y.device).cuda_stream)  # per stream: concurrent streams must not share G(t)
         workspace = _rhs_ws_cache.get(key)
         if workspace is None:
             workspace = torch.empty(workspace_bytes(WS_RHS, n, K, B), dtype=torch.uint8, device=y.device)

@@ -111,7 +111,6 @@ size_t qdb_workspace_bytes(int kind, int n, int K, int B, int S) {
         default:
             return 0;
     }
-    (void)K;
 }
 
 int qdb_pack_operators(int n, int count, const qdb_c128* src, qdb_c128* dst, void* stream) {

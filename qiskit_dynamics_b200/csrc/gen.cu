@@ -130,15 +130,24 @@ int launch_generator(int n, int K, int T, int layout, const double2* ops, const 
     const int npad = round_up8(n);
     const size_t elems = layout != QDB_LAYOUT_ROWMAJOR ? (size_t)npad * round_up16(n) : (size_t)n * n;
     const size_t smem = mu ? (size_t)n * sizeof(double2) : 0;
-    dim3 grid((unsigned)((elems + 511) / 512), T);
-    if (coeff_complex) {
-        if (smem > 48 * 1024)
+    if (smem > 48 * 1024) {
+        if (coeff_complex)
             QDB_CUDA(cudaFuncSetAttribute(generator_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        generator_kernel<true><<<grid, 256, smem, st>>>(n, npad, K, layout, elems, ops, stat, coeff, mu, times, t_scalar, scale, out);
-    } else {
-        if (smem > 48 * 1024)
+        else
             QDB_CUDA(cudaFuncSetAttribute(generator_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        generator_kernel<false><<<grid, 256, smem, st>>>(n, npad, K, layout, elems, ops, stat, coeff, mu, times, t_scalar, scale, out);
+    }
+    // gridDim.y is capped at 65535: long intervals (T = 2 S + 1 stage times) go up in slices of the time axis
+    const size_t out_stride = layout == QDB_LAYOUT_PACKED3M ? elems + elems / 2 : elems;
+    for (int ts = 0; ts < T; ts += kMaxGridY) {
+        const int Tc = T - ts < kMaxGridY ? T - ts : kMaxGridY;
+        dim3 grid((unsigned)((elems + 511) / 512), (unsigned)Tc);
+        const double* cs = coeff ? coeff + (size_t)ts * K * (coeff_complex ? 2 : 1) : nullptr;
+        const double* tms = times ? times + ts : nullptr;
+        double2* os = out + (size_t)ts * out_stride;
+        if (coeff_complex)
+            generator_kernel<true><<<grid, 256, smem, st>>>(n, npad, K, layout, elems, ops, stat, cs, mu, tms, t_scalar, scale, os);
+        else
+            generator_kernel<false><<<grid, 256, smem, st>>>(n, npad, K, layout, elems, ops, stat, cs, mu, tms, t_scalar, scale, os);
     }
     QDB_LAUNCH_CHECK("generator_kernel");
     return QDB_OK;

@@ -33,6 +33,7 @@ int sm_count();  // SMs of the current device (148 on B200 when the query fails)
 // element (r, c) lives at ((r/8)*(kpad/4) + c/4)*32 + (r%8)*4 + c%4
 __host__ __device__ inline int round_up8(int n) { return (n + 7) & ~7; }
 __host__ __device__ inline int round_up16(int n) { return (n + 15) & ~15; }
+constexpr int kMaxGridY = 65535;  // CUDA limit of gridDim.y / gridDim.z: launchers slice longer axes
 __host__ __device__ inline size_t packed_index(int kpad, int r, int c) {
     return ((size_t)(r >> 3) * (kpad >> 2) + (c >> 2)) * 32 + ((r & 7) << 2) + (c & 3);
 }

@@ -89,8 +89,12 @@ int launch_signal_table(int T, int K, int B, int nterms, const int* chan, const 
     SignalTerms tm{chan, samp_off, samp_len, dt, t0, freq, phase, params_per_col};
     const int ncol = B > 0 ? B : 1;
     const int threads = ncol >= 256 ? 256 : (ncol >= 64 ? 64 : 32);
-    dim3 grid((unsigned)((ncol + threads - 1) / threads), (unsigned)T);
-    signal_table_kernel<<<grid, threads, 0, st>>>(T, K, B, nterms, tm, samples, col_stride, scale, times, t_scalar, out);
+    for (int ts = 0; ts < T; ts += kMaxGridY) {  // gridDim.y is capped at 65535: slices of the time axis
+        const int Tc = T - ts < kMaxGridY ? T - ts : kMaxGridY;
+        dim3 grid((unsigned)((ncol + threads - 1) / threads), (unsigned)Tc);
+        signal_table_kernel<<<grid, threads, 0, st>>>(Tc, K, B, nterms, tm, samples, col_stride, scale, times ? times + ts : nullptr,
+                                                      t_scalar, out + (size_t)ts * K * ncol);
+    }
     QDB_LAUNCH_CHECK("signal_table_kernel");
     return QDB_OK;
 }

@@ -55,13 +55,16 @@ def all_gather_columns(local: torch.Tensor, num_columns: int) -> torch.Tensor:
         pad = torch.zeros(buf.shape[:-1] + (max_w - buf.shape[-1],), dtype=buf.dtype, device=buf.device)
         buf = torch.cat([buf, pad], dim=-1)
     send = torch.view_as_real(buf.contiguous()) if is_complex else buf.contiguous()
-    recv = [torch.empty_like(send) for _ in range(w)]
-    dist.all_gather(recv, send)
-    parts = []
-    for r, (lo, hi) in enumerate(widths):
-        part = torch.view_as_complex(recv[r]) if is_complex else recv[r]
-        parts.append(part[..., : hi - lo])
-    return torch.cat(parts, dim=-1)
+    # ONE collective into ONE preallocated tensor (rank-major), no per-rank list of receive buffers
+    recv = torch.empty(w * send.numel(), dtype=send.dtype, device=send.device)
+    dist.all_gather_into_tensor(recv, send.reshape(-1))
+    recv = recv.reshape((w,) + tuple(send.shape))
+    full = torch.view_as_complex(recv) if is_complex else recv  # (w, ..., max_w)
+    if full.ndim == 2 and num_columns == w * max_w:  # 1-d observables, even split: already in column order
+        return full.reshape(-1)
+    if num_columns == w * max_w:
+        return torch.movedim(full, 0, -2).reshape(full.shape[1:-1] + (num_columns,))
+    return torch.cat([full[r][..., : hi - lo] for r, (lo, hi) in enumerate(widths)], dim=-1)
 
 
 def solve_lmde_sharded(generator, t_span, y0: torch.Tensor, gather: bool = True, **kwargs):

@@ -18,7 +18,7 @@ import torch
 from .. import _abi
 from ..arrays import asarray, asreal, stage_to_device
 from ..exceptions import QiskitError
-from ..signals import Signal, SignalList, compile_signal_program
+from ..signals import Signal, SignalList, compile_signal_program, mutation_epoch
 from .operator_collections import OperatorCollection, _as_columns
 from .rotating_frame import RotatingFrame
 
@@ -172,8 +172,9 @@ class GeneratorModel(BaseGeneratorModel):
     def _program(self):
         """Device program of the current signals (compiled once per assignment), or None when a term is an
         arbitrary Python envelope."""
-        if getattr(self, "_signal_program", False) is False:
+        if getattr(self, "_signal_program", False) is False or getattr(self, "_signal_program_epoch", -1) != mutation_epoch():
             self._signal_program = compile_signal_program(self._signals) if self._signals is not None else None
+            self._signal_program_epoch = mutation_epoch()
         return self._signal_program
 
     def _device_coefficients(self, time, device):

@@ -23,6 +23,21 @@ from .exceptions import QiskitError
 
 _TWO_PI_J = 2j * np.pi
 
+# Mutation epoch: bumped by every in-place change of a signal (carrier_freq / phase setters, add_samples).  Models cache the
+# compiled device program of their signals together with the epoch it was compiled at and recompile when it has moved, so
+# that the device route sees in-place edits exactly as the host route -- and the reference, which re-reads the signal
+# objects on every evaluation (signals/signals.py:148-155) -- does.
+_epoch = 0
+
+
+def _bump_epoch() -> None:
+    global _epoch
+    _epoch += 1
+
+
+def mutation_epoch() -> int:
+    return _epoch
+
 
 def _scalar_like(x) -> bool:
     return isinstance(x, (int, float, complex, np.number)) or (hasattr(x, "ndim") and np.ndim(x) == 0)
@@ -63,6 +78,7 @@ class Signal:
 
     @carrier_freq.setter
     def carrier_freq(self, value):
+        _bump_epoch()
         self._carrier_freq = np.asarray(value)
         self._carrier_arg = _TWO_PI_J * self._carrier_freq
 
@@ -72,6 +88,7 @@ class Signal:
 
     @phase.setter
     def phase(self, value):
+        _bump_epoch()
         self._phase = np.asarray(value)
         self._phase_arg = 1j * self._phase
 
@@ -173,6 +190,7 @@ class DiscreteSignal(Signal):
                               carrier_freq=-self.carrier_freq, phase=-self.phase)
 
     def add_samples(self, start_sample: int, samples):
+        _bump_epoch()
         samples = np.asarray(samples)
         if len(samples) < 1:
             return

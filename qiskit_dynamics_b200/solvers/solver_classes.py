@@ -19,7 +19,7 @@ import numpy as np
 import torch
 from scipy.integrate._ivp.ivp import OdeResult
 
-from ..arrays import asarray
+from ..arrays import asarray, wait_pending_copies
 from ..exceptions import QiskitError
 from ..models import HamiltonianModel, LindbladModel, RotatingFrame
 from ..signals import Signal, SignalList, SignalSum, compile_signal_program
@@ -76,6 +76,7 @@ class Solver:
                 results = self._solve_list(t_span_list, y0_list, signals_list, **kwargs)
         finally:
             self._set_new_signals(None)
+            wait_pending_copies()  # pinned-host inputs may be reused by the caller from here on
         return results if multiple else results[0]
 
     def _solve_list(self, t_span_list, y0_list, signals_list, **kwargs) -> List[OdeResult]:

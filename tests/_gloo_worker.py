@@ -24,6 +24,11 @@ assert gathered.shape == full.shape
 assert torch.equal(gathered, full * (2.0 + 1j))
 obs = D.all_gather_columns(evolved.abs().sum(dim=(0, 1)), B)  # real per-column observable
 assert torch.allclose(obs, (full * (2.0 + 1j)).abs().sum(dim=(0, 1)))
+# even split (the bench's case): one all_gather_into_tensor, rank-major blocks land in column order
+full8 = torch.randn(T, n, 8, dtype=torch.float64) + 1j * torch.randn(T, n, 8, dtype=torch.float64)
+assert torch.equal(D.all_gather_columns(D.shard_columns(full8), 8), full8)
+assert torch.equal(D.all_gather_columns(D.shard_columns(full8[0].real.contiguous()), 8), full8[0].real)
+assert torch.equal(D.all_gather_columns(D.shard_columns(full8[0, 0].real.contiguous()), 8), full8[0, 0].real)
 
 # a list of simulations split over the ranks (cfg5: parameter sweep sharded over the GPUs): every rank solves its block
 # through the Solver protocol (a stand-in here: the product has no CPU path), one gather of final states / observables

@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 import oracle.ref_shim as ref_shim  # noqa: E402
 
 if not ref_shim.reference_available():
-    raise SystemExit("reference not mounted at /root/reference; cannot regenerate goldens")
+    raise SystemExit("reference not available (baseline/_ref or /root/reference); cannot regenerate goldens")
 
 from qiskit_dynamics import Signal, DiscreteSignal, solve_lmde, Solver  # noqa: E402
 from qiskit_dynamics.signals import SignalList, SignalSum  # noqa: E402
@@ -437,6 +437,74 @@ def gen_measurement():
     out["tf"] = np.array(tf)
     save("measurement", **out)
 
+def gen_fullsize():
+    """Column subsets of the FULL-SIZE BASELINE configurations solved by the unmodified reference: the GPU tests run the
+    whole batch at the stated sizes (cfg2 n=32 B=1024 1000 steps sweep; cfg3 729 x 4096 expm T=0.2; cfg4 n=128 B=4096
+    1000 steps; cfg5-like n=81, 8 DiscreteSignal channels, 8192 sweep points) and compare these columns.  Every column
+    evolves independently in the reference (no inter-column term), so solving the chosen columns alone is
+    what `results[:, cols]` of the full batch would hold."""
+    import bench_workloads as W
+    out = {}
+    # cfg4: 32 columns of the 4096, 1000 RK4 steps
+    H0, Hs, Y, sig = W.cfg4()
+    cols = W.parity_columns(Y.shape[1])
+    m = HamiltonianModel(static_operator=H0, operators=Hs, signals=sigs(sig), rotating_frame=H0)
+    out["cfg4_cols"] = cols
+    out["cfg4_check"] = checksum(H0, Hs, Y)
+    out["cfg4_y"] = solve_lmde(m, t_span=[0, 1.0], y0=Y[:, cols], method="RK4", max_dt=W.MAX_DT).y[-1]
+    # a ragged batch (4090 columns: the last octet of the tiling is partial) shares the operators; its tail columns
+    colsr = np.arange(4080, 4090)
+    out["cfg4_ragged_cols"] = colsr
+    out["cfg4_ragged_y"] = solve_lmde(m, t_span=[0, 0.1], y0=Y[:, colsr], method="RK4", max_dt=W.MAX_DT).y[-1]
+    # cfg2: 32 of the 1024 sweep points through Solver.solve's sequential list loop, 1000 RK4 steps
+    H0, Hs, y0, per_col = W.cfg2()
+    cols = W.parity_columns(len(per_col))
+    s = Solver(static_hamiltonian=H0, hamiltonian_operators=Hs, rotating_frame=H0)
+    res = s.solve(t_span=[0, 1.0], y0=y0, signals=[sigs(per_col[b]) for b in cols], method="RK4", max_dt=W.MAX_DT)
+    out["cfg2_cols"] = cols
+    out["cfg2_check"] = checksum(H0, Hs, y0)
+    out["cfg2_y"] = np.stack([r.y[-1] for r in res], axis=-1)
+    # cfg3: 16 of the 4096 density matrices, 20 exponential steps
+    H0, Hs, Ls, Y, sig = W.cfg3()
+    cols = W.parity_columns(Y.shape[1], count=16)[:16]
+    mv = LindbladModel(static_hamiltonian=H0, hamiltonian_operators=Hs, hamiltonian_signals=sigs(sig),
+                       static_dissipators=Ls, rotating_frame=np.diag(H0).real, vectorized=True)
+    out["cfg3_cols"] = cols
+    out["cfg3_check"] = checksum(H0, Hs, Ls, Y)
+    out["cfg3_y"] = solve_lmde(mv, t_span=[0, 0.2], y0=Y[:, cols], method="scipy_expm", max_dt=1e-2).y[-1]
+    # cfg5-like: 32 of 8192 sweep points, DiscreteSignal Gaussian-square tables, max_dt = sample width (every stage
+    # time on a bin edge), 64 RK4 steps; final states and the memory-slot probabilities of the reference's
+    # post-processing chain (backend_utils)
+    from qiskit_dynamics.backend import backend_utils as bu
+    nsim, nsamp = 8192, 64
+    H0, ops, freqs = W.cfg5_system()
+    cols = W.parity_columns(nsim)
+    s = Solver(static_hamiltonian=H0, hamiltonian_operators=list(ops), rotating_frame=H0)
+    y0 = np.zeros(H0.shape[0], dtype=complex)
+    y0[0] = 1.0
+    lists = [[DiscreteSignal(dt=W.CFG5_DT, samples=smp, carrier_freq=float(freqs[j]), phase=ph)
+              for j, (smp, ph) in enumerate(W.cfg5_point(int(k), nsim, nsamp))] for k in cols]
+    tf = nsamp * W.CFG5_DT
+    res = s.solve(t_span=[0, tf], y0=y0, signals=lists, method="RK4", max_dt=W.CFG5_DT)
+    finals = np.stack([r.y[-1] for r in res], axis=-1)
+    dims, msub, mslots = W.cfg5_measurement()
+    lab_h = bu._get_lab_frame_static_hamiltonian(s.model)
+    _, dressed = bu._get_dressed_state_decomposition(lab_h)
+    dicts = []
+    for b in range(finals.shape[1]):
+        yf = np.array(s.model.rotating_frame.state_out_of_frame(t=tf, y=finals[:, b]))
+        yf = dressed.conj().T @ yf
+        yf = yf / np.linalg.norm(yf)
+        pd = orc.subsystem_probabilities_dict(np.abs(yf) ** 2, dims, msub)
+        dicts.append(bu._get_memory_slot_probabilities(pd, mslots, max_outcome_value=1))
+    labels = sorted(set().union(*[d.keys() for d in dicts]))
+    out["cfg5_cols"] = cols
+    out["cfg5_check"] = checksum(H0, ops)
+    out["cfg5_y"] = finals
+    out["cfg5_labels"] = np.array(labels)
+    out["cfg5_probs"] = np.array([[d.get(lab, 0.0) for d in dicts] for lab in labels])
+    save("fullsize", **out)
+
 
 if __name__ == "__main__":
     only = set(sys.argv[1:])  # e.g. `make_golden.py magnus` regenerates one file
@@ -453,3 +521,4 @@ if __name__ == "__main__":
     gen_hamiltonian_model()
     gen_rk4_solves()
     gen_lindblad()
+    gen_fullsize()

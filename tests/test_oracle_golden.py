@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import numpy_oracle as orc
-from conftest import MEASUREMENT_CASES, load_golden
+from conftest import MEASUREMENT_CASES, load_golden, max_col_l2
 
 TOL = 1e-12
 
@@ -314,3 +314,30 @@ def test_parallel_template_agrees_with_sequential():
         t, ys = orc.solve_hamiltonian_parallel(H0, Hs, sp, H0, [0.5, 0.0], Y, 0.04, kind="expm", magnus_order=order,
                                                t_eval=[0.5, 0.31, 0.1])
         close(ys, gm[f"h_full_teval_back_o{order}"], 1e-11)
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size configurations: the oracle on the chosen columns == the unmodified reference on the same columns
+# (tests/golden/fullsize.npz); the GPU side of the same comparison is tests/test_fullsize_gpu.py
+# ---------------------------------------------------------------------------------------------
+
+
+def test_fullsize_columns_oracle_equals_reference():
+    import bench_workloads as W
+    import fullsize_cases as fc
+    g = load_golden("fullsize")
+    assert np.array_equal(g["cfg4_cols"], W.parity_columns(4096)) and g["cfg4_cols"].size == 32
+    assert max_col_l2(fc.oracle_cfg4(g["cfg4_cols"]), g["cfg4_y"]) < 1e-12       # 1000 RK4 steps, n = 128
+    assert max_col_l2(fc.oracle_cfg4(g["cfg4_ragged_cols"], t_end=0.1), g["cfg4_ragged_y"]) < 1e-12
+    assert max_col_l2(fc.oracle_cfg2(g["cfg2_cols"][:8]), g["cfg2_y"][:, :8]) < 1e-12  # 1000 steps each, per-column signals
+    assert max_col_l2(fc.oracle_cfg3(g["cfg3_cols"][:4]), g["cfg3_y"][:, :4]) < 1e-12  # 20 exponentials of 729 x 729
+    assert max_col_l2(fc.oracle_cfg5(g["cfg5_cols"]), g["cfg5_y"]) < 1e-12       # bin-edge stage times, 64 steps
+    # memory-slot probabilities of the reference's post-processing chain
+    H0, ops, freqs = W.cfg5_system()
+    dims, msub, mslots = W.cfg5_measurement()
+    _, dressed = orc.dressed_state_decomposition(H0)
+    labels = [str(x) for x in g["cfg5_labels"]]
+    for i in (0, 7, 31):
+        pd = orc.final_state_memory_probabilities(g["cfg5_y"][:, i], fc.CFG5_NSAMP * W.CFG5_DT, H0, dressed, dims, msub, mslots,
+                                                  max_outcome_value=1)
+        close(np.array([pd.get(lab, 0.0) for lab in labels]), g["cfg5_probs"][:, i])
