@@ -127,6 +127,7 @@ bool rk4_fused_tiling(int n, int B, int sweep_K, int* out);
 int launch_rk4_fused_shared(int n, int B, int S, const double2* gen_table, int table_layout, double h,
                             double2* y, int ldy, cudaStream_t st);
 int rk4_fused_table_layout(int n, int B);
+int launch_rk4_rowsplit3m(int n, int B, int S, const double2* gen_table, double h, double2* y, int ldy, cudaStream_t st);
 int launch_rk4_fused_sweep(int n, int K, int B, int S, const double2* stat_packed /*or null*/,
                            const double2* ops_packed /*[K]*/, const double* coeff, int ldc,
                            const double* mu, const double* times_dev,

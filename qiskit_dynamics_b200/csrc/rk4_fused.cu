@@ -1260,6 +1260,13 @@ int launch_3m_t(const Config& cfg, int B, int S, const double2* gen, double h, d
     return QDB_OK;
 }
 
+// QDB_ROWSPLIT_OLD=1 pins rk4_shared3m_kernel<2,0,split> for small batches at n = 121..128 (the bit-level reference of
+// rk4_rowsplit3m_kernel in the tests: same products in the same order per accumulator, k halves swapped on rank 1)
+bool rowsplit_enabled() {
+    const char* e = getenv("QDB_ROWSPLIT_OLD");
+    return !(e && e[0] == '1');
+}
+
 #define QDB_DISPATCH(MRv, NCWv, CALL)                \
     if (cfg.MR == MRv && cfg.NCW == NCWv) return CALL
 
@@ -1305,6 +1312,7 @@ int launch_rk4_fused_shared(int n, int B, int S, const double2* gen_table, int t
         const bool static128 = cfg.geo.KT == 32 && cfg.geo.RT == 16 && cfg.geo.npad == 128;
         if (cfg.split) {
             if (static128) QDB_DISPATCH(2, 3, (launch_3m_t<2, 3, true, 32>(ARGS)));
+            if (static128 && cfg.NCW == 0 && rowsplit_enabled()) return launch_rk4_rowsplit3m(n, B, S, gen_table, h, y, ldy, st);
             if (static128) QDB_DISPATCH(2, 0, (launch_3m_t<2, 0, true, 32>(ARGS)));
             QDB_DISPATCH(2, 0, (launch_3m_t<2, 0, true, 0>(ARGS)));
             QDB_DISPATCH(2, 1, (launch_3m_t<2, 1, true, 0>(ARGS)));

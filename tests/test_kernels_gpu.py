@@ -232,6 +232,9 @@ def test_rk4_split_clusters_bit_identical(abi, n, B, S):
     (128, 512, 2),    # pure row split: one octet per 2-CTA cluster, deep fragment ring (static geometry)
     (100, 300, 2),    # pure row split, dynamic geometry, rank 1 owns 5 of 8 row tiles
     (128, 5, 3),      # a single partial octet
+    (121, 300, 3),    # row-split kernel with padded rows (n < 128)
+    (125, 520, 5),    # row-split kernel, 65 octets, odd number of steps
+    (128, 64, 6),     # row-split kernel, 8 clusters
     (128, 1024, 2),   # whole-column CTAs, one column tile per warp
     (64, 4096, 2),    # one row tile per warp
     (72, 100, 2),     # 9 row tiles on 8 row warps
@@ -264,6 +267,36 @@ def test_rk4_three_product_kernel(abi, n, B, S):
         k4 = G2 @ (y + h * k3)
         y = y + (1.0 / 6) * h * (k1 + 2 * k2 + 2 * k3 + k4)
     assert torch.linalg.vector_norm(y3[:, cols] - y, dim=0).max().item() < 1e-12 * scale
+
+
+@pytest.mark.parametrize("n,B,S", [(128, 512, 7), (128, 20, 3), (122, 333, 4)])
+def test_rowsplit_kernel_against_previous_tiling(abi, n, B, S):
+    """rk4_rowsplit3m_kernel (16-deep fragment ring, own k half first, mid-stage mbarrier wait) against
+    rk4_shared3m_kernel<2,0,split> (QDB_ROWSPLIT_OLD=1): rank 0 of every cluster performs the identical DMMA sequence
+    (rows 0..63 bit for bit), rank 1 sums the two k halves in the other order (rounding only)."""
+    import os
+    rng = np.random.default_rng(n + 7 * B)
+    A = rng.standard_normal((2 * S + 1, n, n)) + 1j * rng.standard_normal((2 * S + 1, n, n))
+    table = dev((A - A.conj().transpose(0, 2, 1)) * (5.0 / np.sqrt(2 * n)))
+    packed3 = abi.to_packed3m(abi.pack_operators(table))
+    y0 = dev(rng.standard_normal((n, B)) + 1j * rng.standard_normal((n, B)))
+    assert abi.rk4_tiling(n, B)["col_tiles_per_warp"] == 0 and abi.rk4_tiling(n, B)["split"] == 1
+    old = os.environ.pop("QDB_ROWSPLIT_OLD", None)
+    try:
+        y_new = y0.clone()
+        abi.rk4_table_steps(n, packed3, 1e-2, y_new, S, layout=abi.LAYOUT_PACKED3M)
+        os.environ["QDB_ROWSPLIT_OLD"] = "1"
+        y_old = y0.clone()
+        abi.rk4_table_steps(n, packed3, 1e-2, y_old, S, layout=abi.LAYOUT_PACKED3M)
+    finally:
+        os.environ.pop("QDB_ROWSPLIT_OLD", None)
+        if old is not None:
+            os.environ["QDB_ROWSPLIT_OLD"] = old
+    torch.cuda.synchronize()
+    scale = torch.linalg.vector_norm(y0, dim=0).max().item()
+    assert torch.linalg.vector_norm(y_new - y_old, dim=0).max().item() < 1e-13 * scale
+    if S == 1:
+        assert torch.equal(y_new[:64], y_old[:64])
 
 
 def test_generator_packed3m_layout(abi):
