@@ -62,6 +62,23 @@ __device__ __forceinline__ void st_async_s(uint32_t dst, uint32_t bar, double v)
                  : "memory");
 }
 
+// The k loop is scheduled by hand: every load and every DMMA is a volatile asm, so ptxas keeps the written order
+// (A fragment 15 k-tiles ahead, B fragment 3 ahead, then the three DMMAs of the k-tile).  Left to itself the compiler
+// sinks the shared-memory loads to three DMMAs before their use (ncu: 15 % short-scoreboard stalls).
+__device__ __forceinline__ void dmma_v(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double2 lds_c(const double2* p) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+}
+__device__ __forceinline__ double lds_s(const double* p) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+}
+
 // stage-buffer slot of (row tile rt, row g, column cin) of the octet: B-fragment order, k-tile = 2 rt + g / 4
 __device__ __forceinline__ int slot(int rt, int g, int cin) {
     return (2 * rt + (g >> 2)) * 32 + frag_swizzle((g & 3) + 4 * cin);
@@ -150,53 +167,56 @@ rk4_rowsplit3m_kernel(int n, int B, int S, const double2* __restrict__ gen, doub
         const double* ns = reinterpret_cast<const double*>(gen + (size_t)nentry * entry_stride + entry_elems) + aoff + lo;
         if (tid == 0 && !final_stage) mbar_expect_tx(mbar + (sidx & 1), tx_bytes);  // rows of stage sidx + 1 from the peer
 
-        // one half of the k dimension: HALF k-tiles starting at element offset `koff` of the stage planes / the entry.
-        // Ring slot u holds sequence position (block, u); position + 15 is fetched into slot (u + 15) % 16.
-        auto half = [&](auto second_tag, int koff) {
-            constexpr bool SECOND = decltype(second_tag)::value;
-            const double2* bc = &sh_c[cur][koff + swl];
-            const double* bs = &sh_s[cur][koff + swl];
-            F3 b[3];
-            b[0].c = bc[0];
-            b[0].s = bs[0];
-            b[1].c = bc[32];
-            b[1].s = bs[32];
+        // The 32 k-tiles of the stage as one sequence: positions 0..15 = own half, 16..31 = peer half.  Ring slot p % 16
+        // holds the A fragment of position p; position p + 15 is fetched into the slot position p - 1 released.  B fragments
+        // run BD positions ahead through a small register ring; the mbarrier wait for the peer's rows sits right before
+        // the first B load of the second half, where it has long completed.
+        {
+            constexpr int BD = 4;
+            const double2* bc_lo = &sh_c[cur][lo + swl];
+            const double* bs_lo = &sh_s[cur][lo + swl];
+            const double2* bc_hi = &sh_c[cur][hi + swl];
+            const double* bs_hi = &sh_s[cur][hi + swl];
+            F3 b[BD];
 #pragma unroll
-            for (int u = 0; u < HALF; ++u) {
+            for (int j = 0; j < BD - 1; ++j) {
+                b[j].c = lds_c(bc_lo + j * 32);
+                b[j].s = lds_s(bs_lo + j * 32);
+            }
+#pragma unroll
+            for (int p = 0; p < 2 * HALF; ++p) {
                 {   // A prefetch, 15 positions ahead
-                    F3& dst = ring[(u + HALF - 1) % HALF];
-                    if (!SECOND) {
-                        if (u == 0) {  // last k-tile of this (own) half
-                            dst.c = ldg_stream(ec + lo + (HALF - 1) * 32);
-                            dst.s = ldg_f64(es + lo + (HALF - 1) * 32);
-                        } else {       // peer half of the same entry
-                            dst.c = ldg_stream(ec + hi + (u - 1) * 32);
-                            dst.s = ldg_f64(es + hi + (u - 1) * 32);
-                        }
+                    F3& dst = ring[(p + HALF - 1) % HALF];
+                    const int t = p + HALF - 1;  // target position: < 32 this entry, else next entry (own half first)
+                    if (t < HALF) {
+                        dst.c = ldg_stream(ec + lo + t * 32);
+                        dst.s = ldg_f64(es + lo + t * 32);
+                    } else if (t < 2 * HALF) {
+                        dst.c = ldg_stream(ec + hi + (t - HALF) * 32);
+                        dst.s = ldg_f64(es + hi + (t - HALF) * 32);
                     } else {
-                        if (u == 0) {  // last k-tile of the peer half
-                            dst.c = ldg_stream(ec + hi + (HALF - 1) * 32);
-                            dst.s = ldg_f64(es + hi + (HALF - 1) * 32);
-                        } else {       // own half of the NEXT entry
-                            dst.c = ldg_stream(nc + (u - 1) * 32);
-                            dst.s = ldg_f64(ns + (u - 1) * 32);
-                        }
+                        dst.c = ldg_stream(nc + (t - 2 * HALF) * 32);
+                        dst.s = ldg_f64(ns + (t - 2 * HALF) * 32);
                     }
                 }
-                if (u + 2 < HALF) {  // B fragments two k-tiles ahead
-                    b[(u + 2) % 3].c = bc[(u + 2) * 32];
-                    b[(u + 2) % 3].s = bs[(u + 2) * 32];
+                {   // B prefetch, BD - 1 positions ahead
+                    const int t = p + BD - 1;
+                    if (t == HALF && sidx > 0) mbar_wait(mbar + ((sidx - 1) & 1), ((sidx - 1) >> 1) & 1);
+                    if (t < HALF) {
+                        b[t % BD].c = lds_c(bc_lo + t * 32);
+                        b[t % BD].s = lds_s(bs_lo + t * 32);
+                    } else if (t < 2 * HALF) {
+                        b[t % BD].c = lds_c(bc_hi + (t - HALF) * 32);
+                        b[t % BD].s = lds_s(bs_hi + (t - HALF) * 32);
+                    }
                 }
-                const F3& a = ring[u];
-                const F3& bb = b[u % 3];
-                dmma(p0[0], p0[1], a.c.x, bb.c.x);
-                dmma(p1[0], p1[1], a.c.y, bb.c.y);
-                dmma(p2[0], p2[1], a.s, bb.s);
+                const F3& a = ring[p % HALF];
+                const F3& bb = b[p % BD];
+                dmma_v(p0[0], p0[1], a.c.x, bb.c.x);
+                dmma_v(p1[0], p1[1], a.c.y, bb.c.y);
+                dmma_v(p2[0], p2[1], a.s, bb.s);
             }
-        };
-        half(std::false_type{}, lo);
-        if (sidx > 0) mbar_wait(mbar + ((sidx - 1) & 1), ((sidx - 1) >> 1) & 1);  // the peer's rows of this stage have landed
-        half(std::true_type{}, hi);
+        }
 
         // ---- epilogue: RK4 stage combine; next stage input to both CTAs ----
         const StageCoef sc(stage, h);
