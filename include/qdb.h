@@ -266,6 +266,36 @@ int qdb_signal_table_f64(int T, int K, int B, int nterms,
 int qdb_outcome_probabilities_f64(int n, int B, int n_out, const qdb_c128* y, int ldy, const int* outcome_of,
                                   int normalize, double* out, void* stream);
 
+/* f2: the non-vectorised Lindblad equation on a batch of density matrices rho (B, n, n) row-major -- batch = LEADING axis,
+ * as in the reference -- evaluated as
+ *     rhs(X) = M1 X + X M2 + sum_j g_j L_j X L_j^dag,   M1 = A + B,  M2 = A - B,  B = -i H(t),  A = -1/2 sum_j g_j L_j^dag L_j
+ * (g_j = 1 for static dissipators), with the frame phases around it: X = rho .* (p_i conj p_k), out = rhs(X) .* (conj p_i p_k),
+ * p = exp(-i mu t); mu == NULL: no frame.  O(n^3) per density matrix (the vectorised form is O(n^4)).
+ *   m1_packed / m2t_packed : M1(t) and the TRANSPOSE of M2(t) in QDB_LAYOUT_PACKED -- entries of generator tables the caller
+ *                  builds with qdb_generator_c128 from [-i H_j ; -1/2 L_j^dag L_j] (M1) and their transposes with +i H_j (M2^T)
+ *   diss_packed  : [J] dissipators L_j (static and time dependent ones alike), QDB_LAYOUT_PACKED
+ *   gamma        : device [J] coefficients g_j(t), or NULL (all 1)
+ * One CTA per density matrix, operands in shared memory, operators streamed from L2; n <= 32 (qdb_lindblad_supported).
+ * Replaces LindbladCollection.evaluate_rhs (models/operator_collections.py:451-567, batch broadcast :506-510) inside
+ * LindbladModel.evaluate_rhs (models/lindblad_model.py:477-538) with RotatingFrame.operator_out_of_frame / operator_into_frame
+ * (models/rotating_frame.py:286-370). */
+int qdb_lindblad_supported(int n);
+int qdb_lindblad_rhs_c128(int n, int J, int B,
+                          const qdb_c128* m1_packed, const qdb_c128* m2t_packed, const qdb_c128* diss_packed,
+                          const double* gamma, const double* mu, double t,
+                          const qdb_c128* rho_in, qdb_c128* rho_out, void* stream);
+
+/* f2 + a7 + a8: S fixed RK4 steps of the same equation with every density matrix resident on chip for the whole launch.
+ *   m1_table / m2t_table : [2S+1] entries at the stage times t_0, t_0 + h/2, t_1, ... (QDB_LAYOUT_PACKED)
+ *   gamma_table  : device [2S+1][J], or NULL;   times_dev : device [2S+1] stage times (needed when mu != NULL)
+ *   rho          : (B, n, n), in/out
+ * Replaces RK4_solver.take_step + the fixed_step_solver_template loop (solvers/fixed_step_solvers.py:43-77, 441-454) applied
+ * to LindbladModel.evaluate_rhs with vectorized=False (the route solve_lmde(method="RK4") takes, solvers/solver_functions.py:315-327). */
+int qdb_lindblad_rk4_steps_c128(int n, int J, int B, int S,
+                                const qdb_c128* m1_table, const qdb_c128* m2t_table, const qdb_c128* diss_packed,
+                                const double* gamma_table, const double* mu, const double* times_dev, double h,
+                                qdb_c128* rho, void* stream);
+
 /* Number of kernels this library has launched on the calling process since load (bench.py's
  * "gpu_launches" evidence). */
 unsigned long long qdb_launch_count(void);

@@ -59,6 +59,9 @@ SIGNATURES = {
     "qdb_magnus_steps_c128": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _i, _vp, _sz, _vp]),
     "qdb_magnus_terms_c128": (_i, [_i, _i, _vp, _d, _d, _vp, _vp, _sz, _vp]),
     "qdb_step_propagators_c128": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _vp, _sz, _vp]),
+    "qdb_lindblad_supported": (_i, [_i]),
+    "qdb_lindblad_rhs_c128": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _vp, _vp, _vp]),
+    "qdb_lindblad_rk4_steps_c128": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _vp]),
     "qdb_launch_count": (ctypes.c_ulonglong, []),
 }
 
@@ -379,6 +382,36 @@ def outcome_probabilities(y, outcome_of, n_out: int, normalize: bool = True, out
                                                int(bool(normalize)), _ptr(out, F, "out"), _stream()),
            "qdb_outcome_probabilities_f64")
     return out
+
+
+def lindblad_supported(n: int) -> bool:
+    """True when the on-chip non-vectorised Lindblad kernels take this dimension (n <= 32)."""
+    return bool(lib().qdb_lindblad_supported(int(n)))
+
+
+def lindblad_rhs(n, m1_packed, m2t_packed, diss_packed, gamma, mu, t, rho, out=None):
+    """One Lindblad RHS evaluation on rho (B, n, n); m1 / m2t: packed M1(t), M2(t)^T; diss_packed (J, npad*kpad) or None."""
+    B = rho.shape[0]
+    J = 0 if diss_packed is None else diss_packed.shape[0]
+    if out is None:
+        out = torch.empty_like(rho)
+    _check(lib().qdb_lindblad_rhs_c128(n, J, B, _ptr(m1_packed, C, "m1"), _ptr(m2t_packed, C, "m2t"), _ptr(diss_packed, C, "diss"),
+                                       _ptr(gamma, F, "gamma"), _ptr(mu, F, "mu"), float(t), _ptr(rho, C, "rho_in"),
+                                       _ptr(out, C, "rho_out"), _stream()), "qdb_lindblad_rhs_c128")
+    return out
+
+
+def lindblad_rk4_steps(n, m1_table, m2t_table, diss_packed, gamma_table, mu, times_dev, h, rho, S):
+    """S fused RK4 steps in place on rho (B, n, n); tables (2S+1, npad*kpad) packed, gamma_table (2S+1, J) or None."""
+    B = rho.shape[0]
+    J = 0 if diss_packed is None else diss_packed.shape[0]
+    if m1_table.shape[0] < 2 * S + 1 or m2t_table.shape[0] < 2 * S + 1:
+        raise QdbError(f"lindblad_rk4_steps: tables have {m1_table.shape[0]} / {m2t_table.shape[0]} entries, need {2 * S + 1}")
+    _check(lib().qdb_lindblad_rk4_steps_c128(n, J, B, S, _ptr(m1_table, C, "m1_table"), _ptr(m2t_table, C, "m2t_table"),
+                                             _ptr(diss_packed, C, "diss"), _ptr(gamma_table, F, "gamma_table"), _ptr(mu, F, "mu"),
+                                             _ptr(times_dev, F, "times"), float(h), _ptr(rho, C, "rho"), _stream()),
+           "qdb_lindblad_rk4_steps_c128")
+    return rho
 
 
 def dmma_probe(iters: int = 20000, reps: int = 5) -> float:

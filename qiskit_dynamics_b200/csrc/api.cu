@@ -345,6 +345,39 @@ int qdb_outcome_probabilities_f64(int n, int B, int n_out, const qdb_c128* y, in
     return launch_outcome_probabilities(n, B, n_out, D2(y), ldy, outcome_of, normalize, out, (cudaStream_t)stream);
 }
 
+int qdb_lindblad_supported(int n) { return lindblad_fused_supported(n) ? 1 : 0; }
+
+int qdb_lindblad_rhs_c128(int n, int J, int B, const qdb_c128* m1_packed, const qdb_c128* m2t_packed, const qdb_c128* diss_packed,
+                          const double* gamma, const double* mu, double t, const qdb_c128* rho_in, qdb_c128* rho_out, void* stream) {
+    QDB_REQUIRE(n >= 1 && J >= 0 && B >= 0, "qdb_lindblad_rhs_c128: bad n=%d J=%d B=%d", n, J, B);
+    if (B == 0) return QDB_OK;
+    QDB_REQUIRE(m1_packed && m2t_packed && rho_in && rho_out, "qdb_lindblad_rhs_c128: null pointer");
+    QDB_REQUIRE(J == 0 || diss_packed, "qdb_lindblad_rhs_c128: J=%d but no dissipators", J);
+    QDB_REQUIRE(rho_in != rho_out, "qdb_lindblad_rhs_c128: rho_in and rho_out must not alias");
+    if (!lindblad_fused_supported(n)) {
+        set_error("qdb_lindblad_rhs_c128: on-chip path needs n <= 32 (got %d)", n);
+        return QDB_E_UNSUPPORTED;
+    }
+    return launch_lindblad_rhs(n, J, B, D2(m1_packed), D2(m2t_packed), D2(diss_packed), gamma, mu, t, D2(rho_in), D2(rho_out),
+                               (cudaStream_t)stream);
+}
+
+int qdb_lindblad_rk4_steps_c128(int n, int J, int B, int S, const qdb_c128* m1_table, const qdb_c128* m2t_table,
+                                const qdb_c128* diss_packed, const double* gamma_table, const double* mu, const double* times_dev,
+                                double h, qdb_c128* rho, void* stream) {
+    QDB_REQUIRE(n >= 1 && J >= 0 && B >= 0 && S >= 0, "qdb_lindblad_rk4_steps_c128: bad n=%d J=%d B=%d S=%d", n, J, B, S);
+    if (B == 0 || S == 0) return QDB_OK;
+    QDB_REQUIRE(m1_table && m2t_table && rho, "qdb_lindblad_rk4_steps_c128: null pointer");
+    QDB_REQUIRE(J == 0 || diss_packed, "qdb_lindblad_rk4_steps_c128: J=%d but no dissipators", J);
+    QDB_REQUIRE(!mu || times_dev, "qdb_lindblad_rk4_steps_c128: frame given without stage times");
+    if (!lindblad_fused_supported(n)) {
+        set_error("qdb_lindblad_rk4_steps_c128: on-chip path needs n <= 32 (got %d)", n);
+        return QDB_E_UNSUPPORTED;
+    }
+    return launch_lindblad_rk4(n, J, B, S, D2(m1_table), D2(m2t_table), D2(diss_packed), gamma_table, mu, times_dev, h, D2(rho),
+                               (cudaStream_t)stream);
+}
+
 int qdb_rk4_tiling(int n, int B, int sweep_K, int* out) {
     QDB_REQUIRE(out && n >= 1 && B >= 1, "qdb_rk4_tiling: bad arguments");
     if (!rk4_fused_tiling(n, B, sweep_K, out)) {

@@ -149,6 +149,13 @@ bool rk4_sweep_small_supported(int n, int K, bool has_static);
 int launch_rk4_sweep_small(int n, int K, int B, int S, const double2* stat, const double2* ops, const double* coeff,
                            int ldc, const double* mu, const double* times, double h, double2* y, int ldy,
                            cudaStream_t st);
+// non-vectorised Lindblad on (B, n, n) batches (lindblad.cu), n <= 32
+bool lindblad_fused_supported(int n);
+int launch_lindblad_rhs(int n, int J, int B, const double2* m1, const double2* m2t, const double2* diss, const double* gam,
+                        const double* mu, double t, const double2* rho_in, double2* rho_out, cudaStream_t st);
+int launch_lindblad_rk4(int n, int J, int B, int S, const double2* m1_table, const double2* m2t_table, const double2* diss,
+                        const double* gam_table, const double* mu, const double* times_dev, double h, double2* rho,
+                        cudaStream_t st);
 int launch_axpby(size_t count, double2* dst, const double2* x, double a, const double2* y, double b,
                  cudaStream_t st);
 }  // namespace qdb

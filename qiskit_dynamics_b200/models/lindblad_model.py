@@ -170,6 +170,14 @@ class LindbladModel(BaseGeneratorModel):
             return None
         return np.ascontiguousarray(np.concatenate(parts, axis=-1))
 
+    def _signal_table_parts(self, times: np.ndarray):
+        """(Hamiltonian signal table (T, Kh) or None, dissipator signal table (T, Kd) or None) on a time grid."""
+        self._require_signals()
+        c = self._operator_collection
+        ham = None if c.hamiltonian_operators is None else np.ascontiguousarray(self._hamiltonian_signals.table(times))
+        dis = None if c.dissipator_operators is None else np.ascontiguousarray(self._dissipator_signals.table(times))
+        return ham, dis
+
     def _require_signals(self):
         if self._hamiltonian_signals is None and self._operator_collection.hamiltonian_operators is not None:
             raise QiskitError(

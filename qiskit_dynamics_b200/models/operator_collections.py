@@ -292,21 +292,111 @@ class LindbladCollection:
         l, n, _ = rho.shape
         return _abi.zgemm(rho.reshape(l * n, n).contiguous(), X).reshape(l, n, n)
 
+    # -- device operands of the fused kernels (csrc/lindblad.cu) --------------------------------------
+    @property
+    def dim(self) -> int:
+        for ops in (self._static_hamiltonian, self._hamiltonian_operators, self._static_dissipators, self._dissipator_operators):
+            if ops is not None:
+                return int(ops.shape[-1])
+        raise QiskitError("empty LindbladCollection")
+
+    def fused_operands(self):
+        """Operands of qdb_lindblad_*: rhs(X) = M1 X + X M2 + sum_j g_j L_j X L_j^dag with
+        M1 = stat1 + sum_k c_k ops1[k], M2^T = stat2t + sum_k c_k ops2t[k], c = [ham coefficients, dis coefficients],
+        ops1 = [-i H_k ; -1/2 L_k^dag L_k], ops2t = [(+i H_k)^T ; (-1/2 L_k^dag L_k)^T], and the dissipator stack
+        [static D_j ; L_k] with g = [1, ..., dis coefficients].  Everything QDB_LAYOUT_PACKED, built once."""
+        if getattr(self, "_fused", None) is None:
+            n = self.dim
+            dev = next(x for x in (self._static_hamiltonian, self._hamiltonian_operators, self._static_dissipators,
+                                   self._dissipator_operators) if x is not None).device
+            stat1 = torch.zeros((n, n), dtype=CDTYPE, device=dev)
+            stat2 = torch.zeros((n, n), dtype=CDTYPE, device=dev)
+            if self._static_hamiltonian is not None:
+                stat1 = stat1 - 1j * self._static_hamiltonian
+                stat2 = stat2 + 1j * self._static_hamiltonian
+            if self._static_product_sum is not None:
+                stat1 = stat1 + self._static_product_sum
+                stat2 = stat2 + self._static_product_sum
+            o1, o2 = [], []
+            if self._hamiltonian_operators is not None:
+                o1.append(-1j * self._hamiltonian_operators)
+                o2.append(1j * self._hamiltonian_operators)
+            if self._dissipator_operators is not None:
+                prods = self._dis_products.operators
+                o1.append(prods)
+                o2.append(prods)
+            ops1 = torch.cat(o1, dim=0).contiguous() if o1 else None
+            ops2t = torch.cat(o2, dim=0).transpose(-1, -2).contiguous() if o2 else None
+            diss = [x for x in (self._static_dissipators, self._dissipator_operators) if x is not None]
+            diss = torch.cat(diss, dim=0).contiguous() if diss else None
+            self._fused = dict(
+                stat1=_abi.pack_operators(stat1.unsqueeze(0).contiguous())[0],
+                stat2t=_abi.pack_operators(stat2.transpose(0, 1).contiguous().unsqueeze(0))[0],
+                ops1=None if ops1 is None else _abi.pack_operators(ops1),
+                ops2t=None if ops2t is None else _abi.pack_operators(ops2t),
+                diss=None if diss is None else _abi.pack_operators(diss),
+                n_static=0 if self._static_dissipators is None else int(self._static_dissipators.shape[0]),
+                n_ham=0 if self._hamiltonian_operators is None else int(self._hamiltonian_operators.shape[0]),
+                n_dis=0 if self._dissipator_operators is None else int(self._dissipator_operators.shape[0]))
+        return self._fused
+
+    def fused_tables(self, ham_table, dis_table, device):
+        """(M1 table, M2^T table, gamma table) on the device for T times; ham_table (T, Kh) / dis_table (T, Kd) are real
+        host arrays or device tensors (None when the collection has no such operators)."""
+        f = self.fused_operands()
+        parts = []
+        T = None
+        for tab, cnt in ((ham_table, f["n_ham"]), (dis_table, f["n_dis"])):
+            if cnt:
+                if tab is None:
+                    raise QiskitError("coefficients required for a collection with operators.")
+                t = asreal(tab, device).reshape(-1, cnt)
+                T = t.shape[0]
+                parts.append(t)
+        T = 1 if T is None else T
+        coeff = torch.cat(parts, dim=1).contiguous() if parts else None
+        n = self.dim
+        m1 = _abi.generator(n, f["ops1"], f["stat1"], coeff, None, None, layout=_abi.LAYOUT_PACKED)
+        m2t = _abi.generator(n, f["ops2t"], f["stat2t"], coeff, None, None, layout=_abi.LAYOUT_PACKED)
+        if coeff is None and T > 1:
+            m1, m2t = m1.expand(T, -1).contiguous(), m2t.expand(T, -1).contiguous()
+        gamma = None
+        if f["n_dis"]:
+            ones = torch.ones((T, f["n_static"]), dtype=RDTYPE, device=coeff.device)
+            gamma = torch.cat([ones, parts[-1]], dim=1).contiguous()
+        return m1, m2t, gamma
+
     def evaluate_rhs(self, ham_coefficients, dis_coefficients, y):
         y = asarray(y)
         single = y.ndim == 2
         rho = y.unsqueeze(0) if single else y
         rho = rho.contiguous()
+        has_ham = self._ham is not None
+        has_dis = self._static_dissipators is not None or self._dissipator_operators is not None
+        if not has_ham and not has_dis:
+            raise QiskitError(
+                "LindbladCollection with None for static_hamiltonian, hamiltonian_operators, "
+                "static_dissipators, and dissipator_operators, cannot evaluate rhs."
+            )
+        n = self.dim
+        if rho.ndim != 3 or tuple(rho.shape[-2:]) != (n, n):
+            raise QiskitError(f"state must be (n, n) or (l, n, n) with n = {n}, got {tuple(y.shape)}.")
+        if _abi.lindblad_supported(n):
+            # fused: two generator launches (M1, M2^T at this time) + ONE kernel for the whole batch; coefficients never
+            # come back to the host
+            f = self.fused_operands()
+            m1, m2t, gamma = self.fused_tables(ham_coefficients, dis_coefficients, rho.device)
+            out = _abi.lindblad_rhs(n, m1[0], m2t[0], f["diss"], None if gamma is None else gamma[0].contiguous(), None, 0.0, rho)
+            return out[0].contiguous() if single else out
+        return self._evaluate_rhs_gemm(ham_coefficients, dis_coefficients, rho, single)
+
+    def _evaluate_rhs_gemm(self, ham_coefficients, dis_coefficients, rho, single):
+        """n > 32: the same sum as a sequence of DMMA GEMMs with the batch folded into the free dimension."""
         B = None
         if self._ham is not None:
             B = -1j * self._ham.evaluate(ham_coefficients)
         has_dis = self._static_dissipators is not None or self._dissipator_operators is not None
         if not has_dis:
-            if B is None:
-                raise QiskitError(
-                    "LindbladCollection with None for static_hamiltonian, hamiltonian_operators, "
-                    "static_dissipators, and dissipator_operators, cannot evaluate rhs."
-                )
             out = self._left(B, rho) - self._right(rho, B)
             return out[0].contiguous() if single else out.contiguous()
         if self._dissipator_operators is None:
@@ -321,9 +411,9 @@ class LindbladCollection:
             for D, Dadj in zip(self._static_dissipators, self._static_adj):
                 out = out + self._left(D.contiguous(), self._right(rho, Dadj.contiguous()))
         if self._dissipator_operators is not None:
-            g = np.real(np.atleast_1d(np.asarray(_host(dis_coefficients))))
-            for gj, L, Ladj in zip(g, self._dissipator_operators, self._dis_adj):
-                out = out + float(gj) * self._left(L.contiguous(), self._right(rho, Ladj.contiguous()))
+            g = asreal(dis_coefficients, rho.device).reshape(-1)  # stays on the device: no host round trip
+            for j, (L, Ladj) in enumerate(zip(self._dissipator_operators, self._dis_adj)):
+                out = out + g[j] * self._left(L.contiguous(), self._right(rho, Ladj.contiguous()))
         return out[0].contiguous() if single else out.contiguous()
 
     def __call__(self, ham_coefficients, dis_coefficients, y=None):

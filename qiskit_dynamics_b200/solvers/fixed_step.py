@@ -20,7 +20,7 @@ import torch
 from scipy.integrate._ivp.ivp import OdeResult
 
 from .. import _abi
-from ..arrays import asarray, asreal
+from ..arrays import asarray, asreal, stage_to_device
 from ..exceptions import QiskitError
 
 EXPM_THETA = 0.7  # 1-norm radius of the degree-16 Taylor polynomial (csrc/expm.cu)
@@ -151,6 +151,42 @@ def rk4_model_solve(model, t_span, y0_fb: torch.Tensor, max_dt, t_eval=None,
                 ws = torch.empty(need, dtype=torch.uint8, device=y.device)
             _abi.rk4_steps(n, ops, stat, ops_p, stat_p, coeff, mu, times, float(h), y, S, per_col=False, workspace=ws)
         ys.append(y.reshape(shape).clone())
+    return trim_t_results(OdeResult(t=np.array(t_list), y=torch.stack(ys)), t_eval)
+
+
+def lindblad_rk4_model_solve(model, t_span, y0_fb: torch.Tensor, max_dt, t_eval=None, table_bytes: int = 1 << 28) -> OdeResult:
+    """RK4 on a NON-vectorised LindbladModel (dim <= 32), density matrices already in the frame basis: y0 (n, n) or a
+    batch (l, n, n).  Per integration interval (chunked so that the two generator tables stay below ``table_bytes``):
+    the signal values on the stage-time grid go up once, two qdb_generator_c128 launches build M1(t) = A + B and
+    M2(t)^T = (A - B)^T for every stage time, and ONE qdb_lindblad_rk4_steps_c128 launch runs the steps with every density
+    matrix resident on chip -- replacing the host loop of RK4_solver over LindbladModel.evaluate_rhs
+    (solvers/fixed_step_solvers.py:43-77, 441-454; models/lindblad_model.py:477-538)."""
+    coll = model._operator_collection
+    n = model.dim
+    single = y0_fb.ndim == 2
+    rho = (y0_fb.unsqueeze(0) if single else y0_fb).contiguous().clone()
+    if rho.ndim != 3 or tuple(rho.shape[-2:]) != (n, n):
+        raise QiskitError(f"y0 must be (n, n) or (l, n, n) with n = {n}.")
+    f = coll.fused_operands()
+    mu = model.rotating_frame.frame_freqs
+    t_list, h_list, n_list = get_fixed_step_sizes(t_span, t_eval, max_dt)
+    per_step = 2 * 2 * _abi.packed_elems(n) * 16
+    ys = [rho[0].clone() if single else rho.clone()]
+    for t0, h, S in zip(t_list, h_list, n_list):
+        S = int(S)
+        times = stage_time_grid(t0, h, S)
+        ham_tab, dis_tab = model._signal_table_parts(times)
+        chunk = max(1, min(S, int(table_bytes // per_step)))
+        for s0 in range(0, S, chunk):
+            Sc = min(chunk, S - s0)
+            sl = slice(2 * s0, 2 * (s0 + Sc) + 1)
+            m1, m2t, gamma = coll.fused_tables(None if ham_tab is None else ham_tab[sl], None if dis_tab is None else dis_tab[sl],
+                                               rho.device)
+            if m1.shape[0] == 1:  # no time-dependent operator at all: one entry serves every stage
+                m1, m2t = m1.expand(2 * Sc + 1, -1).contiguous(), m2t.expand(2 * Sc + 1, -1).contiguous()
+            times_dev = None if mu is None else stage_to_device(times[sl], rho.device)
+            _abi.lindblad_rk4_steps(n, m1, m2t, f["diss"], gamma, mu, times_dev, float(h), rho, Sc)
+        ys.append(rho[0].clone() if single else rho.clone())
     return trim_t_results(OdeResult(t=np.array(t_list), y=torch.stack(ys)), t_eval)
 
 

@@ -21,7 +21,8 @@ from .. import _abi
 from ..arrays import asarray, wait_pending_copies
 from ..exceptions import QiskitError
 from ..models import BaseGeneratorModel, GeneratorModel, LindbladModel
-from .fixed_step import RK4_solver, expm_model_solve, parallel_model_solve, rk4_model_solve, scipy_expm_solver
+from .fixed_step import (RK4_solver, expm_model_solve, lindblad_rk4_model_solve, parallel_model_solve, rk4_model_solve,
+                         scipy_expm_solver)
 
 ODE_METHODS = ["RK4", "jax_RK4"]
 LMDE_METHODS = ["scipy_expm", "jax_expm", "expm", "jax_RK4_parallel", "jax_expm_parallel"]
@@ -100,7 +101,10 @@ def solve_ode(rhs: Union[Callable, BaseGeneratorModel], t_span, y0, method="RK4"
     try:
         if _has_linear_generator(rhs):
             results = rk4_model_solve(rhs, t_span, y0_fb, t_eval=t_eval, **kwargs)
-        else:  # non-vectorised Lindblad: host-driven RK4 over the GEMM-based collection
+        elif is_lindblad_model_not_vectorized(rhs) and _abi.lindblad_supported(rhs.dim) and y0_fb.ndim in (2, 3):
+            # non-vectorised Lindblad, dim <= 32: step loop on the device, density matrices resident on chip
+            results = lindblad_rk4_model_solve(rhs, t_span, y0_fb, t_eval=t_eval, **kwargs)
+        else:  # larger non-vectorised Lindblad systems: host-driven RK4 over the GEMM-based collection
             results = RK4_solver(solver_rhs, t_span, y0_fb, t_eval=t_eval, **kwargs)
         if not was_in_frame_basis:
             results.y = results_y_out_of_frame_basis(rhs, results.y, y0.ndim)

@@ -472,6 +472,28 @@ def gen_fullsize():
     out["cfg3_cols"] = cols
     out["cfg3_check"] = checksum(H0, Hs, Ls, Y)
     out["cfg3_y"] = solve_lmde(mv, t_span=[0, 0.2], y0=Y[:, cols], method="scipy_expm", max_dt=1e-2).y[-1]
+    # row f2 at the cfg3 system: NON-vectorised LindbladModel, RK4 (max_dt = 1e-3, 20 steps) on 8 of the 4096 density
+    # matrices as a (l, n, n) batch -- batch = leading axis (models/operator_collections.py:506-510)
+    colsm = cols[:8]
+    n3 = H0.shape[0]
+    rho = np.array([Y[:, b].reshape(n3, n3, order="F") for b in colsm])
+    mm = LindbladModel(static_hamiltonian=H0, hamiltonian_operators=Hs, hamiltonian_signals=sigs(sig),
+                       static_dissipators=Ls, rotating_frame=np.diag(H0).real, vectorized=False)
+    out["cfg3_mat_cols"] = colsm
+    out["cfg3_mat_rk4_y"] = solve_lmde(mm, t_span=[0, 0.02], y0=rho, method="RK4", max_dt=1e-3).y[-1]
+    out["cfg3_mat_rhs"] = mm(0.013, rho)
+    # time-dependent dissipators + full (non-diagonal) frame at dim 20, batch of 5
+    H20, Hs20, Ls20, Y20, sig20 = orc.synthetic_lindblad(20, 2, 5, 5, 2020)
+    Lst20, Ldy20 = Ls20[:2], Ls20[2:] * (1 + 0.3j)
+    dsig20 = [(0.7, 0.0, 0.0), (0.4, 0.31, 0.2), (0.9, 0.05, -0.4)]
+    rho20 = np.array([Y20[:, b].reshape(20, 20, order="F") for b in range(5)])
+    m20 = LindbladModel(static_hamiltonian=H20, hamiltonian_operators=Hs20, hamiltonian_signals=sigs(sig20),
+                        static_dissipators=Lst20, dissipator_operators=Ldy20, dissipator_signals=sigs(dsig20),
+                        rotating_frame=H20, vectorized=False)
+    out["l20_check"] = checksum(H20, Hs20, Ls20, Y20)
+    out["l20_rk4_y"] = solve_lmde(m20, t_span=[0, 0.1], y0=rho20, method="RK4", max_dt=2e-3).y[-1]
+    out["l20_rk4_single_y"] = solve_lmde(m20, t_span=[0, 0.1], y0=rho20[1], method="RK4", max_dt=2e-3).y[-1]
+    out["l20_rhs"] = m20(0.37, rho20)
     # cfg5-like: 32 of 8192 sweep points, DiscreteSignal Gaussian-square tables, max_dt = sample width (every stage
     # time on a bin edge), 64 RK4 steps; final states and the memory-slot probabilities of the reference's
     # post-processing chain (backend_utils)
@@ -503,6 +525,23 @@ def gen_fullsize():
     out["cfg5_y"] = finals
     out["cfg5_labels"] = np.array(labels)
     out["cfg5_probs"] = np.array([[d.get(lab, 0.0) for d in dicts] for lab in labels])
+    # the same system swept over 65 536 points (BASELINE configs[4] at size; bench.py's cfg5 record): 8 points
+    nbig = 65536
+    pts = np.array([0, 1, 4097, 8191, nbig // 3, nbig // 2, nbig - 9, nbig - 1])
+    lists = [[DiscreteSignal(dt=W.CFG5_DT, samples=smp, carrier_freq=float(freqs[j]), phase=ph)
+              for j, (smp, ph) in enumerate(W.cfg5_point(int(k), nbig, nsamp))] for k in pts]
+    res = s.solve(t_span=[0, tf], y0=y0, signals=lists, method="RK4", max_dt=W.CFG5_DT)
+    dicts = []
+    for r in res:
+        yf = np.array(s.model.rotating_frame.state_out_of_frame(t=tf, y=r.y[-1]))
+        yf = dressed.conj().T @ yf
+        yf = yf / np.linalg.norm(yf)
+        dicts.append(bu._get_memory_slot_probabilities(orc.subsystem_probabilities_dict(np.abs(yf) ** 2, dims, msub), mslots,
+                                                       max_outcome_value=1))
+    labels_big = sorted(set().union(*[d.keys() for d in dicts]))
+    out["cfg5_big_points"] = pts
+    out["cfg5_big_labels"] = np.array(labels_big)
+    out["cfg5_big_probs"] = np.array([[d.get(lab, 0.0) for d in dicts] for lab in labels_big])
     save("fullsize", **out)
 
 

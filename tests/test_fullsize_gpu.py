@@ -154,3 +154,72 @@ def test_long_interval_exceeds_grid_y(qd):
     res = qd.solve_lmde(model, t_span=span2, y0=Y, method="scipy_expm", max_dt=dt2)
     _, ye = orc.solve_hamiltonian(H0, Hs, fc.specs(sig), H0, span2, Y, dt2, method="scipy_expm")
     assert max_col_l2(res.y[-1].cpu().numpy(), ye[-1]) < 1e-9
+
+
+# ---------------------------------------------------------------------------------------------
+# row f2: non-vectorised Lindblad on (l, n, n) batches -- qdb_lindblad_rhs_c128 / qdb_lindblad_rk4_steps_c128
+# ---------------------------------------------------------------------------------------------
+
+
+def _cfg3_models(qd, vectorized):
+    H0, Hs, Ls, Y, sig = W.cfg3()
+    model = qd.LindbladModel(static_hamiltonian=H0, hamiltonian_operators=Hs,
+                             hamiltonian_signals=[qd.Signal(a, nu, ph) for a, nu, ph in sig], static_dissipators=Ls,
+                             rotating_frame=np.diag(H0).real, vectorized=vectorized)
+    return model, Y
+
+
+def test_lindblad_matrix_form_full_batch(qd):
+    """cfg3's system in NON-vectorised form: 4096 density matrices as a (4096, 27, 27) batch, RK4 max_dt = 1e-3, 20 steps,
+    in ONE fused launch per interval -- against the unmodified reference (8 matrices) and against the vectorised path
+    (729 x 4096 columns through the Schrodinger-shaped kernels) on the whole batch."""
+    g = load_golden("fullsize")
+    mm, Y = _cfg3_models(qd, False)
+    n, B = 27, Y.shape[1]
+    rho = np.ascontiguousarray(Y.T.reshape(B, n, n).transpose(0, 2, 1))  # vec_F(rho)[i + k n] = rho[i, k]
+    assert qd._abi.lindblad_supported(n)
+    before = qd._abi.launch_count()
+    res = qd.solve_lmde(mm, t_span=[0, 0.02], y0=rho, method="RK4", max_dt=1e-3)
+    launches = qd._abi.launch_count() - before
+    assert res.y.shape == (2, B, n, n) and launches <= 6, launches  # 2 generator tables + 1 fused RK4 launch (+ set-up)
+    cols = g["cfg3_mat_cols"]
+    got = res.y[-1][torch.from_numpy(cols).to(res.y.device)].cpu().numpy()
+    assert np.max(np.linalg.norm((got - g["cfg3_mat_rk4_y"]).reshape(len(cols), -1), axis=1)) < TOL
+    # the whole batch against the vectorised model (same equation, O(n^4) form)
+    mv, _ = _cfg3_models(qd, True)
+    resv = qd.solve_lmde(mv, t_span=[0, 0.02], y0=Y, method="RK4", max_dt=1e-3)
+    vec = res.y[-1].permute(2, 1, 0).reshape(n * n, B)  # rho[b, i, k] -> row i + k n, column b
+    assert float(torch.linalg.vector_norm(vec - resv.y[-1], dim=0).max()) < TOL
+    # one RHS evaluation of the whole batch
+    rhs = mm(0.013, rho)
+    assert np.max(np.abs(rhs[torch.from_numpy(cols).to(rhs.device)].cpu().numpy() - g["cfg3_mat_rhs"])) < TOL
+    # trace and Hermiticity are preserved
+    tr = torch.diagonal(res.y[-1], dim1=-2, dim2=-1).sum(-1)
+    assert float((tr - 1).abs().max()) < 1e-12
+    assert float((res.y[-1] - res.y[-1].transpose(-1, -2).conj()).abs().max()) < 1e-12
+
+
+def test_lindblad_matrix_form_dynamic_dissipators_full_frame(qd):
+    """dim 20, 2 static + 3 time-dependent dissipators with complex entries, full rotating frame, (l, n, n) batch and a
+    single (n, n) matrix, against the unmodified reference."""
+    from oracle import numpy_oracle as orc
+    g = load_golden("fullsize")
+    H, Hs, Ls, Y, sig = orc.synthetic_lindblad(20, 2, 5, 5, 2020)
+    Lst, Ldy = Ls[:2], Ls[2:] * (1 + 0.3j)
+    dsig = [(0.7, 0.0, 0.0), (0.4, 0.31, 0.2), (0.9, 0.05, -0.4)]
+    rho = np.array([Y[:, b].reshape(20, 20, order="F") for b in range(5)])
+    m = qd.LindbladModel(static_hamiltonian=H, hamiltonian_operators=Hs, hamiltonian_signals=[qd.Signal(*s) for s in sig],
+                         static_dissipators=Lst, dissipator_operators=Ldy, dissipator_signals=[qd.Signal(*s) for s in dsig],
+                         rotating_frame=H, vectorized=False)
+    res = qd.solve_lmde(m, t_span=[0, 0.1], y0=rho, method="RK4", max_dt=2e-3)
+    assert np.max(np.abs(res.y[-1].cpu().numpy() - g["l20_rk4_y"])) < TOL
+    res1 = qd.solve_lmde(m, t_span=[0, 0.1], y0=rho[1], method="RK4", max_dt=2e-3)
+    assert res1.y.shape == (2, 20, 20)
+    assert np.max(np.abs(res1.y[-1].cpu().numpy() - g["l20_rk4_single_y"])) < TOL
+    assert np.max(np.abs(m(0.37, rho).cpu().numpy() - g["l20_rhs"])) < TOL
+    # t_eval and backwards integration go through the same fused route
+    r2 = qd.solve_lmde(m, t_span=[0, 0.1], y0=rho, method="RK4", max_dt=2e-3, t_eval=[0.0, 0.05, 0.1])
+    assert r2.y.shape == (3, 5, 20, 20)
+    assert np.max(np.abs(r2.y[-1].cpu().numpy() - g["l20_rk4_y"])) < TOL
+    back = qd.solve_lmde(m, t_span=[0.1, 0.0], y0=res.y[-1], method="RK4", max_dt=2e-3)
+    assert float((back.y[-1] - qd.asarray(rho)).abs().max()) < 1e-7  # RK4 is not exactly reversible
