@@ -244,6 +244,23 @@ class LindbladModel(BaseGeneratorModel):
             return restore(out)
         # non-vectorised: rho (n,n) or (l,n,n)
         rho = asarray(y)
+        coll = self._operator_collection
+        n = self.dim
+        if _abi.lindblad_supported(n) and rho.ndim in (2, 3) and tuple(rho.shape[-2:]) == (n, n):
+            # one fused launch for the whole batch: frame phases, both one-sided products and every dissipator term
+            # (qdb_lindblad_rhs_c128); M1(t), M2(t)^T come from two generator launches, coefficients stay on the device
+            single = rho.ndim == 2
+            r3 = (rho.unsqueeze(0) if single else rho).contiguous()
+            change_basis = (not self._in_frame_basis) and rf.frame_basis is not None
+            if change_basis:  # U^dag rho U through the DMMA GEMM (batch folded into the free dimension)
+                r3 = coll._left(rf.frame_basis_adjoint.contiguous(), coll._right(r3, rf.frame_basis.contiguous())).contiguous()
+            f = coll.fused_operands()
+            m1, m2t, gamma = coll.fused_tables(h, d, r3.device)
+            out = _abi.lindblad_rhs(n, m1[0], m2t[0], f["diss"], None if gamma is None else gamma[0].contiguous(),
+                                    rf.frame_freqs, float(time), r3)
+            if change_basis:
+                out = coll._left(rf.frame_basis.contiguous(), coll._right(out, rf.frame_basis_adjoint.contiguous())).contiguous()
+            return out[0].contiguous() if single else out
         if rf.frame_diag is not None:
             rho = rf.operator_out_of_frame(time, rho, operator_in_frame_basis=self._in_frame_basis,
                                            return_in_frame_basis=True)

@@ -169,7 +169,11 @@ class RotatingFrame:
         if op.ndim == 2:
             times = torch.tensor([t], dtype=torch.float64, device=op.device)
             return _abi.generator(n, None, op.contiguous(), None, self._mu, times).reshape(n, n)
-        return torch.stack([self._phase_operator(t, o) for o in op])
+        # a stack of operators: one broadcast multiply with the (n, n) phase matrix (set-up / API glue; the solvers and
+        # LindbladModel.evaluate_rhs apply these phases inside their kernels and never come here)
+        ang = self._mu * float(t)
+        e = torch.complex(torch.cos(ang), -torch.sin(ang))  # exp(-i mu t) = exp(frame_diag t)
+        return (op * (e.conj()[:, None] * e[None, :])).contiguous()
 
     def _conjugate_and_add(self, t, operator, op_to_add_in_fb=None, operator_in_frame_basis=False,
                            return_in_frame_basis=False, vectorized_operators=False):
