@@ -87,7 +87,9 @@ size_t qdb_workspace_bytes(int kind, int n, int K, int B, int S) {
                                      (rk4_sweepf_supported(n, K) ? align_up(rk4_sweepf_workspace_bytes(n, K)) : 0);
                 return shared > sweep ? shared : sweep;
             }
-            return 3 * align_up(n2) + 3 * align_up(yb) + align_up(3 * sizeof(double));
+            // generic path: three generators + three state buffers (shared signals), or four state buffers + two phase
+            // vectors (per-column signals: one GEMM per operator and stage with the column scale in its epilogue)
+            return 3 * align_up(n2) + 4 * align_up(yb) + 2 * align_up((size_t)n * sizeof(double2)) + align_up(3 * sizeof(double));
         case QDB_WS_EXPM: {
             // S = 1: one step at a time.  S > 1: room to build the propagators of up to S steps side by side (batched
             // Taylor exponentials) before they are applied one after the other -- capped at 1 GiB of matrices
@@ -268,16 +270,56 @@ int qdb_rk4_steps_c128(int n, int K, int B, int S, const qdb_c128* ops_rm, const
         return QDB_OK;
     }
 
-    // ---- generic path for large n: one GEMM per stage with the RK4 combine fused in its epilogue ----
-    if (sig_mode == 1) {
-        set_error("qdb_rk4_steps_c128: per-column signals need n <= 256 (got %d)", n);
-        return QDB_E_UNSUPPORTED;
-    }
+    // ---- generic path for large n ----
     QDB_REQUIRE(stat_rm || (ops_rm && K > 0), "qdb_rk4_steps_c128: row-major operators missing");
     QDB_REQUIRE(ldy == B, "qdb_rk4_steps_c128: generic path needs ldy == B");
     if (ws_bytes < qdb_workspace_bytes(QDB_WS_RK4, n, K, B, 1)) {
         set_error("qdb_rk4_steps_c128: workspace too small (%zu < %zu)", ws_bytes, qdb_workspace_bytes(QDB_WS_RK4, n, K, B, 1));
         return QDB_E_WORKSPACE;
+    }
+    if (sig_mode == 1) {
+        // per-column signals, n > 256 (vectorised Lindblad sweeps): sum_j G_j (c_jb y_b) -- one DMMA GEMM per operator and
+        // stage, the column's signal value as the GEMM's column scale, the frame phases as its pre / post vectors, accumulated
+        // in k; then the RK4 combine.  Same arithmetic as rk4_sweep_kernel, operands in HBM instead of on chip.
+        QDB_REQUIRE(ldc >= B, "qdb_rk4_steps_c128: ldc < B");
+        const size_t ybs = align_up((size_t)n * B * sizeof(double2)), pv = align_up((size_t)n * sizeof(double2));
+        double2* kbuf = (double2*)ws;
+        double2* ya = (double2*)(ws + ybs);
+        double2* yb2 = (double2*)(ws + 2 * ybs);
+        double2* acc = (double2*)(ws + 3 * ybs);
+        double2* pre = (double2*)(ws + 4 * ybs);
+        double2* post = (double2*)(ws + 4 * ybs + pv);
+        const double2 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0);
+        const size_t nn = (size_t)n * n, cnt = (size_t)n * B;
+        double2* Y = D2(y);
+        auto stage = [&](int entry, const double2* yin, double2* yout, double a_next, double w, int first) -> int {
+            const double2 *prep = nullptr, *postp = nullptr;
+            if (mu) {
+                if ((rc = launch_phase_vectors(n, mu, times_host[entry], pre, post, st)) != QDB_OK) return rc;
+                prep = pre;
+                postp = post;
+            }
+            bool started = false;
+            if (stat_rm) {
+                if ((rc = launch_zgemm(n, B, n, D2(stat_rm), n, yin, ldy, kbuf, ldy, one, zero, nullptr, prep, postp, st)) != QDB_OK) return rc;
+                started = true;
+            }
+            for (int j = 0; j < K; ++j) {
+                rc = launch_zgemm(n, B, n, D2(ops_rm) + (size_t)j * nn, n, yin, ldy, kbuf, ldy, one, started ? one : zero,
+                                  coeff + ((size_t)entry * K + j) * ldc, prep, postp, st);
+                if (rc != QDB_OK) return rc;
+                started = true;
+            }
+            return launch_rk4_combine(cnt, Y, kbuf, yout, acc, a_next, w, first, st);
+        };
+        for (int s = 0; s < S; ++s) {
+            if ((rc = stage(2 * s, Y, ya, 0.5 * h, 1.0, 1)) != QDB_OK) return rc;
+            if ((rc = stage(2 * s + 1, ya, yb2, 0.5 * h, 2.0, 0)) != QDB_OK) return rc;
+            if ((rc = stage(2 * s + 1, yb2, ya, h, 2.0, 0)) != QDB_OK) return rc;
+            if ((rc = stage(2 * s + 2, ya, yb2, 0.0, 1.0, 0)) != QDB_OK) return rc;
+            if ((rc = launch_axpby(cnt, Y, acc, (1.0 / 6) * h, Y, 1.0, st)) != QDB_OK) return rc;
+        }
+        return QDB_OK;
     }
     const size_t n2 = align_up((size_t)n * n * sizeof(double2));
     const size_t yb = align_up((size_t)n * B * sizeof(double2));

@@ -168,6 +168,28 @@ __global__ void axpby_kernel(size_t count, double2* dst, const double2* x, doubl
     dst[i] = v;
 }
 
+// RK4 stage combine after a multi-launch stage product k (generic large-n sweep path):
+//   yout = ybase + a_next * k ;  acc = (first ? 0 : acc) + w * k
+__global__ void rk4_combine_kernel(size_t count, const double2* __restrict__ ybase, const double2* __restrict__ k,
+                                   double2* __restrict__ yout, double2* __restrict__ acc, double a_next, double w, int first) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const double2 kv = k[i], yb = ybase[i];
+    yout[i] = make_double2(fma(a_next, kv.x, yb.x), fma(a_next, kv.y, yb.y));
+    double2 a = first ? make_double2(0.0, 0.0) : acc[i];
+    a.x = fma(w, kv.x, a.x);
+    a.y = fma(w, kv.y, a.y);
+    acc[i] = a;
+}
+
+int launch_rk4_combine(size_t count, const double2* ybase, const double2* k, double2* yout, double2* acc, double a_next,
+                       double w, int first, cudaStream_t st) {
+    if (count == 0) return QDB_OK;
+    rk4_combine_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(count, ybase, k, yout, acc, a_next, w, first);
+    QDB_LAUNCH_CHECK("rk4_combine_kernel");
+    return QDB_OK;
+}
+
 int launch_axpby(size_t count, double2* dst, const double2* x, double a, const double2* y, double b, cudaStream_t st) {
     if (count == 0) return QDB_OK;
     axpby_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(count, dst, x, a, y, b);

@@ -156,6 +156,8 @@ int launch_lindblad_rhs(int n, int J, int B, const double2* m1, const double2* m
 int launch_lindblad_rk4(int n, int J, int B, int S, const double2* m1_table, const double2* m2t_table, const double2* diss,
                         const double* gam_table, const double* mu, const double* times_dev, double h, double2* rho,
                         cudaStream_t st);
+int launch_rk4_combine(size_t count, const double2* ybase, const double2* k, double2* yout, double2* acc, double a_next,
+                       double w, int first, cudaStream_t st);
 int launch_axpby(size_t count, double2* dst, const double2* x, double a, const double2* y, double b,
                  cudaStream_t st);
 }  // namespace qdb

@@ -89,17 +89,22 @@ class Solver:
         return out
 
     def _solve_batched(self, t_span_list, y0_list, signals_list, **kwargs) -> Optional[List[OdeResult]]:
-        """One sweep-mode launch for a list of simulations, when they qualify; else None."""
+        """The list-of-simulations loop of the reference (solvers/solver_classes.py:556-590) as batched launches, when the
+        simulations qualify; else None (the caller then runs the sequential loop).
+
+        * ONE signal specification shared by all simulations (a list of initial states): the states become the columns
+          (vectors or matrices, concatenated) of one shared-signal solve -- any method and any keyword ``solve_lmde``
+          accepts (RK4, scipy_expm with magnus_order, the time-parallel solvers); density matrices of a non-vectorised
+          LindbladModel become one (l, n, n) batch.
+        * per-simulation signals with RK4 on a Hamiltonian or vectorised Lindblad model: every simulation is a group of
+          state columns with its own signal values (sweep mode), one launch per chunk of steps, at any dimension.
+        """
         nsim = len(signals_list)
         model = self.model
-        if nsim < 2 or kwargs.get("method", None) not in ODE_METHODS or "max_dt" not in kwargs:
+        method = kwargs.get("method", None)
+        if nsim < 2 or "max_dt" not in kwargs:
             return None
-        if not (isinstance(model, HamiltonianModel) or is_lindblad_model_vectorized(model)):
-            return None
-        if any(s is None for s in signals_list) or model._collection().num_operators == 0:
-            return None
-        if model._collection().dim > 256:
-            return None
+        linear = isinstance(model, HamiltonianModel) or is_lindblad_model_vectorized(model)
         spans = np.asarray(t_span_list, dtype=float)
         if not np.all(spans == spans[0]):
             return None
@@ -112,13 +117,40 @@ class Solver:
             if key not in converted:
                 converted[key] = validate_and_format_initial_state(y, model)
             y0s.append(converted[key])
-        if any(y.ndim != 1 for y in converted.values()):
+        shapes = {tuple(y.shape) for y in converted.values()}
+        if len(shapes) != 1:
+            return None
+        shape = next(iter(shapes))
+
+        # ---- one signal specification, many initial states: a state ensemble on the shared-signal kernels ----
+        if all(sg is signals_list[0] for sg in signals_list):
+            if linear and len(shape) in (1, 2):
+                m = 1 if len(shape) == 1 else shape[1]
+                Y0 = (torch.stack(y0s, dim=1) if len(shape) == 1 else torch.cat(y0s, dim=1)).contiguous()  # (n, nsim * m)
+                self._set_new_signals(signals_list[0])
+                res = solve_lmde(generator=model, t_span=spans[0], y0=Y0, **kwargs)
+                per_sim = res.y.reshape(res.y.shape[0], res.y.shape[1], nsim, m).permute(2, 0, 1, 3).contiguous()
+                if len(shape) == 1:
+                    per_sim = per_sim[..., 0]
+                return [OdeResult(t=res.t, y=per_sim[b]) for b in range(nsim)]
+            if is_lindblad_model_not_vectorized(model) and len(shape) == 2 and method in ODE_METHODS:
+                self._set_new_signals(signals_list[0])
+                res = solve_lmde(generator=model, t_span=spans[0], y0=torch.stack(y0s, dim=0).contiguous(), **kwargs)
+                per_sim = res.y.transpose(0, 1).contiguous()  # (nsim, T, n, n)
+                return [OdeResult(t=res.t, y=per_sim[b]) for b in range(nsim)]
+            return None
+
+        # ---- per-simulation signals: sweep mode (RK4) ----
+        if method not in ODE_METHODS or not linear or len(shape) not in (1, 2):
+            return None
+        if any(sg is None for sg in signals_list) or model._collection().num_operators == 0:
             return None
         t_eval = kwargs.get("t_eval", None)
         max_dt = kwargs["max_dt"]
         extra = {k: v for k, v in kwargs.items() if k not in ("method", "max_dt", "t_eval")}
         if extra:
             return None
+        mcols = 1 if len(shape) == 1 else shape[1]  # state columns per simulation
 
         # device route (row f3): when every term of every simulation is a sampled or constant-envelope signal
         # and the simulations share their structure, one kernel builds the (T, K, B) table in HBM.
@@ -147,7 +179,8 @@ class Solver:
 
         def column_coefficients(times: np.ndarray):
             if program is not None:
-                return program.table(times, Y0.device)
+                table = program.table(times, Y0.device)
+                return table if mcols == 1 else table.repeat_interleave(mcols, dim=-1)
             cols = []
             for sl in sig_lists:
                 if isinstance(model, LindbladModel):
@@ -155,9 +188,12 @@ class Solver:
                     cols.append(np.concatenate(parts, axis=-1))
                 else:
                     cols.append(sl.table(times))
-            return np.stack(cols, axis=-1)  # (T, K, B)
+            table = np.stack(cols, axis=-1)  # (T, K, B)
+            return table if mcols == 1 else np.repeat(table, mcols, axis=-1)
 
-        if len(converted) == 1:
+        if len(shape) == 2:
+            Y0 = torch.cat(y0s, dim=1).contiguous()  # (n, nsim * m): the columns of simulation b are b m .. b m + m - 1
+        elif len(converted) == 1:
             Y0 = y0s[0].reshape(-1, 1).expand(-1, nsim).contiguous()  # (n, B): the shared state in every column
         else:
             Y0 = torch.stack(y0s, dim=1).contiguous()  # (n, B): one column per simulation
@@ -168,7 +204,10 @@ class Solver:
                 res.y = results_y_out_of_frame_basis(model, res.y, 2)
         finally:
             model.in_frame_basis = was
-        per_sim = res.y.permute(2, 0, 1).contiguous()  # one transpose; per_sim[b] is the contiguous (T, n) result of simulation b
+        if len(shape) == 2:
+            per_sim = res.y.reshape(res.y.shape[0], res.y.shape[1], nsim, mcols).permute(2, 0, 1, 3).contiguous()
+        else:
+            per_sim = res.y.permute(2, 0, 1).contiguous()  # one transpose; per_sim[b] is the contiguous (T, n) result of simulation b
         return [OdeResult(t=res.t, y=per_sim[b]) for b in range(nsim)]
 
 
