@@ -215,10 +215,16 @@ constexpr size_t T_BS = (size_t)BK * TBS_LD * sizeof(double);    //  8704
 constexpr size_t T_STAGE = T_AC + T_AS + T_BC + T_BS;            // 56320
 constexpr size_t T_SMEM = T_STAGES * T_STAGE;                    // 168960
 
-template <typename Epi>
+// SPLIT = 1: one CTA per 64 x 64 tile, 2-D grid (tiles with linear index >= tile_limit, when tile_limit > 0, are left to
+// the tail launch).  SPLIT = 2, 4, 8: the TAIL of a product whose tile count leaves the last wave mostly empty -- a cluster of
+// SPLIT CTAs shares one tile, each CTA multiplies 1 / SPLIT of the k range, the partial tiles are summed through
+// distributed shared memory in FIXED rank order (every CTA reduces its band of rows, reading the bands of the others), so
+// the result does not depend on scheduling.  729 x 4096 x 729: 768 tiles = 5 waves + 28 tiles; those 28 run as 28 x 4 CTAs.
+template <typename Epi, int SPLIT>
 __global__ void __launch_bounds__(256, 1) zgemm3m_kernel(int M, int N, int Kd, const double2* __restrict__ A0, int lda,
                                                           const double2* __restrict__ Bm0, int ldb,
-                                                          const double2* __restrict__ pre, Epi epi, BatchStride bs) {
+                                                          const double2* __restrict__ pre, Epi epi, BatchStride bs,
+                                                          int tile_limit, int tile0, int ntx) {
     const double2* __restrict__ A = A0 + (size_t)blockIdx.z * (size_t)bs.sA;
     const double2* __restrict__ Bm = Bm0 + (size_t)blockIdx.z * (size_t)bs.sB;
     epi.shift(blockIdx.z);
@@ -227,14 +233,28 @@ __global__ void __launch_bounds__(256, 1) zgemm3m_kernel(int M, int N, int Kd, c
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int wm = warp & 3, wn = warp >> 2;  // 4 x 2 warps
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int numK = (Kd + BK - 1) / BK;
+    int bx = blockIdx.x, by = blockIdx.y;
+    unsigned krank = 0;
+    if constexpr (SPLIT > 1) {
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(krank));
+        const int tile = tile0 + (int)(blockIdx.x / SPLIT);
+        by = tile / ntx;
+        bx = tile - by * ntx;
+    } else if (tile_limit > 0 && (int)(blockIdx.y * gridDim.x + blockIdx.x) >= tile_limit) {
+        return;
+    }
+    const int m0 = by * BM, n0 = bx * BN;
+    const int numK_all = (Kd + BK - 1) / BK;
+    // this CTA's share of the k chunks
+    const int kc0 = SPLIT > 1 ? (int)((long long)numK_all * krank / SPLIT) : 0;
+    const int kc1 = SPLIT > 1 ? (int)((long long)numK_all * (krank + 1) / SPLIT) : numK_all;
+    const int numK = kc1 - kc0;
 
     // staging map: A element (ar + 16 i, ac), B element (br + 4 i, bc), i < 4
     const int ar = tid >> 4, ac = tid & 15, br = tid >> 6, bc = tid & 63;
     double2 ra[4], rb[4], rp;
     auto gload = [&](int kt) {
-        const int k0 = kt * BK;
+        const int k0 = (kc0 + kt) * BK;
         const bool kok = k0 + ac < Kd;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -320,8 +340,10 @@ __global__ void __launch_bounds__(256, 1) zgemm3m_kernel(int M, int N, int Kd, c
     // so its first fragments can be fetched in the last k4-step of chunk kt, ahead of the barrier.  The barrier at
     // the end of iteration kt publishes chunk kt+2 (stored in the middle of the iteration, while DMMAs are queued)
     // and retires every read of stage kt % 3 before iteration kt+1 overwrites it with chunk kt+3.
-    gload(0);
-    sstore(0);
+    if (numK > 0) {
+        gload(0);
+        sstore(0);
+    }
     if (numK > 1) {
         gload(1);
         sstore(1);
@@ -329,7 +351,7 @@ __global__ void __launch_bounds__(256, 1) zgemm3m_kernel(int M, int N, int Kd, c
     if (numK > 2) gload(2);
     __syncthreads();
     Frags f0, f1;
-    load_frags(0, 0, f0);
+    if (numK > 0) load_frags(0, 0, f0);
     int slot = 0;
 #pragma unroll 1
     for (int kt = 0; kt < numK; ++kt) {
@@ -348,18 +370,52 @@ __global__ void __launch_bounds__(256, 1) zgemm3m_kernel(int M, int N, int Kd, c
         slot = nslot;
     }
 
+    if constexpr (SPLIT > 1) {
+        // partial tile of this k range -> own shared memory (the stage buffers are free now), [64][65] complex
+        constexpr int PLD = 65;
+        double2* part = reinterpret_cast<double2*>(smem_raw);
 #pragma unroll
-    for (int m = 0; m < 2; ++m) {
-        const int r = m0 + wm * 16 + m * 8 + g;
-        if (r >= M) continue;
+        for (int m = 0; m < 2; ++m)
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+            for (int c = 0; c < 4; ++c)
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int col = n0 + wn * 32 + c * 8 + 2 * q + i;
-                if (col < N)
-                    epilogue(epi, r, col, make_double2(p[0][m][c][i] - p[1][m][c][i], (p[2][m][c][i] - p[0][m][c][i]) - p[1][m][c][i]));
+                for (int i = 0; i < 2; ++i)
+                    part[(wm * 16 + m * 8 + g) * PLD + wn * 32 + c * 8 + 2 * q + i] =
+                        make_double2(p[0][m][c][i] - p[1][m][c][i], (p[2][m][c][i] - p[0][m][c][i]) - p[1][m][c][i]);
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        // rank r reduces rows [r * 64 / SPLIT, (r + 1) * 64 / SPLIT) over all ranks, in rank order
+        constexpr int ROWS = 64 / SPLIT;
+        const uint32_t base = (uint32_t)__cvta_generic_to_shared(part);
+        for (int e = tid; e < ROWS * 64; e += 256) {
+            const int rl = (int)krank * ROWS + e / 64, cl = e % 64;
+            double2 sum = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int rk = 0; rk < SPLIT; ++rk) {
+                uint32_t ra_;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra_) : "r"(base + (uint32_t)((rl * PLD + cl) * sizeof(double2))), "r"(rk));
+                double2 v;
+                asm volatile("ld.shared::cluster.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(ra_));
+                sum.x += v.x;
+                sum.y += v.y;
             }
+            const int r = m0 + rl, col = n0 + cl;
+            if (r < M && col < N) epilogue(epi, r, col, sum);
+        }
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    } else {
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const int r = m0 + wm * 16 + m * 8 + g;
+            if (r >= M) continue;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int col = n0 + wn * 32 + c * 8 + 2 * q + i;
+                    if (col < N)
+                        epilogue(epi, r, col, make_double2(p[0][m][c][i] - p[1][m][c][i], (p[2][m][c][i] - p[0][m][c][i]) - p[1][m][c][i]));
+                }
+        }
     }
 }
 
@@ -374,14 +430,61 @@ int launch_bn(int M, int N, int Kd, const double2* A, int lda, const double2* B,
     return QDB_OK;
 }
 
+template <typename Epi, int SPLIT>
+int launch_3m_tail(int M, int N, int Kd, const double2* A, int lda, const double2* B, int ldb, const double2* pre,
+                   const Epi& epi, BatchStride bs, int tile0, int tail, int ntx, cudaStream_t st) {
+    auto kern = zgemm3m_kernel<Epi, SPLIT>;
+    QDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM));
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(tail * SPLIT);
+    lc.blockDim = dim3(256);
+    lc.dynamicSmemBytes = T_SMEM;
+    lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = SPLIT;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    QDB_CUDA(cudaLaunchKernelEx(&lc, kern, M, N, Kd, A, lda, B, ldb, pre, epi, bs, 0, tile0, ntx));
+    QDB_LAUNCH_CHECK("zgemm3m_kernel<split>");
+    return QDB_OK;
+}
+
+// QDB_ZGEMM_NO_TAIL=1 switches the split-k tail off (the whole product on one-CTA-per-tile launches: the bit-level reference)
+bool zgemm_tail_enabled() {
+    const char* e = getenv("QDB_ZGEMM_NO_TAIL");
+    return !(e && e[0] == '1');
+}
+
 template <typename Epi>
 int launch_3m(int M, int N, int Kd, const double2* A, int lda, const double2* B, int ldb, const double2* pre,
               const Epi& epi, BatchStride bs, int count, cudaStream_t st) {
-    QDB_CUDA(cudaFuncSetAttribute(zgemm3m_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM));
-    dim3 grid((N + 63) / 64, (M + BM - 1) / BM, count);
-    zgemm3m_kernel<Epi><<<grid, 256, T_SMEM, st>>>(M, N, Kd, A, lda, B, ldb, pre, epi, bs);
+    QDB_CUDA(cudaFuncSetAttribute(zgemm3m_kernel<Epi, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM));
+    const int ntx = (N + 63) / 64, nty = (M + BM - 1) / BM;
+    dim3 grid(ntx, nty, count);
+    // Wave quantisation: with one CTA per SM a product of T tiles takes ceil(T / #SM) tile times.  When the last wave is
+    // less than half full, its tiles are split along k over clusters of 2 / 4 / 8 CTAs (deterministic reduction through
+    // DSMEM) so that it costs 1/2 .. 1/8 of a tile time instead of a whole one.
+    const int SMS = sm_count();
+    const int tiles = ntx * nty;
+    const int tail = tiles % SMS;
+    int split = 1;
+    if (count == 1 && tiles > SMS && tail > 0 && 2 * tail <= SMS && Kd >= 256 && zgemm_tail_enabled()) {
+        split = 2;
+        while (split < 8 && 2 * split * tail <= SMS) split *= 2;
+    }
+    if (split == 1) {
+        zgemm3m_kernel<Epi, 1><<<grid, 256, T_SMEM, st>>>(M, N, Kd, A, lda, B, ldb, pre, epi, bs, 0, 0, ntx);
+        QDB_LAUNCH_CHECK("zgemm3m_kernel");
+        return QDB_OK;
+    }
+    zgemm3m_kernel<Epi, 1><<<grid, 256, T_SMEM, st>>>(M, N, Kd, A, lda, B, ldb, pre, epi, bs, tiles - tail, 0, ntx);
     QDB_LAUNCH_CHECK("zgemm3m_kernel");
-    return QDB_OK;
+    if (split == 2) return launch_3m_tail<Epi, 2>(M, N, Kd, A, lda, B, ldb, pre, epi, bs, tiles - tail, tail, ntx, st);
+    if (split == 4) return launch_3m_tail<Epi, 4>(M, N, Kd, A, lda, B, ldb, pre, epi, bs, tiles - tail, tail, ntx, st);
+    return launch_3m_tail<Epi, 8>(M, N, Kd, A, lda, B, ldb, pre, epi, bs, tiles - tail, tail, ntx, st);
 }
 
 // QDB_ZGEMM_4M=1 pins the 4-product kernel (bit-level reference of the 3-product one in the tests)
