@@ -106,8 +106,8 @@ struct ColumnsInFlight {
     static constexpr int value = (MR * NCW <= 2) ? 4 : 2;  // cfg2 (one tile per warp): 15.8 / 10.4 / 11.6 us per step with 2 / 4 / 8
 };
 
-template <int MR, int NCW, int KS, bool KSPLIT>
-__global__ void __launch_bounds__(256, 1)
+template <int MR, int NCW, int KS, bool KSPLIT, int NTHR>
+__global__ void __launch_bounds__(NTHR, 1)
 rk4_sweepf_kernel(FGeo geo, int K, int B, int S, const double2* __restrict__ statf /*or null*/,
                   const double2* __restrict__ opsf, const double* __restrict__ coeff /*[2S+1][K][ldc]*/, int ldc,
                   const double* __restrict__ mu, const double* __restrict__ times /*[2S+1]*/, double h,
@@ -417,13 +417,17 @@ rk4_sweepf_kernel(FGeo geo, int K, int B, int S, const double2* __restrict__ sta
 struct FConfig {
     FGeo geo;
     int MR, NCW, KS, threads, grid;
+    double wave_cost;  // busiest SM of one wave, in column tiles of the reference tiling (see pick_sweepf)
     size_t smem;
 };
 
 constexpr size_t kSmemLimitF = 227 * 1024;
 
-bool pick_sweepf(int n, int B, int K, FConfig& cfg) {
-    if (n < 1 || round_up8(n) > 256 || K < 1 || K > 16) return false;
+// max_ctas > 0: only tilings whose grid fits that many CTAs (one wave); need_C2 > 0: only tilings that read the operator copy
+// packed for that column padding, without the warp-group split (the second launch of a wave-balanced pair, see
+// launch_rk4_sweepf)
+bool pick_sweepf(int n, int B, int K, FConfig& cfg, int max_ctas = 0, int need_C2 = 0) {
+    if (n < 1 || round_up8(n) > 256 || K < 1 || K > 16 || B < 1) return false;
     const int SMS = sm_count();
     FGeo geo;
     geo.n = n;
@@ -450,61 +454,83 @@ bool pick_sweepf(int n, int B, int K, FConfig& cfg) {
     }
     if (const char* force = getenv("QDB_FORCE_SWEEPF")) {  // "WR,WC,MR" (profiling only)
         int fwr, fwc, fmr;
-        if (sscanf(force, "%d,%d,%d", &fwr, &fwc, &fmr) == 3 && fwr * fmr >= geo.RT && fwr * fwc <= 8 && fmr >= 1 && fmr <= 4) {
+        if (sscanf(force, "%d,%d,%d", &fwr, &fwc, &fmr) == 3 && fwr * fmr >= geo.RT && fwr * fwc <= 12 && fmr >= 1 && fmr <= 4) {
             WR = fwr;
             WC = fwc;
             MR = fmr;
         }
     }
-    static const int ncw_opts[5][3] = {{0, 0, 0}, {4, 2, 1}, {3, 2, 1}, {2, 1, 0}, {1, 0, 0}};
+    static const int ncw_opts[5][4] = {{0, 0, 0, 0}, {4, 3, 2, 1}, {3, 2, 1, 0}, {2, 1, 0, 0}, {1, 0, 0, 0}};
+    int force_ncw = 0;
+    if (const char* fn = getenv("QDB_FORCE_SWEEPF_NCW")) force_ncw = atoi(fn);
     bool found = false;
     double best = 0;
     // fewer column warps when the batch is too small to give every SM a CTA; CTAs that end up with at most four warps
     // then split the matrix columns over two warp groups (WK = 2) so that every sub-partition still holds two warps
     const char* nok = getenv("QDB_SWEEPF_NO_KSPLIT");
     const bool ksplit_ok = !(nok && nok[0] == '1');
-    for (int wc = WC; wc >= 1; wc /= 2) {
-        for (int o = 0; o < 3; ++o) {
-            const int NCW = ncw_opts[MR][o];
-            if (NCW == 0) continue;
-            const int NCT = NCW * wc, threads0 = 32 * WR * wc;
-            const int ctas = (CT + NCT - 1) / NCT;
-            const int cu = (MR * NCW <= 2) ? 4 : 2;  // ColumnsInFlight<MR, NCW>
-            const int WK = (ksplit_ok && MR * NCW <= 4 && threads0 <= 128 && ctas <= SMS && n >= 2 * cu) ? 2 : 1;
-            const int threads = threads0 * WK;
-            const size_t smem = ((size_t)geo.npad * (8 * NCT + 1) + (size_t)(WK == 2 ? 3 : 2) * MR * NCW * 2 * threads0) * sizeof(double2);
-            if (smem > kSmemLimitF) continue;
-            // busiest SM: waves x (fixed per-stage part + pipe time of its column tiles).  A sub-partition with two warps
-            // keeps the fp64 pipe full; a lone warp (128-thread CTAs) reaches about 0.65 of it but leaves twice as many
-            // CTAs for a batch that cannot fill the chip.
-            const double wps = threads / 128.0;
-            const double cost = (double)((ctas + SMS - 1) / SMS) * (0.5 + NCW * (threads0 / 128.0) / (wps >= 2.0 ? 1.0 : 0.65));
-            if (!found || cost < best - 1e-9) {
-                found = true;
-                best = cost;
-                cfg.geo = geo;
-                cfg.geo.WR = WR;
-                cfg.geo.WC = wc;
-                cfg.geo.NCT = NCT;
-                cfg.geo.WK = WK;
-                cfg.geo.C2 = (n + cu * WK - 1) / (cu * WK) * (cu * WK);
-                cfg.MR = MR;
-                cfg.NCW = NCW;
-                cfg.KS = K <= 2 ? -K : (K + 3) / 4;  // K <= 2: formation on the FMA pipe
-                cfg.threads = threads;
-                cfg.grid = ctas;
-                cfg.smem = smem;
-            }
+    const int MR0 = MR;
+    auto consider = [&](int wr, int wc, int mr, int NCW) {
+        if (NCW == 0 || (force_ncw > 0 && NCW != force_ncw)) return;
+        const int threads0 = 32 * wr * wc;
+        if (threads0 > 256 && (K <= 2 || mr * NCW > 4 || threads0 > 384)) return;  // 12-warp CTAs: 168 registers per thread
+        const int NCT = NCW * wc;
+        const int ctas = (CT + NCT - 1) / NCT;
+        if (max_ctas > 0 && ctas > max_ctas) return;
+        const int cu = (mr * NCW <= 2) ? 4 : 2;  // ColumnsInFlight<MR, NCW>
+        const int WK = (ksplit_ok && need_C2 == 0 && mr * NCW <= 4 && threads0 <= 128 && ctas <= SMS && n >= 2 * cu) ? 2 : 1;
+        const int C2 = (n + cu * WK - 1) / (cu * WK) * (cu * WK);
+        if (need_C2 > 0 && C2 != need_C2) return;
+        const int threads = threads0 * WK;
+        const size_t smem = ((size_t)geo.npad * (8 * NCT + 1) + (size_t)(WK == 2 ? 3 : 2) * mr * NCW * 2 * threads0) * sizeof(double2);
+        if (smem > kSmemLimitF) return;
+        // busiest SM of a wave: fixed per-stage part + pipe time of the column tiles of its busiest sub-partition, in units
+        // of the rule-based tiling's row tiles (so that those tilings keep the cost they were tuned with).  A sub-partition
+        // with two or three warps keeps the fp64 pipe full; a lone warp (128-thread CTAs) reaches about 0.65 of it but leaves
+        // twice as many CTAs for a batch that cannot fill the chip.  Measured at n = 81, K = 8: 12 units 208 us, 9 units 152 us.
+        const double wq = threads0 <= 256 ? threads0 / 128.0 : (double)((threads0 / 32 + 3) / 4);  // warps of the busiest sub-partition
+        const double wave = 0.5 + (double)NCW * mr * wq / MR0 / (threads >= 256 ? 1.0 : 0.65);
+        const double cost = (double)((ctas + SMS - 1) / SMS) * wave;
+        if (!found || cost < best - 1e-9) {
+            found = true;
+            best = cost;
+            cfg.geo = geo;
+            cfg.geo.WR = wr;
+            cfg.geo.WC = wc;
+            cfg.geo.NCT = NCT;
+            cfg.geo.WK = WK;
+            cfg.geo.C2 = C2;
+            cfg.MR = mr;
+            cfg.NCW = NCW;
+            cfg.KS = K <= 2 ? -K : (K + 3) / 4;  // K <= 2: formation on the FMA pipe
+            cfg.threads = threads;
+            cfg.grid = ctas;
+            cfg.smem = smem;
+            cfg.wave_cost = wave;
         }
-    }
+    };
+    for (int wc = WC; wc >= 1; wc /= 2)
+        for (int o = 0; o < 4; ++o) consider(WR, wc, MR, ncw_opts[MR][o]);
+    // one row tile per warp on 9 .. 12 row warps (three warps per sub-partition): tilings with 3 octets per CTA, which the
+    // 8-warp family cannot offer at these sizes -- the second launch of a wave-balanced pair usually needs exactly that
+    if (geo.RT > 8 && geo.RT <= 12 && !getenv("QDB_FORCE_SWEEPF"))
+        for (int o = 0; o < 4; ++o) consider(12, 1, 1, ncw_opts[1][o]);
     return found;
 }
 
 template <int MR, int NCW, int KS, bool KSPLIT>
 int launch_sweepf_k(const FConfig& cfg, int K, int B, int S, const double2* statf, const double2* opsf, const double* coeff, int ldc,
                     const double* mu, const double* times, double h, double2* y, int ldy, cudaStream_t st) {
-    QDB_CUDA(cudaFuncSetAttribute(rk4_sweepf_kernel<MR, NCW, KS, KSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-    rk4_sweepf_kernel<MR, NCW, KS, KSPLIT><<<cfg.grid, cfg.threads, cfg.smem, st>>>(cfg.geo, K, B, S, statf, opsf, coeff, ldc, mu, times, h, y, ldy);
+    if constexpr (!KSPLIT && KS > 0 && MR * NCW <= 4) {
+        if (cfg.threads > 256) {  // 12-warp CTAs (three warps per sub-partition)
+            QDB_CUDA(cudaFuncSetAttribute(rk4_sweepf_kernel<MR, NCW, KS, false, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+            rk4_sweepf_kernel<MR, NCW, KS, false, 384><<<cfg.grid, cfg.threads, cfg.smem, st>>>(cfg.geo, K, B, S, statf, opsf, coeff, ldc, mu, times, h, y, ldy);
+            QDB_LAUNCH_CHECK("rk4_sweepf_kernel");
+            return QDB_OK;
+        }
+    }
+    QDB_CUDA(cudaFuncSetAttribute(rk4_sweepf_kernel<MR, NCW, KS, KSPLIT, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+    rk4_sweepf_kernel<MR, NCW, KS, KSPLIT, 256><<<cfg.grid, cfg.threads, cfg.smem, st>>>(cfg.geo, K, B, S, statf, opsf, coeff, ldc, mu, times, h, y, ldy);
     QDB_LAUNCH_CHECK("rk4_sweepf_kernel");
     return QDB_OK;
 }
@@ -552,9 +578,38 @@ size_t rk4_sweepf_workspace_bytes(int n, int K) {
     return (RT * C2 * KS * 32 + RT * C2 * 16) * sizeof(double2);
 }
 
+// Wave balancing.  Columns are independent and a CTA owns whole columns, so a batch whose CTA count is not a multiple of the
+// SM count pays for a whole last wave (cfg5: 1024 column octets in CTAs of 4 = 256 CTAs on 148 SMs, 1.73 waves at the price
+// of 2).  The batch is then cut in two: the full waves with the chosen tiling, and the remaining columns with the cheapest
+// tiling that fits ONE wave (usually fewer octets per CTA: 148 x 4 + 144 x 3 octets at cfg5, 7 octets per SM instead of 8).
+// QDB_SWEEPF_NO_BALANCE=1 switches it off.
+static bool plan_sweepf(int n, int K, int B, FConfig& a, FConfig& b, int& colsA) {
+    if (!pick_sweepf(n, B, K, a)) return false;
+    colsA = B;
+    b.grid = 0;
+    const int SMS = sm_count();
+    const char* nb = getenv("QDB_SWEEPF_NO_BALANCE");
+    if ((nb && nb[0] == '1') || a.geo.WK != 1 || a.grid <= SMS || a.grid % SMS == 0) return true;
+    const int full = a.grid / SMS * SMS;
+    const int cols_full = full * 8 * a.geo.NCT;
+    if (cols_full >= B) return true;
+    FConfig c;
+    if (!pick_sweepf(n, B - cols_full, K, c, SMS, a.geo.C2) || c.KS != a.KS) return true;
+    const double whole = (double)((a.grid + SMS - 1) / SMS) * a.wave_cost;
+    const double cut = (double)(a.grid / SMS) * a.wave_cost + c.wave_cost;
+    if (cut < 0.97 * whole) {
+        a.grid = full;
+        b = c;
+        colsA = cols_full;
+    }
+    return true;
+}
+
 bool rk4_sweepf_tiling(int n, int B, int K, int* out) {
-    FConfig cfg;
-    if (!pick_sweepf(n, B, K, cfg)) return false;
+    FConfig cfg, cfg2;
+    int colsA = B;
+    if (!plan_sweepf(n, K, B, cfg, cfg2, colsA)) return false;
+    if (cfg2.grid > 0) cfg.grid += cfg2.grid;  // CTAs of both launches of a wave-balanced pair
     out[0] = cfg.geo.WR;
     out[1] = cfg.geo.WC * cfg.geo.WK;  // column warps x warp groups sharing the matrix columns
     out[2] = cfg.MR;
@@ -567,19 +622,9 @@ bool rk4_sweepf_tiling(int n, int B, int K, int* out) {
     return true;
 }
 
-int launch_rk4_sweepf(int n, int K, int B, int S, const double2* stat_packed, const double2* ops_packed, const double* coeff,
-                      int ldc, const double* mu, const double* times_dev, double h, double2* y, int ldy, void* ws, cudaStream_t st) {
-    FConfig cfg;
-    if (!pick_sweepf(n, B, K, cfg)) {
-        set_error("rk4 formed sweep: unsupported shape n=%d B=%d K=%d", n, B, K);
-        return QDB_E_UNSUPPORTED;
-    }
-    const size_t nops = cfg.KS > 0 ? (size_t)cfg.geo.RT * cfg.geo.C2 * cfg.KS * 32 : (size_t)cfg.geo.RT * cfg.geo.C2 * K * 8, nstat = (size_t)cfg.geo.RT * cfg.geo.C2 * 8;  // static entries (2 double2 each)
-    double2* opsf = (double2*)ws;
-    double2* statf = stat_packed ? opsf + nops : nullptr;
-    const size_t total = nops + (stat_packed ? nstat : 0);
-    pack_sweepf_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n, K, cfg.KS, cfg.geo.C2, cfg.geo.RT, ops_packed, stat_packed, opsf, statf);
-    QDB_LAUNCH_CHECK("pack_sweepf_kernel");
+// One launch of the formed-generator kernel on columns [0, B) of y / coeff with tiling cfg (operator copy already packed).
+static int launch_sweepf_cfg(const FConfig& cfg, int K, int B, int S, const double2* statf, const double2* opsf, const double* coeff,
+                             int ldc, const double* mu, const double* times_dev, double h, double2* y, int ldy, cudaStream_t st) {
 #define QDB_F(mr, ncw)                                                                                                     \
     if (cfg.MR == mr && cfg.NCW == ncw) {                                                                                  \
         if (cfg.KS == -1) return launch_sweepf_t<mr, ncw, -1>(cfg, K, B, S, statf, opsf, coeff, ldc, mu, times_dev, h, y, ldy, st); \
@@ -591,6 +636,7 @@ int launch_rk4_sweepf(int n, int K, int B, int S, const double2* stat_packed, co
     }
     QDB_F(1, 1)
     QDB_F(1, 2)
+    QDB_F(1, 3)
     QDB_F(1, 4)
     QDB_F(2, 1)
     QDB_F(2, 2)
@@ -601,6 +647,25 @@ int launch_rk4_sweepf(int n, int K, int B, int S, const double2* stat_packed, co
 #undef QDB_F
     set_error("rk4 formed sweep: no kernel for MR=%d NCW=%d", cfg.MR, cfg.NCW);
     return QDB_E_UNSUPPORTED;
+}
+
+int launch_rk4_sweepf(int n, int K, int B, int S, const double2* stat_packed, const double2* ops_packed, const double* coeff,
+                      int ldc, const double* mu, const double* times_dev, double h, double2* y, int ldy, void* ws, cudaStream_t st) {
+    FConfig cfg, cfg2;
+    int colsA = B;
+    if (!plan_sweepf(n, K, B, cfg, cfg2, colsA)) {
+        set_error("rk4 formed sweep: unsupported shape n=%d B=%d K=%d", n, B, K);
+        return QDB_E_UNSUPPORTED;
+    }
+    const size_t nops = cfg.KS > 0 ? (size_t)cfg.geo.RT * cfg.geo.C2 * cfg.KS * 32 : (size_t)cfg.geo.RT * cfg.geo.C2 * K * 8, nstat = (size_t)cfg.geo.RT * cfg.geo.C2 * 8;  // static entries (2 double2 each)
+    double2* opsf = (double2*)ws;
+    double2* statf = stat_packed ? opsf + nops : nullptr;
+    const size_t total = nops + (stat_packed ? nstat : 0);
+    pack_sweepf_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n, K, cfg.KS, cfg.geo.C2, cfg.geo.RT, ops_packed, stat_packed, opsf, statf);
+    QDB_LAUNCH_CHECK("pack_sweepf_kernel");
+    int rc = launch_sweepf_cfg(cfg, K, colsA, S, statf, opsf, coeff, ldc, mu, times_dev, h, y, ldy, st);
+    if (rc != QDB_OK || cfg2.grid == 0) return rc;
+    return launch_sweepf_cfg(cfg2, K, B - colsA, S, statf, opsf, coeff + colsA, ldc, mu, times_dev, h, y + colsA, ldy, st);
 }
 
 }  // namespace qdb
