@@ -472,7 +472,7 @@ rk4_shared3m_kernel(Geometry geo_rt, int B, int S, const double2* __restrict__ g
     // are so short (3 DMMAs per warp) that the fragment ring is deepened to stay ahead of the L2 latency.
     constexpr int NC1 = NCW > 0 ? NCW : 1;             // array extents
     constexpr int MA = NCW > 0 ? MR : MS;              // row tiles of A a warp loads
-    constexpr int RG = (NCW <= 1 && SKT > 0 && SKT % 8 == 0) ? 8 : RING;  // few DMMAs per k-tile: deeper ring against the L2 latency
+    constexpr int RG = (NCW <= 2 && !(SPLIT && NCW == 2) && SKT > 0 && SKT % 8 == 0) ? 8 : RING;  // few DMMAs per k-tile: deeper ring against the L2 latency
     extern __shared__ __align__(16) double2 sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
@@ -1320,6 +1320,7 @@ int launch_rk4_fused_shared(int n, int B, int S, const double2* gen_table, int t
             QDB_DISPATCH(2, 3, (launch_3m_t<2, 3, true, 0>(ARGS)));
         } else {
             if (static128) QDB_DISPATCH(2, 1, (launch_3m_t<2, 1, false, 32>(ARGS)));
+            if (static128) QDB_DISPATCH(2, 2, (launch_3m_t<2, 2, false, 32>(ARGS)));
             QDB_DISPATCH(1, 1, (launch_3m_t<1, 1, false, 0>(ARGS)));
             QDB_DISPATCH(1, 2, (launch_3m_t<1, 2, false, 0>(ARGS)));
             QDB_DISPATCH(1, 3, (launch_3m_t<1, 3, false, 0>(ARGS)));
