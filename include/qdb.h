@@ -152,6 +152,15 @@ int qdb_rk4_steps_c128(int n, int K, int B, int S,
 int qdb_rk4_table_steps_c128(int n, int B, int S, const qdb_c128* gen_table, int table_layout, double h,
                              qdb_c128* y, int ldy, void* stream);
 
+/* The same S steps with the fp64 contraction emulated on the int8 tensor cores (tcgen05.mma kind::i8, accumulators and
+ * generator slices in TMEM): every real operand is split error-free into 6 signed 7-bit slices against a per-row /
+ * per-column power-of-two scale, slice products are exact in int32, 21 slice pairs are kept (normwise error 2^-42 per
+ * operand and RHS evaluation).  n = 121..128; gen_table_rowmajor: 2S+1 entries in QDB_LAYOUT_ROWMAJOR;
+ * workspace: qdb_rk4_ozaki_workspace_bytes(S) (the int8 slice planes of the table). */
+size_t qdb_rk4_ozaki_workspace_bytes(int S);
+int qdb_rk4_ozaki_steps_c128(int n, int B, int S, const qdb_c128* gen_table_rowmajor, double h,
+                             qdb_c128* y, int ldy, void* workspace, size_t ws_bytes, void* stream);
+
 /* Table layout qdb_rk4_steps_c128 uses for this shape (QDB_LAYOUT_PACKED or QDB_LAYOUT_PACKED3M), and the
  * bytes of one table entry in a layout. */
 int qdb_rk4_table_layout(int n, int B);

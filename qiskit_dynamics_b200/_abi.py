@@ -48,6 +48,8 @@ SIGNATURES = {
     "qdb_rk4_steps_c128": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _d, _vp, _i, _vp, _sz, _vp]),
     "qdb_expm_steps_c128": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _i, _vp, _sz, _vp]),
     "qdb_rk4_table_steps_c128": (_i, [_i, _i, _i, _vp, _i, _d, _vp, _i, _vp]),
+    "qdb_rk4_ozaki_workspace_bytes": (_sz, [_i]),
+    "qdb_rk4_ozaki_steps_c128": (_i, [_i, _i, _i, _vp, _d, _vp, _i, _vp, _sz, _vp]),
     "qdb_rk4_table_layout": (_i, [_i, _i]),
     "qdb_table_entry_bytes": (_sz, [_i, _i]),
     "qdb_rk4_tiling": (_i, [_i, _i, _i, _vp]),
@@ -347,6 +349,20 @@ def rk4_table_steps(n, table, h, y, S, layout=LAYOUT_PACKED):
         raise QdbError(f"rk4_table_steps: table entries have {table.shape[1]} elements, layout {layout} needs {want}")
     _check(lib().qdb_rk4_table_steps_c128(n, B, S, _ptr(table, C, "table"), int(layout), float(h), _ptr(y, C, "y"), B,
                                           _stream()), "qdb_rk4_table_steps_c128")
+    return y
+
+
+def rk4_ozaki_steps(n, table_rowmajor, h, y, S, workspace=None):
+    """S RK4 steps from a ROW-MAJOR generator table (2S+1, n*n) with the contraction emulated on the int8 tensor cores."""
+    B = y.shape[1]
+    if table_rowmajor.shape[0] < 2 * S + 1 or table_rowmajor.shape[1] != n * n:
+        raise QdbError(f"rk4_ozaki_steps: table shape {tuple(table_rowmajor.shape)}, need ({2 * S + 1}, {n * n})")
+    need = int(lib().qdb_rk4_ozaki_workspace_bytes(S))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=y.device)
+    _check(lib().qdb_rk4_ozaki_steps_c128(n, B, S, _ptr(table_rowmajor, C, "table"), float(h), _ptr(y, C, "y"), B,
+                                          ctypes.c_void_p(workspace.data_ptr()), workspace.numel(), _stream()),
+           "qdb_rk4_ozaki_steps_c128")
     return y
 
 

@@ -363,6 +363,26 @@ int qdb_rk4_table_steps_c128(int n, int B, int S, const qdb_c128* gen_table_pack
     return launch_rk4_fused_shared(n, B, S, D2(gen_table_packed), table_layout, h, D2(y), ldy, (cudaStream_t)stream);
 }
 
+void qdb_ozaki_debug(long long* host64) { qdb::rk4_ozaki_debug(host64); }
+
+size_t qdb_rk4_ozaki_workspace_bytes(int S) { return rk4_ozaki_table_bytes(2 * (S < 1 ? 1 : S) + 1); }
+
+int qdb_rk4_ozaki_steps_c128(int n, int B, int S, const qdb_c128* gen_table_rowmajor, double h, qdb_c128* y, int ldy, void* workspace,
+                             size_t ws_bytes, void* stream) {
+    QDB_REQUIRE(n >= 1 && B >= 0 && S >= 0, "qdb_rk4_ozaki_steps_c128: bad n=%d B=%d S=%d", n, B, S);
+    if (B == 0 || S == 0) return QDB_OK;
+    QDB_REQUIRE(gen_table_rowmajor && y && ldy >= B && workspace, "qdb_rk4_ozaki_steps_c128: null pointer / bad ldy");
+    if (!rk4_ozaki_supported(n)) {
+        set_error("qdb_rk4_ozaki_steps_c128: the int8 tensor-core emulation exists for n = 121..128 (got %d)", n);
+        return QDB_E_UNSUPPORTED;
+    }
+    if (ws_bytes < rk4_ozaki_table_bytes(2 * S + 1)) {
+        set_error("qdb_rk4_ozaki_steps_c128: workspace too small (%zu < %zu)", ws_bytes, rk4_ozaki_table_bytes(2 * S + 1));
+        return QDB_E_WORKSPACE;
+    }
+    return launch_rk4_ozaki(n, B, S, D2(gen_table_rowmajor), h, D2(y), ldy, workspace, (cudaStream_t)stream);
+}
+
 int qdb_signal_table_f64(int T, int K, int B, int nterms, const int* chan, const long long* samp_off, const int* samp_len,
                          const double* dt, const double* t0, const double* freq, const double* phase, int params_per_col,
                          const qdb_c128* samples, long long samp_col_stride, const qdb_c128* scale, const double* times,

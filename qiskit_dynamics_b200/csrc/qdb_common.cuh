@@ -127,6 +127,11 @@ bool rk4_fused_tiling(int n, int B, int sweep_K, int* out);
 int launch_rk4_fused_shared(int n, int B, int S, const double2* gen_table, int table_layout, double h,
                             double2* y, int ldy, cudaStream_t st);
 int rk4_fused_table_layout(int n, int B);
+// fp64 emulation on the int8 tensor cores (rk4_ozaki.cu), n = 121..128
+bool rk4_ozaki_supported(int n);
+size_t rk4_ozaki_table_bytes(int T);
+void rk4_ozaki_debug(long long* host64);
+int launch_rk4_ozaki(int n, int B, int S, const double2* gen_rowmajor, double h, double2* y, int ldy, void* ws, cudaStream_t st);
 int launch_rk4_rowsplit3m(int n, int B, int S, const double2* gen_table, double h, double2* y, int ldy, cudaStream_t st);
 int launch_rk4_fused_sweep(int n, int K, int B, int S, const double2* stat_packed /*or null*/,
                            const double2* ops_packed /*[K]*/, const double* coeff, int ldc,
