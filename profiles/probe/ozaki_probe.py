@@ -40,7 +40,7 @@ try:
     t = list(buf)
     base = t[0]
     print(json.dumps({"mma_wait_a": t[1] - t[0], "mma_wait_b": t[2] - t[1], "mma_issue_and_drain_waits": t[3] - t[2],
-                      "epi_stage_start_rel": t[8] - base, "epi_group_done_rel": [t[8 + g] - base for g in range(2, 8)],
+                      "epi_stage_start_rel": t[8] - base, "epi_group_done_rel_g_descending": [t[8 + g] - base for g in range(7, 1, -1) if t[8 + g]],
                       "epi_combine_done_rel": t[20] - base, "epi_slice_done_rel": t[21] - base, "mma_stage_end_rel": t[3] - base}))
 except Exception as ex:
     print("no debug", ex)

@@ -2,75 +2,95 @@
 // and the generator operand in TMEM) -- an Ozaki-style error-free split.  n = 121..128.
 //
 // Why.  tcgen05 has no fp64 kind; DMMA is the fp64 tensor pipe of sm_100a and rk4_shared3m_kernel already runs it at 85 %.
-// The only way past that roof is to leave the fp64 pipe: every real operand is cut into NS = 6 signed 7-bit slices against a
+// The only way past that roof is to leave the fp64 pipe: every real operand is cut into NS = 5 signed BYTES against a
 // per-row (generator) / per-column (stage vector) power-of-two scale,
-//     x = 2^e (q_1 2^-7 + q_2 2^-14 + ... + q_6 2^-42) + O(2^(e-43)),     q_p integers, |q_1| <= 127, |q_p| <= 64,
-// so that the products of slices are EXACT in int32 (K = 128: |sum| < 2^25) and G y = sum over slice pairs.  Pairs of equal
-// weight 2^(-7 (p + q)) share an accumulator ("group" g = p + q); pairs with g > NS + 1 lie below the truncation error of the
-// operands and are dropped: 21 pairs x 4 real products (re = Ar Br + Ai (-Bi), im = Ar Bi + Ai Br).  Error per RHS
-// evaluation: normwise 2^-42 per operand (measured against the DMMA kernel in tests/test_ozaki_gpu.py).
+//     x = 2^e (q_1 2^-8 + q_2 2^-16 + ... + q_NS 2^(-8 NS)) + O(2^(e - 8 NS - 1)),     q_p integers in [-128, 127],
+// so that the products of slices are EXACT in int32 (K = 128, <= NS pairs per accumulator: |sum| < 2^24) and G y = sum over
+// slice pairs.  Pairs of equal weight 2^(-8 (p + q)) share an accumulator ("group" g = p + q); pairs with g > NS + 1 lie
+// below the truncation error of the operands and are dropped: 15 pairs x 4 real products (re = Ar Br + Ai (-Bi),
+// im = Ar Bi + Ai Br).  Error per RHS evaluation: normwise 2^-40 per operand (measured against the DMMA kernel in
+// tests/test_ozaki_gpu.py).  Balanced byte digits cost nothing to extract: with X = rint(x 2^(8 NS - e)) the bytes of
+// (X + 0x80808080) ^ 0x80808080 ARE the signed digits, and a plane word (the same slice of four columns) is a 4 x 4 byte
+// transpose -- eight PRMT.
 //
 // Hardware mapping (measured first: profiles/probe/umma_i8_probe.cu -> profiles/r02_m_umma_i8_probe.jsonl).  With both
 // operands in shared memory an M128 x N x K32 int8 MMA costs (4096 + 32 N) / 128 cycles -- the operand READ, 41 cycles at
 // N = 32 -- so the generator slices live in TMEM (A operand from TMEM: 21 cycles at N = 32, 33 at N = 64 = the peak of
 // 8192 MAC/clk/SM).  A CTA owns 32 whole columns for the launch (4096 columns = 128 CTAs):
-//   TMEM (512 columns): [0, 128) four int32 accumulators (re, im) x two groups in flight; [128, 512) the 12 generator
-//     slice planes (2 parts x 6 slices x 32 columns of packed int8), reloaded when the stage time changes (every other stage);
-//   shared memory: the 18 stage-vector slice planes (re, im, -im) in the no-swizzle K-major core-matrix layout the MMA
-//     reads (72 KB), y and the RK4 k-sum as fp64 (128 KB);
+//   TMEM: columns [0, 128) four int32 accumulators (re, im) x two groups in flight; [128, 128 + 64 NS) the 2 NS generator
+//     slice planes (32 columns of packed int8 each), reloaded when the stage time changes (every other stage);
+//   shared memory: the 3 NS stage-vector slice planes (re, im, -im) in the no-swizzle MN-major core-matrix layout the MMA
+//     reads, y and the RK4 k-sum as fp64 (128 KB);
 //   warps 0-15: epilogue -- drain a group (tcgen05.ld), combine the groups in int64, one conversion to fp64, RK4 combine, column
-//     scales (warp REDUX + one named barrier), re-slice the next stage vector (integer digits) into shared memory; warp 16:
-//     issues the MMAs of a stage group by group; warps 17-24: load the next generator entry's slices from L2 and tcgen05.st
-//     them into TMEM while the epilogue runs.
-//   Pipelines: full / empty mbarriers per accumulator buffer (MMA <-> epilogue), b_ready (stage vector sliced), a_ready /
-//     a_free (generator slices in TMEM).
+//     scales (warp REDUX + one named barrier), re-slice the next stage vector into shared memory; warp 16: issues the MMAs
+//     of a stage, LEAST significant group first; warps 17-20: load the next generator entry's planes from L2 and
+//     tcgen05.st them into TMEM.  Slice plane p is last read by group p + 1, so with the groups in descending order the
+//     planes are released one by one DURING the stage (p_free mbarriers) and the reload hides behind the MMAs and the
+//     epilogue tail instead of following them.
+//   Pipelines: full / empty mbarriers per accumulator buffer (MMA <-> epilogue), b_ready (stage vector sliced), a_ready
+//     (generator planes in TMEM), p_free[p] (plane p no longer read).
 #include <cstdint>
+#include <cstdlib>
 
 #include "qdb_common.cuh"
 #include "rk4_device.cuh"
 
 namespace qdb {
 
+// -DQDB_OZ_TIMELINE: clock64() stamps of one stage of CTA 0 (profiles/probe/ozaki_probe.py prints them)
 __device__ long long g_oz_dbg[64];
+__device__ int g_oz_dbg_stage = 8;
 
 namespace {
 
-#define OZ_DBG(i) do { if (blockIdx.x == 0 && sidx == 8 && (threadIdx.x & 31) == 0) g_oz_dbg[i] = clock64(); } while (0)
+#ifdef QDB_OZ_TIMELINE
+#define OZ_DBG(i) do { if (blockIdx.x == 0 && sidx == g_oz_dbg_stage && (threadIdx.x & 31) == 0) g_oz_dbg[i] = clock64(); } while (0)
+#else
+#define OZ_DBG(i) do { } while (0)
+#endif
 
-constexpr int NS = 6;        // slices per operand
+constexpr int NS = 5;        // byte slices per operand: 2^-40, 15 slice pairs
 constexpr int NCOL = 32;     // columns per CTA (MMA N)
 constexpr int KD = 128;      // padded dimension (MMA M and K)
-constexpr int EPI_WARPS = 16, MMA_WARP = 16, LOADERS = 4, NWARPS = 20;  // warp 16: MMA issuer + loader of lane quarter 0; 17-19: loaders
-constexpr uint32_t TMEM_A = 128;  // TMEM columns [128, 512): generator slice planes; [0, 128): accumulators (the allocation is the whole TMEM: base 0)
-constexpr int BPLANE = NCOL * KD;  // bytes of one stage-vector slice plane
+constexpr int EPI_WARPS = 16, MMA_WARP = 16, LOADERS = 4, NWARPS = 21;  // warp 16: MMA issuer; 17-20: loaders of lane quarters 1, 2, 3, 0
+constexpr int NACC = 3;           // accumulator buffers (re | im: 64 columns each): a stage's five groups never wait for a drain
+constexpr uint32_t TMEM_A = NACC * 2 * NCOL;  // TMEM columns [192, 512): generator slice planes; [0, 192): accumulators (the allocation is the whole TMEM: base 0)
+static_assert(TMEM_A + 2 * NS * 32 <= 512, "TMEM");
+__host__ __device__ constexpr int acc_of_group(int g) { return (NS + 1 - g) % NACC; }
+constexpr int BPLANE = 2 * NCOL * KD;  // bytes of one stage-vector operand plane: 128 k x 64 "columns" = two parts side by side
 
 // shared-memory carve-up (bytes)
-constexpr int SM_B = 0;                                   // [NS][3][BPLANE] int8
-constexpr int SM_Y = SM_B + NS * 3 * BPLANE;              // [NCOL][KD] double2
+constexpr int SM_B = 0;                                   // [NS][2][BPLANE] int8: (re | im) and (-im | re) of every slice
+constexpr int SM_Y = SM_B + NS * 2 * BPLANE;              // [NCOL][KD] double2
 constexpr int SM_K = SM_Y + NCOL * KD * 16;               // [NCOL][KD] double2
 constexpr int SM_RED = SM_K + NCOL * KD * 16;             // [4][NCOL] unsigned (high words of the column maxima)
-constexpr int SM_EA = SM_RED + 4 * NCOL * 8;              // [2][KD] int
-constexpr int SM_BAR = SM_EA + 2 * KD * 4;                // 8 mbarriers
-constexpr int SM_TMEM = SM_BAR + 8 * 8;
+constexpr int SM_EA = SM_RED + 4 * NCOL * 8;              // [4][KD] int: row exponents of generator entry e in slot e & 3 (the loaders run up to two entries ahead of the epilogue)
+constexpr int SM_BAR = SM_EA + 4 * KD * 4;                // 2 NACC + 2 + NS mbarriers
+constexpr int SM_TMEM = SM_BAR + 16 * 8;
 constexpr int SM_TOTAL = SM_TMEM + 16;
 
-// Stage-vector slice planes (the MMA's B operand, 32 columns x 128 k int8) in the MN-major no-swizzle layout: core matrix =
-// 8 k-rows of 16 consecutive columns.  A thread (one k, eight consecutive columns) owns 8 contiguous bytes of every plane:
-// one 64-bit store instead of eight byte stores.
-__device__ __forceinline__ int bplane_off8(int oc, int k) { return ((k >> 3) * (NCOL >> 4) + (oc >> 1)) * 128 + (k & 7) * 16 + (oc & 1) * 8; }
+// Stage-vector operand planes (the MMA's B operand, 128 k x 64 int8) in the MN-major no-swizzle layout: core matrix = 8 k-rows
+// of 16 consecutive columns, four cores side by side (SBO = 128 B), sixteen k groups (LBO = 512 B).  One N = 64 MMA computes
+// both accumulators: (re | im) += A_re x (B_re | B_im) and += A_im x (-B_im | B_re) -- half the MMA count of N = 32 at the
+// peak rate of the TMEM-operand path.  A thread (one k, eight consecutive columns of one part) owns 8 contiguous bytes:
+// `half` = 0 / 1 selects the left / right 32 columns of the plane.
+__device__ __forceinline__ int bplane_off8(int oc, int k, int half) {
+    return ((k >> 3) * 4 + 2 * half + (oc >> 1)) * 128 + (k & 7) * 16 + (oc & 1) * 8;
+}
 
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
            ((uint64_t)1 << 46);
 }
-constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(KD >> 4) << 24);  // s32 += s8 x s8, A K-major (TMEM), B MN-major, M128 N32
+constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(2 * NCOL >> 3) << 17) | ((uint32_t)(KD >> 4) << 24);  // s32 += s8 x s8, A K-major (TMEM), B MN-major, M128 N64
 
 // executed by a whole warp in uniform control flow; one elected lane issues
-__device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
+// (the shared-memory descriptor arrives as two words: only the low one -- the address field -- varies between the MMAs)
+__device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t db_lo, uint32_t db_hi, uint32_t accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(kIdesc),
-        "r"(accumulate), "r"(0u)
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\tmov.b64 db, {%2, %6};\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], db, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "r"(db_lo), "r"(kIdesc),
+        "r"(accumulate), "r"(0u), "r"(db_hi)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* b) {
@@ -87,34 +107,36 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // 2^e as a double (|e| < 1000)
 __device__ __forceinline__ double pow2(int e) { return __longlong_as_double((long long)(1023 + e) << 52); }
 
-// Slice exponent from the HIGH WORD of max |x| (sign cleared): e with |x| 2^(7 - e) < 127 for every x <= that maximum, so
-// that the leading slice fits a signed byte (the top six mantissa bits set: one more bit of head room); zero / denormal -> 0
+// Slice exponent from the HIGH WORD of max |x| (sign cleared): e with |x| 2^-e < 1/2 - 2^-8 for every |x| <= that maximum,
+// so that the leading digit of X + bias (below) fits a signed byte; zero / denormal -> 0
 __device__ __forceinline__ int slice_exponent_hi(unsigned hi) {
     if (hi < 0x00100000u) return 0;
-    int e = (int)(hi >> 20) - 1022;  // 2^(e-1) <= m < 2^e
+    int e = (int)(hi >> 20) - 1021;  // 2^(e-2) <= m < 2^(e-1)
     if ((hi & 0xFFFFFu) >= 0xFC000u) ++e;
     return e;
 }
 __device__ __forceinline__ unsigned abs_hi(double x) { return (unsigned)(__double_as_longlong(x) >> 32) & 0x7FFFFFFFu; }
 
-// x -> NS signed 7-bit slices against 2^e: x 2^-e = sum_p q_p 2^(-7p) + O(2^(-7 NS - 1)).  One fp64 multiply and one
-// conversion (X = rint(x 2^(7 NS - e)), |X| < 2^42), then balanced base-128 digits on the INTEGER pipe -- the fp64 pipe is the
-// scarce one (16 lanes per clock and sub-partition): q_NS .. q_2 in [-64, 63], q_1 in [-127, 127].
-__device__ __forceinline__ void slice7(double x, double scale /* 2^(7 NS - e) */, int (&q)[NS]) {
-    static_assert(NS == 6, "digit extraction is written for six slices");
-    // balanced digits of X = plain base-128 digits of X + 64 (1 + 128 + ... + 128^4), minus 64 each; the leading one is the rest
-    const long long Y = __double2ll_rn(x * scale) + 17315143744LL;
-    const unsigned lo = (unsigned)Y, hi = (unsigned)((unsigned long long)Y >> 32);
-    q[5] = (int)(lo & 127u) - 64;
-    q[4] = (int)((lo >> 7) & 127u) - 64;
-    q[3] = (int)((lo >> 14) & 127u) - 64;
-    q[2] = (int)((lo >> 21) & 127u) - 64;
-    q[1] = (int)(__funnelshift_r(lo, hi, 28) & 127u) - 64;
-    q[0] = (int)hi >> 3;
+// x -> NS signed byte slices against 2^e: x 2^-e = sum_p q_p 2^(-8p) + O(2^(-8 NS - 1)).  With X = rint(x 2^(8 NS - e)),
+// |X| < 2^(8 NS - 1) - 2^(8 NS - 8), the balanced base-256 digits of X are the bytes of X + bias (bias = 0x80 in each of the
+// NS - 1 low bytes) minus 128 each, i.e. with the top bit flipped: byte j of (X + bias) ^ bias = q_(NS - j) as a signed
+// byte, j = 0 .. NS - 1.  X comes from t = fma(x, scale, 1.5 2^52): the integer sits in the low mantissa bits of t
+// (|X| < 2^51), so rounding, conversion and bias are one fp64 FMA and one 64-bit integer add -- no F2I (a quarter-rate
+// instruction).
+constexpr long long kBias = 0x80808080LL;
+static_assert(NS == 5, "bias: 0x80 in the NS - 1 low bytes");
+constexpr double kMagic = 6755399441055744.0;
+constexpr long long kMagicBits = 0x4338000000000000LL;
+__device__ __forceinline__ long long digits_of(double x, double scale) {
+    return (__double_as_longlong(fma(x, scale, kMagic)) + (kBias - kMagicBits)) ^ kBias;
+}
+__device__ __forceinline__ long long digits_of_negated(double x, double scale) {
+    return ((kMagicBits + kBias) - __double_as_longlong(fma(x, scale, kMagic))) ^ kBias;
 }
 
 // ---- generator table (row-major fp64, as generator_kernel writes it) -> int8 slice planes + row exponents ----
-// planes[t][part][p][row][k] (128 B rows = the TMEM image of the row), expo[t][row]; one block per (row, t)
+// planes[t][part][p][k / 16][row][k % 16] (a loader lane = a row reads 16 B next to its neighbours': coalesced; the eight
+// chunks of a row are its TMEM image), expo[t][row]; one block per (row, t)
 __global__ void __launch_bounds__(128) ozaki_gslice_kernel(int n, const double2* __restrict__ gen, int8_t* __restrict__ planes,
                                                            int* __restrict__ expo) {
     const int row = blockIdx.x, t = blockIdx.y, k = threadIdx.x;
@@ -128,16 +150,24 @@ __global__ void __launch_bounds__(128) ozaki_gslice_kernel(int n, const double2*
     m = max(max(wmax[0], wmax[1]), max(wmax[2], wmax[3]));
     const int e = slice_exponent_hi(m);
     if (k == 0) expo[(size_t)t * KD + row] = e;
-    const double scale = pow2(7 * NS - e);
-    int qr[NS], qi[NS];
-    slice7(v.x, scale, qr);
-    slice7(v.y, scale, qi);
-    int8_t* base = planes + (size_t)t * 2 * NS * KD * KD + (size_t)row * KD + k;
+    const double scale = pow2(8 * NS - e);
+    const long long dr = digits_of(v.x, scale), di = digits_of(v.y, scale);
+    int8_t* base = planes + (size_t)t * 2 * NS * KD * KD + (size_t)(k >> 4) * (KD * 16) + row * 16 + (k & 15);
 #pragma unroll
     for (int p = 0; p < NS; ++p) {
-        base[(size_t)(0 * NS + p) * KD * KD] = (int8_t)qr[p];
-        base[(size_t)(1 * NS + p) * KD * KD] = (int8_t)qi[p];
+        base[(size_t)(0 * NS + p) * KD * KD] = (int8_t)(dr >> (8 * (NS - 1 - p)));
+        base[(size_t)(1 * NS + p) * KD * KD] = (int8_t)(di >> (8 * (NS - 1 - p)));
     }
+}
+
+// the same slice of four columns in one word: w[j] = {a.byte j, b.byte j, c.byte j, d.byte j} (a = lowest address)
+__device__ __forceinline__ void transpose4(unsigned a, unsigned b, unsigned c, unsigned d, unsigned (&w)[4]) {
+    const unsigned t0 = __byte_perm(a, b, 0x5140), t1 = __byte_perm(a, b, 0x7362);
+    const unsigned t2 = __byte_perm(c, d, 0x5140), t3 = __byte_perm(c, d, 0x7362);
+    w[0] = __byte_perm(t0, t2, 0x5410);
+    w[1] = __byte_perm(t0, t2, 0x7632);
+    w[2] = __byte_perm(t1, t3, 0x5410);
+    w[3] = __byte_perm(t1, t3, 0x7632);
 }
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
@@ -167,20 +197,22 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
     unsigned* red = reinterpret_cast<unsigned*>(sm + SM_RED);
     int* ea_s = reinterpret_cast<int*>(sm + SM_EA);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM_BAR);
-    uint64_t *full = bars, *empty = bars + 2, *b_ready = bars + 4, *a_ready = bars + 5, *a_free = bars + 6;
+    uint64_t *full = bars, *empty = bars + NACC, *b_ready = bars + 2 * NACC, *a_ready = b_ready + 1, *p_free = b_ready + 2;  // full[NACC], empty[NACC], p_free[NS]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + SM_TMEM);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int col0 = blockIdx.x * NCOL;
     const int total = 4 * S;
 
     if (tid == 0) {
-        mbar_init(full, 1);
-        mbar_init(full + 1, 1);
-        mbar_init(empty, EPI_WARPS);
-        mbar_init(empty + 1, EPI_WARPS);
+#pragma unroll
+        for (int b = 0; b < NACC; ++b) {
+            mbar_init(full + b, 1);
+            mbar_init(empty + b, EPI_WARPS);
+        }
         mbar_init(b_ready, EPI_WARPS);
         mbar_init(a_ready, LOADERS);
-        mbar_init(a_free, 1);
+#pragma unroll
+        for (int p = 0; p < NS; ++p) mbar_init(p_free + p, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) {
@@ -210,32 +242,46 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
                 for (int j = 0; j < 8; ++j) red[qd * NCOL + 8 * oc + j] = m[j];
             }
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-            unsigned wl[NS * 3], wh[NS * 3];  // the thread's 8 bytes of each of the 18 planes (columns 0-3 / 4-7 of its octet)
+            unsigned wl[3][NS];  // columns 0-3 of the octet: digits of re, im, -im, slice p at [p - 1]
 #pragma unroll
-            for (int i = 0; i < NS * 3; ++i) wl[i] = wh[i] = 0u;
+            for (int hh = 0; hh < 2; ++hh) {  // four columns at a time: one 32-bit word of every plane
+                unsigned lo[3][4], hi[3][4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int c = 8 * oc + j;
-                const unsigned mm = max(max(red[c], red[NCOL + c]), max(red[2 * NCOL + c], red[3 * NCOL + c]));
-                eb[j] = slice_exponent_hi(mm);
-                const double scale = pow2(7 * NS - eb[j]);
-                int qr[NS], qi[NS];
-                slice7(x[j].x, scale, qr);
-                slice7(x[j].y, scale, qi);
-#pragma unroll
-                for (int p = 0; p < NS; ++p) {
-                    unsigned& w0 = j < 4 ? wl[p * 3 + 0] : wh[p * 3 + 0];
-                    unsigned& w1 = j < 4 ? wl[p * 3 + 1] : wh[p * 3 + 1];
-                    unsigned& w2 = j < 4 ? wl[p * 3 + 2] : wh[p * 3 + 2];
-                    asm("bfi.b32 %0, %1, %0, %2, 8;" : "+r"(w0) : "r"(qr[p]), "r"(8 * (j & 3)));
-                    asm("bfi.b32 %0, %1, %0, %2, 8;" : "+r"(w1) : "r"(qi[p]), "r"(8 * (j & 3)));
-                    asm("bfi.b32 %0, %1, %0, %2, 8;" : "+r"(w2) : "r"(-qi[p]), "r"(8 * (j & 3)));
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = 4 * hh + jj, c = 8 * oc + j;
+                    const unsigned mm = max(max(red[c], red[NCOL + c]), max(red[2 * NCOL + c], red[3 * NCOL + c]));
+                    eb[j] = slice_exponent_hi(mm);
+                    const double scale = pow2(8 * NS - eb[j]);
+                    const long long d0 = digits_of(x[j].x, scale), d1 = digits_of(x[j].y, scale), d2 = digits_of_negated(x[j].y, scale);
+                    lo[0][jj] = (unsigned)d0, hi[0][jj] = (unsigned)((unsigned long long)d0 >> 32);
+                    lo[1][jj] = (unsigned)d1, hi[1][jj] = (unsigned)((unsigned long long)d1 >> 32);
+                    lo[2][jj] = (unsigned)d2, hi[2][jj] = (unsigned)((unsigned long long)d2 >> 32);
                 }
-            }
-            {
-                const int off = bplane_off8(oc, row);
 #pragma unroll
-                for (int i = 0; i < NS * 3; ++i) *reinterpret_cast<uint2*>(bsl + i * BPLANE + off) = make_uint2(wl[i], wh[i]);
+                for (int part = 0; part < 3; ++part) {
+                    unsigned wlo[4], whi[4];  // byte j of the digits = slice NS - j
+                    transpose4(lo[part][0], lo[part][1], lo[part][2], lo[part][3], wlo);
+                    transpose4(hi[part][0], hi[part][1], hi[part][2], hi[part][3], whi);
+#pragma unroll
+                    for (int p = 1; p <= NS; ++p) {
+                        const int byte = NS - p;
+                        const unsigned w = byte < 4 ? wlo[byte] : whi[byte - 4];
+                        if (hh == 0) {
+                            wl[part][p - 1] = w;
+                        } else {
+                            const uint2 v = make_uint2(wl[part][p - 1], w);
+                            int8_t* sl = bsl + (p - 1) * 2 * BPLANE;
+                            if (part == 0) {  // re: left half of (re | im), right half of (-im | re)
+                                *reinterpret_cast<uint2*>(sl + bplane_off8(oc, row, 0)) = v;
+                                *reinterpret_cast<uint2*>(sl + BPLANE + bplane_off8(oc, row, 1)) = v;
+                            } else if (part == 1) {
+                                *reinterpret_cast<uint2*>(sl + bplane_off8(oc, row, 1)) = v;
+                            } else {
+                                *reinterpret_cast<uint2*>(sl + BPLANE + bplane_off8(oc, row, 0)) = v;
+                            }
+                        }
+                    }
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
             __syncwarp();
@@ -254,19 +300,19 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
         }
         slice_stage(x);
 
-        unsigned pf[2] = {0u, 0u};
+        unsigned pf[NACC] = {};
 #pragma unroll 1
         for (int sidx = 0; sidx < total; ++sidx) {
             const int stage = sidx & 3, entry = stage_entry(sidx);
-            // groups g = 2 .. NS + 1 arrive in order of decreasing weight 2^(-7g): T = sum_g D_g 128^(NS + 1 - g) by Horner in
-            // int64 (|D_g| < 2^25, |T| < 2^61: exact), ONE conversion to fp64 per value at the end
+            // groups g = NS + 1 .. 2 arrive in order of increasing weight 2^(-8g): T = sum_g D_g 256^(NS + 1 - g) in int64
+            // (|D_g| < 2^24, |T| < 2^(24 + 8 (NS - 1)): exact), ONE conversion to fp64 per value at the end
             long long tr[8], ti[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) tr[j] = ti[j] = 0;
             if (warp == 0) OZ_DBG(8);
-#pragma unroll 1
-            for (int g = 2; g <= NS + 1; ++g) {
-                const int b = g & 1;
+#pragma unroll
+            for (int g = NS + 1; g >= 2; --g) {
+                const int b = acc_of_group(g), sh = 8 * (NS + 1 - g);
                 mbar_wait(full + b, pf[b]);
                 pf[b] ^= 1u;
                 tc_fence_after();
@@ -279,17 +325,17 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
                 if (warp == 0) OZ_DBG(8 + g);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    tr[j] = (tr[j] << 7) + vr[j];
-                    ti[j] = (ti[j] << 7) + vi[j];
+                    tr[j] += (long long)vr[j] << sh;
+                    ti[j] += (long long)vi[j] << sh;
                 }
             }
             // k = 2^(eA[row] + eB[col]) acc; RK4 combine; next stage input
-            const int ea = ea_s[(entry & 1) * KD + row];
+            const int ea = ea_s[(entry & 3) * KD + row];
             const StageCoef sc(stage, h);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int c = 8 * oc + j;
-                const double s = pow2(ea + eb[j] - 7 * (NS + 1));
+                const double s = pow2(ea + eb[j] - 8 * (NS + 1));
                 const double k_r = (double)tr[j] * s, k_i = (double)ti[j] * s;
                 double2 ks = stage == 0 ? make_double2(0.0, 0.0) : ksm[c * KD + row];
                 ks.x = sc.keep * ks.x + sc.wk * k_r;
@@ -309,59 +355,61 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
             if (row < n && col < B) y[(size_t)row * ldy + col] = ysm[c * KD + row];
         }
     } else {
-        // ============ warp 16: MMA issuer (+ generator loader of lane quarter 0); warps 17-19: loaders of quarters 1-3 ============
-        // thread = row of the generator: its 12 slice planes (128 B each) go global -> registers -> TMEM (tcgen05.st), one plane
-        // ahead; the first plane of the next entry is requested before the previous entry is released
-        const int qd = warp & 3;  // 16 -> 0, 17 -> 1, 18 -> 2, 19 -> 3
-        const int row = 32 * qd + lane;
-        const uint32_t a_lane_base = TMEM_A + ((uint32_t)(32 * qd) << 16);
-        auto load_entry = [&](int e) {
-            const int8_t* src = planes + (size_t)e * 2 * NS * KD * KD + (size_t)row * KD;
-            uint4 w[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) w[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
-            ea_s[(e & 1) * KD + row] = expo[(size_t)e * KD + row];
-#pragma unroll 1
-            for (int pl = 0; pl < 2 * NS; ++pl) {
-                uint4 wn[8];
-                const int8_t* nxt = src + (size_t)(pl + 1 < 2 * NS ? pl + 1 : pl) * KD * KD;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) wn[i] = __ldg(reinterpret_cast<const uint4*>(nxt) + i);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t v[8] = {w[2 * i].x, w[2 * i].y, w[2 * i].z, w[2 * i].w, w[2 * i + 1].x, w[2 * i + 1].y, w[2 * i + 1].z, w[2 * i + 1].w};
-                    tmem_st8(a_lane_base + (uint32_t)(pl * 32 + 8 * i), v);
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) w[i] = wn[i];
-            }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(a_ready);
-        };
+        // ============ warp 16: MMA issuer; warps 17-20: generator loaders of TMEM lane quarters 1, 2, 3, 0 ============
         const int last_entry = 2 * S;
         if (warp != MMA_WARP) {
-            unsigned pfree = 0u;
+            // thread = row of the generator: its 2 NS slice planes (128 B each) go global -> registers -> TMEM (tcgen05.st), one
+            // plane ahead, least significant slice first: slice p of the previous entry is free once group p + 1 of the
+            // previous entry's last stage has completed (p_free[p - 1], one completion per entry change)
+            const int qd = warp & 3;
+            const int row = 32 * qd + lane;
+            const uint32_t a_lane_base = TMEM_A + ((uint32_t)(32 * qd) << 16);
 #pragma unroll 1
             for (int e = 0; e <= last_entry; ++e) {
-                if (e > 0) {
-                    mbar_wait(a_free, pfree);
-                    pfree ^= 1u;
-                    tc_fence_after();
+                const int8_t* src = planes + (size_t)e * 2 * NS * KD * KD + (size_t)row * 16;  // chunk i of the row: + i KD 16
+                const unsigned par = (unsigned)(e - 1) & 1u;
+                uint4 w[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(NS - 1) * KD * KD) + i * KD);
+                ea_s[(e & 3) * KD + row] = expo[(size_t)e * KD + row];
+#pragma unroll 1
+                for (int it = 0; it < 2 * NS; ++it) {
+                    const int p = NS - (it >> 1), part = it & 1;  // plane (part, p); next: (1, p) or (0, p - 1)
+                    const int pn = part == 0 ? p : (p > 1 ? p - 1 : 1), partn = part ^ 1;
+                    uint4 wn[8];
+                    const int8_t* nxt = src + (size_t)(partn * NS + pn - 1) * KD * KD;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) wn[i] = __ldg(reinterpret_cast<const uint4*>(nxt) + i * KD);
+                    if (e > 0 && part == 0) {
+                        mbar_wait(p_free + (p - 1), par);
+                        tc_fence_after();
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t v[8] = {w[2 * i].x, w[2 * i].y, w[2 * i].z, w[2 * i].w, w[2 * i + 1].x, w[2 * i + 1].y, w[2 * i + 1].z, w[2 * i + 1].w};
+                        tmem_st8(a_lane_base + (uint32_t)((part * NS + p - 1) * 32 + 8 * i), v);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) w[i] = wn[i];
                 }
-                load_entry(e);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_ready);
             }
         } else {
             const uint32_t bs_addr = (uint32_t)__cvta_generic_to_shared(bsl);
-            constexpr uint32_t LBO = (NCOL / 16) * 128, SBO = 128;  // between the 8-row k groups / between the 16-column cores
+            constexpr uint32_t LBO = 4 * 128, SBO = 128;  // between the 8-row k groups / between the 16-column cores
             const uint64_t bdesc0 = smem_desc(bs_addr, LBO, SBO);
-            unsigned pe[2] = {1u, 1u}, pb = 0u, pa = 0u, pfree = 0u;
-            load_entry(0);
+            const uint32_t bd_hi = (uint32_t)(bdesc0 >> 32);
+            uint32_t bd_lo = (uint32_t)bdesc0;
+            unsigned pe[NACC] = {1u, 1u, 1u}, pb = 0u, pa = 0u;
 #pragma unroll 1
             for (int sidx = 0; sidx < total; ++sidx) {
                 const int entry = stage_entry(sidx);
+                asm volatile("" : "+r"(bd_lo));  // opaque per stage: the 40 descriptor words are base + immediate, not 40 hoisted registers
+                const bool release = sidx + 1 < total && stage_entry(sidx + 1) != entry;  // the loaders refill behind this stage
                 OZ_DBG(0);
                 if (sidx == 0 || stage_entry(sidx - 1) != entry) {
                     mbar_wait(a_ready, pa);
@@ -375,40 +423,28 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
                 // fully unrolled: every TMEM / shared-memory operand is a constant or a base plus a compile-time offset (the
                 // descriptor's address field is bits [0, 14) of its low word in 16 B units: an offset never carries out of it)
 #pragma unroll
-                for (int g = 2; g <= NS + 1; ++g) {
-                    const int b = g & 1;
+                for (int g = NS + 1; g >= 2; --g) {
+                    const int b = acc_of_group(g);
                     mbar_wait(empty + b, pe[b]);
                     pe[b] ^= 1u;
                     tc_fence_after();
-                    constexpr uint32_t dummy = 0;
-                    (void)dummy;
-                    const uint32_t d_re = (uint32_t)((2 * b) * NCOL), d_im = (uint32_t)((2 * b + 1) * NCOL);
+                    const uint32_t d = (uint32_t)(2 * b * NCOL);  // (re | im): 64 accumulator columns
 #pragma unroll
                     for (int p = 1; p < g; ++p) {
                         const int q = g - p;
                         const uint32_t a_re = TMEM_A + (uint32_t)((0 * NS + (p - 1)) * 32), a_im = TMEM_A + (uint32_t)((1 * NS + (p - 1)) * 32);
 #pragma unroll
                         for (int ks = 0; ks < KD / 32; ++ks) {
-                            const uint64_t dre = bdesc0 + (uint64_t)((((q - 1) * 3 + 0) * BPLANE + ks * 4 * (int)LBO) >> 4);
-                            const uint64_t dim = bdesc0 + (uint64_t)((((q - 1) * 3 + 1) * BPLANE + ks * 4 * (int)LBO) >> 4);
-                            const uint64_t dnm = bdesc0 + (uint64_t)((((q - 1) * 3 + 2) * BPLANE + ks * 4 * (int)LBO) >> 4);
-                            const uint32_t acc = (p == 1 && ks == 0) ? 0u : 1u;
-                            mma_ts(d_re, a_re + 8 * ks, dre, acc);
-                            mma_ts(d_re, a_im + 8 * ks, dnm, 1u);
-                            mma_ts(d_im, a_re + 8 * ks, dim, acc);
-                            mma_ts(d_im, a_im + 8 * ks, dre, 1u);
+                            const uint32_t b1 = bd_lo + (uint32_t)((((q - 1) * 2 + 0) * BPLANE + ks * 4 * (int)LBO) >> 4);  // (re | im)
+                            const uint32_t b2 = bd_lo + (uint32_t)((((q - 1) * 2 + 1) * BPLANE + ks * 4 * (int)LBO) >> 4);  // (-im | re)
+                            mma_ts(d, a_re + 8 * ks, b1, bd_hi, (p == 1 && ks == 0) ? 0u : 1u);
+                            mma_ts(d, a_im + 8 * ks, b2, bd_hi, 1u);
                         }
                     }
                     umma_commit(full + b);
+                    if (release) umma_commit(p_free + (g - 2));  // slice plane g - 1 is read by no later group
                 }
                 OZ_DBG(3);
-                if (sidx + 1 < total && stage_entry(sidx + 1) != entry) {
-                    umma_commit(a_free);  // completes when every MMA that reads this entry is done
-                    mbar_wait(a_free, pfree);
-                    pfree ^= 1u;
-                    tc_fence_after();
-                    load_entry(stage_entry(sidx + 1));  // this warp's quarter of the next entry
-                }
             }
         }
     }
@@ -437,6 +473,10 @@ int launch_rk4_ozaki(int n, int B, int S, const double2* gen_rowmajor, double h,
         ozaki_gslice_kernel<<<dim3(KD, Tc), 128, 0, st>>>(n, gen_rowmajor + (size_t)t0 * n * n, planes + (size_t)t0 * 2 * NS * KD * KD,
                                                           expo + (size_t)t0 * KD);
         QDB_LAUNCH_CHECK("ozaki_gslice_kernel");
+    }
+    if (const char* ds = getenv("QDB_OZ_DBG_STAGE")) {
+        const int v = atoi(ds);
+        cudaMemcpyToSymbolAsync(g_oz_dbg_stage, &v, sizeof(int), 0, cudaMemcpyHostToDevice, st);
     }
     QDB_CUDA(cudaFuncSetAttribute(rk4_ozaki_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     rk4_ozaki_kernel<<<(B + NCOL - 1) / NCOL, NWARPS * 32, SM_TOTAL, st>>>(n, B, S, planes, expo, h, y, ldy);
