@@ -41,6 +41,6 @@ try:
     base = t[0]
     print(json.dumps({"mma_wait_a": t[1] - t[0], "mma_wait_b": t[2] - t[1], "mma_issue_and_drain_waits": t[3] - t[2],
                       "epi_stage_start_rel": t[8] - base, "epi_group_done_rel_g_descending": [t[8 + g] - base for g in range(7, 1, -1) if t[8 + g]],
-                      "epi_combine_done_rel": t[20] - base, "epi_slice_done_rel": t[21] - base, "mma_stage_end_rel": t[3] - base}))
+                      "epi_combine_done_rel": t[20] - base, "epi_combine_done_warp15_rel": t[25] - base, "slice_before_bar_rel": t[22] - base, "slice_after_bar_rel": t[23] - base, "slice_stored_rel": t[24] - base, "per_warp_after_bar": [t[48 + w] - base for w in range(16)], "per_warp_stored": [t[32 + w] - base for w in range(16)], "epi_slice_done_rel": t[21] - base, "mma_stage_end_rel": t[3] - base}))
 except Exception as ex:
     print("no debug", ex)

@@ -82,7 +82,10 @@ size_t qdb_workspace_bytes(int kind, int n, int K, int B, int S) {
             if (rk4_fused_supported(n)) {
                 // shared signals: generator table + stage times; per-column signals: stage times + the formed-sweep
                 // operator copy (the caller does not say which mode it will ask for: the larger of the two)
-                const size_t shared = align_up((size_t)(2 * S + 1) * np2) + align_up((size_t)(2 * S + 1) * sizeof(double));
+                size_t entry = np2;  // ... or a PACKED entry plus its int8 slice planes (rk4_ozaki_kernel)
+                if (rk4_ozaki_supported(n) && qdb_packed_elems(n) * 16 + rk4_ozaki_table_bytes(1) > entry)
+                    entry = qdb_packed_elems(n) * 16 + rk4_ozaki_table_bytes(1);
+                const size_t shared = align_up((size_t)(2 * S + 1) * entry) + align_up((size_t)(2 * S + 1) * sizeof(double));
                 const size_t sweep = align_up((size_t)(2 * S + 1) * sizeof(double)) +
                                      (rk4_sweepf_supported(n, K) ? align_up(rk4_sweepf_workspace_bytes(n, K)) : 0);
                 return shared > sweep ? shared : sweep;
@@ -241,8 +244,10 @@ int qdb_rk4_steps_c128(int n, int K, int B, int S, const qdb_c128* ops_rm, const
             return launch_rk4_fused_sweep(n, K, B, S, D2(stat_packed), D2(ops_packed), coeff, ldc, mu, times_dev, h, D2(y), ldy, fws, st);
         }
         // shared signals: chunk the step loop so that the generator table fits the workspace
-        const int table_layout = rk4_fused_table_layout(n, B);
-        const size_t per_entry = qdb_table_entry_bytes(n, table_layout);
+        // (large batches at n = 121..128: the int8 tensor-core emulation, whose slice planes sit behind the packed table)
+        const bool int8_path = rk4_ozaki_preferred(n, B);
+        const int table_layout = int8_path ? QDB_LAYOUT_PACKED : rk4_fused_table_layout(n, B);
+        const size_t per_entry = qdb_table_entry_bytes(n, table_layout) + (int8_path ? rk4_ozaki_table_bytes(1) : 0);
         // largest Sc whose 2 Sc + 1 table entries (+ their stage times) fit the workspace
         auto fits = [&](long long Sc) {
             const size_t E = (size_t)(2 * Sc + 1);
@@ -257,6 +262,7 @@ int qdb_rk4_steps_c128(int n, int K, int B, int S, const qdb_c128* ops_rm, const
         if (Sc_max > S) Sc_max = S;
         double2* table = (double2*)ws;
         double* times_dev = (double*)(ws + align_up((size_t)(2 * Sc_max + 1) * per_entry));
+        void* planes_ws = ws + (size_t)(2 * Sc_max + 1) * qdb_table_entry_bytes(n, table_layout);
         for (int s0 = 0; s0 < S; s0 += (int)Sc_max) {
             const int Sc = (S - s0 < Sc_max) ? S - s0 : (int)Sc_max;
             const int T = 2 * Sc + 1;
@@ -264,7 +270,8 @@ int qdb_rk4_steps_c128(int n, int K, int B, int S, const qdb_c128* ops_rm, const
             rc = launch_generator(n, K, T, table_layout, D2(ops_packed), D2(stat_packed),
                                   coeff ? coeff + (size_t)2 * s0 * K : nullptr, 0, mu, times_dev, 0.0, 1.0, table, st);
             if (rc != QDB_OK) return rc;
-            rc = launch_rk4_fused_shared(n, B, Sc, table, table_layout, h, D2(y), ldy, st);
+            rc = int8_path ? launch_rk4_ozaki(n, B, Sc, table, table_layout, h, D2(y), ldy, planes_ws, st)
+                           : launch_rk4_fused_shared(n, B, Sc, table, table_layout, h, D2(y), ldy, st);
             if (rc != QDB_OK) return rc;
         }
         return QDB_OK;
@@ -380,7 +387,7 @@ int qdb_rk4_ozaki_steps_c128(int n, int B, int S, const qdb_c128* gen_table_rowm
         set_error("qdb_rk4_ozaki_steps_c128: workspace too small (%zu < %zu)", ws_bytes, rk4_ozaki_table_bytes(2 * S + 1));
         return QDB_E_WORKSPACE;
     }
-    return launch_rk4_ozaki(n, B, S, D2(gen_table_rowmajor), h, D2(y), ldy, workspace, (cudaStream_t)stream);
+    return launch_rk4_ozaki(n, B, S, D2(gen_table_rowmajor), QDB_LAYOUT_ROWMAJOR, h, D2(y), ldy, workspace, (cudaStream_t)stream);
 }
 
 int qdb_signal_table_f64(int T, int K, int B, int nterms, const int* chan, const long long* samp_off, const int* samp_len,

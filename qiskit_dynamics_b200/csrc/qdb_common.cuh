@@ -131,7 +131,8 @@ int rk4_fused_table_layout(int n, int B);
 bool rk4_ozaki_supported(int n);
 size_t rk4_ozaki_table_bytes(int T);
 void rk4_ozaki_debug(long long* host64);
-int launch_rk4_ozaki(int n, int B, int S, const double2* gen_rowmajor, double h, double2* y, int ldy, void* ws, cudaStream_t st);
+bool rk4_ozaki_preferred(int n, int B);
+int launch_rk4_ozaki(int n, int B, int S, const double2* gen, int gen_layout, double h, double2* y, int ldy, void* ws, cudaStream_t st);
 int launch_rk4_rowsplit3m(int n, int B, int S, const double2* gen_table, double h, double2* y, int ldy, cudaStream_t st);
 int launch_rk4_fused_sweep(int n, int K, int B, int S, const double2* stat_packed /*or null*/,
                            const double2* ops_packed /*[K]*/, const double* coeff, int ldc,

@@ -137,12 +137,14 @@ __device__ __forceinline__ long long digits_of_negated(double x, double scale) {
 // ---- generator table (row-major fp64, as generator_kernel writes it) -> int8 slice planes + row exponents ----
 // planes[t][part][p][k / 16][row][k % 16] (a loader lane = a row reads 16 B next to its neighbours': coalesced; the eight
 // chunks of a row are its TMEM image), expo[t][row]; one block per (row, t)
+// the table comes row-major (generator_kernel's QDB_LAYOUT_ROWMAJOR) or in the packed DMMA-fragment layout (QDB_LAYOUT_PACKED)
+template <bool PACKED>
 __global__ void __launch_bounds__(128) ozaki_gslice_kernel(int n, const double2* __restrict__ gen, int8_t* __restrict__ planes,
                                                            int* __restrict__ expo) {
     const int row = blockIdx.x, t = blockIdx.y, k = threadIdx.x;
     __shared__ unsigned wmax[4];
     double2 v = make_double2(0.0, 0.0);
-    if (row < n && k < n) v = gen[((size_t)t * n + row) * n + k];
+    if (row < n && k < n) v = PACKED ? gen[(size_t)t * KD * KD + packed_index(KD, row, k)] : gen[((size_t)t * n + row) * n + k];
     unsigned m = max(abs_hi(v.x), abs_hi(v.y));
     m = __reduce_max_sync(0xffffffffu, m);
     if ((k & 31) == 0) wmax[k >> 5] = m;
@@ -233,7 +235,8 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
         int eb[8];  // column exponents of the current stage vector (this thread's 8 columns)
 
         // slices the stage vector x (this thread's 8 elements) into shared memory; returns through eb the column scales
-        auto slice_stage = [&](const double2 (&x)[8]) {
+        auto slice_stage = [&](const double2 (&x)[8], int sidx) {
+            (void)sidx;
             unsigned m[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) m[j] = __reduce_max_sync(0xffffffffu, max(abs_hi(x[j].x), abs_hi(x[j].y)));  // over the warp's 32 rows
@@ -241,7 +244,10 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
 #pragma unroll
                 for (int j = 0; j < 8; ++j) red[qd * NCOL + 8 * oc + j] = m[j];
             }
+            if (warp == 0) OZ_DBG(22);
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+            if (warp == 0) OZ_DBG(23);
+            OZ_DBG(48 + warp);
             unsigned wl[3][NS];  // columns 0-3 of the octet: digits of re, im, -im, slice p at [p - 1]
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {  // four columns at a time: one 32-bit word of every plane
@@ -283,6 +289,8 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
                     }
                 }
             }
+            if (warp == 0) OZ_DBG(24);
+            OZ_DBG(32 + warp);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
             __syncwarp();
             if (lane == 0) mbar_arrive(b_ready);
@@ -298,7 +306,7 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
             ysm[c * KD + row] = v;
             ksm[c * KD + row] = make_double2(0.0, 0.0);
         }
-        slice_stage(x);
+        slice_stage(x, -1);
 
         unsigned pf[NACC] = {};
 #pragma unroll 1
@@ -346,7 +354,8 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
                 if (sc.last) ysm[c * KD + row] = x[j]; else ksm[c * KD + row] = ks;
             }
             if (warp == 0) OZ_DBG(20);
-            if (sidx + 1 < total) slice_stage(x);
+            if (warp == 15) OZ_DBG(25);
+            if (sidx + 1 < total) slice_stage(x, sidx);
             if (warp == 0) OZ_DBG(21);
         }
 #pragma unroll
@@ -458,20 +467,36 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
 
 bool rk4_ozaki_supported(int n) { return n >= 121 && n <= 128; }
 
+// The emulated path is the faster one once its single wave of 32-column CTAs beats the DMMA kernels' time for the batch
+// (measured at n = 128: 23.8 us per step for any B <= 4736 against 17.9 / 30.2 / 51.8 us at B = 1024 / 2048 / 4096).
+// QDB_RK4_INT8=0 keeps every batch on the fp64 DMMA kernels.
+bool rk4_ozaki_preferred(int n, int B) {
+    static const bool enabled = [] {
+        const char* e = getenv("QDB_RK4_INT8");
+        return !(e && e[0] == '0');
+    }();
+    return enabled && rk4_ozaki_supported(n) && B >= 1536;
+}
+
 void rk4_ozaki_debug(long long* host64) { cudaMemcpyFromSymbol(host64, g_oz_dbg, sizeof(long long) * 64); }
 
 // bytes of the int8 slice planes + row exponents of T table entries
 size_t rk4_ozaki_table_bytes(int T) { return (size_t)T * (2 * NS * KD * KD + KD * sizeof(int)); }
 
-// gen_rowmajor: [2S+1][n][n] generator table (QDB_LAYOUT_ROWMAJOR); ws: rk4_ozaki_table_bytes(2S+1) of scratch
-int launch_rk4_ozaki(int n, int B, int S, const double2* gen_rowmajor, double h, double2* y, int ldy, void* ws, cudaStream_t st) {
+// gen: [2S+1] generator table entries, row-major n x n (QDB_LAYOUT_ROWMAJOR) or packed (QDB_LAYOUT_PACKED: 128 x 128 for these
+// n); ws: rk4_ozaki_table_bytes(2S+1) of scratch
+int launch_rk4_ozaki(int n, int B, int S, const double2* gen, int gen_layout, double h, double2* y, int ldy, void* ws, cudaStream_t st) {
     const int T = 2 * S + 1;
     int8_t* planes = reinterpret_cast<int8_t*>(ws);
     int* expo = reinterpret_cast<int*>(planes + (size_t)T * 2 * NS * KD * KD);
     for (int t0 = 0; t0 < T; t0 += kMaxGridY) {
         const int Tc = T - t0 < kMaxGridY ? T - t0 : kMaxGridY;
-        ozaki_gslice_kernel<<<dim3(KD, Tc), 128, 0, st>>>(n, gen_rowmajor + (size_t)t0 * n * n, planes + (size_t)t0 * 2 * NS * KD * KD,
-                                                          expo + (size_t)t0 * KD);
+        if (gen_layout == QDB_LAYOUT_PACKED)
+            ozaki_gslice_kernel<true><<<dim3(KD, Tc), 128, 0, st>>>(n, gen + (size_t)t0 * KD * KD, planes + (size_t)t0 * 2 * NS * KD * KD,
+                                                                    expo + (size_t)t0 * KD);
+        else
+            ozaki_gslice_kernel<false><<<dim3(KD, Tc), 128, 0, st>>>(n, gen + (size_t)t0 * n * n, planes + (size_t)t0 * 2 * NS * KD * KD,
+                                                                     expo + (size_t)t0 * KD);
         QDB_LAUNCH_CHECK("ozaki_gslice_kernel");
     }
     if (const char* ds = getenv("QDB_OZ_DBG_STAGE")) {
