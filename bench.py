@@ -14,9 +14,12 @@ second, whole job (sum over the N ranks; headline = weak scaling: B columns per 
   e2e       : the same workload through the public API (`solve_lmde(model, ...)`) from a pinned HOST y0 to a pinned
               HOST final state -- signal table, H2D, basis changes, D2H and (N > 1) the single NCCL gather of final
               observables are all inside the timed region.
-  roofline  : the dominant kernel (rk4_shared3m_kernel) against the fp64 tensor pipe: algorithmic flops per launch /
-              its mean CUDA-event duration, over the live-measured DMMA peak, with a cuBLAS ZGEMM 4096^3 timed in the
-              same run as the second witness of that peak (MEASURED_PEAKS.json has no fp64 entry).
+  roofline  : the dominant kernel against the fp64 tensor pipe: algorithmic flops per launch / its mean CUDA-event
+              duration, over the live-measured DMMA peak, with a cuBLAS ZGEMM 4096^3 timed in the same run as the second
+              witness of that peak (MEASURED_PEAKS.json has no fp64 entry).  At the headline shape the dominant kernel is
+              rk4_ozaki_kernel -- the fp64 contraction emulated on the int8 tensor cores (tcgen05.mma kind::i8) -- so frac
+              exceeds 1 against the fp64 roof; roofline.int8_pipe states the executed int8 MACs against the int8 tensor
+              roof, and roofline.fp64_kernel the DMMA kernel (rk4_shared3m_kernel) it replaced, timed in the same run.
   parity    : max column-L2 error of the timed solve's final states on 32 chosen columns against the answers of the
               unmodified reference (committed fixture tests/golden/fullsize.npz).
   strong_scaling : the same solve on a TOTAL batch of 4096 (4096 / N columns per GPU), device-resident and e2e.
@@ -381,27 +384,41 @@ def run_b200(args):
     value = 4.0 * S * B * world / (dev_ms * 1e-3)
     e2e_value = 4.0 * S * B * world / (e2e_ms * 1e-3)
 
-    # the dominant kernel alone (one launch = one chunk of steps from a prebuilt table), CUDA events on its stream
+    # the dominant kernel alone (one launch = one chunk of steps from a prebuilt table), CUDA events on its stream:
+    # the fp64 DMMA stepper always, and the int8 tensor-core stepper when the solve above took it
     layout = abi.rk4_table_layout(n, B)
+    int8_path = abi.rk4_int8_preferred(n, B)
     S_k = 100
     entry_elems = abi.packed_elems(n) * (3 if layout == abi.LAYOUT_PACKED3M else 2) // 2
     table = torch.empty((2 * S_k + 1, entry_elems), dtype=torch.complex128, device=dev)
     times_k = torch.from_numpy(case["times"][: 2 * S_k + 1]).to(dev)
     abi.generator(n, case["ops_p"], case["stat_p"], case["coeff"][: 2 * S_k + 1].contiguous(), case["mu"], times_k,
                   layout=layout, out=table)
-    kern_ms = []
-    for it in range(3 + 10):
-        case["y_work"].copy_(case["y_fb"])
-        flush.zero_()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record()
-        abi.rk4_table_steps(n, table, MAX_DT, case["y_work"], S_k, layout=layout)
-        k1.record()
-        torch.cuda.synchronize()
-        if it >= 3:
-            kern_ms.append(k0.elapsed_time(k1))
-    kern_mean_ms = float(np.mean(kern_ms))
+
+    def time_kernel(launch):
+        ms = []
+        for it in range(3 + 10):
+            case["y_work"].copy_(case["y_fb"])
+            flush.zero_()
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record()
+            launch()
+            k1.record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                ms.append(k0.elapsed_time(k1))
+        return float(np.mean(ms))
+
+    dmma_kern_ms = time_kernel(lambda: abi.rk4_table_steps(n, table, MAX_DT, case["y_work"], S_k, layout=layout))
     del table
+    kern_mean_ms = dmma_kern_ms
+    if int8_path:
+        tpk = abi.generator(n, case["ops_p"], case["stat_p"], case["coeff"][: 2 * S_k + 1].contiguous(), case["mu"], times_k,
+                            layout=abi.LAYOUT_PACKED)
+        planes = abi.rk4_ozaki_slice(n, tpk, layout=abi.LAYOUT_PACKED)
+        del tpk
+        kern_mean_ms = time_kernel(lambda: abi.rk4_ozaki_steps(n, None, MAX_DT, case["y_work"], S_k, workspace=planes))
+        del planes
 
     # ---------------- strong scaling: 4096 columns in TOTAL ----------------
     if world == 1:
@@ -518,8 +535,38 @@ def run_b200(args):
         except Exception:  # noqa: BLE001
             traffic = None
     tiling = abi.rk4_tiling(n, B)
-    kernel_name = (f"{'rk4_shared3m_kernel' if tiling['m3'] else 'rk4_shared_kernel'}<{tiling['row_tiles_per_warp']},"
-                   f"{tiling['col_tiles_per_warp']},{'split' if tiling['split'] else 'whole'}>")
+    dmma_name = (f"{'rk4_shared3m_kernel' if tiling['m3'] else 'rk4_shared_kernel'}<{tiling['row_tiles_per_warp']},"
+                 f"{tiling['col_tiles_per_warp']},{'split' if tiling['split'] else 'whole'}>")
+    dmma_tf = flops_launch / (dmma_kern_ms * 1e-3) * 1e-12
+    fp64_kernel = {"kernel": dmma_name, "tiling": tiling, "kernel_ms": dmma_kern_ms, "achieved": dmma_tf, "frac": dmma_tf / peak_tf,
+                   "pipe_frac": dmma_tf * (0.75 if tiling["m3"] else 1.0) / peak_tf, "traffic": traffic,
+                   "note": "the fp64 DMMA stepper on the same table (QDB_RK4_INT8=0 makes it the solve's kernel); the "
+                           "3-product kernel issues 6 flops per complex multiply-add, pipe_frac = executed DMMA flops / peak"}
+    kernel_name = dmma_name
+    int8_pipe = None
+    if int8_path:
+        # rk4_ozaki_kernel: per column tile of 32 and RHS evaluation 15 slice pairs x 4 k-steps x 2 MMAs of
+        # M128 x N64 x K32 int8 (A from TMEM).  Roof: the measured TMEM-operand issue rate of 8192 MAC/clk/SM
+        # (profiles/r02_m_umma_i8_probe.jsonl) x 148 SMs x the SM clock under load.
+        kernel_name = "rk4_ozaki_kernel<5 byte slices, 32 columns per CTA>"
+        ctas = (B + 31) // 32
+        macs = float(S_k) * 4 * ctas * 15 * 4 * 2 * (128 * 64 * 32)
+        sm_mhz = float((clocks or {}).get("sm_mhz") or 1900.0)
+        peak_tops = 2 * 8192 * 148 * sm_mhz * 1e6 * 1e-12
+        int8_pipe = {"executed_tops": 2 * macs / (kern_mean_ms * 1e-3) * 1e-12, "peak_tops": peak_tops,
+                     "frac": 2 * macs / (kern_mean_ms * 1e-3) * 1e-12 / peak_tops, "ctas": ctas, "sms": 148,
+                     "slices": 5, "slice_pairs": 15,
+                     "note": "int8 tensor-pipe utilisation of the emulation: a CTA's stage is MMA phase (~45 %) then drain + "
+                             "RK4 combine + re-slicing of the next stage vector (serial per column tile), and 4096 columns "
+                             "fill 128 of the 148 SMs; peak = measured 8192 MAC/clk/SM x 148 SMs x SM clock under load"}
+        traffic = None
+        tprof = os.path.join(ROOT, "profiles", "rk4_ozaki_traffic.json")
+        if os.path.exists(tprof):
+            try:
+                pj = json.load(open(tprof))
+                traffic = float(pj["dram_bytes_fixed"]) + float(pj["dram_bytes_per_table_entry"]) * (2 * S_k + 1)
+            except Exception:  # noqa: BLE001
+                traffic = None
 
     # parity of the TIMED configuration: final states of the e2e solve (1000 steps) on 32 chosen columns against the
     # answers of the UNMODIFIED reference on the same inputs (tests/golden/fullsize.npz, generated by make_golden.py)
@@ -649,13 +696,14 @@ def run_b200(args):
                      "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
                      "flops_per_launch": flops_launch, "kernel_ms": kern_mean_ms, "rk4_steps_per_launch": S_k,
                      "kernel_share_of_step": kern_mean_ms * (S / S_k) / dev_ms,
-                     "executed_tflops": achieved_tf * (0.75 if tiling["m3"] else 1.0),
-                     "pipe_frac": achieved_tf * (0.75 if tiling["m3"] else 1.0) / peak_tf,
                      "peak_cublas_zgemm": cublas_tf,
-                     "note": ("achieved = ALGORITHMIC flops (8 per complex multiply-add, SURVEY 8(d)) / kernel time; the "
-                              "3-product kernel issues 6 per complex multiply-add (re*re, im*im, (re+im)*(re+im)), so "
-                              "frac can exceed 1; pipe_frac = executed DMMA flops / peak is the tensor-pipe utilisation")
-                     if tiling["m3"] else "achieved = algorithmic = executed flops",
+                     "int8_pipe": int8_pipe, "fp64_kernel": fp64_kernel,
+                     "note": ("achieved = ALGORITHMIC fp64 flops (8 per complex multiply-add, SURVEY 8(d)) / kernel time, "
+                              "peak = the fp64 DMMA tensor roof.  The kernel leaves the fp64 pipe -- the contraction runs as "
+                              "exact int8 slice products on tcgen05 (int8_pipe: executed int8 ops against the int8 roof) -- "
+                              "so frac > 1 is the speed-up over a perfect fp64 tensor kernel, not a utilisation; "
+                              "fp64_kernel is the DMMA stepper on the same table in the same run")
+                     if int8_path else fp64_kernel["note"],
                      "peak_source": "live DMMA m8n8k4 issue-rate probe (qdb_dmma_probe); second witness peak_cublas_zgemm = "
                                     "torch.matmul complex128 4096^3 in the same run; MEASURED_PEAKS.json has no fp64 entry; "
                                     "B200 datasheet fp64 tensor 37-40 TFLOP/s"},

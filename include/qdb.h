@@ -153,11 +153,20 @@ int qdb_rk4_table_steps_c128(int n, int B, int S, const qdb_c128* gen_table, int
                              qdb_c128* y, int ldy, void* stream);
 
 /* The same S steps with the fp64 contraction emulated on the int8 tensor cores (tcgen05.mma kind::i8, accumulators and
- * generator slices in TMEM): every real operand is split error-free into 6 signed 7-bit slices against a per-row /
- * per-column power-of-two scale, slice products are exact in int32, 21 slice pairs are kept (normwise error 2^-42 per
- * operand and RHS evaluation).  n = 121..128; gen_table_rowmajor: 2S+1 entries in QDB_LAYOUT_ROWMAJOR;
- * workspace: qdb_rk4_ozaki_workspace_bytes(S) (the int8 slice planes of the table). */
+ * generator slices in TMEM): every real operand is split error-free into 5 signed byte slices against a per-row /
+ * per-column power-of-two scale, slice products are exact in int32, the 15 slice pairs above the operands' truncation
+ * error are kept (normwise error 2^-40 per operand and RHS evaluation; measured 3e-12 against the DMMA kernel after
+ * 1000 steps of the headline problem).  n = 121..128.
+ * qdb_rk4_int8_preferred: 1 when qdb_rk4_steps_c128 takes this kernel for a shared-signal solve of this shape (B >= 1536;
+ *   the environment variable QDB_RK4_INT8=0 keeps every batch on the fp64 DMMA kernels).
+ * qdb_rk4_ozaki_slice_c128: T table entries (QDB_LAYOUT_ROWMAJOR or QDB_LAYOUT_PACKED) -> int8 slice planes + row
+ *   exponents in `workspace` (qdb_rk4_ozaki_workspace_bytes(S) for T = 2S+1 entries).
+ * qdb_rk4_ozaki_steps_c128: gen_table_rowmajor = 2S+1 entries in QDB_LAYOUT_ROWMAJOR, sliced into `workspace` first; or
+ *   NULL: `workspace` already holds the planes of these 2S+1 entries (the stepper alone, for timing / profiling). */
 size_t qdb_rk4_ozaki_workspace_bytes(int S);
+int qdb_rk4_int8_preferred(int n, int B);
+int qdb_rk4_ozaki_slice_c128(int n, int T, const qdb_c128* gen_table, int table_layout, void* workspace, size_t ws_bytes,
+                             void* stream);
 int qdb_rk4_ozaki_steps_c128(int n, int B, int S, const qdb_c128* gen_table_rowmajor, double h,
                              qdb_c128* y, int ldy, void* workspace, size_t ws_bytes, void* stream);
 

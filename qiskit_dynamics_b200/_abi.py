@@ -49,6 +49,8 @@ SIGNATURES = {
     "qdb_expm_steps_c128": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _i, _vp, _sz, _vp]),
     "qdb_rk4_table_steps_c128": (_i, [_i, _i, _i, _vp, _i, _d, _vp, _i, _vp]),
     "qdb_rk4_ozaki_workspace_bytes": (_sz, [_i]),
+    "qdb_rk4_int8_preferred": (_i, [_i, _i]),
+    "qdb_rk4_ozaki_slice_c128": (_i, [_i, _i, _vp, _i, _vp, _sz, _vp]),
     "qdb_rk4_ozaki_steps_c128": (_i, [_i, _i, _i, _vp, _d, _vp, _i, _vp, _sz, _vp]),
     "qdb_rk4_table_layout": (_i, [_i, _i]),
     "qdb_table_entry_bytes": (_sz, [_i, _i]),
@@ -352,13 +354,32 @@ def rk4_table_steps(n, table, h, y, S, layout=LAYOUT_PACKED):
     return y
 
 
+def rk4_int8_preferred(n, B) -> bool:
+    """True when a shared-signal RK4 solve of this shape runs on the int8 tensor-core emulation (rk4_ozaki_kernel)."""
+    return bool(lib().qdb_rk4_int8_preferred(int(n), int(B)))
+
+
+def rk4_ozaki_slice(n, table, layout=LAYOUT_ROWMAJOR, workspace=None):
+    """Generator table (T, entry) -> the int8 slice planes rk4_ozaki_steps(..., table=None) consumes."""
+    T = table.shape[0]
+    need = int(lib().qdb_rk4_ozaki_workspace_bytes(max(1, (T - 1) // 2 + (T - 1) % 2)))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=table.device)
+    _check(lib().qdb_rk4_ozaki_slice_c128(n, T, _ptr(table, C, "table"), int(layout), ctypes.c_void_p(workspace.data_ptr()),
+                                          workspace.numel(), _stream()), "qdb_rk4_ozaki_slice_c128")
+    return workspace
+
+
 def rk4_ozaki_steps(n, table_rowmajor, h, y, S, workspace=None):
-    """S RK4 steps from a ROW-MAJOR generator table (2S+1, n*n) with the contraction emulated on the int8 tensor cores."""
+    """S RK4 steps with the contraction emulated on the int8 tensor cores, from a ROW-MAJOR generator table (2S+1, n*n) --
+    or, with ``table_rowmajor=None``, from a ``workspace`` rk4_ozaki_slice filled with exactly 2S+1 entries."""
     B = y.shape[1]
-    if table_rowmajor.shape[0] < 2 * S + 1 or table_rowmajor.shape[1] != n * n:
+    if table_rowmajor is not None and (table_rowmajor.shape[0] != 2 * S + 1 or table_rowmajor.shape[1] != n * n):
         raise QdbError(f"rk4_ozaki_steps: table shape {tuple(table_rowmajor.shape)}, need ({2 * S + 1}, {n * n})")
     need = int(lib().qdb_rk4_ozaki_workspace_bytes(S))
     if workspace is None or workspace.numel() < need:
+        if table_rowmajor is None:
+            raise QdbError("rk4_ozaki_steps: no table and no sliced workspace")
         workspace = torch.empty(need, dtype=torch.uint8, device=y.device)
     _check(lib().qdb_rk4_ozaki_steps_c128(n, B, S, _ptr(table_rowmajor, C, "table"), float(h), _ptr(y, C, "y"), B,
                                           ctypes.c_void_p(workspace.data_ptr()), workspace.numel(), _stream()),

@@ -373,12 +373,31 @@ int qdb_rk4_table_steps_c128(int n, int B, int S, const qdb_c128* gen_table_pack
 void qdb_ozaki_debug(long long* host64) { qdb::rk4_ozaki_debug(host64); }
 
 size_t qdb_rk4_ozaki_workspace_bytes(int S) { return rk4_ozaki_table_bytes(2 * (S < 1 ? 1 : S) + 1); }
+int qdb_rk4_int8_preferred(int n, int B) { return n >= 1 && B >= 1 && rk4_ozaki_preferred(n, B) ? 1 : 0; }
+
+int qdb_rk4_ozaki_slice_c128(int n, int T, const qdb_c128* gen_table, int table_layout, void* workspace, size_t ws_bytes,
+                             void* stream) {
+    QDB_REQUIRE(n >= 1 && T >= 0, "qdb_rk4_ozaki_slice_c128: bad n=%d T=%d", n, T);
+    QDB_REQUIRE(table_layout == QDB_LAYOUT_ROWMAJOR || table_layout == QDB_LAYOUT_PACKED, "qdb_rk4_ozaki_slice_c128: bad table layout %d",
+                table_layout);
+    if (T == 0) return QDB_OK;
+    QDB_REQUIRE(gen_table && workspace, "qdb_rk4_ozaki_slice_c128: null pointer");
+    if (!rk4_ozaki_supported(n)) {
+        set_error("qdb_rk4_ozaki_slice_c128: the int8 tensor-core emulation exists for n = 121..128 (got %d)", n);
+        return QDB_E_UNSUPPORTED;
+    }
+    if (ws_bytes < rk4_ozaki_table_bytes(T)) {
+        set_error("qdb_rk4_ozaki_slice_c128: workspace too small (%zu < %zu)", ws_bytes, rk4_ozaki_table_bytes(T));
+        return QDB_E_WORKSPACE;
+    }
+    return launch_ozaki_slice(n, T, D2(gen_table), table_layout, workspace, (cudaStream_t)stream);
+}
 
 int qdb_rk4_ozaki_steps_c128(int n, int B, int S, const qdb_c128* gen_table_rowmajor, double h, qdb_c128* y, int ldy, void* workspace,
                              size_t ws_bytes, void* stream) {
     QDB_REQUIRE(n >= 1 && B >= 0 && S >= 0, "qdb_rk4_ozaki_steps_c128: bad n=%d B=%d S=%d", n, B, S);
     if (B == 0 || S == 0) return QDB_OK;
-    QDB_REQUIRE(gen_table_rowmajor && y && ldy >= B && workspace, "qdb_rk4_ozaki_steps_c128: null pointer / bad ldy");
+    QDB_REQUIRE(y && ldy >= B && workspace, "qdb_rk4_ozaki_steps_c128: null pointer / bad ldy");
     if (!rk4_ozaki_supported(n)) {
         set_error("qdb_rk4_ozaki_steps_c128: the int8 tensor-core emulation exists for n = 121..128 (got %d)", n);
         return QDB_E_UNSUPPORTED;

@@ -132,6 +132,7 @@ bool rk4_ozaki_supported(int n);
 size_t rk4_ozaki_table_bytes(int T);
 void rk4_ozaki_debug(long long* host64);
 bool rk4_ozaki_preferred(int n, int B);
+int launch_ozaki_slice(int n, int T, const double2* gen, int gen_layout, void* ws, cudaStream_t st);
 int launch_rk4_ozaki(int n, int B, int S, const double2* gen, int gen_layout, double h, double2* y, int ldy, void* ws, cudaStream_t st);
 int launch_rk4_rowsplit3m(int n, int B, int S, const double2* gen_table, double h, double2* y, int ldy, cudaStream_t st);
 int launch_rk4_fused_sweep(int n, int K, int B, int S, const double2* stat_packed /*or null*/,

@@ -483,10 +483,9 @@ void rk4_ozaki_debug(long long* host64) { cudaMemcpyFromSymbol(host64, g_oz_dbg,
 // bytes of the int8 slice planes + row exponents of T table entries
 size_t rk4_ozaki_table_bytes(int T) { return (size_t)T * (2 * NS * KD * KD + KD * sizeof(int)); }
 
-// gen: [2S+1] generator table entries, row-major n x n (QDB_LAYOUT_ROWMAJOR) or packed (QDB_LAYOUT_PACKED: 128 x 128 for these
-// n); ws: rk4_ozaki_table_bytes(2S+1) of scratch
-int launch_rk4_ozaki(int n, int B, int S, const double2* gen, int gen_layout, double h, double2* y, int ldy, void* ws, cudaStream_t st) {
-    const int T = 2 * S + 1;
+// gen: T generator table entries, row-major n x n (QDB_LAYOUT_ROWMAJOR) or packed (QDB_LAYOUT_PACKED: 128 x 128 for these n)
+// -> ws: int8 slice planes + row exponents (rk4_ozaki_table_bytes(T))
+int launch_ozaki_slice(int n, int T, const double2* gen, int gen_layout, void* ws, cudaStream_t st) {
     int8_t* planes = reinterpret_cast<int8_t*>(ws);
     int* expo = reinterpret_cast<int*>(planes + (size_t)T * 2 * NS * KD * KD);
     for (int t0 = 0; t0 < T; t0 += kMaxGridY) {
@@ -499,10 +498,24 @@ int launch_rk4_ozaki(int n, int B, int S, const double2* gen, int gen_layout, do
                                                                      expo + (size_t)t0 * KD);
         QDB_LAUNCH_CHECK("ozaki_gslice_kernel");
     }
+    return QDB_OK;
+}
+
+// S steps from the sliced table of 2S+1 entries in ws; gen == nullptr: ws was filled by launch_ozaki_slice
+int launch_rk4_ozaki(int n, int B, int S, const double2* gen, int gen_layout, double h, double2* y, int ldy, void* ws, cudaStream_t st) {
+    const int T = 2 * S + 1;
+    if (gen) {
+        const int rc = launch_ozaki_slice(n, T, gen, gen_layout, ws, st);
+        if (rc != QDB_OK) return rc;
+    }
+    int8_t* planes = reinterpret_cast<int8_t*>(ws);
+    int* expo = reinterpret_cast<int*>(planes + (size_t)T * 2 * NS * KD * KD);
+#ifdef QDB_OZ_TIMELINE
     if (const char* ds = getenv("QDB_OZ_DBG_STAGE")) {
         const int v = atoi(ds);
         cudaMemcpyToSymbolAsync(g_oz_dbg_stage, &v, sizeof(int), 0, cudaMemcpyHostToDevice, st);
     }
+#endif
     QDB_CUDA(cudaFuncSetAttribute(rk4_ozaki_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     rk4_ozaki_kernel<<<(B + NCOL - 1) / NCOL, NWARPS * 32, SM_TOTAL, st>>>(n, B, S, planes, expo, h, y, ldy);
     QDB_LAUNCH_CHECK("rk4_ozaki_kernel");
