@@ -50,46 +50,54 @@ namespace {
 #endif
 
 constexpr int NS = 5;        // byte slices per operand: 2^-40, 15 slice pairs
-constexpr int NCOL = 32;     // columns per CTA (MMA N)
 constexpr int KD = 128;      // padded dimension (MMA M and K)
-constexpr int EPI_WARPS = 16, MMA_WARP = 16, LOADERS = 4, NWARPS = 21;  // warp 16: MMA issuer; 17-20: loaders of lane quarters 1, 2, 3, 0
-constexpr int NACC = 3;           // accumulator buffers (re | im: 64 columns each): a stage's five groups never wait for a drain
-constexpr uint32_t TMEM_A = NACC * 2 * NCOL;  // TMEM columns [192, 512): generator slice planes; [0, 192): accumulators (the allocation is the whole TMEM: base 0)
+constexpr int LOADERS = 4;   // generator loader warps (one per TMEM lane quarter)
+constexpr int NACC = 3;           // accumulator buffers per set (re | im: 32 columns each): a stage's five groups never wait for a drain
+constexpr uint32_t TMEM_A = 192;  // TMEM columns [192, 512): generator slice planes; [0, 192): accumulators (the allocation is the whole TMEM: base 0)
 static_assert(TMEM_A + 2 * NS * 32 <= 512, "TMEM");
 __host__ __device__ constexpr int acc_of_group(int g) { return (NS + 1 - g) % NACC; }
-constexpr int BPLANE = 2 * NCOL * KD;  // bytes of one stage-vector operand plane: 128 k x 64 "columns" = two parts side by side
 
-// shared-memory carve-up (bytes)
-constexpr int SM_B = 0;                                   // [NS][2][BPLANE] int8: (re | im) and (-im | re) of every slice
-constexpr int SM_Y = SM_B + NS * 2 * BPLANE;              // [NCOL][KD] double2
-constexpr int SM_K = SM_Y + NCOL * KD * 16;               // [NCOL][KD] double2
-constexpr int SM_RED = SM_K + NCOL * KD * 16;             // [4][NCOL] unsigned (high words of the column maxima)
-constexpr int SM_EA = SM_RED + 4 * NCOL * 8;              // [4][KD] int: row exponents of generator entry e in slot e & 3 (the loaders run up to two entries ahead of the epilogue)
-constexpr int SM_BAR = SM_EA + 4 * KD * 4;                // 2 NACC + 2 + NS mbarriers
-constexpr int SM_TMEM = SM_BAR + 16 * 8;
-constexpr int SM_TOTAL = SM_TMEM + 16;
+// shared-memory carve-up (bytes) of a CTA with SETS column sets of CS columns; a stage-vector operand plane is 128 k x 2 CS
+// "columns" (two parts side by side): 2 CS KD bytes
+struct Smem {
+    int b, y, k, red, ea, bar, tmem, total;
+    __host__ __device__ constexpr Smem(int cs, int sets)
+        : b(0),                                  // [SETS][NS][2][2 CS KD] int8: (re | im) and (-im | re) of every slice
+          y(b + sets * NS * 2 * 2 * cs * KD),    // [SETS CS][KD] double2
+          k(y + sets * cs * KD * 16),            // [SETS CS][KD] double2
+          red(k + sets * cs * KD * 16),          // [SETS][4][CS] unsigned (high words of the column maxima)
+          ea(red + sets * 4 * cs * 4),           // [4][KD] int: row exponents of generator entry e in slot e & 3 (the loaders run up to two entries ahead of the epilogue)
+          bar(ea + 4 * KD * 4),                  // SETS (2 NACC + 1) + 1 + NS mbarriers
+          tmem(bar + 32 * 8),
+          total(tmem + 16) {}
+};
 
-// Stage-vector operand planes (the MMA's B operand, 128 k x 64 int8) in the MN-major no-swizzle layout: core matrix = 8 k-rows
-// of 16 consecutive columns, four cores side by side (SBO = 128 B), sixteen k groups (LBO = 512 B).  One N = 64 MMA computes
-// both accumulators: (re | im) += A_re x (B_re | B_im) and += A_im x (-B_im | B_re) -- half the MMA count of N = 32 at the
-// peak rate of the TMEM-operand path.  A thread (one k, eight consecutive columns of one part) owns 8 contiguous bytes:
-// `half` = 0 / 1 selects the left / right 32 columns of the plane.
+// Stage-vector operand planes (the MMA's B operand, 128 k x 2 CS int8) in the MN-major no-swizzle layout: core matrix = 8 k-rows
+// of 16 consecutive columns, CS / 8 cores side by side (SBO = 128 B), sixteen k groups (LBO = CS / 8 x 128 B).  One N = 2 CS
+// MMA computes both accumulators of a set: (re | im) += A_re x (B_re | B_im) and += A_im x (-B_im | B_re) -- half the MMA
+// count, and at CS = 32 the peak rate of the TMEM-operand path.  A thread (one k, eight consecutive columns of one part) owns
+// 8 contiguous bytes: `half` = 0 / 1 selects the left / right CS columns of the plane.
+template <int CS>
 __device__ __forceinline__ int bplane_off8(int oc, int k, int half) {
-    return ((k >> 3) * 4 + 2 * half + (oc >> 1)) * 128 + (k & 7) * 16 + (oc & 1) * 8;
+    return ((k >> 3) * (CS / 8) + half * (CS / 16) + (oc >> 1)) * 128 + (k & 7) * 16 + (oc & 1) * 8;
 }
 
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
            ((uint64_t)1 << 46);
 }
-constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(2 * NCOL >> 3) << 17) | ((uint32_t)(KD >> 4) << 24);  // s32 += s8 x s8, A K-major (TMEM), B MN-major, M128 N64
+// s32 += s8 x s8, A K-major (TMEM), B MN-major, M = 128, N = ncols
+__host__ __device__ constexpr uint32_t idesc_for(int ncols) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)(KD >> 4) << 24);
+}
 
 // executed by a whole warp in uniform control flow; one elected lane issues
 // (the shared-memory descriptor arrives as two words: only the low one -- the address field -- varies between the MMAs)
+template <uint32_t IDESC>
 __device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t db_lo, uint32_t db_hi, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\tmov.b64 db, {%2, %6};\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], db, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "r"(db_lo), "r"(kIdesc),
+        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], db, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "r"(db_lo), "r"(IDESC),
         "r"(accumulate), "r"(0u), "r"(db_hi)
         : "memory");
 }
@@ -189,29 +197,41 @@ __device__ __forceinline__ int stage_entry(int sidx) {
     return 2 * step + (stage == 0 ? 0 : (stage == 3 ? 2 : 1));
 }
 
-__global__ void __launch_bounds__(NWARPS * 32, 1)
+// A CTA owns SETS independent column sets of CS columns (CS / 2 epilogue warps each) that share the generator in TMEM and the
+// MMA warp.  Instantiated: <32, 1> (one wave of 32-column CTAs: batches above 16 columns per SM), <16, 1> (smaller batches:
+// twice the CTAs, and a stage whose serial epilogue handles half the columns) and <16, 2> (two sets whose stages interleave;
+// measured SLOWER than <32, 1> -- the per-thread epilogue chain, not the data volume, sets the stage time -- kept for the record).
+template <int CS, int SETS>
+__global__ void __launch_bounds__((SETS * (CS / 2) + 1 + LOADERS) * 32, 1)
 rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const int* __restrict__ expo, double h, double2* __restrict__ y,
                  int ldy) {
+    constexpr Smem L(CS, SETS);
+    constexpr int SET_WARPS = CS / 2, EPI_WARPS = SETS * SET_WARPS, MMA_WARP = EPI_WARPS, BPLANE = 2 * CS * KD;
+    static_assert(SETS * NACC * 2 * CS <= (int)TMEM_A, "accumulators");
     extern __shared__ __align__(1024) uint8_t sm[];
-    int8_t* bsl = reinterpret_cast<int8_t*>(sm + SM_B);
-    double2* ysm = reinterpret_cast<double2*>(sm + SM_Y);
-    double2* ksm = reinterpret_cast<double2*>(sm + SM_K);
-    unsigned* red = reinterpret_cast<unsigned*>(sm + SM_RED);
-    int* ea_s = reinterpret_cast<int*>(sm + SM_EA);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM_BAR);
-    uint64_t *full = bars, *empty = bars + NACC, *b_ready = bars + 2 * NACC, *a_ready = b_ready + 1, *p_free = b_ready + 2;  // full[NACC], empty[NACC], p_free[NS]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + SM_TMEM);
+    int8_t* bsl = reinterpret_cast<int8_t*>(sm + L.b);
+    double2* ysm = reinterpret_cast<double2*>(sm + L.y);
+    double2* ksm = reinterpret_cast<double2*>(sm + L.k);
+    int* ea_s = reinterpret_cast<int*>(sm + L.ea);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bar);
+    // per set: full[NACC], empty[NACC], b_ready; then a_ready, p_free[NS]
+    constexpr int PER_SET = 2 * NACC + 1;
+    uint64_t *a_ready = bars + SETS * PER_SET, *p_free = a_ready + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.tmem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int col0 = blockIdx.x * NCOL;
+    const int col0 = blockIdx.x * (SETS * CS);
     const int total = 4 * S;
 
     if (tid == 0) {
 #pragma unroll
-        for (int b = 0; b < NACC; ++b) {
-            mbar_init(full + b, 1);
-            mbar_init(empty + b, EPI_WARPS);
+        for (int s = 0; s < SETS; ++s) {
+#pragma unroll
+            for (int b = 0; b < NACC; ++b) {
+                mbar_init(bars + s * PER_SET + b, 1);
+                mbar_init(bars + s * PER_SET + NACC + b, SET_WARPS);
+            }
+            mbar_init(bars + s * PER_SET + 2 * NACC, SET_WARPS);
         }
-        mbar_init(b_ready, EPI_WARPS);
         mbar_init(a_ready, LOADERS);
 #pragma unroll
         for (int p = 0; p < NS; ++p) mbar_init(p_free + p, 1);
@@ -228,10 +248,14 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
     constexpr uint32_t tmem = 0u;
 
     if (warp < EPI_WARPS) {
-        // =========================== epilogue warps: thread = (row, 8 columns) ===========================
-        const int qd = warp & 3, oc = warp >> 2;
+        // =========================== epilogue warps: thread = (row, 8 columns of the warp's set) ===========================
+        const int set = warp / SET_WARPS, qd = warp & 3, oc = (warp % SET_WARPS) >> 2;
         const int row = 32 * qd + lane;
-        const uint32_t lane_base = ((uint32_t)(32 * qd) << 16);
+        const uint32_t lane_base = ((uint32_t)(32 * qd) << 16) + (uint32_t)(set * NACC * 2 * CS);
+        uint64_t *full = bars + set * PER_SET, *empty = full + NACC, *b_ready = full + 2 * NACC;
+        unsigned* red = reinterpret_cast<unsigned*>(sm + L.red) + set * 4 * CS;
+        int8_t* bset = bsl + set * (NS * 2 * BPLANE);
+        const int cbase = set * CS + 8 * oc;  // first of the thread's columns within the CTA
         int eb[8];  // column exponents of the current stage vector (this thread's 8 columns)
 
         // slices the stage vector x (this thread's 8 elements) into shared memory; returns through eb the column scales
@@ -242,10 +266,10 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
             for (int j = 0; j < 8; ++j) m[j] = __reduce_max_sync(0xffffffffu, max(abs_hi(x[j].x), abs_hi(x[j].y)));  // over the warp's 32 rows
             if (lane == 0) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) red[qd * NCOL + 8 * oc + j] = m[j];
+                for (int j = 0; j < 8; ++j) red[qd * CS + 8 * oc + j] = m[j];
             }
             if (warp == 0) OZ_DBG(22);
-            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + set), "n"(SET_WARPS * 32) : "memory");  // the set's warps
             if (warp == 0) OZ_DBG(23);
             OZ_DBG(48 + warp);
             unsigned wl[3][NS];  // columns 0-3 of the octet: digits of re, im, -im, slice p at [p - 1]
@@ -255,7 +279,7 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     const int j = 4 * hh + jj, c = 8 * oc + j;
-                    const unsigned mm = max(max(red[c], red[NCOL + c]), max(red[2 * NCOL + c], red[3 * NCOL + c]));
+                    const unsigned mm = max(max(red[c], red[CS + c]), max(red[2 * CS + c], red[3 * CS + c]));
                     eb[j] = slice_exponent_hi(mm);
                     const double scale = pow2(8 * NS - eb[j]);
                     const long long d0 = digits_of(x[j].x, scale), d1 = digits_of(x[j].y, scale), d2 = digits_of_negated(x[j].y, scale);
@@ -276,14 +300,14 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
                             wl[part][p - 1] = w;
                         } else {
                             const uint2 v = make_uint2(wl[part][p - 1], w);
-                            int8_t* sl = bsl + (p - 1) * 2 * BPLANE;
+                            int8_t* sl = bset + (p - 1) * 2 * BPLANE;
                             if (part == 0) {  // re: left half of (re | im), right half of (-im | re)
-                                *reinterpret_cast<uint2*>(sl + bplane_off8(oc, row, 0)) = v;
-                                *reinterpret_cast<uint2*>(sl + BPLANE + bplane_off8(oc, row, 1)) = v;
+                                *reinterpret_cast<uint2*>(sl + bplane_off8<CS>(oc, row, 0)) = v;
+                                *reinterpret_cast<uint2*>(sl + BPLANE + bplane_off8<CS>(oc, row, 1)) = v;
                             } else if (part == 1) {
-                                *reinterpret_cast<uint2*>(sl + bplane_off8(oc, row, 1)) = v;
+                                *reinterpret_cast<uint2*>(sl + bplane_off8<CS>(oc, row, 1)) = v;
                             } else {
-                                *reinterpret_cast<uint2*>(sl + BPLANE + bplane_off8(oc, row, 0)) = v;
+                                *reinterpret_cast<uint2*>(sl + BPLANE + bplane_off8<CS>(oc, row, 0)) = v;
                             }
                         }
                     }
@@ -299,7 +323,7 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
         double2 x[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int c = 8 * oc + j, col = col0 + c;
+            const int c = cbase + j, col = col0 + c;
             double2 v = make_double2(0.0, 0.0);
             if (row < n && col < B) v = y[(size_t)row * ldy + col];
             x[j] = v;
@@ -325,8 +349,8 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
                 pf[b] ^= 1u;
                 tc_fence_after();
                 int vr[8], vi[8];
-                tmem_ld8(lane_base + (uint32_t)((2 * b) * NCOL + 8 * oc), vr);
-                tmem_ld8(lane_base + (uint32_t)((2 * b + 1) * NCOL + 8 * oc), vi);
+                tmem_ld8(lane_base + (uint32_t)(2 * b * CS + 8 * oc), vr);
+                tmem_ld8(lane_base + (uint32_t)((2 * b + 1) * CS + 8 * oc), vi);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 if (lane == 0) mbar_arrive(empty + b);
@@ -342,7 +366,7 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
             const StageCoef sc(stage, h);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int c = 8 * oc + j;
+                const int c = cbase + j;
                 const double s = pow2(ea + eb[j] - 8 * (NS + 1));
                 const double k_r = (double)tr[j] * s, k_i = (double)ti[j] * s;
                 double2 ks = stage == 0 ? make_double2(0.0, 0.0) : ksm[c * KD + row];
@@ -354,17 +378,17 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
                 if (sc.last) ysm[c * KD + row] = x[j]; else ksm[c * KD + row] = ks;
             }
             if (warp == 0) OZ_DBG(20);
-            if (warp == 15) OZ_DBG(25);
+            if (warp == EPI_WARPS - 1) OZ_DBG(25);
             if (sidx + 1 < total) slice_stage(x, sidx);
             if (warp == 0) OZ_DBG(21);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int c = 8 * oc + j, col = col0 + c;
+            const int c = cbase + j, col = col0 + c;
             if (row < n && col < B) y[(size_t)row * ldy + col] = ysm[c * KD + row];
         }
     } else {
-        // ============ warp 16: MMA issuer; warps 17-20: generator loaders of TMEM lane quarters 1, 2, 3, 0 ============
+        // ============ MMA issuer (the first warp after the epilogue); then four generator loaders, one per TMEM lane quarter ============
         const int last_entry = 2 * S;
         if (warp != MMA_WARP) {
             // thread = row of the generator: its 2 NS slice planes (128 B each) go global -> registers -> TMEM (tcgen05.st), one
@@ -409,51 +433,59 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
             }
         } else {
             const uint32_t bs_addr = (uint32_t)__cvta_generic_to_shared(bsl);
-            constexpr uint32_t LBO = 4 * 128, SBO = 128;  // between the 8-row k groups / between the 16-column cores
+            constexpr uint32_t LBO = (CS / 8) * 128, SBO = 128;  // between the 8-row k groups / between the 16-column cores
             const uint64_t bdesc0 = smem_desc(bs_addr, LBO, SBO);
             const uint32_t bd_hi = (uint32_t)(bdesc0 >> 32);
             uint32_t bd_lo = (uint32_t)bdesc0;
-            unsigned pe[NACC] = {1u, 1u, 1u}, pb = 0u, pa = 0u;
+            unsigned pe[SETS][NACC], pb = 0u, pa = 0u;
+#pragma unroll
+            for (int s = 0; s < SETS; ++s)
+#pragma unroll
+                for (int b = 0; b < NACC; ++b) pe[s][b] = 1u;
 #pragma unroll 1
             for (int sidx = 0; sidx < total; ++sidx) {
                 const int entry = stage_entry(sidx);
-                asm volatile("" : "+r"(bd_lo));  // opaque per stage: the 40 descriptor words are base + immediate, not 40 hoisted registers
                 const bool release = sidx + 1 < total && stage_entry(sidx + 1) != entry;  // the loaders refill behind this stage
+                asm volatile("" : "+r"(bd_lo));  // opaque per stage: the descriptor words are base + immediate, not hoisted registers
                 OZ_DBG(0);
                 if (sidx == 0 || stage_entry(sidx - 1) != entry) {
                     mbar_wait(a_ready, pa);
                     pa ^= 1u;
                 }
                 OZ_DBG(1);
-                mbar_wait(b_ready, pb);
-                pb ^= 1u;
-                tc_fence_after();
-                OZ_DBG(2);
                 // fully unrolled: every TMEM / shared-memory operand is a constant or a base plus a compile-time offset (the
                 // descriptor's address field is bits [0, 14) of its low word in 16 B units: an offset never carries out of it)
 #pragma unroll
-                for (int g = NS + 1; g >= 2; --g) {
-                    const int b = acc_of_group(g);
-                    mbar_wait(empty + b, pe[b]);
-                    pe[b] ^= 1u;
+                for (int set = 0; set < SETS; ++set) {
+                    uint64_t *full = bars + set * PER_SET, *empty = full + NACC, *b_ready = full + 2 * NACC;
+                    mbar_wait(b_ready, pb);
                     tc_fence_after();
-                    const uint32_t d = (uint32_t)(2 * b * NCOL);  // (re | im): 64 accumulator columns
+                    if (set == 0) OZ_DBG(2);
 #pragma unroll
-                    for (int p = 1; p < g; ++p) {
-                        const int q = g - p;
-                        const uint32_t a_re = TMEM_A + (uint32_t)((0 * NS + (p - 1)) * 32), a_im = TMEM_A + (uint32_t)((1 * NS + (p - 1)) * 32);
+                    for (int g = NS + 1; g >= 2; --g) {
+                        const int b = acc_of_group(g);
+                        mbar_wait(empty + b, pe[set][b]);
+                        pe[set][b] ^= 1u;
+                        tc_fence_after();
+                        const uint32_t d = (uint32_t)((set * NACC + b) * 2 * CS);  // (re | im): 2 CS accumulator columns
 #pragma unroll
-                        for (int ks = 0; ks < KD / 32; ++ks) {
-                            const uint32_t b1 = bd_lo + (uint32_t)((((q - 1) * 2 + 0) * BPLANE + ks * 4 * (int)LBO) >> 4);  // (re | im)
-                            const uint32_t b2 = bd_lo + (uint32_t)((((q - 1) * 2 + 1) * BPLANE + ks * 4 * (int)LBO) >> 4);  // (-im | re)
-                            mma_ts(d, a_re + 8 * ks, b1, bd_hi, (p == 1 && ks == 0) ? 0u : 1u);
-                            mma_ts(d, a_im + 8 * ks, b2, bd_hi, 1u);
+                        for (int p = 1; p < g; ++p) {
+                            const int q = g - p;
+                            const uint32_t a_re = TMEM_A + (uint32_t)((0 * NS + (p - 1)) * 32), a_im = TMEM_A + (uint32_t)((1 * NS + (p - 1)) * 32);
+#pragma unroll
+                            for (int ks = 0; ks < KD / 32; ++ks) {
+                                const uint32_t b1 = bd_lo + (uint32_t)((((set * NS + q - 1) * 2 + 0) * BPLANE + ks * 4 * (int)LBO) >> 4);  // (re | im)
+                                const uint32_t b2 = bd_lo + (uint32_t)((((set * NS + q - 1) * 2 + 1) * BPLANE + ks * 4 * (int)LBO) >> 4);  // (-im | re)
+                                mma_ts<idesc_for(2 * CS)>(d, a_re + 8 * ks, b1, bd_hi, (p == 1 && ks == 0) ? 0u : 1u);
+                                mma_ts<idesc_for(2 * CS)>(d, a_im + 8 * ks, b2, bd_hi, 1u);
+                            }
                         }
+                        umma_commit(full + b);
+                        if (release && set == SETS - 1) umma_commit(p_free + (g - 2));  // slice plane g - 1 is read by no later group
                     }
-                    umma_commit(full + b);
-                    if (release) umma_commit(p_free + (g - 2));  // slice plane g - 1 is read by no later group
+                    if (set == 0) OZ_DBG(3);
                 }
-                OZ_DBG(3);
+                pb ^= 1u;
             }
         }
     }
@@ -467,15 +499,15 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
 
 bool rk4_ozaki_supported(int n) { return n >= 121 && n <= 128; }
 
-// The emulated path is the faster one once its single wave of 32-column CTAs beats the DMMA kernels' time for the batch
-// (measured at n = 128: 23.8 us per step for any B <= 4736 against 17.9 / 30.2 / 51.8 us at B = 1024 / 2048 / 4096).
-// QDB_RK4_INT8=0 keeps every batch on the fp64 DMMA kernels.
+// The emulated path is the faster one once its single wave of CTAs beats the DMMA kernels' time for the batch (measured at
+// n = 128: 17.9 us per step for any B <= 2368 -- 16 columns per CTA -- and 23.8 us up to 4736, against 9.0 / 17.9 / 30.2 /
+// 51.8 us of the DMMA kernels at B = 512 / 1024 / 2048 / 4096).  QDB_RK4_INT8=0 keeps every batch on the fp64 DMMA kernels.
 bool rk4_ozaki_preferred(int n, int B) {
     static const bool enabled = [] {
         const char* e = getenv("QDB_RK4_INT8");
         return !(e && e[0] == '0');
     }();
-    return enabled && rk4_ozaki_supported(n) && B >= 1536;
+    return enabled && rk4_ozaki_supported(n) && B > 1024;
 }
 
 void rk4_ozaki_debug(long long* host64) { cudaMemcpyFromSymbol(host64, g_oz_dbg, sizeof(long long) * 64); }
@@ -516,8 +548,24 @@ int launch_rk4_ozaki(int n, int B, int S, const double2* gen, int gen_layout, do
         cudaMemcpyToSymbolAsync(g_oz_dbg_stage, &v, sizeof(int), 0, cudaMemcpyHostToDevice, st);
     }
 #endif
-    QDB_CUDA(cudaFuncSetAttribute(rk4_ozaki_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-    rk4_ozaki_kernel<<<(B + NCOL - 1) / NCOL, NWARPS * 32, SM_TOTAL, st>>>(n, B, S, planes, expo, h, y, ldy);
+    // 32 columns per CTA once 16 per CTA would no longer fit one wave of the SMs (QDB_OZ_TWO_SETS=1: two sets of 16, for the record)
+    static const bool two_sets = [] {
+        const char* e = getenv("QDB_OZ_TWO_SETS");
+        return e && e[0] == '1';
+    }();
+    if (B <= sm_count() * 16) {
+        constexpr Smem L(16, 1);
+        QDB_CUDA(cudaFuncSetAttribute(rk4_ozaki_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        rk4_ozaki_kernel<16, 1><<<(B + 15) / 16, (8 + 1 + LOADERS) * 32, L.total, st>>>(n, B, S, planes, expo, h, y, ldy);
+    } else if (two_sets) {
+        constexpr Smem L(16, 2);
+        QDB_CUDA(cudaFuncSetAttribute(rk4_ozaki_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        rk4_ozaki_kernel<16, 2><<<(B + 31) / 32, (16 + 1 + LOADERS) * 32, L.total, st>>>(n, B, S, planes, expo, h, y, ldy);
+    } else {
+        constexpr Smem L(32, 1);
+        QDB_CUDA(cudaFuncSetAttribute(rk4_ozaki_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        rk4_ozaki_kernel<32, 1><<<(B + 31) / 32, (16 + 1 + LOADERS) * 32, L.total, st>>>(n, B, S, planes, expo, h, y, ldy);
+    }
     QDB_LAUNCH_CHECK("rk4_ozaki_kernel");
     return QDB_OK;
 }
