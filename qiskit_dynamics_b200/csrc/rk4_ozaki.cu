@@ -16,22 +16,26 @@
 // Hardware mapping (measured first: profiles/probe/umma_i8_probe.cu -> profiles/r02_m_umma_i8_probe.jsonl).  With both
 // operands in shared memory an M128 x N x K32 int8 MMA costs (4096 + 32 N) / 128 cycles -- the operand READ, 41 cycles at
 // N = 32 -- so the generator slices live in TMEM (A operand from TMEM: 21 cycles at N = 32, 33 at N = 64 = the peak of
-// 8192 MAC/clk/SM).  A CTA owns 32 whole columns for the launch (4096 columns = 128 CTAs):
-//   TMEM: columns [0, 128) four int32 accumulators (re, im) x two groups in flight; [128, 128 + 64 NS) the 2 NS generator
-//     slice planes (32 columns of packed int8 each), reloaded when the stage time changes (every other stage);
-//   shared memory: the 3 NS stage-vector slice planes (re, im, -im) in the no-swizzle MN-major core-matrix layout the MMA
-//     reads, y and the RK4 k-sum as fp64 (128 KB);
-//   warps 0-15: epilogue -- drain a group (tcgen05.ld), combine the groups in int64, one conversion to fp64, RK4 combine, column
-//     scales (warp REDUX + one named barrier), re-slice the next stage vector into shared memory; warp 16: issues the MMAs
-//     of a stage, LEAST significant group first; warps 17-20: load the next generator entry's planes from L2 and
-//     tcgen05.st them into TMEM.  Slice plane p is last read by group p + 1, so with the groups in descending order the
-//     planes are released one by one DURING the stage (p_free mbarriers) and the reload hides behind the MMAs and the
-//     epilogue tail instead of following them.
+// 8192 MAC/clk/SM), and one N = 64 MMA computes (re | im) of 32 columns at once from the operand planes (B_re | B_im) and
+// (-B_im | B_re).  A CTA owns 32 whole columns for the launch (4096 columns = 128 CTAs; 16 per CTA for small batches):
+//   TMEM: columns [0, 192) three int32 accumulator buffers (re | im), so that the five groups of a stage never wait for a
+//     drain; [192, 512) the 2 NS generator slice planes (32 columns of packed int8 each), reloaded when the stage time
+//     changes (every other stage);
+//   shared memory: the 2 NS stage-vector operand planes in the no-swizzle MN-major core-matrix layout the MMA reads
+//     (80 KB), y and the RK4 k-sum as fp64 (128 KB);
+//   warps 0-15: epilogue, thread = (row, 8 columns) -- drain a group (tcgen05.ld), combine the groups in int64, one
+//     conversion to fp64, RK4 combine, column scales (warp REDUX + one named barrier), re-slice the next stage vector into
+//     shared memory; warp 16: issues the 120 MMAs of a stage, LEAST significant group first; warps 17-20: load the next
+//     generator entry's planes from L2 (coalesced: the planes are stored chunk-major) and tcgen05.st them into TMEM.  Slice
+//     plane p is last read by group p + 1, so with the groups in descending order the planes are released one by one
+//     DURING the stage (p_free mbarriers) and the reload hides behind the MMAs and the epilogue instead of following them.
 //   Pipelines: full / empty mbarriers per accumulator buffer (MMA <-> epilogue), b_ready (stage vector sliced), a_ready
 //     (generator planes in TMEM), p_free[p] (plane p no longer read).
+// A stage is serial per column tile (MMA phase ~4.7K cycles, then last drain + combine + re-slice ~5.3K: measured with
+// -DQDB_OZ_TIMELINE, profiles/r02_o_ozaki_variants.jsonl); the tensor pipe is busy 27 % of the time (ncu,
+// profiles/r02_n_rk4_ozaki_ncu.json).
 #include <cstdint>
 #include <cstdlib>
-#include <type_traits>
 
 #include "qdb_common.cuh"
 #include "rk4_device.cuh"
@@ -187,9 +191,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
                  : "r"(taddr)
                  : "memory");
 }
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, int (&v)[4]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
-}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
                  "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
@@ -202,18 +203,16 @@ __device__ __forceinline__ int stage_entry(int sidx) {
 }
 
 // A CTA owns SETS independent column sets of CS columns (CS / 2 epilogue warps each) that share the generator in TMEM and the
-// MMA warp.  Instantiated: <32, 1> (one wave of 32-column CTAs: batches above 16 columns per SM), <16, 1> (smaller batches:
-// twice the CTAs, and a stage whose serial epilogue handles half the columns) and <16, 2> (two sets whose stages interleave;
-// measured SLOWER than <32, 1> -- the per-thread epilogue chain, not the data volume, sets the stage time -- kept for the record).
-// ALT (with <16, 2>): all 16 epilogue warps serve BOTH sets in turn, four columns per thread -- half the per-thread chain per set,
-// so that one set's drain / combine / re-slice runs under the other set's MMAs.
-template <int CS, int SETS, bool ALT>
-__global__ void __launch_bounds__(((ALT ? 16 : SETS * (CS / 2)) + 1 + LOADERS) * 32, 1)
+// MMA warp.  Instantiated: <32, 1> (one wave of 32-column CTAs: batches above 16 columns per SM) and <16, 1> (smaller batches:
+// twice the CTAs).  Two 16-column sets per CTA whose stages interleave on the MMA warp -- eight epilogue warps per set, or all
+// sixteen alternating with four columns per thread -- were built and measured SLOWER than <32, 1> (27.0 / 30.2 against 23.8 us
+// per step, profiles/r02_o_ozaki_variants.jsonl): the sets' epilogues collide and the N = 32 MMA costs 27.6 cycles.
+template <int CS, int SETS>
+__global__ void __launch_bounds__((SETS * (CS / 2) + 1 + LOADERS) * 32, 1)
 rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const int* __restrict__ expo, double h, double2* __restrict__ y,
                  int ldy) {
     constexpr Smem L(CS, SETS);
-    constexpr int SET_WARPS = ALT ? 16 : CS / 2, EPI_WARPS = ALT ? 16 : SETS * SET_WARPS, MMA_WARP = EPI_WARPS, BPLANE = 2 * CS * KD;
-    static_assert(!ALT || (CS == 16 && SETS == 2), "ALT serves two 16-column sets");
+    constexpr int SET_WARPS = CS / 2, EPI_WARPS = SETS * SET_WARPS, MMA_WARP = EPI_WARPS, BPLANE = 2 * CS * KD;
     static_assert(SETS * NACC * 2 * CS <= (int)TMEM_A, "accumulators");
     extern __shared__ __align__(1024) uint8_t sm[];
     int8_t* bsl = reinterpret_cast<int8_t*>(sm + L.b);
@@ -254,141 +253,7 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
     if (*tmem_slot != 0u) __trap();  // all 512 columns of the only resident CTA: the allocation starts at column 0, lane 0
     constexpr uint32_t tmem = 0u;
 
-    if constexpr (ALT) {
-      if (warp < EPI_WARPS) {
-        // =========== epilogue warps, alternating sets: thread = (row, 4 columns of set 0), then (row, 4 columns of set 1) ===========
-        constexpr int CPT = 4;
-        const int qd = warp & 3, oc = warp >> 2;
-        const int row = 32 * qd + lane;
-        const uint32_t lane_q = (uint32_t)(32 * qd) << 16;
-        const int boff = ((row >> 3) * (CS / 8)) * 128 + (row & 7) * 16 + CPT * oc;  // + half (CS / 16) 128
-        int eb[SETS][CPT];
-        unsigned pf[SETS][NACC] = {};
-        double2 x[CPT];
-
-        // slices the stage vector x (this thread's 4 elements of the set) into shared memory; the column scales go to eb[set]
-        auto slice_set = [&](auto set_c) {
-            constexpr int set = decltype(set_c)::value;
-            unsigned* red = reinterpret_cast<unsigned*>(sm + L.red) + set * 4 * CS;
-            int8_t* bset = bsl + set * (NS * 2 * BPLANE);
-            unsigned m[CPT];
-#pragma unroll
-            for (int j = 0; j < CPT; ++j) m[j] = __reduce_max_sync(0xffffffffu, max(abs_hi(x[j].x), abs_hi(x[j].y)));
-            if (lane == 0) {
-#pragma unroll
-                for (int j = 0; j < CPT; ++j) red[qd * CS + CPT * oc + j] = m[j];
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-            unsigned lo[3][4], hi[3][4];
-#pragma unroll
-            for (int j = 0; j < CPT; ++j) {
-                const int c = CPT * oc + j;
-                const unsigned mm = max(max(red[c], red[CS + c]), max(red[2 * CS + c], red[3 * CS + c]));
-                eb[set][j] = slice_exponent_hi(mm);
-                const double scale = pow2(8 * NS - eb[set][j]);
-                const long long d0 = digits_of(x[j].x, scale), d1 = digits_of(x[j].y, scale), d2 = digits_of_negated(x[j].y, scale);
-                lo[0][j] = (unsigned)d0, hi[0][j] = (unsigned)((unsigned long long)d0 >> 32);
-                lo[1][j] = (unsigned)d1, hi[1][j] = (unsigned)((unsigned long long)d1 >> 32);
-                lo[2][j] = (unsigned)d2, hi[2][j] = (unsigned)((unsigned long long)d2 >> 32);
-            }
-#pragma unroll
-            for (int part = 0; part < 3; ++part) {
-                unsigned wlo[4], whi[4];  // byte j of the digits = slice NS - j
-                transpose4(lo[part][0], lo[part][1], lo[part][2], lo[part][3], wlo);
-                transpose4(hi[part][0], hi[part][1], hi[part][2], hi[part][3], whi);
-#pragma unroll
-                for (int p = 1; p <= NS; ++p) {
-                    const int byte = NS - p;
-                    const unsigned w = byte < 4 ? wlo[byte] : whi[byte - 4];
-                    int8_t* sl = bset + (p - 1) * 2 * BPLANE + boff;
-                    constexpr int HALF = (CS / 16) * 128;
-                    if (part == 0) {  // re: left half of (re | im), right half of (-im | re)
-                        *reinterpret_cast<unsigned*>(sl) = w;
-                        *reinterpret_cast<unsigned*>(sl + BPLANE + HALF) = w;
-                    } else if (part == 1) {
-                        *reinterpret_cast<unsigned*>(sl + HALF) = w;
-                    } else {
-                        *reinterpret_cast<unsigned*>(sl + BPLANE) = w;
-                    }
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bars + set * PER_SET + 2 * NACC);
-        };
-        auto load_set = [&](auto set_c) {
-            constexpr int set = decltype(set_c)::value;
-#pragma unroll
-            for (int j = 0; j < CPT; ++j) {
-                const int c = set * CS + CPT * oc + j, col = col0 + c;
-                double2 v = make_double2(0.0, 0.0);
-                if (row < n && col < B) v = y[(size_t)row * ldy + col];
-                x[j] = v;
-                ysm[c * KD + row] = v;
-                ksm[c * KD + row] = make_double2(0.0, 0.0);
-            }
-            slice_set(set_c);
-        };
-        load_set(std::integral_constant<int, 0>{});
-        load_set(std::integral_constant<int, 1>{});
-
-        auto stage_set = [&](auto set_c, int sidx) {
-            constexpr int set = decltype(set_c)::value;
-            uint64_t *full = bars + set * PER_SET, *empty = full + NACC;
-            const int stage = sidx & 3, entry = stage_entry(sidx);
-            long long tr[CPT], ti[CPT];
-#pragma unroll
-            for (int j = 0; j < CPT; ++j) tr[j] = ti[j] = 0;
-#pragma unroll
-            for (int g = NS + 1; g >= 2; --g) {
-                const int b = acc_of_group(g), sh = 8 * (NS + 1 - g);
-                mbar_wait(full + b, pf[set][b]);
-                pf[set][b] ^= 1u;
-                tc_fence_after();
-                int vr[CPT], vi[CPT];
-                tmem_ld4(lane_q + (uint32_t)((set * NACC + b) * 2 * CS + CPT * oc), vr);
-                tmem_ld4(lane_q + (uint32_t)((set * NACC + b) * 2 * CS + CS + CPT * oc), vi);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                tc_fence_before();
-                if (lane == 0) mbar_arrive(empty + b);
-#pragma unroll
-                for (int j = 0; j < CPT; ++j) {
-                    tr[j] += (long long)vr[j] << sh;
-                    ti[j] += (long long)vi[j] << sh;
-                }
-            }
-            const int ea = ea_s[(entry & 3) * KD + row];
-            const StageCoef sc(stage, h);
-#pragma unroll
-            for (int j = 0; j < CPT; ++j) {
-                const int c = set * CS + CPT * oc + j;
-                const double s = pow2(ea + eb[set][j] - 8 * (NS + 1));
-                const double k_r = (double)tr[j] * s, k_i = (double)ti[j] * s;
-                double2 ks = stage == 0 ? make_double2(0.0, 0.0) : ksm[c * KD + row];
-                ks.x = sc.keep * ks.x + sc.wk * k_r;
-                ks.y = sc.keep * ks.y + sc.wk * k_i;
-                const double v_r = sc.last ? ks.x : k_r, v_i = sc.last ? ks.y : k_i;
-                const double2 yv = ysm[c * KD + row];
-                x[j] = make_double2(yv.x + sc.astep * v_r, yv.y + sc.astep * v_i);
-                if (sc.last) ysm[c * KD + row] = x[j]; else ksm[c * KD + row] = ks;
-            }
-            if (sidx + 1 < total) slice_set(set_c);
-        };
-#pragma unroll 1
-        for (int sidx = 0; sidx < total; ++sidx) {
-            stage_set(std::integral_constant<int, 0>{}, sidx);
-            stage_set(std::integral_constant<int, 1>{}, sidx);
-        }
-#pragma unroll
-        for (int s2 = 0; s2 < SETS; ++s2)
-#pragma unroll
-            for (int j = 0; j < CPT; ++j) {
-                const int c = s2 * CS + CPT * oc + j, col = col0 + c;
-                if (row < n && col < B) y[(size_t)row * ldy + col] = ysm[c * KD + row];
-            }
-      }
-    }
-    if (!ALT && warp < EPI_WARPS) {
+    if (warp < EPI_WARPS) {
         // =========================== epilogue warps: thread = (row, 8 columns of the warp's set) ===========================
         const int set = warp / SET_WARPS, qd = warp & 3, oc = (warp % SET_WARPS) >> 2;
         const int row = 32 * qd + lane;
@@ -528,7 +393,7 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
             const int c = cbase + j, col = col0 + c;
             if (row < n && col < B) y[(size_t)row * ldy + col] = ysm[c * KD + row];
         }
-    } else if (warp >= EPI_WARPS) {
+    } else {
         // ============ MMA issuer (the first warp after the epilogue); then four generator loaders, one per TMEM lane quarter ============
         const int last_entry = 2 * S;
         if (warp != MMA_WARP) {
@@ -689,27 +554,15 @@ int launch_rk4_ozaki(int n, int B, int S, const double2* gen, int gen_layout, do
         cudaMemcpyToSymbolAsync(g_oz_dbg_stage, &v, sizeof(int), 0, cudaMemcpyHostToDevice, st);
     }
 #endif
-    // 32 columns per CTA once 16 per CTA would no longer fit one wave of the SMs (QDB_OZ_TWO_SETS=1: two sets of 16, for the record)
-    static const int two_sets = [] {
-        const char* e = getenv("QDB_OZ_TWO_SETS");
-        return e ? atoi(e) : 0;
-    }();
+    // 32 columns per CTA once 16 per CTA would no longer fit one wave of the SMs
     if (B <= sm_count() * 16) {
         constexpr Smem L(16, 1);
-        QDB_CUDA(cudaFuncSetAttribute(rk4_ozaki_kernel<16, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-        rk4_ozaki_kernel<16, 1, false><<<(B + 15) / 16, (8 + 1 + LOADERS) * 32, L.total, st>>>(n, B, S, planes, expo, h, y, ldy);
-    } else if (two_sets == 2) {
-        constexpr Smem L(16, 2);
-        QDB_CUDA(cudaFuncSetAttribute(rk4_ozaki_kernel<16, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-        rk4_ozaki_kernel<16, 2, true><<<(B + 31) / 32, (16 + 1 + LOADERS) * 32, L.total, st>>>(n, B, S, planes, expo, h, y, ldy);
-    } else if (two_sets == 1) {
-        constexpr Smem L(16, 2);
-        QDB_CUDA(cudaFuncSetAttribute(rk4_ozaki_kernel<16, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-        rk4_ozaki_kernel<16, 2, false><<<(B + 31) / 32, (16 + 1 + LOADERS) * 32, L.total, st>>>(n, B, S, planes, expo, h, y, ldy);
+        QDB_CUDA(cudaFuncSetAttribute(rk4_ozaki_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        rk4_ozaki_kernel<16, 1><<<(B + 15) / 16, (8 + 1 + LOADERS) * 32, L.total, st>>>(n, B, S, planes, expo, h, y, ldy);
     } else {
         constexpr Smem L(32, 1);
-        QDB_CUDA(cudaFuncSetAttribute(rk4_ozaki_kernel<32, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-        rk4_ozaki_kernel<32, 1, false><<<(B + 31) / 32, (16 + 1 + LOADERS) * 32, L.total, st>>>(n, B, S, planes, expo, h, y, ldy);
+        QDB_CUDA(cudaFuncSetAttribute(rk4_ozaki_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        rk4_ozaki_kernel<32, 1><<<(B + 31) / 32, (16 + 1 + LOADERS) * 32, L.total, st>>>(n, B, S, planes, expo, h, y, ldy);
     }
     QDB_LAUNCH_CHECK("rk4_ozaki_kernel");
     return QDB_OK;
