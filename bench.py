@@ -436,6 +436,7 @@ def run_b200(args):
         s_e2e = time_e2e(scase, ssteps)
         strong = {"total_batch": BATCH, "batch_per_gpu": hi - lo, "ms_per_step": s_ms, "value": 4.0 * S * BATCH / (s_ms * 1e-3),
                   "e2e_ms_per_step": s_e2e, "e2e_value": 4.0 * S * BATCH / (s_e2e * 1e-3), "steps": ssteps,
+                  "kernel": ("rk4_ozaki_kernel (int8 tensor cores)" if abi.rk4_int8_preferred(n, hi - lo) else "fp64 DMMA, tiling below"),
                   "tiling": abi.rk4_tiling(n, hi - lo),
                   "note": "same 1000-step solve, total batch fixed at 4096 columns, split over the ranks; value = whole-job "
                           "state-RHS/s; strong-scaling efficiency = value(N) / (N * value(1))"}
