@@ -244,7 +244,7 @@ int qdb_rk4_steps_c128(int n, int K, int B, int S, const qdb_c128* ops_rm, const
             return launch_rk4_fused_sweep(n, K, B, S, D2(stat_packed), D2(ops_packed), coeff, ldc, mu, times_dev, h, D2(y), ldy, fws, st);
         }
         // shared signals: chunk the step loop so that the generator table fits the workspace
-        // (large batches at n = 121..128: the int8 tensor-core emulation, whose slice planes sit behind the packed table)
+        // (large batches at n = 80..128: the int8 tensor-core emulation, whose slice planes sit behind the packed table)
         const bool int8_path = rk4_ozaki_preferred(n, B);
         const int table_layout = int8_path ? QDB_LAYOUT_PACKED : rk4_fused_table_layout(n, B);
         const size_t per_entry = qdb_table_entry_bytes(n, table_layout) + (int8_path ? rk4_ozaki_table_bytes(1) : 0);
@@ -383,7 +383,7 @@ int qdb_rk4_ozaki_slice_c128(int n, int T, const qdb_c128* gen_table, int table_
     if (T == 0) return QDB_OK;
     QDB_REQUIRE(gen_table && workspace, "qdb_rk4_ozaki_slice_c128: null pointer");
     if (!rk4_ozaki_supported(n)) {
-        set_error("qdb_rk4_ozaki_slice_c128: the int8 tensor-core emulation exists for n = 121..128 (got %d)", n);
+        set_error("qdb_rk4_ozaki_slice_c128: the int8 tensor-core emulation exists for n = 65..128 (got %d)", n);
         return QDB_E_UNSUPPORTED;
     }
     if (ws_bytes < rk4_ozaki_table_bytes(T)) {
@@ -399,7 +399,7 @@ int qdb_rk4_ozaki_steps_c128(int n, int B, int S, const qdb_c128* gen_table_rowm
     if (B == 0 || S == 0) return QDB_OK;
     QDB_REQUIRE(y && ldy >= B && workspace, "qdb_rk4_ozaki_steps_c128: null pointer / bad ldy");
     if (!rk4_ozaki_supported(n)) {
-        set_error("qdb_rk4_ozaki_steps_c128: the int8 tensor-core emulation exists for n = 121..128 (got %d)", n);
+        set_error("qdb_rk4_ozaki_steps_c128: the int8 tensor-core emulation exists for n = 65..128 (got %d)", n);
         return QDB_E_UNSUPPORTED;
     }
     if (ws_bytes < rk4_ozaki_table_bytes(2 * S + 1)) {

@@ -1,5 +1,5 @@
 // Fused shared-signal RK4 with the fp64 contraction EMULATED on the int8 tensor cores (tcgen05.mma kind::i8, accumulators
-// and the generator operand in TMEM) -- an Ozaki-style error-free split.  n = 121..128.
+// and the generator operand in TMEM) -- an Ozaki-style error-free split.  n = 65..128 (rows and k padded to 128).
 //
 // Why.  tcgen05 has no fp64 kind; DMMA is the fp64 tensor pipe of sm_100a and rk4_shared3m_kernel already runs it at 85 %.
 // The only way past that roof is to leave the fp64 pipe: every real operand is cut into NS = 5 signed BYTES against a
@@ -55,6 +55,7 @@ namespace {
 #endif
 
 constexpr int NS = 5;        // byte slices per operand: 2^-40, 15 slice pairs
+constexpr int OZ_MIN_N = 65; // rows and k are padded to 128 (k chunks of 32 past n are skipped): below this the DMMA kernels win
 constexpr int KD = 128;      // padded dimension (MMA M and K)
 constexpr int LOADERS = 4;   // generator loader warps (one per TMEM lane quarter)
 constexpr int NACC = 3;           // accumulator buffers per set (re | im: 32 columns each): a stage's five groups never wait for a drain
@@ -157,7 +158,10 @@ __global__ void __launch_bounds__(128) ozaki_gslice_kernel(int n, const double2*
     const int row = blockIdx.x, t = blockIdx.y, k = threadIdx.x;
     __shared__ unsigned wmax[4];
     double2 v = make_double2(0.0, 0.0);
-    if (row < n && k < n) v = PACKED ? gen[(size_t)t * KD * KD + packed_index(KD, row, k)] : gen[((size_t)t * n + row) * n + k];
+    if (row < n && k < n) {
+        const int kpad = round_up16(n);
+        v = PACKED ? gen[(size_t)t * round_up8(n) * kpad + packed_index(kpad, row, k)] : gen[((size_t)t * n + row) * n + k];
+    }
     unsigned m = max(abs_hi(v.x), abs_hi(v.y));
     m = __reduce_max_sync(0xffffffffu, m);
     if ((k & 31) == 0) wmax[k >> 5] = m;
@@ -227,6 +231,7 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int col0 = blockIdx.x * (SETS * CS);
     const int total = 4 * S;
+    const int nks = (n + 31) >> 5;  // k chunks of 32 that hold data
 
     if (tid == 0) {
 #pragma unroll
@@ -480,6 +485,7 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
                             const uint32_t a_re = TMEM_A + (uint32_t)((0 * NS + (p - 1)) * 32), a_im = TMEM_A + (uint32_t)((1 * NS + (p - 1)) * 32);
 #pragma unroll
                             for (int ks = 0; ks < KD / 32; ++ks) {
+                                if (ks >= nks) continue;  // k chunks past n hold zeros (uniform: n is a kernel argument)
                                 const uint32_t b1 = bd_lo + (uint32_t)((((set * NS + q - 1) * 2 + 0) * BPLANE + ks * 4 * (int)LBO) >> 4);  // (re | im)
                                 const uint32_t b2 = bd_lo + (uint32_t)((((set * NS + q - 1) * 2 + 1) * BPLANE + ks * 4 * (int)LBO) >> 4);  // (-im | re)
                                 mma_ts<idesc_for(2 * CS)>(d, a_re + 8 * ks, b1, bd_hi, (p == 1 && ks == 0) ? 0u : 1u);
@@ -503,17 +509,22 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
 
 }  // namespace
 
-bool rk4_ozaki_supported(int n) { return n >= 121 && n <= 128; }
+bool rk4_ozaki_supported(int n) { return n >= OZ_MIN_N && n <= 128; }
 
 // The emulated path is the faster one once its single wave of CTAs beats the DMMA kernels' time for the batch (measured at
 // n = 128: 17.9 us per step for any B <= 2368 -- 16 columns per CTA -- and 23.8 us up to 4736, against 9.0 / 17.9 / 30.2 /
-// 51.8 us of the DMMA kernels at B = 512 / 1024 / 2048 / 4096).  QDB_RK4_INT8=0 keeps every batch on the fp64 DMMA kernels.
+// 51.8 us of the DMMA kernels at B = 512 / 1024 / 2048 / 4096).  Smaller n pay the padding to 128 rows: at B = 4096 the
+// emulation wins 1.64x at n = 100..112, 1.44x at 96, 1.24x at 80 and 65; at B = 2048 1.07x at n = 96 and 0.88x at 80
+// (profiles/r02_r_ozaki_small_n.jsonl).  QDB_RK4_INT8=0 keeps every batch on the fp64 DMMA kernels.
 bool rk4_ozaki_preferred(int n, int B) {
     static const bool enabled = [] {
         const char* e = getenv("QDB_RK4_INT8");
         return !(e && e[0] == '0');
     }();
-    return enabled && rk4_ozaki_supported(n) && B > 1024;
+    if (!enabled || !rk4_ozaki_supported(n)) return false;
+    if (n >= 121) return B > 1024;
+    if (n >= 96) return B >= 1536;
+    return n >= 80 && B > sm_count() * 16;
 }
 
 void rk4_ozaki_debug(long long* host64) { cudaMemcpyFromSymbol(host64, g_oz_dbg, sizeof(long long) * 64); }
@@ -529,7 +540,7 @@ int launch_ozaki_slice(int n, int T, const double2* gen, int gen_layout, void* w
     for (int t0 = 0; t0 < T; t0 += kMaxGridY) {
         const int Tc = T - t0 < kMaxGridY ? T - t0 : kMaxGridY;
         if (gen_layout == QDB_LAYOUT_PACKED)
-            ozaki_gslice_kernel<true><<<dim3(KD, Tc), 128, 0, st>>>(n, gen + (size_t)t0 * KD * KD, planes + (size_t)t0 * 2 * NS * KD * KD,
+            ozaki_gslice_kernel<true><<<dim3(KD, Tc), 128, 0, st>>>(n, gen + (size_t)t0 * round_up8(n) * round_up16(n), planes + (size_t)t0 * 2 * NS * KD * KD,
                                                                     expo + (size_t)t0 * KD);
         else
             ozaki_gslice_kernel<false><<<dim3(KD, Tc), 128, 0, st>>>(n, gen + (size_t)t0 * n * n, planes + (size_t)t0 * 2 * NS * KD * KD,
