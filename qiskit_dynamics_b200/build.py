@@ -6,7 +6,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["api.cu", "gen.cu", "zgemm.cu", "rk4_fused.cu", "rk4_rowsplit.cu", "rk4_ozaki.cu", "rk4_sweep_small.cu", "rk4_sweepf.cu", "lindblad.cu", "expm.cu", "propagator.cu", "signals.cu", "measure.cu"]
+SOURCES = ["api.cu", "gen.cu", "zgemm.cu", "rk4_fused.cu", "rk4_rowsplit.cu", "rk4_ozaki.cu", "zgemm_ozaki.cu", "rk4_sweep_small.cu", "rk4_sweepf.cu", "lindblad.cu", "expm.cu", "propagator.cu", "signals.cu", "measure.cu"]
 OUT = os.path.join(CSRC, "libqdb.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--threads", "0",
               "-Xcompiler", "-fPIC", "-shared"]

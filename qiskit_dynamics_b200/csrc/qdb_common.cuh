@@ -127,6 +127,10 @@ bool rk4_fused_tiling(int n, int B, int sweep_K, int* out);
 int launch_rk4_fused_shared(int n, int B, int S, const double2* gen_table, int table_layout, double h,
                             double2* y, int ldy, cudaStream_t st);
 int rk4_fused_table_layout(int n, int B);
+// complex GEMM emulated on the int8 tensor cores (zgemm_ozaki.cu)
+bool zgemm_int8_preferred(int M, int N, int Kd);
+int launch_zgemm_int8(int M, int N, int Kd, const double2* A, int lda, const double2* B, int ldb, double2* C, int ldc, double2 alpha,
+                      double2 beta, const double* colscale, const double2* pre, const double2* post, cudaStream_t st);
 // fp64 emulation on the int8 tensor cores (rk4_ozaki.cu), n = 121..128
 bool rk4_ozaki_supported(int n);
 size_t rk4_ozaki_table_bytes(int T);

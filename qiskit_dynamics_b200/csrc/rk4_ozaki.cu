@@ -37,8 +37,7 @@
 #include <cstdint>
 #include <cstdlib>
 
-#include "qdb_common.cuh"
-#include "rk4_device.cuh"
+#include "ozaki_device.cuh"
 
 namespace qdb {
 
@@ -54,14 +53,6 @@ namespace {
 #define OZ_DBG(i) do { } while (0)
 #endif
 
-constexpr int NS = 5;        // byte slices per operand: 2^-40, 15 slice pairs
-constexpr int OZ_MIN_N = 65; // rows and k are padded to 128 (k chunks of 32 past n are skipped): below this the DMMA kernels win
-constexpr int KD = 128;      // padded dimension (MMA M and K)
-constexpr int LOADERS = 4;   // generator loader warps (one per TMEM lane quarter)
-constexpr int NACC = 3;           // accumulator buffers per set (re | im: 32 columns each): a stage's five groups never wait for a drain
-constexpr uint32_t TMEM_A = 192;  // TMEM columns [192, 512): generator slice planes; [0, 192): accumulators (the allocation is the whole TMEM: base 0)
-static_assert(TMEM_A + 2 * NS * 32 <= 512, "TMEM");
-__host__ __device__ constexpr int acc_of_group(int g) { return (NS + 1 - g) % NACC; }
 
 // shared-memory carve-up (bytes) of a CTA with SETS column sets of CS columns; a stage-vector operand plane is 128 k x 2 CS
 // "columns" (two parts side by side): 2 CS KD bytes
@@ -78,75 +69,6 @@ struct Smem {
           total(tmem + 16) {}
 };
 
-// Stage-vector operand planes (the MMA's B operand, 128 k x 2 CS int8) in the MN-major no-swizzle layout: core matrix = 8 k-rows
-// of 16 consecutive columns, CS / 8 cores side by side (SBO = 128 B), sixteen k groups (LBO = CS / 8 x 128 B).  One N = 2 CS
-// MMA computes both accumulators of a set: (re | im) += A_re x (B_re | B_im) and += A_im x (-B_im | B_re) -- half the MMA
-// count, and at CS = 32 the peak rate of the TMEM-operand path.  A thread (one k, eight consecutive columns of one part) owns
-// 8 contiguous bytes: `half` = 0 / 1 selects the left / right CS columns of the plane.
-template <int CS>
-__device__ __forceinline__ int bplane_off8(int oc, int k, int half) {
-    return ((k >> 3) * (CS / 8) + half * (CS / 16) + (oc >> 1)) * 128 + (k & 7) * 16 + (oc & 1) * 8;
-}
-
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
-           ((uint64_t)1 << 46);
-}
-// s32 += s8 x s8, A K-major (TMEM), B MN-major, M = 128, N = ncols
-__host__ __device__ constexpr uint32_t idesc_for(int ncols) {
-    return (2u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)(KD >> 4) << 24);
-}
-
-// executed by a whole warp in uniform control flow; one elected lane issues
-// (the shared-memory descriptor arrives as two words: only the low one -- the address field -- varies between the MMAs)
-template <uint32_t IDESC>
-__device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t db_lo, uint32_t db_hi, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\tmov.b64 db, {%2, %6};\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], db, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "r"(db_lo), "r"(IDESC),
-        "r"(accumulate), "r"(0u), "r"(db_hi)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* b) {
-    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(
-                     (uint32_t)__cvta_generic_to_shared(b))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(b)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// 2^e as a double (|e| < 1000)
-__device__ __forceinline__ double pow2(int e) { return __longlong_as_double((long long)(1023 + e) << 52); }
-
-// Slice exponent from the HIGH WORD of max |x| (sign cleared): e with |x| 2^-e < 1/2 - 2^-8 for every |x| <= that maximum,
-// so that the leading digit of X + bias (below) fits a signed byte; zero / denormal -> 0
-__device__ __forceinline__ int slice_exponent_hi(unsigned hi) {
-    if (hi < 0x00100000u) return 0;
-    int e = (int)(hi >> 20) - 1021;  // 2^(e-2) <= m < 2^(e-1)
-    if ((hi & 0xFFFFFu) >= 0xFC000u) ++e;
-    return e;
-}
-__device__ __forceinline__ unsigned abs_hi(double x) { return (unsigned)(__double_as_longlong(x) >> 32) & 0x7FFFFFFFu; }
-
-// x -> NS signed byte slices against 2^e: x 2^-e = sum_p q_p 2^(-8p) + O(2^(-8 NS - 1)).  With X = rint(x 2^(8 NS - e)),
-// |X| < 2^(8 NS - 1) - 2^(8 NS - 8), the balanced base-256 digits of X are the bytes of X + bias (bias = 0x80 in each of the
-// NS - 1 low bytes) minus 128 each, i.e. with the top bit flipped: byte j of (X + bias) ^ bias = q_(NS - j) as a signed
-// byte, j = 0 .. NS - 1.  X comes from t = fma(x, scale, 1.5 2^52): the integer sits in the low mantissa bits of t
-// (|X| < 2^51), so rounding, conversion and bias are one fp64 FMA and one 64-bit integer add -- no F2I (a quarter-rate
-// instruction).
-constexpr long long kBias = 0x80808080LL;
-static_assert(NS == 5, "bias: 0x80 in the NS - 1 low bytes");
-constexpr double kMagic = 6755399441055744.0;
-constexpr long long kMagicBits = 0x4338000000000000LL;
-__device__ __forceinline__ long long digits_of(double x, double scale) {
-    return (__double_as_longlong(fma(x, scale, kMagic)) + (kBias - kMagicBits)) ^ kBias;
-}
-__device__ __forceinline__ long long digits_of_negated(double x, double scale) {
-    return ((kMagicBits + kBias) - __double_as_longlong(fma(x, scale, kMagic))) ^ kBias;
-}
 
 // ---- generator table (row-major fp64, as generator_kernel writes it) -> int8 slice planes + row exponents ----
 // planes[t][part][p][k / 16][row][k % 16] (a loader lane = a row reads 16 B next to its neighbours': coalesced; the eight
@@ -179,27 +101,6 @@ __global__ void __launch_bounds__(128) ozaki_gslice_kernel(int n, const double2*
     }
 }
 
-// the same slice of four columns in one word: w[j] = {a.byte j, b.byte j, c.byte j, d.byte j} (a = lowest address)
-__device__ __forceinline__ void transpose4(unsigned a, unsigned b, unsigned c, unsigned d, unsigned (&w)[4]) {
-    const unsigned t0 = __byte_perm(a, b, 0x5140), t1 = __byte_perm(a, b, 0x7362);
-    const unsigned t2 = __byte_perm(c, d, 0x5140), t3 = __byte_perm(c, d, 0x7362);
-    w[0] = __byte_perm(t0, t2, 0x5410);
-    w[1] = __byte_perm(t0, t2, 0x7632);
-    w[2] = __byte_perm(t1, t3, 0x5410);
-    w[3] = __byte_perm(t1, t3, 0x7632);
-}
-
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
-                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-                 : "memory");
-}
 
 __device__ __forceinline__ int stage_entry(int sidx) {
     const int step = sidx >> 2, stage = sidx & 3;

@@ -513,6 +513,8 @@ int launch_zgemm(int M, int N, int Kd, const double2* A, int lda, const double2*
                  double2 alpha, double2 beta, const double* colscale, const double2* pre, const double2* post,
                  cudaStream_t st) {
     if (M == 0 || N == 0) return QDB_OK;
+    // large products: the int8 tensor-core emulation (zgemm_ozaki.cu)
+    if (zgemm_int8_preferred(M, N, Kd)) return launch_zgemm_int8(M, N, Kd, A, lda, B, ldb, C, ldc, alpha, beta, colscale, pre, post, st);
     EpiStd e{C, ldc, alpha, beta, colscale, post, 0};
     return launch(M, N, Kd, A, lda, B, ldb, pre, e, st);
 }
