@@ -78,14 +78,22 @@ __device__ __forceinline__ unsigned abs_hi(double x) { return (unsigned)(__doubl
 // byte, j = 0 .. NS - 1.  X comes from t = fma(x, scale, 1.5 2^52): the integer sits in the low mantissa bits of t
 // (|X| < 2^51), so rounding, conversion and bias are one fp64 FMA and one 64-bit integer add -- no F2I (a quarter-rate
 // instruction).
-constexpr long long kBias = 0x80808080LL;
-static_assert(NS == 5, "bias: 0x80 in the NS - 1 low bytes");
+template <int NSL>
+__host__ __device__ constexpr long long bias_of() {  // 0x80 in the NSL - 1 low bytes
+    long long b = 0;
+    for (int j = 0; j < NSL - 1; ++j) b |= 0x80LL << (8 * j);
+    return b;
+}
 constexpr double kMagic = 6755399441055744.0;
 constexpr long long kMagicBits = 0x4338000000000000LL;
+template <int NSL = NS>
 __device__ __forceinline__ long long digits_of(double x, double scale) {
+    constexpr long long kBias = bias_of<NSL>();
     return (__double_as_longlong(fma(x, scale, kMagic)) + (kBias - kMagicBits)) ^ kBias;
 }
+template <int NSL = NS>
 __device__ __forceinline__ long long digits_of_negated(double x, double scale) {
+    constexpr long long kBias = bias_of<NSL>();
     return ((kMagicBits + kBias) - __double_as_longlong(fma(x, scale, kMagic))) ^ kBias;
 }
 

@@ -9,9 +9,9 @@
 // Three launches:
 //   zg_aslice_kernel   A (M x K) -> int8 planes per (row tile of 128, k chunk of 128), chunk-major like the generator planes
 //                      of rk4_ozaki.cu (a loader lane = a row reads 16 B next to its neighbours'), + row exponents;
-//   zg_colmax_kernel + zg_bslice_kernel   B (K x N, rows scaled by `pre`) -> per (column tile of 32, k chunk) the 80 KB
-//                      shared-memory IMAGE of the ten operand planes (B_re | B_im), (-B_im | B_re) in the MN-major
-//                      no-swizzle core-matrix layout, + column exponents;
+//   zg_colmax_kernel + zg_bslice_kernel   B (K x N, rows scaled by `pre`) -> per (column tile of 32, k chunk) the
+//                      shared-memory IMAGE of the operand planes (B_re | B_im), (-B_im | B_re) of every slice in the MN-major
+//                      no-swizzle core-matrix layout (12 KB per slice: the two planes overlap in B_re), + column exponents;
 //   zgemm_ozaki_kernel one CTA per 128 x 32 tile of C: per k chunk the A planes go L2 -> (TMA, four-deep shared-memory ring)
 //                      -> registers -> TMEM (four loader warps; a plane of the previous chunk is overwritten as soon as
 //                      its last group has completed), the B image arrives by ONE TMA bulk copy into a double-buffered slot, warp 16 issues 120 N = 64 MMAs, sixteen
@@ -26,10 +26,32 @@ namespace qdb {
 namespace {
 
 constexpr int TN = 32;                 // columns of C per CTA (MMA N = 64: re | im)
-constexpr int BPL = 2 * TN * KD;       // bytes of one B operand plane of a k chunk
-constexpr int BCHUNK = NS * 2 * BPL;   // bytes of the B image of a (column tile, k chunk): 81920
+// B image of a (column tile, k chunk), per slice: sixteen k groups (8 k-rows) of SIX cores (16 columns x 8 k, 128 B each)
+// [-im(0:16) -im(16:32) | re(0:16) re(16:32) | im(0:16) im(16:32)] -- the operand plane (re | im) is cores 2..5 and
+// (-im | re) is cores 0..3 of every k group (LBO = 768 B, SBO = 128 B), so re is stored once: 12 KB per slice instead of 16
+constexpr int BKG = 6 * 128;           // bytes of a k group
+constexpr int BSL = (KD / 8) * BKG;    // bytes of a slice of the image: 12288
+__device__ __forceinline__ int bimg_off8(int oc, int k, int which /* 0: -im, 1: re, 2: im */) {
+    return (k >> 3) * BKG + (2 * which + (oc >> 1)) * 128 + (k & 7) * 16 + (oc & 1) * 8;
+}
 constexpr int APL = KD * KD;           // bytes of one A plane of a (row tile, k chunk)
-constexpr int ACHUNK = 2 * NS * APL;   // 163840
+constexpr int Z_EPI_WARPS = 16, Z_MMA_WARP = 16, Z_PRODUCER = 21, Z_NWARPS = 22;  // 17-20: loaders (smem -> TMEM), 21: TMA producer of the A planes
+
+// NSL byte slices per operand: 5 -> 2^-40, 15 slice pairs, three accumulator buffers, a six-deep A ring;
+// 6 -> 2^-48, 21 pairs -- TMEM (12 A planes) then leaves room for two accumulator buffers, shared memory (two 72 KB B images)
+// for a five-deep A ring
+template <int NSL>
+struct ZCfg {
+    static constexpr int NACC = NSL == 5 ? 3 : 2;
+    static constexpr int ASTAGES = NSL == 5 ? 6 : 5;
+    static constexpr int BCHUNK = NSL * BSL;       // bytes of the B image of a (column tile, k chunk)
+    static constexpr int ACHUNK = 2 * NSL * APL;
+    static constexpr uint32_t TMEM_A = NACC * 2 * TN;  // accumulators below, A planes above
+    static_assert(TMEM_A + 2 * NSL * 32 <= 512, "TMEM");
+    static constexpr int S_B = 0, S_A = 2 * BCHUNK, S_BAR = S_A + ASTAGES * APL, S_TMEM = S_BAR + 32 * 8, S_TOTAL = S_TMEM + 16;
+    static_assert(S_TOTAL <= 232448, "shared memory");
+    __host__ __device__ static constexpr int acc(int g) { return (NSL + 1 - g) % NACC; }
+};
 
 struct EpiZ {
     double2* C;
@@ -40,6 +62,7 @@ struct EpiZ {
 };
 
 // ---- A -> planes[rt][kc][part][p][k/16][row][k%16], expo[row]; one block per (padded) row ----
+template <int NSL>
 __global__ void __launch_bounds__(128) zg_aslice_kernel(int M, int K, int KC, const double2* __restrict__ A, int lda,
                                                          int8_t* __restrict__ planes, int* __restrict__ expo) {
     const int row = blockIdx.x, tid = threadIdx.x;
@@ -56,18 +79,18 @@ __global__ void __launch_bounds__(128) zg_aslice_kernel(int M, int K, int KC, co
     m = max(max(wmax[0], wmax[1]), max(wmax[2], wmax[3]));
     const int e = slice_exponent_hi(m);
     if (tid == 0) expo[row] = e;
-    const double scale = pow2(8 * NS - e);
+    const double scale = pow2(8 * NSL - e);
     const int rt = row >> 7, r = row & 127;
     for (int kc = 0; kc < KC; ++kc) {
         const int k = kc * KD + tid;
         double2 v = make_double2(0.0, 0.0);
         if (row < M && k < K) v = A[(size_t)row * lda + k];
-        const long long dr = digits_of(v.x, scale), di = digits_of(v.y, scale);
-        int8_t* base = planes + (size_t)(rt * KC + kc) * ACHUNK + (size_t)(tid >> 4) * (KD * 16) + r * 16 + (tid & 15);
+        const long long dr = digits_of<NSL>(v.x, scale), di = digits_of<NSL>(v.y, scale);
+        int8_t* base = planes + (size_t)(rt * KC + kc) * ZCfg<NSL>::ACHUNK + (size_t)(tid >> 4) * (KD * 16) + r * 16 + (tid & 15);
 #pragma unroll
-        for (int p = 0; p < NS; ++p) {
-            base[(size_t)(0 * NS + p) * APL] = (int8_t)(dr >> (8 * (NS - 1 - p)));
-            base[(size_t)(1 * NS + p) * APL] = (int8_t)(di >> (8 * (NS - 1 - p)));
+        for (int p = 0; p < NSL; ++p) {
+            base[(size_t)(0 * NSL + p) * APL] = (int8_t)(dr >> (8 * (NSL - 1 - p)));
+            base[(size_t)(1 * NSL + p) * APL] = (int8_t)(di >> (8 * (NSL - 1 - p)));
         }
     }
 }
@@ -92,14 +115,17 @@ __global__ void __launch_bounds__(256) zg_colmax_kernel(int K, int N, const doub
     atomicMax(colmax + c, m);
 }
 
-// ---- diag(pre) B -> images[ct][kc] (80 KB each: [slice][(re | im), (-im | re)][8 KB]), expo[c]; thread = (k, column octet) ----
+// ---- diag(pre) B -> images[ct][kc][slice] (12 KB each), expo[c].  Block = column tile x 32 k rows; a warp = one k group of 8
+// rows, lane = (k row, column octet): a store instruction of the warp fills two adjacent cores (256 contiguous bytes) ----
+template <int NSL>
 __global__ void __launch_bounds__(128) zg_bslice_kernel(int K, int N, int KC, int CT, const double2* __restrict__ B, int ldb,
                                                          const double2* __restrict__ pre, const unsigned* __restrict__ colmax,
                                                          int8_t* __restrict__ images, int* __restrict__ expo) {
-    const int oct = blockIdx.x * 128 + threadIdx.x, k = blockIdx.y;
-    if (oct >= CT * (TN / 8)) return;
-    const int c0 = 8 * oct;
-    unsigned wl[3][NS], wh[3][NS];
+    const int ct = blockIdx.x, lane = threadIdx.x & 31;
+    const int k = (blockIdx.y * 4 + (threadIdx.x >> 5)) * 8 + (lane >> 2), oc = lane & 3;
+    const int c0 = ct * TN + 8 * oc;
+    (void)CT;
+    unsigned wl[3][NSL], wh[3][NSL];
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
         unsigned lo[3][4], hi[3][4];
@@ -115,51 +141,44 @@ __global__ void __launch_bounds__(128) zg_bslice_kernel(int K, int N, int KC, in
             } else if (k == 0) {
                 expo[c] = 0;
             }
-            const double scale = pow2(8 * NS - e);
-            const long long d0 = digits_of(v.x, scale), d1 = digits_of(v.y, scale), d2 = digits_of_negated(v.y, scale);
+            const double scale = pow2(8 * NSL - e);
+            const long long d0 = digits_of<NSL>(v.x, scale), d1 = digits_of<NSL>(v.y, scale), d2 = digits_of_negated<NSL>(v.y, scale);
             lo[0][jj] = (unsigned)d0, hi[0][jj] = (unsigned)((unsigned long long)d0 >> 32);
             lo[1][jj] = (unsigned)d1, hi[1][jj] = (unsigned)((unsigned long long)d1 >> 32);
             lo[2][jj] = (unsigned)d2, hi[2][jj] = (unsigned)((unsigned long long)d2 >> 32);
         }
 #pragma unroll
         for (int part = 0; part < 3; ++part) {
-            unsigned wlo[4], whi[4];  // byte j of the digits = slice NS - j
+            unsigned wlo[4], whi[4];  // byte j of the digits = slice NSL - j
             transpose4(lo[part][0], lo[part][1], lo[part][2], lo[part][3], wlo);
             transpose4(hi[part][0], hi[part][1], hi[part][2], hi[part][3], whi);
 #pragma unroll
-            for (int p = 1; p <= NS; ++p) {
-                const int byte = NS - p;
+            for (int p = 1; p <= NSL; ++p) {
+                const int byte = NSL - p;
                 const unsigned w = byte < 4 ? wlo[byte] : whi[byte - 4];
                 if (hh == 0) wl[part][p - 1] = w; else wh[part][p - 1] = w;
             }
         }
     }
-    const int ct = c0 / TN, oc = (c0 % TN) >> 3, kc = k >> 7, kk = k & 127;
-    int8_t* base = images + (size_t)(ct * KC + kc) * BCHUNK;
-    const int off0 = bplane_off8<TN>(oc, kk, 0), off1 = bplane_off8<TN>(oc, kk, 1);
+    const int kc = k >> 7, kk = k & 127;
+    int8_t* base = images + (size_t)(ct * KC + kc) * ZCfg<NSL>::BCHUNK;
 #pragma unroll
-    for (int p = 0; p < NS; ++p) {
-        int8_t* sl = base + p * 2 * BPL;
-        const uint2 re = make_uint2(wl[0][p], wh[0][p]), im = make_uint2(wl[1][p], wh[1][p]), nim = make_uint2(wl[2][p], wh[2][p]);
-        *reinterpret_cast<uint2*>(sl + off0) = re;          // (re | im)
-        *reinterpret_cast<uint2*>(sl + off1) = im;
-        *reinterpret_cast<uint2*>(sl + BPL + off0) = nim;   // (-im | re)
-        *reinterpret_cast<uint2*>(sl + BPL + off1) = re;
+    for (int p = 0; p < NSL; ++p) {
+        int8_t* sl = base + p * BSL;
+        *reinterpret_cast<uint2*>(sl + bimg_off8(oc, kk, 0)) = make_uint2(wl[2][p], wh[2][p]);  // -im
+        *reinterpret_cast<uint2*>(sl + bimg_off8(oc, kk, 1)) = make_uint2(wl[0][p], wh[0][p]);  // re
+        *reinterpret_cast<uint2*>(sl + bimg_off8(oc, kk, 2)) = make_uint2(wl[1][p], wh[1][p]);  // im
     }
 }
 
-// shared memory: two B images, a four-deep ring of A planes on their way to TMEM, then the mbarriers
-constexpr int ASTAGES = 4;
-constexpr int ZS_B = 0;
-constexpr int ZS_A = 2 * BCHUNK;
-constexpr int ZS_BAR = ZS_A + ASTAGES * APL;
-constexpr int ZS_TMEM = ZS_BAR + 32 * 8;
-constexpr int ZS_TOTAL = ZS_TMEM + 16;
-constexpr int Z_EPI_WARPS = 16, Z_MMA_WARP = 16, Z_PRODUCER = 21, Z_NWARPS = 22;  // 17-20: loaders (smem -> TMEM), 21: TMA producer of the A planes
-
+template <int NSL>
 __global__ void __launch_bounds__(Z_NWARPS * 32, 1)
 zgemm_ozaki_kernel(int M, int N, int KC, const int8_t* __restrict__ aplanes, const int* __restrict__ expoA,
                    const int8_t* __restrict__ bimages, const int* __restrict__ expoB, EpiZ epi) {
+    using Z = ZCfg<NSL>;
+    constexpr int NS = NSL, NACC = Z::NACC, ASTAGES = Z::ASTAGES, BCHUNK = Z::BCHUNK, ACHUNK = Z::ACHUNK;
+    constexpr int ZS_B = Z::S_B, ZS_A = Z::S_A, ZS_BAR = Z::S_BAR, ZS_TMEM = Z::S_TMEM;
+    constexpr uint32_t TMEM_A = Z::TMEM_A;
     extern __shared__ __align__(1024) uint8_t sm[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + ZS_BAR);
     uint64_t *full = bars, *empty = bars + NACC, *a_ready = bars + 2 * NACC, *p_free = a_ready + 1, *b_full = p_free + NS, *b_free = b_full + 2, *as_full = b_free + 2, *as_free = as_full + ASTAGES;
@@ -204,14 +223,16 @@ zgemm_ozaki_kernel(int M, int N, int KC, const int8_t* __restrict__ aplanes, con
         const int row = 32 * qd + lane;
         const uint32_t lane_base = ((uint32_t)(32 * qd) << 16);
         unsigned pf[NACC] = {};
-        long long tr[8], ti[8];  // sums over the k chunks: |.| < KC 2^56
+        // sums over the groups and the k chunks in fp64: every int32 group sum converts exactly, each addition rounds at 2^-53 of
+        // the running sum -- far below the 2^(-8 NS) truncation of the operands (and no int64 range to watch over long k)
+        double sr[8], si[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) tr[j] = ti[j] = 0;
+        for (int j = 0; j < 8; ++j) sr[j] = si[j] = 0.0;
 #pragma unroll 1
         for (int kc = 0; kc < KC; ++kc) {
 #pragma unroll
             for (int g = NS + 1; g >= 2; --g) {
-                const int b = acc_of_group(g), sh = 8 * (NS + 1 - g);
+                const int b = Z::acc(g), sh = 8 * (NS + 1 - g);
                 mbar_wait(full + b, pf[b]);
                 pf[b] ^= 1u;
                 tc_fence_after();
@@ -223,8 +244,8 @@ zgemm_ozaki_kernel(int M, int N, int KC, const int8_t* __restrict__ aplanes, con
                 if (lane == 0) mbar_arrive(empty + b);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    tr[j] += (long long)vr[j] << sh;
-                    ti[j] += (long long)vi[j] << sh;
+                    sr[j] = fma((double)vr[j], pow2(sh), sr[j]);
+                    si[j] = fma((double)vi[j], pow2(sh), si[j]);
                 }
             }
         }
@@ -238,7 +259,7 @@ zgemm_ozaki_kernel(int M, int N, int KC, const int8_t* __restrict__ aplanes, con
                 const int c = ct * TN + 8 * oc + j;
                 if (c < N) {
                     const double s = pow2(ea + expoB[c] - 8 * (NS + 1));
-                    double2 v = make_double2((double)tr[j] * s, (double)ti[j] * s);
+                    double2 v = make_double2(sr[j] * s, si[j] * s);
                     if (epi.post) v = cmul(po, v);
                     double2 a = epi.alpha;
                     if (epi.colscale) {
@@ -323,10 +344,12 @@ zgemm_ozaki_kernel(int M, int N, int KC, const int8_t* __restrict__ aplanes, con
     } else {
         // =========================== MMA issuer ===========================
         const uint32_t bs_addr = (uint32_t)__cvta_generic_to_shared(sm + ZS_B);
-        constexpr uint32_t LBO = (TN / 8) * 128, SBO = 128;
+        constexpr uint32_t LBO = BKG, SBO = 128;
         const uint64_t bdesc0 = smem_desc(bs_addr, LBO, SBO);
         const uint32_t bd_hi = (uint32_t)(bdesc0 >> 32);
-        unsigned pe[NACC] = {1u, 1u, 1u};
+        unsigned pe[NACC];
+#pragma unroll
+        for (int b = 0; b < NACC; ++b) pe[b] = 1u;
 #pragma unroll 1
         for (int kc = 0; kc < KC; ++kc) {
             const int buf = kc & 1;
@@ -338,7 +361,7 @@ zgemm_ozaki_kernel(int M, int N, int KC, const int8_t* __restrict__ aplanes, con
             tc_fence_after();
 #pragma unroll
             for (int g = NS + 1; g >= 2; --g) {
-                const int b = acc_of_group(g);
+                const int b = Z::acc(g);
                 mbar_wait(empty + b, pe[b]);
                 pe[b] ^= 1u;
                 tc_fence_after();
@@ -349,8 +372,8 @@ zgemm_ozaki_kernel(int M, int N, int KC, const int8_t* __restrict__ aplanes, con
                     const uint32_t a_re = TMEM_A + (uint32_t)((0 * NS + (p - 1)) * 32), a_im = TMEM_A + (uint32_t)((1 * NS + (p - 1)) * 32);
 #pragma unroll
                     for (int ks = 0; ks < KD / 32; ++ks) {
-                        const uint32_t b1 = bd_lo + (uint32_t)((((q - 1) * 2 + 0) * BPL + ks * 4 * (int)LBO) >> 4);  // (re | im)
-                        const uint32_t b2 = bd_lo + (uint32_t)((((q - 1) * 2 + 1) * BPL + ks * 4 * (int)LBO) >> 4);  // (-im | re)
+                        const uint32_t b1 = bd_lo + (uint32_t)(((q - 1) * BSL + 256 + ks * 4 * (int)LBO) >> 4);  // (re | im): cores 2..5
+                        const uint32_t b2 = bd_lo + (uint32_t)(((q - 1) * BSL + ks * 4 * (int)LBO) >> 4);        // (-im | re): cores 0..3
                         mma_ts<idesc_for(2 * TN)>(d, a_re + 8 * ks, b1, bd_hi, (p == 1 && ks == 0) ? 0u : 1u);
                         mma_ts<idesc_for(2 * TN)>(d, a_im + 8 * ks, b2, bd_hi, 1u);
                     }
@@ -367,27 +390,12 @@ zgemm_ozaki_kernel(int M, int N, int KC, const int8_t* __restrict__ aplanes, con
     if (warp == Z_MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
-}  // namespace
-
-// The emulated product pays three passes over the operands and a serial five-group drain per k chunk: it wins on products
-// that fill the chip with 128 x 32 tiles and are long enough in k (measured: profiles/r02_s_zgemm_int8.jsonl).
-// QDB_ZGEMM_INT8=0 keeps every product on the fp64 DMMA kernels.
-bool zgemm_int8_preferred(int M, int N, int Kd) {
-    static const int mode = [] {
-        const char* e = getenv("QDB_ZGEMM_INT8");
-        return e ? atoi(e) : 1;
-    }();
-    if (mode == 0) return false;
-    if (Kd > 4096) return false;  // the int64 chunk sums stay below 2^62
-    if (mode == 2) return Kd >= 1 && M >= 1 && N >= 1;  // force (tests)
-    const long tiles = (long)((M + KD - 1) / KD) * ((N + TN - 1) / TN);
-    return Kd >= 256 && tiles >= sm_count() / 2;
-}
-
-int launch_zgemm_int8(int M, int N, int Kd, const double2* A, int lda, const double2* B, int ldb, double2* C, int ldc, double2 alpha,
-                      double2 beta, const double* colscale, const double2* pre, const double2* post, cudaStream_t st) {
+template <int NSL>
+int launch_int8(int M, int N, int Kd, const double2* A, int lda, const double2* B, int ldb, double2* C, int ldc, double2 alpha,
+                double2 beta, const double* colscale, const double2* pre, const double2* post, cudaStream_t st) {
+    using Z = ZCfg<NSL>;
     const int RT = (M + KD - 1) / KD, CT = (N + TN - 1) / TN, KC = (Kd + KD - 1) / KD;
-    const size_t a_bytes = (size_t)RT * KC * ACHUNK, b_bytes = (size_t)CT * KC * BCHUNK;
+    const size_t a_bytes = (size_t)RT * KC * Z::ACHUNK, b_bytes = (size_t)CT * KC * Z::BCHUNK;
     const size_t ea_bytes = (size_t)RT * KD * sizeof(int), eb_bytes = (size_t)CT * TN * sizeof(int), cm_bytes = (size_t)CT * TN * sizeof(unsigned);
     // stream-ordered scratch from the device's default pool, which is told once to keep what it has been given
     static const bool pool_ready = [] {
@@ -408,18 +416,42 @@ int launch_zgemm_int8(int M, int N, int Kd, const double2* A, int lda, const dou
     int* expoB = reinterpret_cast<int*>(ws + a_bytes + b_bytes + ea_bytes);
     unsigned* colmax = reinterpret_cast<unsigned*>(ws + a_bytes + b_bytes + ea_bytes + eb_bytes);
     QDB_CUDA(cudaMemsetAsync(colmax, 0, cm_bytes, st));
-    zg_aslice_kernel<<<RT * KD, 128, 0, st>>>(M, Kd, KC, A, lda, aplanes, expoA);
+    zg_aslice_kernel<NSL><<<RT * KD, 128, 0, st>>>(M, Kd, KC, A, lda, aplanes, expoA);
     QDB_LAUNCH_CHECK("zg_aslice_kernel");
     zg_colmax_kernel<<<dim3((N + 255) / 256, (Kd + 63) / 64), 256, 0, st>>>(Kd, N, B, ldb, pre, colmax);
     QDB_LAUNCH_CHECK("zg_colmax_kernel");
-    zg_bslice_kernel<<<dim3((CT * (TN / 8) + 127) / 128, KC * KD), 128, 0, st>>>(Kd, N, KC, CT, B, ldb, pre, colmax, bimages, expoB);
+    zg_bslice_kernel<NSL><<<dim3(CT, KC * KD / 32), 128, 0, st>>>(Kd, N, KC, CT, B, ldb, pre, colmax, bimages, expoB);
     QDB_LAUNCH_CHECK("zg_bslice_kernel");
-    QDB_CUDA(cudaFuncSetAttribute(zgemm_ozaki_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ZS_TOTAL));
+    QDB_CUDA(cudaFuncSetAttribute(zgemm_ozaki_kernel<NSL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Z::S_TOTAL));
     EpiZ epi{C, ldc, alpha, beta, colscale, post};
-    zgemm_ozaki_kernel<<<dim3(CT, RT), Z_NWARPS * 32, ZS_TOTAL, st>>>(M, N, KC, aplanes, expoA, bimages, expoB, epi);
+    zgemm_ozaki_kernel<NSL><<<dim3(CT, RT), Z_NWARPS * 32, Z::S_TOTAL, st>>>(M, N, KC, aplanes, expoA, bimages, expoB, epi);
     QDB_LAUNCH_CHECK("zgemm_ozaki_kernel");
     QDB_CUDA(cudaFreeAsync(ws, st));
     return QDB_OK;
+}
+
+}  // namespace
+
+// The emulated product pays three passes over the operands and a serial drain of the weight groups per k chunk: it wins on
+// products that fill the chip with 128 x 32 tiles and are long enough in k (measured: profiles/r02_s_zgemm_int8.jsonl).
+// QDB_ZGEMM_INT8=0 keeps every product on the fp64 DMMA kernels, =2 forces the emulation (tests);
+// QDB_ZGEMM_SLICES=5 selects five byte slices per operand (2^-40) instead of six (2^-48).
+bool zgemm_int8_preferred(int M, int N, int Kd) {
+    const char* env = getenv("QDB_ZGEMM_INT8");  // read per call: the tests switch it
+    const int mode = env ? atoi(env) : 1;
+    if (mode == 0) return false;
+    if (Kd > 1 << 20) return false;  // grid.y of the slicing kernel
+    if (mode == 2) return Kd >= 1 && M >= 1 && N >= 1;
+    const long tiles = (long)((M + KD - 1) / KD) * ((N + TN - 1) / TN);
+    return Kd >= 384 && tiles >= sm_count() / 2;
+}
+
+int launch_zgemm_int8(int M, int N, int Kd, const double2* A, int lda, const double2* B, int ldb, double2* C, int ldc, double2 alpha,
+                      double2 beta, const double* colscale, const double2* pre, const double2* post, cudaStream_t st) {
+    const char* env = getenv("QDB_ZGEMM_SLICES");
+    const int slices = env && atoi(env) == 5 ? 5 : 6;
+    if (slices == 5) return launch_int8<5>(M, N, Kd, A, lda, B, ldb, C, ldc, alpha, beta, colscale, pre, post, st);
+    return launch_int8<6>(M, N, Kd, A, lda, B, ldb, C, ldc, alpha, beta, colscale, pre, post, st);
 }
 
 }  // namespace qdb
