@@ -99,7 +99,8 @@ def test_zgemm(abi, M, N, Kd):
 def test_zgemm_three_product_vs_four_product(abi, monkeypatch):
     """The 3-product kernel changes rounding only: against the 4-product kernel (QDB_ZGEMM_4M=1) on the shapes of the
     vectorised-Lindblad propagator (729^3) and its application (729 x 4096 x 729) the difference stays at a few
-    ulp of |A||B| (normwise bound), and both agree with NumPy."""
+    ulp of |A||B| (normwise bound), and both agree with NumPy.  (QDB_ZGEMM_INT8=0: the fp64 DMMA kernels are the subject.)"""
+    monkeypatch.setenv("QDB_ZGEMM_INT8", "0")
     rng = np.random.default_rng(7)
     for M, N, Kd in ((729, 729, 729), (729, 4096, 729), (128, 4096, 128)):
         A = rng.standard_normal((M, Kd)) + 1j * rng.standard_normal((M, Kd))
@@ -121,7 +122,9 @@ def test_zgemm_three_product_vs_four_product(abi, monkeypatch):
 def test_zgemm_split_k_tail(abi, monkeypatch, M, N, Kd):
     """Products whose 64 x 64 tile count leaves the last wave less than half full run that wave as clusters of 2 / 4 / 8
     CTAs splitting k (deterministic DSMEM reduction): same result as the one-CTA-per-tile launch up to the rounding of a
-    different summation order, with every epilogue option, and bit-identical from run to run."""
+    different summation order, with every epilogue option, and bit-identical from run to run.  (QDB_ZGEMM_INT8=0: the fp64
+    DMMA kernels are the subject.)"""
+    monkeypatch.setenv("QDB_ZGEMM_INT8", "0")
     rng = np.random.default_rng(M + N + Kd)
     A = dev(rng.standard_normal((M, Kd)) + 1j * rng.standard_normal((M, Kd)))
     Bm = dev(rng.standard_normal((Kd, N)) + 1j * rng.standard_normal((Kd, N)))
