@@ -112,7 +112,8 @@ __device__ __forceinline__ int stage_entry(int sidx) {
 // twice the CTAs).  Two 16-column sets per CTA whose stages interleave on the MMA warp -- eight epilogue warps per set, or all
 // sixteen alternating with four columns per thread -- were built and measured SLOWER than <32, 1> (27.0 / 30.2 against 23.8 us
 // per step, profiles/r02_o_ozaki_variants.jsonl): the sets' epilogues collide and the N = 32 MMA costs 27.6 cycles.
-template <int CS, int SETS>
+// NKS: k chunks of 32 that hold data (4; 3 for n <= 96 -- a compile-time count: a run-time test per MMA costs 14 % of the step)
+template <int CS, int SETS, int NKS>
 __global__ void __launch_bounds__((SETS * (CS / 2) + 1 + LOADERS) * 32, 1)
 rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const int* __restrict__ expo, double h, double2* __restrict__ y,
                  int ldy) {
@@ -132,7 +133,6 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int col0 = blockIdx.x * (SETS * CS);
     const int total = 4 * S;
-    const int nks = (n + 31) >> 5;  // k chunks of 32 that hold data
 
     if (tid == 0) {
 #pragma unroll
@@ -385,8 +385,7 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
                             const int q = g - p;
                             const uint32_t a_re = TMEM_A + (uint32_t)((0 * NS + (p - 1)) * 32), a_im = TMEM_A + (uint32_t)((1 * NS + (p - 1)) * 32);
 #pragma unroll
-                            for (int ks = 0; ks < KD / 32; ++ks) {
-                                if (ks >= nks) continue;  // k chunks past n hold zeros (uniform: n is a kernel argument)
+                            for (int ks = 0; ks < NKS; ++ks) {  // k chunks past n hold zeros
                                 const uint32_t b1 = bd_lo + (uint32_t)((((set * NS + q - 1) * 2 + 0) * BPLANE + ks * 4 * (int)LBO) >> 4);  // (re | im)
                                 const uint32_t b2 = bd_lo + (uint32_t)((((set * NS + q - 1) * 2 + 1) * BPLANE + ks * 4 * (int)LBO) >> 4);  // (-im | re)
                                 mma_ts<idesc_for(2 * CS)>(d, a_re + 8 * ks, b1, bd_hi, (p == 1 && ks == 0) ? 0u : 1u);
@@ -414,9 +413,9 @@ bool rk4_ozaki_supported(int n) { return n >= OZ_MIN_N && n <= 128; }
 
 // The emulated path is the faster one once its single wave of CTAs beats the DMMA kernels' time for the batch (measured at
 // n = 128: 17.9 us per step for any B <= 2368 -- 16 columns per CTA -- and 23.8 us up to 4736, against 9.0 / 17.9 / 30.2 /
-// 51.8 us of the DMMA kernels at B = 512 / 1024 / 2048 / 4096).  Smaller n pay the padding to 128 rows: at B = 4096 the
-// emulation wins 1.64x at n = 100..112, 1.44x at 96, 1.24x at 80 and 65; at B = 2048 1.07x at n = 96 and 0.88x at 80
-// (profiles/r02_r_ozaki_small_n.jsonl).  QDB_RK4_INT8=0 keeps every batch on the fp64 DMMA kernels.
+// 51.8 us of the DMMA kernels at B = 512 / 1024 / 2048 / 4096).  Smaller n pay the padding to 128 rows (n <= 96 runs three
+// k chunks instead of four): at B = 4096 the emulation wins 1.93x at n = 100, 1.87x at 96, 1.60x at 80; at B = 2048 1.07x
+// at n = 96 and 0.88x at 80 (profiles/r02_r_ozaki_small_n.jsonl).  QDB_RK4_INT8=0 keeps every batch on the fp64 DMMA kernels.
 bool rk4_ozaki_preferred(int n, int B) {
     static const bool enabled = [] {
         const char* e = getenv("QDB_RK4_INT8");
@@ -425,7 +424,7 @@ bool rk4_ozaki_preferred(int n, int B) {
     if (!enabled || !rk4_ozaki_supported(n)) return false;
     if (n >= 121) return B > 1024;
     if (n >= 96) return B >= 1536;
-    return n >= 80 && B > sm_count() * 16;
+    return B > sm_count() * 16;  // n >= 65
 }
 
 void rk4_ozaki_debug(long long* host64) { cudaMemcpyFromSymbol(host64, g_oz_dbg, sizeof(long long) * 64); }
@@ -467,15 +466,17 @@ int launch_rk4_ozaki(int n, int B, int S, const double2* gen, int gen_layout, do
     }
 #endif
     // 32 columns per CTA once 16 per CTA would no longer fit one wave of the SMs
-    if (B <= sm_count() * 16) {
-        constexpr Smem L(16, 1);
-        QDB_CUDA(cudaFuncSetAttribute(rk4_ozaki_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-        rk4_ozaki_kernel<16, 1><<<(B + 15) / 16, (8 + 1 + LOADERS) * 32, L.total, st>>>(n, B, S, planes, expo, h, y, ldy);
-    } else {
-        constexpr Smem L(32, 1);
-        QDB_CUDA(cudaFuncSetAttribute(rk4_ozaki_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-        rk4_ozaki_kernel<32, 1><<<(B + 31) / 32, (16 + 1 + LOADERS) * 32, L.total, st>>>(n, B, S, planes, expo, h, y, ldy);
-    }
+    auto go = [&](auto kernel, int cs, int warps) -> int {
+        const Smem L(cs, 1);
+        QDB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        kernel<<<(B + cs - 1) / cs, warps * 32, L.total, st>>>(n, B, S, planes, expo, h, y, ldy);
+        return QDB_OK;
+    };
+    const bool small = B <= sm_count() * 16, k3 = n <= 96;
+    int rc;
+    if (small) rc = k3 ? go(rk4_ozaki_kernel<16, 1, 3>, 16, 8 + 1 + LOADERS) : go(rk4_ozaki_kernel<16, 1, 4>, 16, 8 + 1 + LOADERS);
+    else rc = k3 ? go(rk4_ozaki_kernel<32, 1, 3>, 32, 16 + 1 + LOADERS) : go(rk4_ozaki_kernel<32, 1, 4>, 32, 16 + 1 + LOADERS);
+    if (rc != QDB_OK) return rc;
     QDB_LAUNCH_CHECK("rk4_ozaki_kernel");
     return QDB_OK;
 }
