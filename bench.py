@@ -25,7 +25,8 @@ second, whole job (sum over the N ranks; headline = weak scaling: B columns per 
   strong_scaling : the same solve on a TOTAL batch of 4096 (4096 / N columns per GPU), device-resident and e2e.
   cfg5      : BASELINE configs[4] at size -- 65 536 sweep points / N per GPU through distributed.solver_solve_sharded
               with one gather of the memory-slot probabilities (FinalStateMeasurement).
-  cfg3      : BASELINE configs[2] -- vectorised Lindblad 729, batch 4096, scipy_expm T = 0.2 -- with its own roofline.
+  cfg3      : BASELINE configs[2] -- vectorised Lindblad 729, batch 4096, scipy_expm T = 0.2 -- with its own roofline (the
+              729^3 and 729 x 4096 x 729 products run on zgemm_ozaki_kernel, the int8 tensor-core GEMM).
   sweep_mode: per-column-signal RK4 kernels (cfg2, cfg5-like) device-resident, against the same roof.
   cpu_baseline : the reference itself (baseline/_ref through oracle/ref_shim.py; the NumPy port when absent) on the
               host cores, bounded sample, all BLAS threads and one thread.
@@ -614,8 +615,12 @@ def run_b200(args):
                 "alg_frac": alg / best * 1e-9 / peak_tf, "squarings_mean": float(np.mean(sq)),
                 "flops_per_step": {"generator": f_gen, "expm": f_expm, "apply": f_apply},
                 "parity_max_col_l2": err3, "parity_columns": int(cols3.size), "parity_against": "tests/golden/fullsize.npz (unmodified reference)",
+                "gemm": "zgemm_ozaki_kernel<6> (int8 tensor cores, six byte slices per operand; QDB_ZGEMM_INT8=0: zgemm3m_kernel, fp64 DMMA)"
+                        if os.environ.get("QDB_ZGEMM_INT8", "1") != "0" else "zgemm3m_kernel (fp64 DMMA)",
                 "note": "solve_lmde(LindbladModel(vectorized=True), method='scipy_expm') from device-resident y0, best of 3 "
-                        "after 1 warm-up, CUDA events, L2 flushed; one 'state RHS' here = one propagator application per column"}
+                        "after 1 warm-up, CUDA events, L2 flushed; one 'state RHS' here = one propagator application per column; "
+                        "alg_frac = fp64-equivalent algorithmic flops over the fp64 DMMA roof (> 1: the products run as exact "
+                        "int8 slice products on tcgen05)"}
 
     cfg3 = cfg3_record()
 
