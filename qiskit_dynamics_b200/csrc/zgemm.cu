@@ -525,15 +525,8 @@ int launch_zgemm(int M, int N, int Kd, const double2* A, int lda, const double2*
 int launch_zgemm_batched(int M, int N, int Kd, const double2* A, int lda, long long sA, const double2* B, int ldb, long long sB,
                          double2* C, int ldc, long long sC, double2 alpha, double2 beta, int count, cudaStream_t st) {
     if (M == 0 || N == 0 || count == 0) return QDB_OK;
-    // products that fill the chip on their own: the int8 tensor-core emulation, one after the other
-    if (zgemm_int8_preferred(M, N, Kd)) {
-        for (int z = 0; z < count; ++z) {
-            const int rc = launch_zgemm_int8(M, N, Kd, A + (size_t)z * sA, lda, B + (size_t)z * sB, ldb, C + (size_t)z * sC, ldc, alpha, beta,
-                                             nullptr, nullptr, nullptr, st);
-            if (rc != QDB_OK) return rc;
-        }
-        return QDB_OK;
-    }
+    // products that are large enough on their own: the int8 tensor-core emulation, side by side
+    if (zgemm_int8_preferred(M, N, Kd)) return launch_zgemm_int8_batched(M, N, Kd, A, lda, sA, B, ldb, sB, C, ldc, sC, alpha, beta, count, st);
     for (int z0 = 0; z0 < count; z0 += 65535) {  // grid.z limit
         const int c = count - z0 < 65535 ? count - z0 : 65535;
         EpiStd e{C + (size_t)z0 * sC, ldc, alpha, beta, nullptr, nullptr, sC};

@@ -61,11 +61,22 @@ struct EpiZ {
     const double2* post;
 };
 
+// independent products side by side (grid.z / grid.y of the slicing kernels): element strides of the operands (0 = shared)
+// and byte / element strides of the sliced scratch
+struct ZBatch {
+    long long sA, sB, sC;
+    size_t a_planes, b_images;  // bytes per product
+    int ea, eb;                 // exponents per product
+};
+
 // ---- A -> planes[rt][kc][part][p][k/16][row][k%16], expo[row]; one block per (padded) row ----
 template <int NSL>
 __global__ void __launch_bounds__(128) zg_aslice_kernel(int M, int K, int KC, const double2* __restrict__ A, int lda,
-                                                         int8_t* __restrict__ planes, int* __restrict__ expo) {
+                                                         int8_t* __restrict__ planes, int* __restrict__ expo, ZBatch zb) {
     const int row = blockIdx.x, tid = threadIdx.x;
+    A += (size_t)blockIdx.y * zb.sA;
+    planes += (size_t)blockIdx.y * zb.a_planes;
+    expo += (size_t)blockIdx.y * zb.ea;
     __shared__ unsigned wmax[4];
     unsigned m = 0u;
     if (row < M)
@@ -103,9 +114,11 @@ __device__ __forceinline__ double2 scaled_b(const double2* __restrict__ B, int l
 
 // ---- column maxima of diag(pre) B: colmax[c] (high words), zeroed by the caller ----
 __global__ void __launch_bounds__(256) zg_colmax_kernel(int K, int N, const double2* __restrict__ B, int ldb, const double2* __restrict__ pre,
-                                                         unsigned* __restrict__ colmax) {
+                                                         unsigned* __restrict__ colmax, ZBatch zb) {
     const int c = blockIdx.x * 256 + threadIdx.x;
     if (c >= N) return;
+    B += (size_t)blockIdx.z * zb.sB;
+    colmax += (size_t)blockIdx.z * zb.eb;
     const int k0 = blockIdx.y * 64, k1 = min(K, k0 + 64);
     unsigned m = 0u;
     for (int k = k0; k < k1; ++k) {
@@ -120,7 +133,11 @@ __global__ void __launch_bounds__(256) zg_colmax_kernel(int K, int N, const doub
 template <int NSL>
 __global__ void __launch_bounds__(128) zg_bslice_kernel(int K, int N, int KC, int CT, const double2* __restrict__ B, int ldb,
                                                          const double2* __restrict__ pre, const unsigned* __restrict__ colmax,
-                                                         int8_t* __restrict__ images, int* __restrict__ expo) {
+                                                         int8_t* __restrict__ images, int* __restrict__ expo, ZBatch zb) {
+    B += (size_t)blockIdx.z * zb.sB;
+    colmax += (size_t)blockIdx.z * zb.eb;
+    images += (size_t)blockIdx.z * zb.b_images;
+    expo += (size_t)blockIdx.z * zb.eb;
     const int ct = blockIdx.x, lane = threadIdx.x & 31;
     const int k = (blockIdx.y * 4 + (threadIdx.x >> 5)) * 8 + (lane >> 2), oc = lane & 3;
     const int c0 = ct * TN + 8 * oc;
@@ -174,7 +191,12 @@ __global__ void __launch_bounds__(128) zg_bslice_kernel(int K, int N, int KC, in
 template <int NSL>
 __global__ void __launch_bounds__(Z_NWARPS * 32, 1)
 zgemm_ozaki_kernel(int M, int N, int KC, const int8_t* __restrict__ aplanes, const int* __restrict__ expoA,
-                   const int8_t* __restrict__ bimages, const int* __restrict__ expoB, EpiZ epi) {
+                   const int8_t* __restrict__ bimages, const int* __restrict__ expoB, EpiZ epi, ZBatch zb) {
+    aplanes += (size_t)blockIdx.z * zb.a_planes;
+    bimages += (size_t)blockIdx.z * zb.b_images;
+    expoA += (size_t)blockIdx.z * zb.ea;
+    expoB += (size_t)blockIdx.z * zb.eb;
+    epi.C += (size_t)blockIdx.z * zb.sC;
     using Z = ZCfg<NSL>;
     constexpr int NS = NSL, NACC = Z::NACC, ASTAGES = Z::ASTAGES, BCHUNK = Z::BCHUNK, ACHUNK = Z::ACHUNK;
     constexpr int ZS_B = Z::S_B, ZS_A = Z::S_A, ZS_BAR = Z::S_BAR, ZS_TMEM = Z::S_TMEM;
@@ -391,12 +413,16 @@ zgemm_ozaki_kernel(int M, int N, int KC, const int8_t* __restrict__ aplanes, con
 }
 
 template <int NSL>
-int launch_int8(int M, int N, int Kd, const double2* A, int lda, const double2* B, int ldb, double2* C, int ldc, double2 alpha,
-                double2 beta, const double* colscale, const double2* pre, const double2* post, cudaStream_t st) {
+int launch_int8(int M, int N, int Kd, const double2* A, int lda, long long sA, const double2* B, int ldb, long long sB, double2* C, int ldc,
+                long long sC, int count, double2 alpha, double2 beta, const double* colscale, const double2* pre, const double2* post,
+                cudaStream_t st) {
     using Z = ZCfg<NSL>;
     const int RT = (M + KD - 1) / KD, CT = (N + TN - 1) / TN, KC = (Kd + KD - 1) / KD;
-    const size_t a_bytes = (size_t)RT * KC * Z::ACHUNK, b_bytes = (size_t)CT * KC * Z::BCHUNK;
-    const size_t ea_bytes = (size_t)RT * KD * sizeof(int), eb_bytes = (size_t)CT * TN * sizeof(int), cm_bytes = (size_t)CT * TN * sizeof(unsigned);
+    const size_t a_one = (size_t)RT * KC * Z::ACHUNK, b_one = (size_t)CT * KC * Z::BCHUNK;
+    const size_t a_bytes = a_one * count, b_bytes = b_one * count;
+    const size_t ea_bytes = (size_t)RT * KD * sizeof(int) * count, eb_bytes = (size_t)CT * TN * sizeof(int) * count,
+                 cm_bytes = (size_t)CT * TN * sizeof(unsigned) * count;
+    const ZBatch zb{sA, sB, sC, a_one, b_one, RT * KD, CT * TN};
     // stream-ordered scratch from the device's default pool, which is told once to keep what it has been given
     static const bool pool_ready = [] {
         int dev = 0;
@@ -416,15 +442,15 @@ int launch_int8(int M, int N, int Kd, const double2* A, int lda, const double2* 
     int* expoB = reinterpret_cast<int*>(ws + a_bytes + b_bytes + ea_bytes);
     unsigned* colmax = reinterpret_cast<unsigned*>(ws + a_bytes + b_bytes + ea_bytes + eb_bytes);
     QDB_CUDA(cudaMemsetAsync(colmax, 0, cm_bytes, st));
-    zg_aslice_kernel<NSL><<<RT * KD, 128, 0, st>>>(M, Kd, KC, A, lda, aplanes, expoA);
+    zg_aslice_kernel<NSL><<<dim3(RT * KD, count), 128, 0, st>>>(M, Kd, KC, A, lda, aplanes, expoA, zb);
     QDB_LAUNCH_CHECK("zg_aslice_kernel");
-    zg_colmax_kernel<<<dim3((N + 255) / 256, (Kd + 63) / 64), 256, 0, st>>>(Kd, N, B, ldb, pre, colmax);
+    zg_colmax_kernel<<<dim3((N + 255) / 256, (Kd + 63) / 64, count), 256, 0, st>>>(Kd, N, B, ldb, pre, colmax, zb);
     QDB_LAUNCH_CHECK("zg_colmax_kernel");
-    zg_bslice_kernel<NSL><<<dim3(CT, KC * KD / 32), 128, 0, st>>>(Kd, N, KC, CT, B, ldb, pre, colmax, bimages, expoB);
+    zg_bslice_kernel<NSL><<<dim3(CT, KC * KD / 32, count), 128, 0, st>>>(Kd, N, KC, CT, B, ldb, pre, colmax, bimages, expoB, zb);
     QDB_LAUNCH_CHECK("zg_bslice_kernel");
     QDB_CUDA(cudaFuncSetAttribute(zgemm_ozaki_kernel<NSL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Z::S_TOTAL));
     EpiZ epi{C, ldc, alpha, beta, colscale, post};
-    zgemm_ozaki_kernel<NSL><<<dim3(CT, RT), Z_NWARPS * 32, Z::S_TOTAL, st>>>(M, N, KC, aplanes, expoA, bimages, expoB, epi);
+    zgemm_ozaki_kernel<NSL><<<dim3(CT, RT, count), Z_NWARPS * 32, Z::S_TOTAL, st>>>(M, N, KC, aplanes, expoA, bimages, expoB, epi, zb);
     QDB_LAUNCH_CHECK("zgemm_ozaki_kernel");
     QDB_CUDA(cudaFreeAsync(ws, st));
     return QDB_OK;
@@ -450,8 +476,25 @@ int launch_zgemm_int8(int M, int N, int Kd, const double2* A, int lda, const dou
                       double2 beta, const double* colscale, const double2* pre, const double2* post, cudaStream_t st) {
     const char* env = getenv("QDB_ZGEMM_SLICES");
     const int slices = env && atoi(env) == 5 ? 5 : 6;
-    if (slices == 5) return launch_int8<5>(M, N, Kd, A, lda, B, ldb, C, ldc, alpha, beta, colscale, pre, post, st);
-    return launch_int8<6>(M, N, Kd, A, lda, B, ldb, C, ldc, alpha, beta, colscale, pre, post, st);
+    if (slices == 5) return launch_int8<5>(M, N, Kd, A, lda, 0, B, ldb, 0, C, ldc, 0, 1, alpha, beta, colscale, pre, post, st);
+    return launch_int8<6>(M, N, Kd, A, lda, 0, B, ldb, 0, C, ldc, 0, 1, alpha, beta, colscale, pre, post, st);
+}
+
+// count independent products side by side (operand strides in elements, 0 = shared): one launch of each of the four kernels,
+// in slices of at most 64 products (scratch: ~17 MB per 729^3 product)
+int launch_zgemm_int8_batched(int M, int N, int Kd, const double2* A, int lda, long long sA, const double2* B, int ldb, long long sB,
+                              double2* C, int ldc, long long sC, double2 alpha, double2 beta, int count, cudaStream_t st) {
+    const char* env = getenv("QDB_ZGEMM_SLICES");
+    const int slices = env && atoi(env) == 5 ? 5 : 6;
+    for (int z0 = 0; z0 < count; z0 += 64) {
+        const int c = count - z0 < 64 ? count - z0 : 64;
+        const double2 *a = A + (size_t)z0 * sA, *b = B + (size_t)z0 * sB;
+        double2* cc = C + (size_t)z0 * sC;
+        const int rc = slices == 5 ? launch_int8<5>(M, N, Kd, a, lda, sA, b, ldb, sB, cc, ldc, sC, c, alpha, beta, nullptr, nullptr, nullptr, st)
+                                   : launch_int8<6>(M, N, Kd, a, lda, sA, b, ldb, sB, cc, ldc, sC, c, alpha, beta, nullptr, nullptr, nullptr, st);
+        if (rc != QDB_OK) return rc;
+    }
+    return QDB_OK;
 }
 
 }  // namespace qdb
