@@ -205,7 +205,8 @@ int qdb_dmma_probe(double* sink, int iters, double* flops_out, void* stream);
  *   workspace      : qdb_workspace_bytes(QDB_WS_EXPM, n, K, B, S).  With the S = 1 size the steps run one at a
  *                    time; with more, the propagators of a chunk of steps are built side by side (one generator
  *                    launch + one batched Taylor exponential, all steps of the chunk sharing the largest number
- *                    of squarings) and then applied in order.
+ *                    of squarings) and then applied in order -- so the result depends on the workspace size at the
+ *                    rounding level (extra squarings on the weaker steps of a chunk).
  * Replaces get_exponential_take_step(magnus_order=1) + scipy.linalg.expm
  * (solvers/fixed_step_solvers.py:343-346,400-401,104). */
 int qdb_expm_steps_c128(int n, int K, int B, int S,

@@ -131,6 +131,8 @@ int rk4_fused_table_layout(int n, int B);
 bool zgemm_int8_preferred(int M, int N, int Kd);
 int launch_zgemm_int8(int M, int N, int Kd, const double2* A, int lda, const double2* B, int ldb, double2* C, int ldc, double2 alpha,
                       double2 beta, const double* colscale, const double2* pre, const double2* post, cudaStream_t st);
+int launch_zgemm_int8_rk4stage(int n, int B, const double2* G, const double2* yin, int ldy, const double2* ybase, double2* yout, double2* acc,
+                               double a_next, double w, int first, cudaStream_t st);
 int launch_zgemm_int8_batched(int M, int N, int Kd, const double2* A, int lda, long long sA, const double2* B, int ldb, long long sB,
                               double2* C, int ldc, long long sC, double2 alpha, double2 beta, int count, cudaStream_t st);
 // fp64 emulation on the int8 tensor cores (rk4_ozaki.cu), n = 121..128

@@ -540,6 +540,7 @@ int launch_zgemm_batched(int M, int N, int Kd, const double2* A, int lda, long l
 int launch_zgemm_rk4stage(int n, int B, const double2* G, const double2* yin, int ldy, const double2* ybase,
                           double2* yout, double2* acc, double a_next, double w, int first, cudaStream_t st) {
     if (n == 0 || B == 0) return QDB_OK;
+    if (zgemm_int8_preferred(n, B, n)) return launch_zgemm_int8_rk4stage(n, B, G, yin, ldy, ybase, yout, acc, a_next, w, first, st);
     EpiRk4 e{ybase, yout, acc, ldy, a_next, w, first};
     return launch(n, B, n, G, n, yin, ldy, (const double2*)nullptr, e, st);
 }

@@ -59,6 +59,12 @@ struct EpiZ {
     double2 alpha, beta;
     const double* colscale;
     const double2* post;
+    // RK4 stage of the generic large-n stepper (zgemm.cu EpiRk4): k = A B;  yout = ybase + a_next k;  acc = (first ? 0 : acc) + w k
+    const double2* ybase;
+    double2* yout;  // non-null selects this epilogue
+    double2* acc;
+    double a_next, w;
+    int first;
 };
 
 // independent products side by side (grid.z / grid.y of the slicing kernels): element strides of the operands (0 = shared)
@@ -282,6 +288,19 @@ zgemm_ozaki_kernel(int M, int N, int KC, const int8_t* __restrict__ aplanes, con
                 if (c < N) {
                     const double s = pow2(ea + expoB[c] - 8 * (NS + 1));
                     double2 v = make_double2(sr[j] * s, si[j] * s);
+                    if (epi.yout) {
+                        const size_t i = (size_t)r * epi.ldc + c;
+                        const double2 yb = epi.ybase[i];
+                        epi.yout[i] = make_double2(fma(epi.a_next, v.x, yb.x), fma(epi.a_next, v.y, yb.y));
+                        double2 a = make_double2(epi.w * v.x, epi.w * v.y);
+                        if (!epi.first) {
+                            const double2 old = epi.acc[i];
+                            a.x += old.x;
+                            a.y += old.y;
+                        }
+                        epi.acc[i] = a;
+                        continue;
+                    }
                     if (epi.post) v = cmul(po, v);
                     double2 a = epi.alpha;
                     if (epi.colscale) {
@@ -415,7 +434,7 @@ zgemm_ozaki_kernel(int M, int N, int KC, const int8_t* __restrict__ aplanes, con
 template <int NSL>
 int launch_int8(int M, int N, int Kd, const double2* A, int lda, long long sA, const double2* B, int ldb, long long sB, double2* C, int ldc,
                 long long sC, int count, double2 alpha, double2 beta, const double* colscale, const double2* pre, const double2* post,
-                cudaStream_t st) {
+                cudaStream_t st, const EpiZ* rk4 = nullptr) {
     using Z = ZCfg<NSL>;
     const int RT = (M + KD - 1) / KD, CT = (N + TN - 1) / TN, KC = (Kd + KD - 1) / KD;
     const size_t a_one = (size_t)RT * KC * Z::ACHUNK, b_one = (size_t)CT * KC * Z::BCHUNK;
@@ -449,7 +468,8 @@ int launch_int8(int M, int N, int Kd, const double2* A, int lda, long long sA, c
     zg_bslice_kernel<NSL><<<dim3(CT, KC * KD / 32, count), 128, 0, st>>>(Kd, N, KC, CT, B, ldb, pre, colmax, bimages, expoB, zb);
     QDB_LAUNCH_CHECK("zg_bslice_kernel");
     QDB_CUDA(cudaFuncSetAttribute(zgemm_ozaki_kernel<NSL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Z::S_TOTAL));
-    EpiZ epi{C, ldc, alpha, beta, colscale, post};
+    EpiZ epi{C, ldc, alpha, beta, colscale, post, nullptr, nullptr, nullptr, 0.0, 0.0, 0};
+    if (rk4) epi = *rk4;
     zgemm_ozaki_kernel<NSL><<<dim3(CT, RT, count), Z_NWARPS * 32, Z::S_TOTAL, st>>>(M, N, KC, aplanes, expoA, bimages, expoB, epi, zb);
     QDB_LAUNCH_CHECK("zgemm_ozaki_kernel");
     QDB_CUDA(cudaFreeAsync(ws, st));
@@ -478,6 +498,17 @@ int launch_zgemm_int8(int M, int N, int Kd, const double2* A, int lda, const dou
     const int slices = env && atoi(env) == 5 ? 5 : 6;
     if (slices == 5) return launch_int8<5>(M, N, Kd, A, lda, 0, B, ldb, 0, C, ldc, 0, 1, alpha, beta, colscale, pre, post, st);
     return launch_int8<6>(M, N, Kd, A, lda, 0, B, ldb, 0, C, ldc, 0, 1, alpha, beta, colscale, pre, post, st);
+}
+
+// one RK4 stage of the generic (n > 256) stepper: k = G yin, yout = ybase + a_next k, acc = (first ? 0 : acc) + w k
+int launch_zgemm_int8_rk4stage(int n, int B, const double2* G, const double2* yin, int ldy, const double2* ybase, double2* yout, double2* acc,
+                               double a_next, double w, int first, cudaStream_t st) {
+    const char* env = getenv("QDB_ZGEMM_SLICES");
+    const int slices = env && atoi(env) == 5 ? 5 : 6;
+    const double2 one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0);
+    const EpiZ e{nullptr, ldy, one, zero, nullptr, nullptr, ybase, yout, acc, a_next, w, first};
+    if (slices == 5) return launch_int8<5>(n, B, n, G, n, 0, yin, ldy, 0, nullptr, ldy, 0, 1, one, zero, nullptr, nullptr, nullptr, st, &e);
+    return launch_int8<6>(n, B, n, G, n, 0, yin, ldy, 0, nullptr, ldy, 0, 1, one, zero, nullptr, nullptr, nullptr, st, &e);
 }
 
 // count independent products side by side (operand strides in elements, 0 = shared): one launch of each of the four kernels,

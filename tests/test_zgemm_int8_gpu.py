@@ -94,3 +94,41 @@ def test_dispatch_and_opt_out(abi, monkeypatch):
     c_fp64 = abi.zgemm(A, B)
     assert abi.launch_count() - before <= 2
     assert rel(c_int8, c_fp64) < 1e-12
+
+
+def test_generic_rk4_stage_takes_the_int8_gemm(abi, monkeypatch):
+    """n > 256 shared-signal RK4 (the path of vectorised Lindblad models with RK4): every stage is one product with the RK4
+    epilogue (k = G y_in, y_out = y + a k, acc += w k).  At n = 400, B = 2048 it runs on the int8 GEMM (per step: generator +
+    4 x 4 launches + axpby); final states against the DMMA route of the same call < 1e-11 and against NumPy < 1e-11."""
+    n, K, B, S, h = 400, 2, 2048, 3, 1e-3
+    rng = np.random.default_rng(12)
+    herm = lambda: (lambda a: (a + a.conj().T) / (2 * np.sqrt(n)))(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+    G = np.array([-1j * herm() for _ in range(K)])
+    Gd = -1j * 5 * herm()
+    Y = rng.standard_normal((n, B)) + 1j * rng.standard_normal((n, B))
+    Y /= np.linalg.norm(Y, axis=0, keepdims=True)
+    times = np.arange(2 * S + 1) * (h / 2)
+    coeff = np.stack([np.cos(3 * times), np.sin(2 * times)], axis=1)
+
+    def run():
+        y = dev(Y)
+        before = abi.launch_count()
+        abi.rk4_steps(n, dev(G), dev(Gd), None, None, dev(coeff), None, times, h, y, S)
+        torch.cuda.synchronize()
+        return y, abi.launch_count() - before
+
+    monkeypatch.setenv("QDB_ZGEMM_INT8", "0")
+    y_fp64, l_fp64 = run()
+    monkeypatch.delenv("QDB_ZGEMM_INT8")
+    y_int8, l_int8 = run()
+    assert l_int8 > l_fp64  # four launches per product instead of one
+    assert float(torch.linalg.vector_norm(y_int8 - y_fp64, dim=0).max()) < 1e-11
+    y = Y[:, :8].copy()
+    gen = lambda i: Gd + coeff[i, 0] * G[0] + coeff[i, 1] * G[1]
+    for s in range(S):
+        k1 = gen(2 * s) @ y
+        k2 = gen(2 * s + 1) @ (y + 0.5 * h * k1)
+        k3 = gen(2 * s + 1) @ (y + 0.5 * h * k2)
+        k4 = gen(2 * s + 2) @ (y + h * k3)
+        y = y + (h / 6) * (k1 + 2 * k2 + 2 * k3 + k4)
+    assert np.linalg.norm(y_int8.cpu().numpy()[:, :8] - y, axis=0).max() < 1e-11
