@@ -20,14 +20,21 @@ static_assert(TMEM_A + 2 * NS * 32 <= 512, "TMEM");
 __host__ __device__ constexpr int acc_of_group(int g) { return (NS + 1 - g) % NACC; }
 
 // Stage-vector operand planes (the MMA's B operand, 128 k x 2 CS int8) in the MN-major no-swizzle layout: core matrix = 8 k-rows
-// of 16 consecutive columns, CS / 8 cores side by side (SBO = 128 B), sixteen k groups (LBO = CS / 8 x 128 B).  One N = 2 CS
-// MMA computes both accumulators of a set: (re | im) += A_re x (B_re | B_im) and += A_im x (-B_im | B_re) -- half the MMA
-// count, and at CS = 32 the peak rate of the TMEM-operand path.  A thread (one k, eight consecutive columns of one part) owns
-// 8 contiguous bytes: `half` = 0 / 1 selects the left / right CS columns of the plane.
+// of 16 consecutive columns.  One N = 2 CS MMA computes both accumulators of a column set: (re | im) += A_re x (B_re | B_im)
+// and += A_im x (-B_im | B_re) -- half the MMA count, and at CS = 32 the peak rate of the TMEM-operand path.  The two planes
+// share B_re: per slice and k group (8 k-rows) the image holds 3 CS / 16 cores [-im | re | im]; (re | im) starts CS / 16 cores
+// in, (-im | re) at the start, both with SBO = 128 B between cores and LBO = the k-group size.  3/4 of the bytes and of the
+// epilogue's stores of two separate planes.  A thread (one k, eight consecutive columns of one part) owns 8 contiguous bytes.
 template <int CS>
-__device__ __forceinline__ int bplane_off8(int oc, int k, int half) {
-    return ((k >> 3) * (CS / 8) + half * (CS / 16) + (oc >> 1)) * 128 + (k & 7) * 16 + (oc & 1) * 8;
-}
+struct BImage {
+    static constexpr int NC = CS / 16;             // cores per part
+    static constexpr int KG = 3 * NC * 128;        // bytes of a k group = LBO
+    static constexpr int SLICE = (KD / 8) * KG;    // bytes of a slice
+    static constexpr int RE_IM = NC * 128;         // start of the (re | im) plane; (-im | re) starts at 0
+    __device__ static __forceinline__ int off8(int oc, int k, int which /* 0: -im, 1: re, 2: im */) {
+        return (k >> 3) * KG + (which * NC + (oc >> 1)) * 128 + (k & 7) * 16 + (oc & 1) * 8;
+    }
+};
 
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |

@@ -17,12 +17,13 @@
 // operands in shared memory an M128 x N x K32 int8 MMA costs (4096 + 32 N) / 128 cycles -- the operand READ, 41 cycles at
 // N = 32 -- so the generator slices live in TMEM (A operand from TMEM: 21 cycles at N = 32, 33 at N = 64 = the peak of
 // 8192 MAC/clk/SM), and one N = 64 MMA computes (re | im) of 32 columns at once from the operand planes (B_re | B_im) and
-// (-B_im | B_re).  A CTA owns 32 whole columns for the launch (4096 columns = 128 CTAs; 16 per CTA for small batches):
+// (-B_im | B_re) (BImage in ozaki_device.cuh).  A CTA owns 32 whole columns for the launch (4096 columns = 128 CTAs; 16 per CTA for small batches):
 //   TMEM: columns [0, 192) three int32 accumulator buffers (re | im), so that the five groups of a stage never wait for a
 //     drain; [192, 512) the 2 NS generator slice planes (32 columns of packed int8 each), reloaded when the stage time
 //     changes (every other stage);
-//   shared memory: the 2 NS stage-vector operand planes in the no-swizzle MN-major core-matrix layout the MMA reads
-//     (80 KB), y and the RK4 k-sum as fp64 (128 KB);
+//   shared memory: the stage-vector operand images of the NS slices in the no-swizzle MN-major core-matrix layout the MMA
+//     reads ([-im | re | im] per k group: the planes (re | im) and (-im | re) overlap in re; 60 KB), y and the RK4 k-sum as
+//     fp64 (128 KB);
 //   warps 0-15: epilogue, thread = (row, 8 columns) -- drain a group (tcgen05.ld), combine the groups in int64, one
 //     conversion to fp64, RK4 combine, column scales (warp REDUX + one named barrier), re-slice the next stage vector into
 //     shared memory; warp 16: issues the 120 MMAs of a stage, LEAST significant group first; warps 17-20: load the next
@@ -54,13 +55,13 @@ namespace {
 #endif
 
 
-// shared-memory carve-up (bytes) of a CTA with SETS column sets of CS columns; a stage-vector operand plane is 128 k x 2 CS
-// "columns" (two parts side by side): 2 CS KD bytes
+// shared-memory carve-up (bytes) of a CTA with SETS column sets of CS columns; the operand image of a slice (BImage<CS>) is
+// 3 CS KD bytes
 struct Smem {
     int b, y, k, red, ea, bar, tmem, total;
     __host__ __device__ constexpr Smem(int cs, int sets)
-        : b(0),                                  // [SETS][NS][2][2 CS KD] int8: (re | im) and (-im | re) of every slice
-          y(b + sets * NS * 2 * 2 * cs * KD),    // [SETS CS][KD] double2
+        : b(0),                                  // [SETS][NS][3 CS KD] int8: [-im | re | im] of every slice
+          y(b + sets * NS * 3 * cs * KD),        // [SETS CS][KD] double2
           k(y + sets * cs * KD * 16),            // [SETS CS][KD] double2
           red(k + sets * cs * KD * 16),          // [SETS][4][CS] unsigned (high words of the column maxima)
           ea(red + sets * 4 * cs * 4),           // [4][KD] int: row exponents of generator entry e in slot e & 3 (the loaders run up to two entries ahead of the epilogue)
@@ -118,7 +119,8 @@ __global__ void __launch_bounds__((SETS * (CS / 2) + 1 + LOADERS) * 32, 1)
 rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const int* __restrict__ expo, double h, double2* __restrict__ y,
                  int ldy) {
     constexpr Smem L(CS, SETS);
-    constexpr int SET_WARPS = CS / 2, EPI_WARPS = SETS * SET_WARPS, MMA_WARP = EPI_WARPS, BPLANE = 2 * CS * KD;
+    constexpr int SET_WARPS = CS / 2, EPI_WARPS = SETS * SET_WARPS, MMA_WARP = EPI_WARPS;
+    using BI = BImage<CS>;
     static_assert(SETS * NACC * 2 * CS <= (int)TMEM_A, "accumulators");
     extern __shared__ __align__(1024) uint8_t sm[];
     int8_t* bsl = reinterpret_cast<int8_t*>(sm + L.b);
@@ -166,7 +168,7 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
         const uint32_t lane_base = ((uint32_t)(32 * qd) << 16) + (uint32_t)(set * NACC * 2 * CS);
         uint64_t *full = bars + set * PER_SET, *empty = full + NACC, *b_ready = full + 2 * NACC;
         unsigned* red = reinterpret_cast<unsigned*>(sm + L.red) + set * 4 * CS;
-        int8_t* bset = bsl + set * (NS * 2 * BPLANE);
+        int8_t* bset = bsl + set * (NS * BI::SLICE);
         const int cbase = set * CS + 8 * oc;  // first of the thread's columns within the CTA
         int eb[8];  // column exponents of the current stage vector (this thread's 8 columns)
 
@@ -211,16 +213,8 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
                         if (hh == 0) {
                             wl[part][p - 1] = w;
                         } else {
-                            const uint2 v = make_uint2(wl[part][p - 1], w);
-                            int8_t* sl = bset + (p - 1) * 2 * BPLANE;
-                            if (part == 0) {  // re: left half of (re | im), right half of (-im | re)
-                                *reinterpret_cast<uint2*>(sl + bplane_off8<CS>(oc, row, 0)) = v;
-                                *reinterpret_cast<uint2*>(sl + BPLANE + bplane_off8<CS>(oc, row, 1)) = v;
-                            } else if (part == 1) {
-                                *reinterpret_cast<uint2*>(sl + bplane_off8<CS>(oc, row, 1)) = v;
-                            } else {
-                                *reinterpret_cast<uint2*>(sl + BPLANE + bplane_off8<CS>(oc, row, 0)) = v;
-                            }
+                            // parts (re, im, -im) -> image positions (1, 2, 0)
+                            *reinterpret_cast<uint2*>(bset + (p - 1) * BI::SLICE + BI::off8(oc, row, (part + 1) % 3)) = make_uint2(wl[part][p - 1], w);
                         }
                     }
                 }
@@ -345,7 +339,7 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
             }
         } else {
             const uint32_t bs_addr = (uint32_t)__cvta_generic_to_shared(bsl);
-            constexpr uint32_t LBO = (CS / 8) * 128, SBO = 128;  // between the 8-row k groups / between the 16-column cores
+            constexpr uint32_t LBO = BI::KG, SBO = 128;  // between the 8-row k groups / between the 16-column cores
             const uint64_t bdesc0 = smem_desc(bs_addr, LBO, SBO);
             const uint32_t bd_hi = (uint32_t)(bdesc0 >> 32);
             uint32_t bd_lo = (uint32_t)bdesc0;
@@ -386,8 +380,8 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
                             const uint32_t a_re = TMEM_A + (uint32_t)((0 * NS + (p - 1)) * 32), a_im = TMEM_A + (uint32_t)((1 * NS + (p - 1)) * 32);
 #pragma unroll
                             for (int ks = 0; ks < NKS; ++ks) {  // k chunks past n hold zeros
-                                const uint32_t b1 = bd_lo + (uint32_t)((((set * NS + q - 1) * 2 + 0) * BPLANE + ks * 4 * (int)LBO) >> 4);  // (re | im)
-                                const uint32_t b2 = bd_lo + (uint32_t)((((set * NS + q - 1) * 2 + 1) * BPLANE + ks * 4 * (int)LBO) >> 4);  // (-im | re)
+                                const uint32_t b1 = bd_lo + (uint32_t)(((set * NS + q - 1) * BI::SLICE + BI::RE_IM + ks * 4 * (int)LBO) >> 4);  // (re | im)
+                                const uint32_t b2 = bd_lo + (uint32_t)(((set * NS + q - 1) * BI::SLICE + ks * 4 * (int)LBO) >> 4);               // (-im | re)
                                 mma_ts<idesc_for(2 * CS)>(d, a_re + 8 * ks, b1, bd_hi, (p == 1 && ks == 0) ? 0u : 1u);
                                 mma_ts<idesc_for(2 * CS)>(d, a_im + 8 * ks, b2, bd_hi, 1u);
                             }

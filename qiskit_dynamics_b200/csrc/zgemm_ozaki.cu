@@ -26,14 +26,10 @@ namespace qdb {
 namespace {
 
 constexpr int TN = 32;                 // columns of C per CTA (MMA N = 64: re | im)
-// B image of a (column tile, k chunk), per slice: sixteen k groups (8 k-rows) of SIX cores (16 columns x 8 k, 128 B each)
-// [-im(0:16) -im(16:32) | re(0:16) re(16:32) | im(0:16) im(16:32)] -- the operand plane (re | im) is cores 2..5 and
-// (-im | re) is cores 0..3 of every k group (LBO = 768 B, SBO = 128 B), so re is stored once: 12 KB per slice instead of 16
-constexpr int BKG = 6 * 128;           // bytes of a k group
-constexpr int BSL = (KD / 8) * BKG;    // bytes of a slice of the image: 12288
-__device__ __forceinline__ int bimg_off8(int oc, int k, int which /* 0: -im, 1: re, 2: im */) {
-    return (k >> 3) * BKG + (2 * which + (oc >> 1)) * 128 + (k & 7) * 16 + (oc & 1) * 8;
-}
+// B image of a (column tile, k chunk): BImage<TN> per slice (ozaki_device.cuh): 12 KB instead of the 16 KB of two planes
+using BI = BImage<TN>;
+constexpr int BKG = BI::KG, BSL = BI::SLICE;
+__device__ __forceinline__ int bimg_off8(int oc, int k, int which) { return BI::off8(oc, k, which); }
 constexpr int APL = KD * KD;           // bytes of one A plane of a (row tile, k chunk)
 constexpr int Z_EPI_WARPS = 16, Z_MMA_WARP = 16, Z_PRODUCER = 21, Z_NWARPS = 22;  // 17-20: loaders (smem -> TMEM), 21: TMA producer of the A planes
 
@@ -413,7 +409,7 @@ zgemm_ozaki_kernel(int M, int N, int KC, const int8_t* __restrict__ aplanes, con
                     const uint32_t a_re = TMEM_A + (uint32_t)((0 * NS + (p - 1)) * 32), a_im = TMEM_A + (uint32_t)((1 * NS + (p - 1)) * 32);
 #pragma unroll
                     for (int ks = 0; ks < KD / 32; ++ks) {
-                        const uint32_t b1 = bd_lo + (uint32_t)(((q - 1) * BSL + 256 + ks * 4 * (int)LBO) >> 4);  // (re | im): cores 2..5
+                        const uint32_t b1 = bd_lo + (uint32_t)(((q - 1) * BSL + BI::RE_IM + ks * 4 * (int)LBO) >> 4);  // (re | im): cores 2..5
                         const uint32_t b2 = bd_lo + (uint32_t)(((q - 1) * BSL + ks * 4 * (int)LBO) >> 4);        // (-im | re): cores 0..3
                         mma_ts<idesc_for(2 * TN)>(d, a_re + 8 * ks, b1, bd_hi, (p == 1 && ks == 0) ? 0u : 1u);
                         mma_ts<idesc_for(2 * TN)>(d, a_im + 8 * ks, b2, bd_hi, 1u);
