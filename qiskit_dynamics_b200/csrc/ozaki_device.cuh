@@ -55,6 +55,23 @@ __device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_
         "r"(accumulate), "r"(0u), "r"(db_hi)
         : "memory");
 }
+// the same issued by ONE thread (the caller has elected it: the whole issue loop runs in that thread)
+template <uint32_t IDESC>
+__device__ __forceinline__ void mma_ts1(uint32_t tmem_d, uint32_t tmem_a, uint32_t db_lo, uint32_t db_hi, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tmov.b64 db, {%2, %6};\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], db, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "r"(db_lo), "r"(IDESC),
+        "r"(accumulate), "r"(0u), "r"(db_hi)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit1(uint64_t* b) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(b)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t x;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(x));
+    return x != 0u;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* b) {
     asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(
                      (uint32_t)__cvta_generic_to_shared(b))

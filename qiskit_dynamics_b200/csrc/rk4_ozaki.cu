@@ -348,6 +348,8 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
             for (int s = 0; s < SETS; ++s)
 #pragma unroll
                 for (int b = 0; b < NACC; ++b) pe[s][b] = 1u;
+            // ONE elected thread runs the whole issue loop (waits, MMAs, commits): no election and predicate shuffling per MMA
+            if (elect_one())
 #pragma unroll 1
             for (int sidx = 0; sidx < total; ++sidx) {
                 const int entry = stage_entry(sidx);
@@ -382,12 +384,12 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
                             for (int ks = 0; ks < NKS; ++ks) {  // k chunks past n hold zeros
                                 const uint32_t b1 = bd_lo + (uint32_t)(((set * NS + q - 1) * BI::SLICE + BI::RE_IM + ks * 4 * (int)LBO) >> 4);  // (re | im)
                                 const uint32_t b2 = bd_lo + (uint32_t)(((set * NS + q - 1) * BI::SLICE + ks * 4 * (int)LBO) >> 4);               // (-im | re)
-                                mma_ts<idesc_for(2 * CS)>(d, a_re + 8 * ks, b1, bd_hi, (p == 1 && ks == 0) ? 0u : 1u);
-                                mma_ts<idesc_for(2 * CS)>(d, a_im + 8 * ks, b2, bd_hi, 1u);
+                                mma_ts1<idesc_for(2 * CS)>(d, a_re + 8 * ks, b1, bd_hi, (p == 1 && ks == 0) ? 0u : 1u);
+                                mma_ts1<idesc_for(2 * CS)>(d, a_im + 8 * ks, b2, bd_hi, 1u);
                             }
                         }
-                        umma_commit(full + b);
-                        if (release && set == SETS - 1) umma_commit(p_free + (g - 2));  // slice plane g - 1 is read by no later group
+                        umma_commit1(full + b);
+                        if (release && set == SETS - 1) umma_commit1(p_free + (g - 2));  // slice plane g - 1 is read by no later group
                     }
                     if (set == 0) OZ_DBG(3);
                 }

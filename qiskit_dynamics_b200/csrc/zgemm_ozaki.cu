@@ -387,6 +387,8 @@ zgemm_ozaki_kernel(int M, int N, int KC, const int8_t* __restrict__ aplanes, con
         unsigned pe[NACC];
 #pragma unroll
         for (int b = 0; b < NACC; ++b) pe[b] = 1u;
+        // ONE elected thread runs the whole issue loop (waits, MMAs, commits): no election and predicate shuffling per MMA
+        if (elect_one())
 #pragma unroll 1
         for (int kc = 0; kc < KC; ++kc) {
             const int buf = kc & 1;
@@ -411,14 +413,14 @@ zgemm_ozaki_kernel(int M, int N, int KC, const int8_t* __restrict__ aplanes, con
                     for (int ks = 0; ks < KD / 32; ++ks) {
                         const uint32_t b1 = bd_lo + (uint32_t)(((q - 1) * BSL + BI::RE_IM + ks * 4 * (int)LBO) >> 4);  // (re | im): cores 2..5
                         const uint32_t b2 = bd_lo + (uint32_t)(((q - 1) * BSL + ks * 4 * (int)LBO) >> 4);        // (-im | re): cores 0..3
-                        mma_ts<idesc_for(2 * TN)>(d, a_re + 8 * ks, b1, bd_hi, (p == 1 && ks == 0) ? 0u : 1u);
-                        mma_ts<idesc_for(2 * TN)>(d, a_im + 8 * ks, b2, bd_hi, 1u);
+                        mma_ts1<idesc_for(2 * TN)>(d, a_re + 8 * ks, b1, bd_hi, (p == 1 && ks == 0) ? 0u : 1u);
+                        mma_ts1<idesc_for(2 * TN)>(d, a_im + 8 * ks, b2, bd_hi, 1u);
                     }
                 }
-                umma_commit(full + b);
-                if (release) umma_commit(p_free + (g - 2));
+                umma_commit1(full + b);
+                if (release) umma_commit1(p_free + (g - 2));
             }
-            umma_commit(b_free + buf);
+            umma_commit1(b_free + buf);
         }
     }
 
