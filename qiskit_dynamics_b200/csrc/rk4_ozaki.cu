@@ -307,6 +307,12 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
             for (int e = 0; e <= last_entry; ++e) {
                 const int8_t* src = planes + (size_t)e * 2 * NS * KD * KD + (size_t)row * 16;  // chunk i of the row: + i KD 16
                 const unsigned par = (unsigned)(e - 1) & 1u;
+                // the table is far larger than L2 in a real solve (1000 steps: 330 MB of planes): the CTAs share out an L2
+                // prefetch of the entry after the next (1280 lines of 128 B), so that every reload finds its planes in L2
+                if (e + 2 <= last_entry) {
+                    const int line = (int)blockIdx.x + (int)gridDim.x * ((warp - MMA_WARP - 1) * 32 + lane);
+                    if (line < 2 * NS * KD) asm volatile("prefetch.global.L2 [%0];" ::"l"(planes + (size_t)(e + 2) * 2 * NS * KD * KD + (size_t)line * 128));
+                }
                 uint4 w[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) w[i] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(NS - 1) * KD * KD) + i * KD);
