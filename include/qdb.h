@@ -103,8 +103,8 @@ int qdb_frame_apply_c128(int n, int B, const double* mu, double t, int conj_phas
  * scipy.linalg.expm (solvers/fixed_step_solvers.py:22,104).
  * Products that fill half the SMs with 128 x 32 tiles and have Kd >= 384 run on the int8 tensor cores (tcgen05.mma
  * kind::i8: six signed byte slices per operand against a power-of-two scale per row of A and per column of Bm, exact int32
- * slice products, normwise error 2^-48 per operand -- measured 9e-14 against cuBLAS ZGEMM; 1.8x its speed at
- * 729 x 4096 x 729); smaller ones on the fp64 DMMA kernels.  Environment: QDB_ZGEMM_INT8=0 keeps every product on the
+ * slice products, normwise error 2^-48 per operand -- measured 9e-14 against cuBLAS ZGEMM; 1.95x its speed at
+ * 729 x 4096 x 729, Kd <= 4096); smaller ones on the fp64 DMMA kernels.  Environment: QDB_ZGEMM_INT8=0 keeps every product on the
  * DMMA kernels, QDB_ZGEMM_SLICES=5 trades accuracy (2^-40) for ~10 % speed.  The emulated path takes its scratch
  * from the device's stream-ordered memory pool (cudaMallocAsync on `stream`). */
 int qdb_zgemm_c128(int M, int N, int Kd,

@@ -247,11 +247,14 @@ zgemm_ozaki_kernel(int M, int N, int KC, const int8_t* __restrict__ aplanes, con
         const int row = 32 * qd + lane;
         const uint32_t lane_base = ((uint32_t)(32 * qd) << 16);
         unsigned pf[NACC] = {};
-        // sums over the groups and the k chunks in fp64: every int32 group sum converts exactly, each addition rounds at 2^-53 of
-        // the running sum -- far below the 2^(-8 NS) truncation of the operands (and no int64 range to watch over long k)
-        double sr[8], si[8];
+        // sums over the groups AND the k chunks in int64 (integer pipe; the conversions of a per-group fp64 sum throttled the
+        // fp64 pipe: 22 % of the stall samples).  Range: a chunk contributes < 2^(24 + 8 (NS - 1)); with six slices the sums are
+        // kept in units of 2^8 -- the least significant group is rounded to its upper 24 bits, an error of 2^-49 of the
+        // operand scales, below their 2^-48 truncation -- so that k <= 4096 stays below 2^60 for either slice count
+        constexpr int DROP = NS == 6 ? 8 : 0;
+        long long tr[8], ti[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sr[j] = si[j] = 0.0;
+        for (int j = 0; j < 8; ++j) tr[j] = ti[j] = 0;
 #pragma unroll 1
         for (int kc = 0; kc < KC; ++kc) {
 #pragma unroll
@@ -268,8 +271,13 @@ zgemm_ozaki_kernel(int M, int N, int KC, const int8_t* __restrict__ aplanes, con
                 if (lane == 0) mbar_arrive(empty + b);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    sr[j] = fma((double)vr[j], pow2(sh), sr[j]);
-                    si[j] = fma((double)vi[j], pow2(sh), si[j]);
+                    if (sh >= DROP) {
+                        tr[j] += (long long)vr[j] << (sh >= DROP ? sh - DROP : 0);
+                        ti[j] += (long long)vi[j] << (sh >= DROP ? sh - DROP : 0);
+                    } else {  // round to nearest, ties up
+                        tr[j] += (long long)((vr[j] + (1 << (DROP - 1))) >> DROP);
+                        ti[j] += (long long)((vi[j] + (1 << (DROP - 1))) >> DROP);
+                    }
                 }
             }
         }
@@ -282,8 +290,8 @@ zgemm_ozaki_kernel(int M, int N, int KC, const int8_t* __restrict__ aplanes, con
             for (int j = 0; j < 8; ++j) {
                 const int c = ct * TN + 8 * oc + j;
                 if (c < N) {
-                    const double s = pow2(ea + expoB[c] - 8 * (NS + 1));
-                    double2 v = make_double2(sr[j] * s, si[j] * s);
+                    const double s = pow2(ea + expoB[c] - 8 * (NS + 1) + DROP);
+                    double2 v = make_double2((double)tr[j] * s, (double)ti[j] * s);
                     if (epi.yout) {
                         const size_t i = (size_t)r * epi.ldc + c;
                         const double2 yb = epi.ybase[i];
@@ -484,7 +492,7 @@ bool zgemm_int8_preferred(int M, int N, int Kd) {
     const char* env = getenv("QDB_ZGEMM_INT8");  // read per call: the tests switch it
     const int mode = env ? atoi(env) : 1;
     if (mode == 0) return false;
-    if (Kd > 1 << 20) return false;  // grid.y of the slicing kernel
+    if (Kd > 4096) return false;  // the int64 sums over the k chunks stay below 2^60
     if (mode == 2) return Kd >= 1 && M >= 1 && N >= 1;
     const long tiles = (long)((M + KD - 1) / KD) * ((N + TN - 1) / TN);
     return Kd >= 384 && tiles >= sm_count() / 2;
