@@ -251,7 +251,7 @@ zgemm_ozaki_kernel(int M, int N, int KC, const int8_t* __restrict__ aplanes, con
         // fp64 pipe: 22 % of the stall samples).  Range: a chunk contributes < 2^(24 + 8 (NS - 1)); with six slices the sums are
         // kept in units of 2^8 -- the least significant group is rounded to its upper 24 bits, an error of 2^-49 of the
         // operand scales, below their 2^-48 truncation -- so that k <= 4096 stays below 2^60 for either slice count
-        constexpr int DROP = NS == 6 ? 8 : 0;
+        constexpr int DROP = NS == 6 ? 8 : 0, HALF = NS == 6 ? 128 : 0;
         long long tr[8], ti[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) tr[j] = ti[j] = 0;
@@ -275,8 +275,8 @@ zgemm_ozaki_kernel(int M, int N, int KC, const int8_t* __restrict__ aplanes, con
                         tr[j] += (long long)vr[j] << (sh >= DROP ? sh - DROP : 0);
                         ti[j] += (long long)vi[j] << (sh >= DROP ? sh - DROP : 0);
                     } else {  // round to nearest, ties up
-                        tr[j] += (long long)((vr[j] + (1 << (DROP - 1))) >> DROP);
-                        ti[j] += (long long)((vi[j] + (1 << (DROP - 1))) >> DROP);
+                        tr[j] += (long long)((vr[j] + HALF) >> DROP);
+                        ti[j] += (long long)((vi[j] + HALF) >> DROP);
                     }
                 }
             }
