@@ -360,6 +360,10 @@ zgemm_ozaki_kernel(int M, int N, int KC, const int8_t* __restrict__ aplanes, con
                 uint4 w[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) w[i] = src[i * KD];
+                // the slot goes back to the TMA producer only when the loads have LANDED: an arrive does not wait for loads
+                // in flight (the empty asm statements consume the registers, i.e. wait on their scoreboard)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) asm volatile("" ::"r"(w[i].x), "r"(w[i].y), "r"(w[i].z), "r"(w[i].w) : "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(as_free + slot);  // the plane is in registers
                 if (kc > 0 && part == 0) {
