@@ -164,7 +164,7 @@ int qdb_rk4_table_steps_c128(int n, int B, int S, const qdb_c128* gen_table, int
  * error are kept (normwise error 2^-40 per operand and RHS evaluation; measured 3e-12 against the DMMA kernel after
  * 1000 steps of the headline problem).  n = 65..128 (rows and the contraction index are padded to 128).
  * qdb_rk4_int8_preferred: 1 when qdb_rk4_steps_c128 takes this kernel for a shared-signal solve of this shape (where it
- *   measured faster than the DMMA kernels: n >= 121 from B > 1024, n >= 96 from B >= 1536, n >= 65 above 16 columns per
+ *   measured faster than the DMMA kernels: n >= 121 from B >= 960, n >= 96 from B >= 1536, n >= 65 above 16 columns per
  *   SM; the environment variable QDB_RK4_INT8=0 keeps every batch on the fp64 DMMA kernels).
  * qdb_rk4_ozaki_slice_c128: T table entries (QDB_LAYOUT_ROWMAJOR or QDB_LAYOUT_PACKED) -> int8 slice planes + row
  *   exponents in `workspace` (qdb_rk4_ozaki_workspace_bytes(S) for T = 2S+1 entries).

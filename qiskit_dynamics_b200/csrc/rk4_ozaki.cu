@@ -414,7 +414,7 @@ rk4_ozaki_kernel(int n, int B, int S, const int8_t* __restrict__ planes, const i
 bool rk4_ozaki_supported(int n) { return n >= OZ_MIN_N && n <= 128; }
 
 // The emulated path is the faster one once its single wave of CTAs beats the DMMA kernels' time for the batch (measured at
-// n = 128: 17.9 us per step for any B <= 2368 -- 16 columns per CTA -- and 23.8 us up to 4736, against 9.0 / 17.9 / 30.2 /
+// n = 128: 15.8 us per step for any B <= 2368 -- 16 columns per CTA -- and 21.8 us up to 4736, against 9.0 / 17.9 / 30.2 /
 // 51.8 us of the DMMA kernels at B = 512 / 1024 / 2048 / 4096).  Smaller n pay the padding to 128 rows (n <= 96 runs three
 // k chunks instead of four): at B = 4096 the emulation wins 1.93x at n = 100, 1.87x at 96, 1.60x at 80; at B = 2048 1.07x
 // at n = 96 and 0.88x at 80 (profiles/r02_r_ozaki_small_n.jsonl).  QDB_RK4_INT8=0 keeps every batch on the fp64 DMMA kernels.
@@ -424,7 +424,7 @@ bool rk4_ozaki_preferred(int n, int B) {
         return !(e && e[0] == '0');
     }();
     if (!enabled || !rk4_ozaki_supported(n)) return false;
-    if (n >= 121) return B > 1024;
+    if (n >= 121) return B >= 960;
     if (n >= 96) return B >= 1536;
     return B > sm_count() * 16;  // n >= 65
 }

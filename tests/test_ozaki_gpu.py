@@ -118,7 +118,7 @@ def test_unsupported_dimension_is_an_error(abi):
 
 @pytest.mark.parametrize("n,B,frame", [(128, 2048, "full"), (123, 1600, "diag"), (128, 4096, "none"), (100, 1600, "full"), (81, 2400, "diag")])
 def test_solver_route_takes_the_int8_path_and_matches_the_oracle(abi, n, B, frame):
-    """qdb_rk4_steps_c128 with shared signals picks the emulated kernel for B > 1024 at n = 121..128 (generator + slicing +
+    """qdb_rk4_steps_c128 with shared signals picks the emulated kernel for B >= 960 at n = 121..128 (generator + slicing +
     stepper = 3 launches for one chunk; the fp64 route is 2); final states against the NumPy oracle on 32 columns.
     Tolerance 1e-10 (the judge's bar; measured ~1e-13 at these step counts)."""
     K, S, t0, h = 4, 20, 0.1, 1e-3
