@@ -55,7 +55,7 @@ def col_err(a, b):
 
 
 @pytest.mark.parametrize("n,B,S", [(128, 4096, 6), (128, 32, 5), (121, 1, 4), (125, 33, 5), (127, 1000, 3), (124, 4100, 3),
-                                    (128, 4737, 2),
+                                    (128, 4737, 2), (128, 2048, 1), (126, 960, 1),
                                     # smaller systems, padded to 128 rows; n <= 96 skips the last k chunk, n = 65 is the smallest
                                     (100, 2500, 3), (96, 2400, 3), (97, 40, 3), (80, 3000, 2), (65, 17, 4)])
 def test_int8_emulation_matches_the_fp64_kernel(abi, n, B, S):
