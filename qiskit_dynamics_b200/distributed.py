@@ -115,7 +115,9 @@ def solver_solve_sharded(solver, t_span, y0, signals: List, measurement=None, ga
     if not gather:
         return local_results, None
     if local_results:
-        finals = torch.stack([r.y[-1] for r in local_results], dim=-1)  # (n, n_local)
+        finals = getattr(local_results, "final_states", None)  # a batched sweep hands over its (n, n_local) final states
+        if finals is None:
+            finals = torch.stack([r.y[-1] for r in local_results], dim=-1)  # (n, n_local)
         t_final = float(local_results[0].t[-1])
         table = measurement.probabilities(t_final, finals) if measurement is not None else finals
     else:

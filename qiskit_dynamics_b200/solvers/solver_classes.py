@@ -28,6 +28,21 @@ from .solver_functions import (ODE_METHODS, is_lindblad_model_not_vectorized, is
                                results_y_out_of_frame_basis, setup_generator_model_rhs_y0_in_frame_basis, solve_lmde)
 
 
+class SweepResults(list):
+    """The list of ``OdeResult`` a batched solve returns (one per simulation, as the reference's list route does), carrying
+    ``final_states``: the last time point of every simulation as ONE ``(n, nsim)`` device tensor -- what a sharded sweep
+    measures and gathers, without re-stacking tens of thousands of per-simulation views."""
+
+    final_states: Optional[torch.Tensor] = None
+
+
+def _per_simulation_results(t, per_sim: torch.Tensor, final_states: Optional[torch.Tensor] = None) -> "SweepResults":
+    """per_sim: (nsim, T, ...) contiguous; one OdeResult per simulation (views, made by ONE unbind)."""
+    out = SweepResults(OdeResult(t=t, y=v) for v in per_sim.unbind(0))
+    out.final_states = final_states
+    return out
+
+
 class Solver:
     def __init__(self, static_hamiltonian=None, hamiltonian_operators=None, static_dissipators=None,
                  dissipator_operators=None, hamiltonian_channels=None, dissipator_channels=None,
@@ -132,12 +147,12 @@ class Solver:
                 per_sim = res.y.reshape(res.y.shape[0], res.y.shape[1], nsim, m).permute(2, 0, 1, 3).contiguous()
                 if len(shape) == 1:
                     per_sim = per_sim[..., 0]
-                return [OdeResult(t=res.t, y=per_sim[b]) for b in range(nsim)]
+                return _per_simulation_results(res.t, per_sim, res.y[-1] if len(shape) == 1 else None)
             if is_lindblad_model_not_vectorized(model) and len(shape) == 2 and method in ODE_METHODS:
                 self._set_new_signals(signals_list[0])
                 res = solve_lmde(generator=model, t_span=spans[0], y0=torch.stack(y0s, dim=0).contiguous(), **kwargs)
                 per_sim = res.y.transpose(0, 1).contiguous()  # (nsim, T, n, n)
-                return [OdeResult(t=res.t, y=per_sim[b]) for b in range(nsim)]
+                return _per_simulation_results(res.t, per_sim)
             return None
 
         # ---- per-simulation signals: sweep mode (RK4) ----
@@ -208,7 +223,7 @@ class Solver:
             per_sim = res.y.reshape(res.y.shape[0], res.y.shape[1], nsim, mcols).permute(2, 0, 1, 3).contiguous()
         else:
             per_sim = res.y.permute(2, 0, 1).contiguous()  # one transpose; per_sim[b] is the contiguous (T, n) result of simulation b
-        return [OdeResult(t=res.t, y=per_sim[b]) for b in range(nsim)]
+        return _per_simulation_results(res.t, per_sim, res.y[-1] if len(shape) == 1 else None)
 
 
 # ---------------------------------------------------------------------------------------------
