@@ -19,7 +19,7 @@ y0 = np.zeros(81, dtype=complex); y0[0] = 1.0
 tf = nsamp * W.CFG5_DT
 def run():
     out = solver.solve(t_span=[0, tf], y0=y0, signals=lists, method="RK4", max_dt=W.CFG5_DT)
-    finals = torch.stack([r.y[-1] for r in out], dim=-1)
+    finals = out.final_states
     P = meas.probabilities(tf, finals)
     torch.cuda.synchronize()
     return P

@@ -15,6 +15,8 @@ from __future__ import annotations
 
 from typing import List, Optional, Tuple, Union
 
+from itertools import chain as _chain
+
 import numpy as np
 import torch
 from scipy.integrate._ivp.ivp import OdeResult
@@ -173,9 +175,14 @@ class Solver:
         # are (length-checked here), without a SignalList -- one DiscreteSignalSum per channel -- per simulation.
         program, sig_lists = None, None
         K = model._collection().num_operators
-        if isinstance(model, HamiltonianModel) and all(
-                isinstance(sl, list) and len(sl) == K and all(isinstance(x, Signal) and not isinstance(x, SignalSum) for x in sl)
-                for sl in signals_list):
+        def plain_signal_lists():
+            # every simulation a plain list of K elementary signals (C-level passes: tens of thousands of simulations)
+            if set(map(type, signals_list)) != {list} or set(map(len, signals_list)) != {K}:
+                return False
+            kinds = set(map(type, _chain.from_iterable(signals_list)))
+            return all(issubclass(k, Signal) and not issubclass(k, SignalSum) for k in kinds)
+
+        if isinstance(model, HamiltonianModel) and plain_signal_lists():
             program = compile_signal_program(signals_list)
             if program is not None:
                 self._set_new_signals(signals_list[0])
