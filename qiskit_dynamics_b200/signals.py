@@ -498,8 +498,9 @@ def _compile_discrete_lists(lists) -> Optional[SignalProgram]:
                     row[offs[j]:offs[j] + pad.shape[0]] = pad
     except (TypeError, ValueError):  # array-valued or complex carrier / phase, object samples: the general route decides
         return None
-    shared_params = bool(np.all(params == params[:1]))
-    shared_samples = bool(np.all(samples == samples[:1]))
+    # (a sweep almost always differs already in its second simulation: look there before comparing everything)
+    shared_params = B == 1 or (bool(np.array_equal(params[1], params[0])) and bool(np.all(params == params[:1])))
+    shared_samples = B == 1 or (bool(np.array_equal(samples[1], samples[0])) and bool(np.all(samples == samples[:1])))
     pick = (lambda k: params[0, :, k].copy()) if shared_params else (lambda k: np.ascontiguousarray(params[:, :, k].T))
     return SignalProgram(K, B, np.arange(K, dtype=np.int32), np.asarray(lens, dtype=np.int32), offs[:-1].copy(),
                          pick(0), pick(1), pick(2), pick(3), samples[0].copy() if shared_samples else samples)
