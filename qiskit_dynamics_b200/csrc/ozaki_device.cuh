@@ -83,8 +83,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// 2^e as a double (|e| < 1000)
-__device__ __forceinline__ double pow2(int e) { return __longlong_as_double((long long)(1023 + e) << 52); }
+// 2^e as a double
+__device__ __forceinline__ double pow2(int e) {
+    e = max(-1022, min(1023, e));  // products of scales beyond the double range saturate instead of wrapping the exponent field
+    return __longlong_as_double((long long)(1023 + e) << 52);
+}
 
 // Slice exponent from the HIGH WORD of max |x| (sign cleared): e with |x| 2^-e < 1/2 - 2^-8 for every |x| <= that maximum,
 // so that the leading digit of X + bias (below) fits a signed byte; zero / denormal -> 0
